@@ -1,0 +1,74 @@
+// common.cuh -- shared device helpers for libb200llama (sm_100a only).
+//
+// Numerics contract: every kernel reproduces the float evaluation order of the reference's
+// CPU path (see DESIGN.md "Exactness").  The translation unit is compiled with -fmad=false
+// and, belt and braces, all order-sensitive arithmetic uses the __f*_rn intrinsics, which
+// the compiler never contracts or reassociates.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define B200_WARP 32
+
+// Device-resident step descriptor read by every kernel of the captured decode graph, so one
+// graph serves every (token, position) and on-device greedy loops need no host round trip.
+struct StepState {
+    int token;    // token consumed by this step
+    int pos;      // sequence position of this step
+    int step;     // index into seq_tokens / out_ids
+    int n_seq;    // number of valid entries in seq_tokens
+    int feedback; // !=0: next token = this step's argmax (greedy generation)
+    int pad[3];
+};
+
+__device__ __forceinline__ float warp_max_f(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Activation quantisation of one 32-element block held one element per lane.
+// Restates Q8_0FloatTensor.dotQ8Activation's per-block quantiser (Q8_0FloatTensor.java:100-117):
+// amax -> qs = amax/127f -> aScale = f16 round trip of qs -> aInv = qs != 0 ? 1/qs : 0 ->
+// aq = (int)(x*aInv + copySign(0.5f, .)).
+__device__ __forceinline__ int quant_block_lane(float v, float &ascale) {
+    float amax = warp_max_f(fabsf(v));
+    float qs = __fdiv_rn(amax, 127.0f);
+    ascale = __half2float(__float2half_rn(qs));
+    float ainv = qs != 0.0f ? __fdiv_rn(1.0f, qs) : 0.0f;
+    float s = __fmul_rn(v, ainv);
+    return __float2int_rz(__fadd_rn(s, copysignf(0.5f, s)));
+}
+
+// 256-bit read-only streaming load (LDG.E.256 on sm_100a): one whole Q8_0 quant block per lane.
+__device__ __forceinline__ void ldg256_stream(const void *p, int (&r)[8]) {
+    asm("ld.global.nc.L1::no_allocate.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+        : "l"(p));
+}
+
+__device__ __forceinline__ int4 ldg128_stream(const void *p) {
+    int4 r;
+    asm("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+// FP16FloatTensor.vectorDot's bit trick (FP16FloatTensor.java:88-98): denormals-are-zero,
+// no inf/nan handling.  Used for FP16 weight matrices only; embedding lookups use IEEE.
+__device__ __forceinline__ float f16_bits_to_f32_daz(unsigned h) {
+    unsigned mask = (h & 0x7C00u) ? 0xFFFFFFFFu : 0u;
+    unsigned bits = ((h & 0x8000u) << 16) | ((((h & 0x7FFFu) + 0x1C000u) << 13) & mask);
+    return __uint_as_float(bits);
+}
+
+// Weight matrix as stored on the device.
+//   Q8_0: qs = int8 [rows][cols] row-major, sc = f16 scale [rows][cols/32]
+//         (GGUF's 34-byte blocks split at upload so the quants are 32-byte aligned: same
+//          1.0625 B/element, one LDG.256 per block).
+//   F16 : qs = f16 [rows][cols], sc unused.  F32: qs = float.
+struct DevMat {
+    const void *qs;
+    const __half *sc;
+    int rows, cols, type;
+};

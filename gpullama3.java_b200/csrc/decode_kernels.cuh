@@ -1,0 +1,491 @@
+// decode_kernels.cuh -- single-token decode kernels (Q8_0 and FP16 weights), bit-exact with the
+// reference's CPU path.  One CUDA graph strings them together per token (plan.cu).
+//
+// Replaces (reference kernel inventory):
+//   k_rmsnorm_quant  <- reductionOneBlockWithLayer + reductionOneBlock2WithLayer / mapContextWithQuantize
+//                       (TransformerComputeKernelsLayered.java:387-454) + convertQ8_0toFP32 embedding
+//   k_matvec_q8      <- fusedQKVMatmulQ8 / matrixVectorGenericWithResidualQ8_0Byte / matrixVectorGenericQ8Byte
+//                       (TransformerComputeKernelsLayered.java:3038-3223, 2888-2906, 2773-2787)
+//   k_gateup_q8      <- fullyFusedRmsNormFFNGateUpQ8 (:3386-3549)
+//   k_rope_kv        <- ropeRotationWithCacheCopy (:495-542), Qwen3 fusedQKRmsNorm + NeoX rope (Qwen3Kernels.java:302-361,973-1064)
+//   k_attention      <- processHeadsFlashAttention (:784-906)
+//   k_argmax_advance <- argmaxLogits (TransformerComputeKernels.java:25-56), with CPU tie-break semantics
+// but the arithmetic they implement is the CPU path's (InferenceCore.java:50-172, 565-697).
+#pragma once
+#include "common.cuh"
+
+enum { MODE_STORE = 0, MODE_RESID = 1 };
+
+// ------------------------------------------------------------------------------------------
+// Embedding row lookup: FloatTensor.copyTo -> getFloat per element (InferenceCore.java:61).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float emb_get(const DevMat &e, int token, int i) {
+    size_t idx = (size_t)token * e.cols + i;
+    if (e.type == 8) { // Q8_0FloatTensor.getFloat: quant * scale (Q8_0FloatTensor.java:55-63)
+        float q = (float)((const int8_t *)e.qs)[idx];
+        return __fmul_rn(q, __half2float(e.sc[idx >> 5]));
+    } else if (e.type == 1) { // FP16FloatTensor.getFloat: Float.float16ToFloat (IEEE, subnormals kept)
+        return __half2float(((const __half *)e.qs)[idx]);
+    }
+    return ((const float *)e.qs)[idx];
+}
+
+// ------------------------------------------------------------------------------------------
+// RMSNorm (+ optional embedding gather, + Q8_0 activation quantisation).
+// InferenceCore.rmsnorm (InferenceCore.java:39-48): ss = sequential float sum of x*x;
+// ss = ss/size + eps; ss = (float)(1.0/Math.sqrt(ss)); out = w * (ss * x).
+// The sum is order-sensitive, so one thread walks it (squares precomputed in parallel).
+// One CTA.  Outputs: xq/xs (Q8_0 activation for the following matvec) and/or xb (float).
+// ------------------------------------------------------------------------------------------
+template <bool EMBED>
+__global__ void __launch_bounds__(1024) k_rmsnorm_quant(float *__restrict__ x, const StepState *__restrict__ st,
+                                                       DevMat emb, const float *__restrict__ w, float eps, int dim,
+                                                       int8_t *__restrict__ xq, float *__restrict__ xs,
+                                                       float *__restrict__ xb) {
+    extern __shared__ __align__(16) float sm[];
+    float *sx = sm, *sq = sm + dim;
+    __shared__ float s_ss;
+    const int tid = threadIdx.x;
+    int token = 0;
+    if (EMBED) token = st->token;
+    for (int i = tid; i < dim; i += blockDim.x) {
+        float v;
+        if (EMBED) { v = emb_get(emb, token, i); x[i] = v; }
+        else v = x[i];
+        sx[i] = v;
+        sq[i] = __fmul_rn(v, v);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float ss = 0.0f;
+        for (int i = 0; i < dim; i += 4) {
+            float4 t = *reinterpret_cast<const float4 *>(sq + i);
+            ss = __fadd_rn(ss, t.x); ss = __fadd_rn(ss, t.y); ss = __fadd_rn(ss, t.z); ss = __fadd_rn(ss, t.w);
+        }
+        ss = __fdiv_rn(ss, (float)dim);
+        ss = __fadd_rn(ss, eps);
+        s_ss = (float)(1.0 / sqrt((double)ss));
+    }
+    __syncthreads();
+    const float ss = s_ss;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    for (int b = warp; b < dim / 32; b += nwarps) {
+        int i = b * 32 + lane;
+        float v = __fmul_rn(w[i], __fmul_rn(ss, sx[i]));
+        if (xb) xb[i] = v;
+        if (xq) {
+            float as;
+            int q = quant_block_lane(v, as);
+            xq[i] = (int8_t)q;
+            if (lane == 0) xs[b] = as;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Q8_0 dequant-matvec, bit-exact with Q8_0FloatTensor.dotQ8Activation (Q8_0FloatTensor.java:90-123):
+//   per 32-block b:  isum_b = sum aq*wq (int32, exact);  term_b = (float)isum_b * (wScale_b * aScale_b)
+//   result = ((term_0 + term_1) + term_2) + ...      strictly in block order.
+// The activation quantisation is row-independent, so it arrives pre-quantised (xq, xs).
+// Mapping: a warp owns R rows; lane l owns blocks l, l+32, ... of each row (one LDG.256 per block,
+// the warp reads 1 KB contiguous per instruction); block terms go to shared memory and lanes
+// 0..R-1 then walk their row's terms in order.
+// ------------------------------------------------------------------------------------------
+template <int R>
+__device__ __forceinline__ void q8_row_terms(const int8_t *__restrict__ qs, const __half *__restrict__ sc, size_t row0,
+                                             int cols, int nb, const int4 *__restrict__ sxq, const float *__restrict__ sxs,
+                                             float *__restrict__ terms, int nbp, int lane) {
+    constexpr int JB = R >= 4 ? 2 : 4; // 64 registers of weights in flight per lane
+    for (int b0 = 0; b0 < nb; b0 += 32 * JB) {
+        int wv[R][JB][8];
+        __half sv[R][JB];
+#pragma unroll
+        for (int r = 0; r < R; r++)
+#pragma unroll
+            for (int j = 0; j < JB; j++) {
+                int b = b0 + j * 32 + lane;
+                if (b < nb) {
+                    ldg256_stream(qs + (row0 + r) * (size_t)cols + (size_t)b * 32, wv[r][j]);
+                    sv[r][j] = sc[(row0 + r) * (size_t)nb + b];
+                }
+            }
+#pragma unroll
+        for (int j = 0; j < JB; j++) {
+            int b = b0 + j * 32 + lane;
+            if (b < nb) {
+                int4 a0 = sxq[b], a1 = sxq[nb + b];
+                float as = sxs[b];
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    int isum = __dp4a(wv[r][j][0], a0.x, 0);
+                    isum = __dp4a(wv[r][j][1], a0.y, isum);
+                    isum = __dp4a(wv[r][j][2], a0.z, isum);
+                    isum = __dp4a(wv[r][j][3], a0.w, isum);
+                    isum = __dp4a(wv[r][j][4], a1.x, isum);
+                    isum = __dp4a(wv[r][j][5], a1.y, isum);
+                    isum = __dp4a(wv[r][j][6], a1.z, isum);
+                    isum = __dp4a(wv[r][j][7], a1.w, isum);
+                    terms[r * nbp + b] = __fmul_rn((float)isum, __fmul_rn(__half2float(sv[r][j]), as));
+                }
+            }
+        }
+    }
+}
+
+// Stage the quantised activation in shared memory as two planes of 16-byte half-blocks
+// (plane p holds bytes [16p,16p+16) of every block) so that lanes reading consecutive
+// blocks hit consecutive 16-byte slots: conflict-free LDS.128.
+__device__ __forceinline__ void stage_activation(const int8_t *__restrict__ xq, const float *__restrict__ xs, int cols,
+                                                 int4 *sxq, float *sxs) {
+    const int nb = cols >> 5;
+    const int4 *src = reinterpret_cast<const int4 *>(xq);
+    for (int c = threadIdx.x; c < cols / 16; c += blockDim.x) sxq[(c & 1) * nb + (c >> 1)] = src[c];
+    for (int b = threadIdx.x; b < nb; b += blockDim.x) sxs[b] = xs[b];
+}
+
+__host__ __device__ inline size_t q8_smem_bytes(int cols, int rows_per_warp, int warps) {
+    int nb = cols / 32, nbp = nb | 1;
+    return (size_t)cols + (size_t)nb * 4 + (size_t)warps * rows_per_warp * nbp * 4 + 64;
+}
+
+template <int R, int MODE>
+__global__ void __launch_bounds__(256) k_matvec_q8(const int8_t *__restrict__ qs, const __half *__restrict__ sc,
+                                                   const int8_t *__restrict__ xq, const float *__restrict__ xs, int rows,
+                                                   int cols, float *__restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const int nb = cols >> 5, nbp = nb | 1;
+    int4 *sxq = reinterpret_cast<int4 *>(smraw);
+    float *sxs = reinterpret_cast<float *>(smraw + cols);
+    float *terms_all = sxs + nb;
+    stage_activation(xq, xs, cols, sxq, sxs);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *terms = terms_all + (size_t)warp * R * nbp;
+    const int nwarps_total = gridDim.x * (blockDim.x >> 5);
+    for (size_t row0 = (size_t)(blockIdx.x * (blockDim.x >> 5) + warp) * R; row0 < (size_t)rows; row0 += (size_t)nwarps_total * R) {
+        q8_row_terms<R>(qs, sc, row0, cols, nb, sxq, sxs, terms, nbp, lane);
+        __syncwarp();
+        if (lane < R) {
+            const float *t = terms + lane * nbp;
+            float acc = 0.0f;
+            for (int b = 0; b < nb; b++) acc = __fadd_rn(acc, t[b]);
+            size_t row = row0 + lane;
+            if (MODE == MODE_RESID) out[row] = __fadd_rn(out[row], acc); // x[i] = x[i] + xb2[i]  (InferenceCore.java:143,164)
+            else out[row] = acc;
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused gate/up projection + SwiGLU + Q8_0 quantisation of the result (the activation of the
+// down projection).  InferenceCore.java:150-158: hb = hb / (float)(1.0 + Math.exp(-hb)); hb *= hb2.
+// One CTA (8 warps) = one 32-element block of hb, so the CTA can quantise it in its epilogue.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float swiglu(float g, float u) {
+    float s = __fdiv_rn(g, (float)(1.0 + exp((double)(-g))));
+    return __fmul_rn(s, u);
+}
+
+__global__ void __launch_bounds__(256) k_gateup_q8(const int8_t *__restrict__ qs1, const __half *__restrict__ sc1,
+                                                   const int8_t *__restrict__ qs3, const __half *__restrict__ sc3,
+                                                   const int8_t *__restrict__ xq, const float *__restrict__ xs, int hidden,
+                                                   int cols, int8_t *__restrict__ hq, float *__restrict__ hs,
+                                                   float *__restrict__ hb_dbg) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    __shared__ float hvals[32];
+    const int nb = cols >> 5, nbp = nb | 1;
+    int4 *sxq = reinterpret_cast<int4 *>(smraw);
+    float *sxs = reinterpret_cast<float *>(smraw + cols);
+    float *terms_all = sxs + nb;
+    stage_activation(xq, xs, cols, sxq, sxs);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *terms = terms_all + (size_t)warp * 4 * nbp; // 2 hidden units x {gate, up}
+    for (int blk = blockIdx.x; blk < hidden / 32; blk += gridDim.x) {
+#pragma unroll 1
+        for (int half = 0; half < 2; half++) {
+            int u0 = blk * 32 + warp * 4 + half * 2; // this warp: hidden units u0, u0+1
+            q8_row_terms<2>(qs1, sc1, (size_t)u0, cols, nb, sxq, sxs, terms, nbp, lane);
+            q8_row_terms<2>(qs3, sc3, (size_t)u0, cols, nb, sxq, sxs, terms + 2 * nbp, nbp, lane);
+            __syncwarp();
+            float acc = 0.0f;
+            if (lane < 4) {
+                const float *t = terms + lane * nbp;
+                for (int b = 0; b < nb; b++) acc = __fadd_rn(acc, t[b]);
+            }
+            float up = __shfl_down_sync(0xffffffffu, acc, 2); // lanes 0,1 = gate(u0,u0+1); lanes 2,3 = up
+            if (lane < 2) hvals[warp * 4 + half * 2 + lane] = swiglu(acc, up);
+            __syncwarp();
+        }
+        __syncthreads();
+        if (warp == 0) {
+            float v = hvals[lane];
+            if (hb_dbg) hb_dbg[blk * 32 + lane] = v;
+            float as;
+            int q = quant_block_lane(v, as);
+            hq[blk * 32 + lane] = (int8_t)q;
+            if (lane == 0) hs[blk] = as;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// FP16 dequant-matvec, bit-exact with FP16FloatTensor.vectorDot (FP16FloatTensor.java:62-110)
+// for an L-lane species: L independent strided FMA chains (fused, as FloatVector.fma), then
+// reduceLanes(ADD) in ascending lane order, then the IEEE scalar tail.
+// A warp owns 32/L rows at a time... see k_matvec_f16 below: thread (r, c) owns chain c of row r;
+// the warp stages 16-byte coalesced loads through shared memory so every thread reads its
+// stride-L elements from there.
+// ------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256) k_matvec_f16(const __half *__restrict__ w, const float *__restrict__ x, int rows,
+                                                    int cols, int lanes, float *__restrict__ out) {
+    // Each warp processes RW = 32/lanes rows at once; thread t of the warp: row r = t / lanes, chain c = t % lanes.
+    // Shared: activation x (cols floats) + per-warp weight tile RW x TC halves.
+    extern __shared__ __align__(16) unsigned char smraw[];
+    float *sx = reinterpret_cast<float *>(smraw);
+    constexpr int TC = 256; // columns per staged tile
+    __half *tiles = reinterpret_cast<__half *>(smraw + (size_t)cols * 4);
+    for (int i = threadIdx.x; i < cols; i += blockDim.x) sx[i] = x[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int L = lanes > 0 ? lanes : 1;
+    const int RW = 32 / L;
+    __half *tile = tiles + (size_t)warp * RW * TC;
+    const int r = lane / L, c = lane % L;
+    const int nwarps_total = gridDim.x * (blockDim.x >> 5);
+    const int upper = lanes > 0 ? cols - (cols % L) : 0;
+    for (size_t row0 = (size_t)(blockIdx.x * (blockDim.x >> 5) + warp) * RW; row0 < (size_t)rows; row0 += (size_t)nwarps_total * RW) {
+        float acc = 0.0f;
+        for (int c0 = 0; c0 < cols; c0 += TC) {
+            int tc = min(TC, cols - c0);
+            // coalesced stage: RW rows x tc halves, 8 halves (16 B) per lane per load
+            int chunks_per_row = tc >> 3;
+            for (int q = lane; q < RW * chunks_per_row; q += 32) {
+                int rr = q / chunks_per_row, cc = q % chunks_per_row;
+                size_t row = row0 + rr;
+                int4 v = make_int4(0, 0, 0, 0);
+                if (row < (size_t)rows) v = ldg128_stream(w + row * (size_t)cols + c0 + cc * 8);
+                *reinterpret_cast<int4 *>(tile + rr * TC + cc * 8) = v;
+            }
+            __syncwarp();
+            if (lanes > 0) {
+                int lim = min(tc, upper - c0);
+                for (int i = c; i < lim; i += L) {
+                    float wf = f16_bits_to_f32_daz(__half_as_ushort(tile[r * TC + i]));
+                    acc = fmaf(wf, sx[c0 + i], acc);
+                }
+            } else {
+                // llama.VectorBitSize=0: FloatTensor.scalarDot, sequential, IEEE conversion, unfused
+                for (int i = 0; i < tc; i++) acc = __fadd_rn(acc, __fmul_rn(__half2float(tile[r * TC + i]), sx[c0 + i]));
+            }
+            __syncwarp();
+        }
+        // reduceLanes(ADD), ascending lane order starting from the identity, then scalar tail
+        float result = acc;
+        if (lanes > 0) {
+            result = 0.0f;
+            for (int k = 0; k < L; k++) {
+                float a = __shfl_sync(0xffffffffu, acc, r * L + k);
+                result = __fadd_rn(result, a);
+            }
+            size_t row = row0 + r;
+            if (row < (size_t)rows)
+                for (int j = upper; j < cols; j++)
+                    result = __fadd_rn(result, __fmul_rn(__half2float(w[row * (size_t)cols + j]), sx[j]));
+        }
+        size_t row = row0 + r;
+        if (c == 0 && row < (size_t)rows) {
+            if (MODE == MODE_RESID) out[row] = __fadd_rn(out[row], result);
+            else out[row] = result;
+        }
+    }
+}
+
+// SwiGLU over separately computed gate/up vectors (FP16 path): hb = silu(hb) * hb2.
+__global__ void k_swiglu(float *__restrict__ hb, const float *__restrict__ hb2, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) hb[i] = swiglu(hb[i], hb2[i]);
+}
+
+// ------------------------------------------------------------------------------------------
+// RoPE + KV-cache write (+ Qwen3 per-head q/k RMSNorm).
+// Llama: interleaved pairs (i, i+1), InferenceCore.java:75-87.  Qwen3: per-head rmsnorm
+// (InferenceCore.java:594-600) then NeoX pairs (ic, ic+half), :604-619.  KV write :92-93.
+// Grid: n_heads + n_kv_heads CTAs (q heads, then k heads which also copy their v head).
+// Block: head_size/2 threads, one rotation pair each.  cos/sin come from the table built at
+// plan creation exactly as RoPE.precomputeFreqsCis does (RoPE.java:6-37).
+// ------------------------------------------------------------------------------------------
+__global__ void k_rope_kv(float *__restrict__ qkv, const StepState *__restrict__ st, const float *__restrict__ cr,
+                          const float *__restrict__ ci, int n_heads, int n_kv_heads, int hs, int arch,
+                          const float *__restrict__ qnorm_w, const float *__restrict__ knorm_w, float eps,
+                          float *__restrict__ kc, float *__restrict__ vc) {
+    extern __shared__ float sh[]; // hs floats
+    __shared__ float s_ss;
+    const int pos = st->pos, half = hs >> 1, p = threadIdx.x;
+    const int slot = blockIdx.x;
+    const bool is_q = slot < n_heads;
+    const int head = is_q ? slot : slot - n_heads;
+    const int qd = n_heads * hs, kvd = n_kv_heads * hs;
+    float *vec = is_q ? qkv + head * hs : qkv + qd + head * hs;
+    const float fcr = cr[(size_t)pos * half + p], fci = ci[(size_t)pos * half + p];
+    int i0, i1;
+    if (arch == 1) { i0 = p; i1 = p + half; } else { i0 = 2 * p; i1 = 2 * p + 1; }
+    float v0 = vec[i0], v1 = vec[i1];
+    if (arch == 1) {
+        const float *nw = is_q ? qnorm_w : knorm_w;
+        sh[i0] = __fmul_rn(v0, v0);
+        sh[i1] = __fmul_rn(v1, v1);
+        __syncthreads();
+        if (p == 0) {
+            float ss = 0.0f;
+            for (int i = 0; i < hs; i++) ss = __fadd_rn(ss, sh[i]);
+            ss = __fdiv_rn(ss, (float)hs);
+            ss = __fadd_rn(ss, eps);
+            s_ss = (float)(1.0 / sqrt((double)ss));
+        }
+        __syncthreads();
+        float ss = s_ss;
+        v0 = __fmul_rn(nw[i0], __fmul_rn(ss, v0));
+        v1 = __fmul_rn(nw[i1], __fmul_rn(ss, v1));
+    }
+    float r0 = __fsub_rn(__fmul_rn(v0, fcr), __fmul_rn(v1, fci));
+    float r1 = __fadd_rn(__fmul_rn(v0, fci), __fmul_rn(v1, fcr));
+    vec[i0] = r0;
+    vec[i1] = r1;
+    if (!is_q) {
+        size_t o = (size_t)pos * kvd + head * hs;
+        kc[o + i0] = r0;
+        kc[o + i1] = r1;
+        const float *v = qkv + qd + kvd + head * hs;
+        vc[o + i0] = v[i0];
+        vc[o + i1] = v[i1];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Attention for one query head per CTA, exact CPU-path order (InferenceCore.java:98-137):
+//   score_t = scalarDot(q, k_t) / sqrt(head)        (sequential unfused mul/add, FloatTensor.java:86-92)
+//   softmaxInPlace: max, (float)Math.exp(f - max), sequential sum, divide   (FloatTensor.java:211-219)
+//   xb = sum_t a_t * v_t, sequentially over t per element (saxpyInPlace, FloatTensor.java:221-227)
+// Output is written as floats (xb) and/or quantised to Q8_0 (activation of the Wo matvec).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_attention(const float *__restrict__ qkv, const float *__restrict__ kc,
+                                                   const float *__restrict__ vc, const StepState *__restrict__ st, int hs,
+                                                   int kvd, int kv_mul, float sqrt_hs, int8_t *__restrict__ xq,
+                                                   float *__restrict__ xs, float *__restrict__ xb) {
+    extern __shared__ __align__(16) float sm[]; // q[hs] | out[hs] | att[ctx]
+    __shared__ float red[4];
+    __shared__ float s_val;
+    float *sq = sm, *so = sm + hs, *att = sm + 2 * hs;
+    const int h = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nt = st->pos + 1;
+    const int kvh = h / kv_mul;
+    for (int i = tid; i < hs; i += blockDim.x) sq[i] = qkv[h * hs + i];
+    __syncthreads();
+    float lmax = -INFINITY;
+    for (int t = tid; t < nt; t += blockDim.x) {
+        const float4 *k = reinterpret_cast<const float4 *>(kc + (size_t)t * kvd + kvh * hs);
+        float acc = 0.0f;
+        for (int j = 0; j < hs / 4; j++) {
+            float4 kk = k[j];
+            acc = __fadd_rn(acc, __fmul_rn(sq[4 * j + 0], kk.x));
+            acc = __fadd_rn(acc, __fmul_rn(sq[4 * j + 1], kk.y));
+            acc = __fadd_rn(acc, __fmul_rn(sq[4 * j + 2], kk.z));
+            acc = __fadd_rn(acc, __fmul_rn(sq[4 * j + 3], kk.w));
+        }
+        float s = __fdiv_rn(acc, sqrt_hs);
+        att[t] = s;
+        lmax = fmaxf(lmax, s);
+    }
+    lmax = warp_max_f(lmax);
+    if (lane == 0) red[warp] = lmax;
+    __syncthreads();
+    const float mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    for (int t = tid; t < nt; t += blockDim.x) att[t] = (float)exp((double)__fsub_rn(att[t], mx));
+    __syncthreads();
+    if (tid == 0) {
+        float sum = 0.0f;
+        for (int t = 0; t < nt; t++) sum = __fadd_rn(sum, att[t]);
+        s_val = sum;
+    }
+    __syncthreads();
+    const float sum = s_val;
+    for (int t = tid; t < nt; t += blockDim.x) att[t] = __fdiv_rn(att[t], sum);
+    __syncthreads();
+    for (int i = tid; i < hs; i += blockDim.x) {
+        const float *v = vc + kvh * hs + i;
+        float acc = 0.0f;
+        for (int t = 0; t < nt; t++) acc = __fadd_rn(__fmul_rn(att[t], v[(size_t)t * kvd]), acc);
+        so[i] = acc;
+        if (xb) xb[h * hs + i] = acc;
+    }
+    __syncthreads();
+    if (xq) {
+        for (int b = warp; b < hs / 32; b += (blockDim.x >> 5)) {
+            float as;
+            int q = quant_block_lane(so[b * 32 + lane], as);
+            xq[h * hs + b * 32 + lane] = (int8_t)q;
+            if (lane == 0) xs[(h * hs) / 32 + b] = as;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Greedy sampler + step advance.  FloatTensor.argmax (FloatTensor.java:138-151): first strict
+// maximum.  One CTA; each thread keeps (max, lowest index) over a strided slice, then a tree
+// merge that prefers the lower index on ties -- equal to the sequential scan for NaN-free input.
+// Also advances the device-resident StepState so graph replays chain without the host.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void argmax_merge(float &v, int &i, float ov, int oi) {
+    if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+}
+
+__global__ void __launch_bounds__(1024) k_argmax_advance(const float *__restrict__ logits, int vocab, StepState *st,
+                                                        const int *__restrict__ seq_tokens, int *__restrict__ out_ids,
+                                                        int do_argmax) {
+    __shared__ float sv[32];
+    __shared__ int si[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int best_i = 0;
+    if (do_argmax) {
+        float best = -INFINITY;
+        best_i = 0x7fffffff;
+        for (int i = tid; i < vocab; i += blockDim.x) {
+            float v = logits[i];
+            if (v > best) { best = v; best_i = i; }
+        }
+        // a thread that saw nothing > -inf keeps INT_MAX; index 0 wins below if all are -inf
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+            argmax_merge(best, best_i, ov, oi);
+        }
+        if (lane == 0) { sv[warp] = best; si[warp] = best_i; }
+        __syncthreads();
+        if (warp == 0) {
+            int nw = blockDim.x >> 5;
+            best = lane < nw ? sv[lane] : -INFINITY;
+            best_i = lane < nw ? si[lane] : 0x7fffffff;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                float ov = __shfl_xor_sync(0xffffffffu, best, o);
+                int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+                argmax_merge(best, best_i, ov, oi);
+            }
+            if (best_i == 0x7fffffff) best_i = 0;
+        }
+    }
+    if (tid == 0) {
+        int step = st->step;
+        if (do_argmax && out_ids) out_ids[step] = best_i;
+        int next = step + 1;
+        if (st->feedback && do_argmax) st->token = best_i;
+        else if (next < st->n_seq) st->token = seq_tokens[next];
+        st->step = next;
+        st->pos = st->pos + 1;
+    }
+}

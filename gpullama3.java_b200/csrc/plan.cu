@@ -1,0 +1,652 @@
+// plan.cu -- libb200llama.so: plan lifecycle, weight upload/repack, CUDA-graph capture and the
+// C ABI declared in include/b200llama.h.  Plays the role of TornadoVMMasterPlan*.java +
+// tornadovm/plan/** + tornadovm/layers/** of the reference (one native context and one CUDA
+// graph per token instead of N+2 TaskGraph executions, TornadoVMMasterPlanSingleToken.java:68-95).
+#include "../../include/b200llama.h"
+#include "decode_kernels.cuh"
+#include "prefill.cuh"
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+namespace {
+
+struct LayerW {
+    DevMat qkv, wo, w1, w3, w2;
+    float *attn_norm = nullptr, *ffn_norm = nullptr, *q_norm = nullptr, *k_norm = nullptr;
+};
+
+} // namespace
+
+struct b200_plan {
+    b200_config cfg{};
+    int device = 0;
+    int wtype = 0; // B200_GGML_Q8_0 or B200_GGML_F16 (matrix type)
+    int qd = 0, kvd = 0;
+    int prefill_batch = 0;
+    cudaStream_t stream = nullptr;
+    std::vector<void *> allocs;
+    int64_t bytes = 0;
+    std::string err;
+
+    DevMat emb{}, out{};
+    float *out_norm = nullptr;
+    std::vector<LayerW> layers;
+    float *rope_cr = nullptr, *rope_ci = nullptr;
+
+    // activations
+    float *x = nullptr, *xb = nullptr, *qkv = nullptr, *hb = nullptr, *hb2 = nullptr, *logits = nullptr;
+    int8_t *xq = nullptr, *hq = nullptr;
+    float *xs = nullptr, *hs = nullptr;
+    float *key_cache = nullptr, *value_cache = nullptr;
+    StepState *st = nullptr;
+    int *seq_tokens = nullptr, *out_ids = nullptr;
+    int seq_cap = 0;
+    StepState *h_st = nullptr; // pinned
+    int *h_ids = nullptr;      // pinned, seq_cap
+
+    cudaGraphExec_t g_decode = nullptr, g_prefill = nullptr;
+    int launches_decode = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    PrefillCtx prefill;
+};
+
+namespace {
+
+int fail(b200_plan *p, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (p) p->err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            return fail(p, e_ == cudaErrorMemoryAllocation ? B200_ERR_OOM : B200_ERR_CUDA, "%s: %s (%s:%d)", #call, \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                                 \
+    } while (0)
+
+template <typename T> int dalloc(b200_plan *p, T **ptr, size_t n_bytes) {
+    void *d = nullptr;
+    if (n_bytes == 0) n_bytes = 16;
+    CK(cudaMalloc(&d, n_bytes));
+    p->allocs.push_back(d);
+    p->bytes += (int64_t)n_bytes;
+    *ptr = reinterpret_cast<T *>(d);
+    return B200_OK;
+}
+
+// GGUF Q8_0 blocks (f16 scale + 32 int8, 34 bytes, GGMLType.java:13) -> split planes.
+// One thread per 16-bit word of the raw stream: word 0 of each block is the scale.
+__global__ void k_repack_q8(const uint16_t *__restrict__ raw, uint16_t *__restrict__ qs, uint16_t *__restrict__ sc,
+                            size_t n_words) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_words) return;
+    size_t blk = i / 17;
+    int w = (int)(i % 17);
+    uint16_t v = raw[i];
+    if (w == 0) sc[blk] = v;
+    else qs[blk * 16 + (w - 1)] = v;
+}
+
+const b200_tensor *find(const b200_tensor *t, int n, const std::string &name) {
+    for (int i = 0; i < n; i++)
+        if (name == t[i].name) return &t[i];
+    return nullptr;
+}
+
+int64_t n_elems(const b200_tensor *t) {
+    int64_t n = 1;
+    for (int i = 0; i < t->n_dims; i++) n *= t->dims[i];
+    return n;
+}
+
+// Upload rows [0, rows) of a [rows][cols] GGUF matrix into dst at row offset `row_off`.
+int upload_matrix(b200_plan *p, const b200_tensor *t, int rows, int cols, DevMat &dst, int row_off, void *stage,
+                  size_t stage_bytes) {
+    if (!t) return fail(p, B200_ERR_BAD_ARG, "missing tensor");
+    if (n_elems(t) != (int64_t)rows * cols)
+        return fail(p, B200_ERR_BAD_ARG, "tensor %s has %lld elements, expected %lld", t->name, (long long)n_elems(t),
+                    (long long)rows * cols);
+    if (t->ggml_type != dst.type)
+        return fail(p, B200_ERR_UNSUPPORTED, "tensor %s has ggml type %d, plan weight type is %d", t->name, t->ggml_type,
+                    dst.type);
+    if (dst.type == B200_GGML_Q8_0) {
+        size_t nblk = (size_t)rows * cols / 32;
+        int8_t *qs = (int8_t *)dst.qs + (size_t)row_off * cols;
+        __half *sc = (__half *)dst.sc + (size_t)row_off * (cols / 32);
+        // chunked through the staging buffer (multiple of 34 bytes)
+        size_t blk_per_chunk = stage_bytes / 34;
+        for (size_t b0 = 0; b0 < nblk; b0 += blk_per_chunk) {
+            size_t nb = nblk - b0 < blk_per_chunk ? nblk - b0 : blk_per_chunk;
+            CK(cudaMemcpyAsync(stage, (const uint8_t *)t->data + b0 * 34, nb * 34, cudaMemcpyHostToDevice, p->stream));
+            size_t words = nb * 17;
+            k_repack_q8<<<(unsigned)((words + 255) / 256), 256, 0, p->stream>>>((const uint16_t *)stage, (uint16_t *)(qs + b0 * 32),
+                                                                                  (uint16_t *)(sc + b0), words);
+            CK(cudaGetLastError());
+            CK(cudaStreamSynchronize(p->stream)); // staging buffer is reused
+        }
+    } else {
+        size_t esz = dst.type == B200_GGML_F16 ? 2 : 4;
+        CK(cudaMemcpy((uint8_t *)dst.qs + (size_t)row_off * cols * esz, t->data, (size_t)rows * cols * esz, cudaMemcpyHostToDevice));
+    }
+    return B200_OK;
+}
+
+int alloc_matrix(b200_plan *p, DevMat &m, int rows, int cols, int type) {
+    m.rows = rows;
+    m.cols = cols;
+    m.type = type;
+    m.sc = nullptr;
+    void *q = nullptr;
+    int rc;
+    if (type == B200_GGML_Q8_0) {
+        if ((rc = dalloc(p, (int8_t **)&q, (size_t)rows * cols))) return rc;
+        __half *s;
+        if ((rc = dalloc(p, &s, (size_t)rows * (cols / 32) * 2))) return rc;
+        m.sc = s;
+    } else {
+        if ((rc = dalloc(p, (uint8_t **)&q, (size_t)rows * cols * (type == B200_GGML_F16 ? 2 : 4)))) return rc;
+    }
+    m.qs = q;
+    return B200_OK;
+}
+
+int upload_f32(b200_plan *p, const b200_tensor *t, int n, float **dst, const char *what) {
+    if (!t) return fail(p, B200_ERR_BAD_ARG, "missing tensor %s", what);
+    if (t->ggml_type != B200_GGML_F32) return fail(p, B200_ERR_UNSUPPORTED, "tensor %s must be F32", what);
+    if (n_elems(t) != n) return fail(p, B200_ERR_BAD_ARG, "tensor %s has wrong size", what);
+    int rc = dalloc(p, dst, (size_t)n * 4);
+    if (rc) return rc;
+    CK(cudaMemcpy(*dst, t->data, (size_t)n * 4, cudaMemcpyHostToDevice));
+    return B200_OK;
+}
+
+template <int MODE> int launch_matvec_q8(b200_plan *p, const DevMat &m, const int8_t *xq, const float *xs, float *out) {
+    int R = (m.rows % 4 == 0 && m.rows >= 32768) ? 4 : (m.rows % 2 == 0 ? 2 : 1);
+    int warps = m.rows / R;
+    int ctas = (warps + 7) / 8;
+    size_t smem = q8_smem_bytes(m.cols, R, 8);
+    const int8_t *qs = (const int8_t *)m.qs;
+    if (R == 4) k_matvec_q8<4, MODE><<<ctas, 256, smem, p->stream>>>(qs, m.sc, xq, xs, m.rows, m.cols, out);
+    else if (R == 2) k_matvec_q8<2, MODE><<<ctas, 256, smem, p->stream>>>(qs, m.sc, xq, xs, m.rows, m.cols, out);
+    else k_matvec_q8<1, MODE><<<ctas, 256, smem, p->stream>>>(qs, m.sc, xq, xs, m.rows, m.cols, out);
+    CK(cudaGetLastError());
+    return B200_OK;
+}
+
+size_t f16_smem_bytes(int cols, int lanes) {
+    int L = lanes > 0 ? lanes : 1;
+    return (size_t)cols * 4 + (size_t)8 * (32 / L) * 256 * 2;
+}
+
+template <int MODE> int launch_matvec_f16(b200_plan *p, const DevMat &m, const float *x, float *out) {
+    int L = p->cfg.fp16_lanes > 0 ? p->cfg.fp16_lanes : 1;
+    int rw = 32 / L;
+    int warps = (m.rows + rw - 1) / rw;
+    int ctas = (warps + 7) / 8;
+    k_matvec_f16<MODE><<<ctas, 256, f16_smem_bytes(m.cols, p->cfg.fp16_lanes), p->stream>>>((const __half *)m.qs, x, m.rows,
+                                                                                            m.cols, p->cfg.fp16_lanes, out);
+    CK(cudaGetLastError());
+    return B200_OK;
+}
+
+// Enqueue one single-token forward on p->stream (captured into a CUDA graph at creation).
+// with_logits=false is the prefill variant (InferenceCoreBatchPrefillDecode.java:166-167).
+int enqueue_forward(b200_plan *p, bool with_logits, int *launches) {
+    const b200_config &c = p->cfg;
+    const bool q8 = p->wtype == B200_GGML_Q8_0;
+    int n = 0;
+    const size_t norm_smem = (size_t)c.dim * 8;
+    int8_t *xq = q8 ? p->xq : nullptr;
+    float *xs = q8 ? p->xs : nullptr;
+    float *xbf = q8 ? nullptr : p->xb;
+    const size_t ctx_kv = (size_t)c.context_length * p->kvd;
+    for (int l = 0; l < c.n_layers; l++) {
+        LayerW &L = p->layers[l];
+        if (l == 0) k_rmsnorm_quant<true><<<1, 1024, norm_smem, p->stream>>>(p->x, p->st, p->emb, L.attn_norm, c.rms_norm_eps, c.dim, xq, xs, xbf);
+        else k_rmsnorm_quant<false><<<1, 1024, norm_smem, p->stream>>>(p->x, p->st, p->emb, L.attn_norm, c.rms_norm_eps, c.dim, xq, xs, xbf);
+        CK(cudaGetLastError()); n++;
+        int rc;
+        if (q8) rc = launch_matvec_q8<MODE_STORE>(p, L.qkv, p->xq, p->xs, p->qkv);
+        else rc = launch_matvec_f16<MODE_STORE>(p, L.qkv, p->xb, p->qkv);
+        if (rc) return rc; n++;
+        float *kc = p->key_cache + (size_t)l * ctx_kv, *vc = p->value_cache + (size_t)l * ctx_kv;
+        k_rope_kv<<<c.n_heads + c.n_kv_heads, c.head_size / 2, c.head_size * 4, p->stream>>>(
+            p->qkv, p->st, p->rope_cr, p->rope_ci, c.n_heads, c.n_kv_heads, c.head_size, c.arch, L.q_norm, L.k_norm, c.rms_norm_eps, kc, vc);
+        CK(cudaGetLastError()); n++;
+        k_attention<<<c.n_heads, 128, (size_t)(2 * c.head_size + c.context_length) * 4, p->stream>>>(
+            p->qkv, kc, vc, p->st, c.head_size, p->kvd, c.n_heads / c.n_kv_heads, (float)sqrt((double)c.head_size), xq, xs, xbf);
+        CK(cudaGetLastError()); n++;
+        if (q8) rc = launch_matvec_q8<MODE_RESID>(p, L.wo, p->xq, p->xs, p->x);
+        else rc = launch_matvec_f16<MODE_RESID>(p, L.wo, p->xb, p->x);
+        if (rc) return rc; n++;
+        k_rmsnorm_quant<false><<<1, 1024, norm_smem, p->stream>>>(p->x, p->st, p->emb, L.ffn_norm, c.rms_norm_eps, c.dim, xq, xs, xbf);
+        CK(cudaGetLastError()); n++;
+        if (q8) {
+            k_gateup_q8<<<c.hidden_dim / 32, 256, q8_smem_bytes(c.dim, 4, 8), p->stream>>>(
+                (const int8_t *)L.w1.qs, L.w1.sc, (const int8_t *)L.w3.qs, L.w3.sc, p->xq, p->xs, c.hidden_dim, c.dim, p->hq, p->hs, p->hb);
+            CK(cudaGetLastError()); n++;
+            if ((rc = launch_matvec_q8<MODE_RESID>(p, L.w2, p->hq, p->hs, p->x))) return rc; n++;
+        } else {
+            if ((rc = launch_matvec_f16<MODE_STORE>(p, L.w1, p->xb, p->hb))) return rc; n++;
+            if ((rc = launch_matvec_f16<MODE_STORE>(p, L.w3, p->xb, p->hb2))) return rc; n++;
+            k_swiglu<<<(c.hidden_dim + 255) / 256, 256, 0, p->stream>>>(p->hb, p->hb2, c.hidden_dim);
+            CK(cudaGetLastError()); n++;
+            if ((rc = launch_matvec_f16<MODE_RESID>(p, L.w2, p->hb, p->x))) return rc; n++;
+        }
+    }
+    if (with_logits) {
+        // rmsnorm(x, x, rms_final_weight) then wcls.matmul (InferenceCore.java:167-169)
+        k_rmsnorm_quant<false><<<1, 1024, norm_smem, p->stream>>>(p->x, p->st, p->emb, p->out_norm, c.rms_norm_eps, c.dim, xq, xs, xbf);
+        CK(cudaGetLastError()); n++;
+        int rc;
+        if (q8) rc = launch_matvec_q8<MODE_STORE>(p, p->out, p->xq, p->xs, p->logits);
+        else rc = launch_matvec_f16<MODE_STORE>(p, p->out, p->xb, p->logits);
+        if (rc) return rc; n++;
+    }
+    k_argmax_advance<<<1, 1024, 0, p->stream>>>(p->logits, c.vocab_size, p->st, p->seq_tokens, p->out_ids, with_logits ? 1 : 0);
+    CK(cudaGetLastError()); n++;
+    if (launches) *launches = n;
+    return B200_OK;
+}
+
+int capture(b200_plan *p, bool with_logits, cudaGraphExec_t *exec, int *launches) {
+    cudaGraph_t g = nullptr;
+    CK(cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = enqueue_forward(p, with_logits, launches);
+    cudaError_t e = cudaStreamEndCapture(p->stream, &g);
+    if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+    if (e != cudaSuccess) return fail(p, B200_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(exec, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return fail(p, B200_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+    return B200_OK;
+}
+
+int set_smem_attrs(b200_plan *p) {
+    const b200_config &c = p->cfg;
+    int maxdyn = 0;
+    CK(cudaDeviceGetAttribute(&maxdyn, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device));
+    size_t need_norm = (size_t)c.dim * 8;
+    size_t need_att = (size_t)(2 * c.head_size + c.context_length) * 4;
+    int maxcols = c.hidden_dim > c.dim ? c.hidden_dim : c.dim;
+    if (p->qd > maxcols) maxcols = p->qd;
+    size_t need_mv = q8_smem_bytes(maxcols, 4, 8);
+    size_t need_f16 = f16_smem_bytes(maxcols, p->cfg.fp16_lanes);
+    if (need_norm > (size_t)maxdyn || need_att > (size_t)maxdyn || (p->wtype == B200_GGML_Q8_0 && need_mv > (size_t)maxdyn) ||
+        (p->wtype == B200_GGML_F16 && need_f16 > (size_t)maxdyn))
+        return fail(p, B200_ERR_UNSUPPORTED, "shape needs more shared memory than the device offers (%d bytes)", maxdyn);
+    CK(cudaFuncSetAttribute(k_rmsnorm_quant<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_norm));
+    CK(cudaFuncSetAttribute(k_rmsnorm_quant<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_norm));
+    CK(cudaFuncSetAttribute(k_attention, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_att));
+    CK(cudaFuncSetAttribute(k_matvec_q8<1, MODE_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_mv));
+    CK(cudaFuncSetAttribute(k_matvec_q8<2, MODE_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_mv));
+    CK(cudaFuncSetAttribute(k_matvec_q8<4, MODE_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_mv));
+    CK(cudaFuncSetAttribute(k_matvec_q8<1, MODE_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_mv));
+    CK(cudaFuncSetAttribute(k_matvec_q8<2, MODE_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_mv));
+    CK(cudaFuncSetAttribute(k_matvec_q8<4, MODE_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_mv));
+    CK(cudaFuncSetAttribute(k_gateup_q8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_mv));
+    CK(cudaFuncSetAttribute(k_matvec_f16<MODE_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_f16));
+    CK(cudaFuncSetAttribute(k_matvec_f16<MODE_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_f16));
+    return B200_OK;
+}
+
+int build(b200_plan *p, const b200_tensor *tensors, int n_tensors) {
+    const b200_config &c = p->cfg;
+    if (c.arch != B200_ARCH_LLAMA && c.arch != B200_ARCH_QWEN3) return fail(p, B200_ERR_UNSUPPORTED, "unknown arch %d", c.arch);
+    if (c.tp_size > 1) return fail(p, B200_ERR_UNSUPPORTED, "tensor parallelism is not built yet (tp_size=%d)", c.tp_size);
+    if (c.dim <= 0 || c.dim % 32 || c.hidden_dim % 32 || c.head_size % 32 || c.head_size > 256 || c.n_heads % c.n_kv_heads ||
+        c.n_layers <= 0 || c.vocab_size <= 0 || c.context_length <= 0)
+        return fail(p, B200_ERR_BAD_ARG, "unsupported shape (dim/hidden/head_size must be multiples of 32, head_size <= 256)");
+    if (c.fp16_lanes != 0 && c.fp16_lanes != 8 && c.fp16_lanes != 16 && c.fp16_lanes != 4 && c.fp16_lanes != 32)
+        return fail(p, B200_ERR_BAD_ARG, "fp16_lanes must be 0, 4, 8, 16 or 32");
+    p->qd = c.n_heads * c.head_size;
+    p->kvd = c.n_kv_heads * c.head_size;
+    if (c.arch == B200_ARCH_LLAMA && p->qd != c.dim) return fail(p, B200_ERR_BAD_ARG, "llama: n_heads*head_size must equal dim");
+
+    const b200_tensor *emb = find(tensors, n_tensors, "token_embd.weight");
+    if (!emb) return fail(p, B200_ERR_BAD_ARG, "missing tensor token_embd.weight");
+    const b200_tensor *wq0 = find(tensors, n_tensors, "blk.0.attn_q.weight");
+    if (!wq0) return fail(p, B200_ERR_BAD_ARG, "missing tensor blk.0.attn_q.weight");
+    p->wtype = wq0->ggml_type;
+    if (p->wtype != B200_GGML_Q8_0 && p->wtype != B200_GGML_F16)
+        return fail(p, B200_ERR_UNSUPPORTED, "Type: %d currently not supported for B200 weights (Q8_0 and F16 only)", p->wtype);
+
+    CK(cudaSetDevice(p->device));
+    CK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&p->ev0));
+    CK(cudaEventCreate(&p->ev1));
+    int rc;
+    void *stage = nullptr;
+    const size_t stage_bytes = (size_t)34 * (8u << 20); // 8 Mi blocks = 272 MiB
+    if (p->wtype == B200_GGML_Q8_0 || emb->ggml_type == B200_GGML_Q8_0) CK(cudaMalloc(&stage, stage_bytes));
+    struct StageGuard { void *s; ~StageGuard() { if (s) cudaFree(s); } } guard{stage};
+
+    // embedding table (+ tied classifier: AbstractModelLoader.java:186-195)
+    if ((rc = alloc_matrix(p, p->emb, c.vocab_size, c.dim, emb->ggml_type))) return rc;
+    if ((rc = upload_matrix(p, emb, c.vocab_size, c.dim, p->emb, 0, stage, stage_bytes))) return rc;
+    const b200_tensor *outw = find(tensors, n_tensors, "output.weight");
+    if (outw) {
+        if ((rc = alloc_matrix(p, p->out, c.vocab_size, c.dim, p->wtype))) return rc;
+        if ((rc = upload_matrix(p, outw, c.vocab_size, c.dim, p->out, 0, stage, stage_bytes))) return rc;
+    } else {
+        if (emb->ggml_type != p->wtype) return fail(p, B200_ERR_UNSUPPORTED, "tied output weight type differs from the matrix type");
+        p->out = p->emb;
+    }
+    if ((rc = upload_f32(p, find(tensors, n_tensors, "output_norm.weight"), c.dim, &p->out_norm, "output_norm.weight"))) return rc;
+
+    p->layers.resize(c.n_layers);
+    for (int l = 0; l < c.n_layers; l++) {
+        LayerW &L = p->layers[l];
+        std::string pre = "blk." + std::to_string(l) + ".";
+        auto T = [&](const char *s) { return find(tensors, n_tensors, pre + s); };
+        if ((rc = upload_f32(p, T("attn_norm.weight"), c.dim, &L.attn_norm, "attn_norm.weight"))) return rc;
+        if ((rc = upload_f32(p, T("ffn_norm.weight"), c.dim, &L.ffn_norm, "ffn_norm.weight"))) return rc;
+        if (c.arch == B200_ARCH_QWEN3) {
+            if ((rc = upload_f32(p, T("attn_q_norm.weight"), c.head_size, &L.q_norm, "attn_q_norm.weight"))) return rc;
+            if ((rc = upload_f32(p, T("attn_k_norm.weight"), c.head_size, &L.k_norm, "attn_k_norm.weight"))) return rc;
+        }
+        // fused [Wq; Wk; Wv] so one launch produces the packed q|k|v vector
+        if ((rc = alloc_matrix(p, L.qkv, p->qd + 2 * p->kvd, c.dim, p->wtype))) return rc;
+        if ((rc = upload_matrix(p, T("attn_q.weight"), p->qd, c.dim, L.qkv, 0, stage, stage_bytes))) return rc;
+        if ((rc = upload_matrix(p, T("attn_k.weight"), p->kvd, c.dim, L.qkv, p->qd, stage, stage_bytes))) return rc;
+        if ((rc = upload_matrix(p, T("attn_v.weight"), p->kvd, c.dim, L.qkv, p->qd + p->kvd, stage, stage_bytes))) return rc;
+        if ((rc = alloc_matrix(p, L.wo, c.dim, p->qd, p->wtype))) return rc;
+        if ((rc = upload_matrix(p, T("attn_output.weight"), c.dim, p->qd, L.wo, 0, stage, stage_bytes))) return rc;
+        if ((rc = alloc_matrix(p, L.w1, c.hidden_dim, c.dim, p->wtype))) return rc;
+        if ((rc = upload_matrix(p, T("ffn_gate.weight"), c.hidden_dim, c.dim, L.w1, 0, stage, stage_bytes))) return rc;
+        if ((rc = alloc_matrix(p, L.w3, c.hidden_dim, c.dim, p->wtype))) return rc;
+        if ((rc = upload_matrix(p, T("ffn_up.weight"), c.hidden_dim, c.dim, L.w3, 0, stage, stage_bytes))) return rc;
+        if ((rc = alloc_matrix(p, L.w2, c.dim, c.hidden_dim, p->wtype))) return rc;
+        if ((rc = upload_matrix(p, T("ffn_down.weight"), c.dim, c.hidden_dim, L.w2, 0, stage, stage_bytes))) return rc;
+    }
+
+    // RoPE table exactly as RoPE.precomputeFreqsCis (RoPE.java:6-37, ropeScaling=false):
+    // freq = (float)(1.0 / Math.pow(theta, i / (double) headSize)); val = pos * freq (float);
+    // cos/sin evaluated in double and narrowed.
+    {
+        int half = c.head_size / 2;
+        std::vector<float> cr((size_t)c.context_length * half), ci((size_t)c.context_length * half);
+        size_t k = 0;
+        for (int pos = 0; pos < c.context_length; pos++)
+            for (int i = 0; i < c.head_size; i += 2) {
+                float freq = (float)(1.0 / pow((double)c.rope_theta, i / (double)c.head_size));
+                float val = (float)pos * freq;
+                cr[k] = (float)cos((double)val);
+                ci[k] = (float)sin((double)val);
+                k++;
+            }
+        if ((rc = dalloc(p, &p->rope_cr, cr.size() * 4))) return rc;
+        if ((rc = dalloc(p, &p->rope_ci, ci.size() * 4))) return rc;
+        CK(cudaMemcpy(p->rope_cr, cr.data(), cr.size() * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(p->rope_ci, ci.data(), ci.size() * 4, cudaMemcpyHostToDevice));
+    }
+
+    int big = c.dim > p->qd ? c.dim : p->qd;
+    if ((rc = dalloc(p, &p->x, (size_t)c.dim * 4))) return rc;
+    if ((rc = dalloc(p, &p->xb, (size_t)big * 4))) return rc;
+    if ((rc = dalloc(p, &p->qkv, (size_t)(p->qd + 2 * p->kvd) * 4))) return rc;
+    if ((rc = dalloc(p, &p->hb, (size_t)c.hidden_dim * 4))) return rc;
+    if ((rc = dalloc(p, &p->hb2, (size_t)c.hidden_dim * 4))) return rc;
+    if ((rc = dalloc(p, &p->logits, (size_t)c.vocab_size * 4))) return rc;
+    if ((rc = dalloc(p, &p->xq, (size_t)big))) return rc;
+    if ((rc = dalloc(p, &p->xs, (size_t)(big / 32) * 4))) return rc;
+    if ((rc = dalloc(p, &p->hq, (size_t)c.hidden_dim))) return rc;
+    if ((rc = dalloc(p, &p->hs, (size_t)(c.hidden_dim / 32) * 4))) return rc;
+    size_t kv_bytes = (size_t)c.n_layers * c.context_length * p->kvd * 4;
+    if ((rc = dalloc(p, &p->key_cache, kv_bytes))) return rc;
+    if ((rc = dalloc(p, &p->value_cache, kv_bytes))) return rc;
+    CK(cudaMemset(p->key_cache, 0, kv_bytes));
+    CK(cudaMemset(p->value_cache, 0, kv_bytes));
+    CK(cudaMemset(p->logits, 0, (size_t)c.vocab_size * 4));
+    p->seq_cap = c.context_length + 8;
+    if ((rc = dalloc(p, &p->st, sizeof(StepState)))) return rc;
+    if ((rc = dalloc(p, &p->seq_tokens, (size_t)p->seq_cap * 4))) return rc;
+    if ((rc = dalloc(p, &p->out_ids, (size_t)p->seq_cap * 4))) return rc;
+    CK(cudaMemset(p->st, 0, sizeof(StepState)));
+    CK(cudaMemset(p->seq_tokens, 0, (size_t)p->seq_cap * 4));
+    CK(cudaMallocHost(&p->h_st, sizeof(StepState)));
+    CK(cudaMallocHost(&p->h_ids, (size_t)p->seq_cap * 4));
+
+    if ((rc = set_smem_attrs(p))) return rc;
+    if ((rc = capture(p, true, &p->g_decode, &p->launches_decode))) return rc;
+    if ((rc = capture(p, false, &p->g_prefill, nullptr))) return rc;
+    if (p->prefill_batch > 1)
+        if ((rc = prefill_init(p->prefill, p->cfg, p->prefill_batch))) return fail(p, rc, "batched prefill init failed");
+    CK(cudaStreamSynchronize(p->stream));
+    return B200_OK;
+}
+
+int set_state(b200_plan *p, int token, int pos, int n_seq, int feedback) {
+    StepState *h = p->h_st;
+    h->token = token; h->pos = pos; h->step = 0; h->n_seq = n_seq; h->feedback = feedback;
+    CK(cudaMemcpyAsync(p->st, h, sizeof(StepState), cudaMemcpyHostToDevice, p->stream));
+    return B200_OK;
+}
+
+int check_pos(b200_plan *p, int token, int pos) {
+    if (token < 0 || token >= p->cfg.vocab_size) return fail(p, B200_ERR_BAD_ARG, "token %d out of range", token);
+    if (pos < 0 || pos >= p->cfg.context_length) return fail(p, B200_ERR_BAD_ARG, "position %d outside the KV cache (%d)", pos, p->cfg.context_length);
+    return B200_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int b200_plan_create(const b200_config *cfg, const b200_tensor *tensors, int32_t n_tensors, int32_t prefill_batch_size,
+                     int32_t device, b200_plan **out, char *err, size_t err_len) {
+    if (out) *out = nullptr;
+    if (!cfg || !tensors || !out || n_tensors <= 0) {
+        if (err && err_len) snprintf(err, err_len, "null argument");
+        return B200_ERR_BAD_ARG;
+    }
+    b200_plan *p = new b200_plan();
+    p->cfg = *cfg;
+    if (p->cfg.tp_size <= 0) p->cfg.tp_size = 1;
+    p->device = device;
+    p->prefill_batch = prefill_batch_size;
+    int rc = build(p, tensors, n_tensors);
+    if (rc != B200_OK) {
+        if (err && err_len) snprintf(err, err_len, "%s", p->err.c_str());
+        b200_plan_free(p);
+        return rc;
+    }
+    *out = p;
+    return B200_OK;
+}
+
+int b200_forward_decode(b200_plan *p, int32_t token, int32_t position, float *logits, int32_t *argmax) {
+    if (!p) return B200_ERR_BAD_ARG;
+    int rc;
+    if ((rc = check_pos(p, token, position))) return rc;
+    CK(cudaSetDevice(p->device));
+    if ((rc = set_state(p, token, position, 0, 0))) return rc;
+    CK(cudaGraphLaunch(p->g_decode, p->stream));
+    if (argmax) CK(cudaMemcpyAsync(p->h_ids, p->out_ids, 4, cudaMemcpyDeviceToHost, p->stream));
+    if (logits) CK(cudaMemcpyAsync(logits, p->logits, (size_t)p->cfg.vocab_size * 4, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    if (argmax) *argmax = p->h_ids[0];
+    return B200_OK;
+}
+
+int b200_forward_prefill(b200_plan *p, int32_t token, int32_t position) {
+    if (!p) return B200_ERR_BAD_ARG;
+    int rc;
+    if ((rc = check_pos(p, token, position))) return rc;
+    CK(cudaSetDevice(p->device));
+    if ((rc = set_state(p, token, position, 0, 0))) return rc;
+    CK(cudaGraphLaunch(p->g_prefill, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return B200_OK;
+}
+
+int b200_forward_batch_prefill(b200_plan *p, const int32_t *tokens, int32_t n, int32_t start_pos) {
+    if (!p || !tokens) return B200_ERR_BAD_ARG;
+    if (n <= 0) return B200_OK;
+    if (p->prefill_batch > 1 && n > p->prefill_batch) return fail(p, B200_ERR_BAD_ARG, "chunk of %d tokens exceeds prefill_batch_size %d", n, p->prefill_batch);
+    if (start_pos < 0 || start_pos + n > p->cfg.context_length) return fail(p, B200_ERR_BAD_ARG, "positions %d..%d outside the KV cache", start_pos, start_pos + n - 1);
+    for (int i = 0; i < n; i++)
+        if (tokens[i] < 0 || tokens[i] >= p->cfg.vocab_size) return fail(p, B200_ERR_BAD_ARG, "token %d out of range", tokens[i]);
+    CK(cudaSetDevice(p->device));
+    // Exact path: the prefill graph token by token (bit-identical KV cache to the CPU
+    // batchForwardJavaPrefill, InferenceCoreBatchPrefillDecode.java:62-168).
+    if (n > p->seq_cap) return fail(p, B200_ERR_BAD_ARG, "chunk too long");
+    memcpy(p->h_ids, tokens, (size_t)n * 4);
+    CK(cudaMemcpyAsync(p->seq_tokens, p->h_ids, (size_t)n * 4, cudaMemcpyHostToDevice, p->stream));
+    int rc;
+    if ((rc = set_state(p, tokens[0], start_pos, n, 0))) return rc;
+    for (int i = 0; i < n; i++) CK(cudaGraphLaunch(p->g_prefill, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return B200_OK;
+}
+
+int b200_decode_sequence(b200_plan *p, const int32_t *tokens, int32_t n, int32_t start_pos, int32_t feedback,
+                         int32_t *out_ids, float *device_ms) {
+    if (!p || !tokens) return B200_ERR_BAD_ARG;
+    if (n <= 0) return B200_OK;
+    if (n > p->seq_cap) return fail(p, B200_ERR_BAD_ARG, "sequence of %d steps exceeds capacity %d", n, p->seq_cap);
+    if (start_pos < 0 || start_pos + n > p->cfg.context_length) return fail(p, B200_ERR_BAD_ARG, "positions %d..%d outside the KV cache (%d)", start_pos, start_pos + n - 1, p->cfg.context_length);
+    int nt = feedback ? 1 : n;
+    for (int i = 0; i < nt; i++)
+        if (tokens[i] < 0 || tokens[i] >= p->cfg.vocab_size) return fail(p, B200_ERR_BAD_ARG, "token %d out of range", tokens[i]);
+    CK(cudaSetDevice(p->device));
+    memcpy(p->h_ids, tokens, (size_t)nt * 4);
+    CK(cudaMemcpyAsync(p->seq_tokens, p->h_ids, (size_t)nt * 4, cudaMemcpyHostToDevice, p->stream));
+    int rc;
+    if ((rc = set_state(p, tokens[0], start_pos, nt, feedback))) return rc;
+    CK(cudaEventRecord(p->ev0, p->stream));
+    for (int i = 0; i < n; i++) CK(cudaGraphLaunch(p->g_decode, p->stream));
+    CK(cudaEventRecord(p->ev1, p->stream));
+    if (out_ids) CK(cudaMemcpyAsync(p->h_ids, p->out_ids, (size_t)n * 4, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    if (out_ids) memcpy(out_ids, p->h_ids, (size_t)n * 4);
+    if (device_ms) CK(cudaEventElapsedTime(device_ms, p->ev0, p->ev1));
+    return B200_OK;
+}
+
+int b200_kv_reset(b200_plan *p) {
+    if (!p) return B200_ERR_BAD_ARG;
+    CK(cudaSetDevice(p->device));
+    size_t kv_bytes = (size_t)p->cfg.n_layers * p->cfg.context_length * p->kvd * 4;
+    CK(cudaMemsetAsync(p->key_cache, 0, kv_bytes, p->stream));
+    CK(cudaMemsetAsync(p->value_cache, 0, kv_bytes, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return B200_OK;
+}
+
+int b200_read_buffer(b200_plan *p, const char *name, int32_t layer, void *dst, size_t bytes) {
+    if (!p || !name || !dst) return B200_ERR_BAD_ARG;
+    const b200_config &c = p->cfg;
+    const void *src = nullptr;
+    size_t sz = 0;
+    std::string s = name;
+    size_t ctx_kv = (size_t)c.context_length * p->kvd;
+    if (s == "x") { src = p->x; sz = (size_t)c.dim * 4; }
+    else if (s == "xb") { src = p->xb; sz = (size_t)(c.dim > p->qd ? c.dim : p->qd) * 4; }
+    else if (s == "q" || s == "qkv") { src = p->qkv; sz = (size_t)(p->qd + 2 * p->kvd) * 4; }
+    else if (s == "hb") { src = p->hb; sz = (size_t)c.hidden_dim * 4; }
+    else if (s == "logits") { src = p->logits; sz = (size_t)c.vocab_size * 4; }
+    else if (s == "xq") { src = p->xq; sz = (size_t)(c.dim > p->qd ? c.dim : p->qd); }
+    else if (s == "xs") { src = p->xs; sz = (size_t)((c.dim > p->qd ? c.dim : p->qd) / 32) * 4; }
+    else if (s == "hq") { src = p->hq; sz = (size_t)c.hidden_dim; }
+    else if (s == "hs") { src = p->hs; sz = (size_t)(c.hidden_dim / 32) * 4; }
+    else if (s == "key_cache" || s == "value_cache") {
+        if (layer < 0 || layer >= c.n_layers) return fail(p, B200_ERR_BAD_ARG, "layer out of range");
+        src = (s == "key_cache" ? p->key_cache : p->value_cache) + (size_t)layer * ctx_kv;
+        sz = ctx_kv * 4;
+    } else return fail(p, B200_ERR_BAD_ARG, "unknown buffer %s", name);
+    if (bytes < sz) sz = bytes;
+    CK(cudaSetDevice(p->device));
+    CK(cudaStreamSynchronize(p->stream));
+    CK(cudaMemcpy(dst, src, sz, cudaMemcpyDeviceToHost));
+    return B200_OK;
+}
+
+int b200_time_kernel(b200_plan *p, int32_t which, int32_t reps, float *avg_ms, int64_t *algorithmic_bytes) {
+    if (!p || !avg_ms || reps <= 0) return B200_ERR_BAD_ARG;
+    const b200_config &c = p->cfg;
+    const bool q8 = p->wtype == B200_GGML_Q8_0;
+    CK(cudaSetDevice(p->device));
+    std::vector<float> save(c.dim);
+    CK(cudaStreamSynchronize(p->stream));
+    CK(cudaMemcpy(save.data(), p->x, (size_t)c.dim * 4, cudaMemcpyDeviceToHost));
+    auto mat_bytes = [&](const DevMat &m) -> int64_t {
+        int64_t e = (int64_t)m.rows * m.cols;
+        return q8 ? e / 32 * 34 : e * 2;
+    };
+    int64_t bytes = 0;
+    int launches = 0;
+    auto one = [&](int l) -> int {
+        LayerW &L = p->layers[l];
+        switch (which) {
+        case 0:
+            if (q8) {
+                k_gateup_q8<<<c.hidden_dim / 32, 256, q8_smem_bytes(c.dim, 4, 8), p->stream>>>(
+                    (const int8_t *)L.w1.qs, L.w1.sc, (const int8_t *)L.w3.qs, L.w3.sc, p->xq, p->xs, c.hidden_dim, c.dim, p->hq, p->hs, p->hb);
+                CK(cudaGetLastError());
+            } else {
+                int rc;
+                if ((rc = launch_matvec_f16<MODE_STORE>(p, L.w1, p->xb, p->hb))) return rc;
+                if ((rc = launch_matvec_f16<MODE_STORE>(p, L.w3, p->xb, p->hb2))) return rc;
+            }
+            bytes = mat_bytes(L.w1) + mat_bytes(L.w3);
+            return B200_OK;
+        case 1: bytes = mat_bytes(L.w2); return q8 ? launch_matvec_q8<MODE_RESID>(p, L.w2, p->hq, p->hs, p->x) : launch_matvec_f16<MODE_RESID>(p, L.w2, p->hb, p->x);
+        case 2: bytes = mat_bytes(L.qkv); return q8 ? launch_matvec_q8<MODE_STORE>(p, L.qkv, p->xq, p->xs, p->qkv) : launch_matvec_f16<MODE_STORE>(p, L.qkv, p->xb, p->qkv);
+        case 3: bytes = mat_bytes(L.wo); return q8 ? launch_matvec_q8<MODE_RESID>(p, L.wo, p->xq, p->xs, p->x) : launch_matvec_f16<MODE_RESID>(p, L.wo, p->xb, p->x);
+        default: bytes = mat_bytes(p->out); return q8 ? launch_matvec_q8<MODE_STORE>(p, p->out, p->xq, p->xs, p->logits) : launch_matvec_f16<MODE_STORE>(p, p->out, p->xb, p->logits);
+        }
+    };
+    if (which < 0 || which > 4) return fail(p, B200_ERR_BAD_ARG, "unknown kernel id %d", which);
+    int rc;
+    for (int l = 0; l < c.n_layers; l++) if ((rc = one(l))) return rc; // warm-up pass (also defeats L2 for pass 1)
+    CK(cudaEventRecord(p->ev0, p->stream));
+    for (int r = 0; r < reps; r++)
+        for (int l = 0; l < c.n_layers; l++) { if ((rc = one(l))) return rc; launches++; }
+    CK(cudaEventRecord(p->ev1, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, p->ev0, p->ev1));
+    *avg_ms = ms / launches;
+    if (algorithmic_bytes) *algorithmic_bytes = bytes;
+    CK(cudaMemcpy(p->x, save.data(), (size_t)c.dim * 4, cudaMemcpyHostToDevice));
+    return B200_OK;
+}
+
+int b200_launches_per_decode(b200_plan *p) { return p ? p->launches_decode : 0; }
+int64_t b200_device_bytes(b200_plan *p) { return p ? p->bytes : 0; }
+
+void b200_plan_free(b200_plan *p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    if (p->stream) cudaStreamSynchronize(p->stream);
+    prefill_free(p->prefill);
+    if (p->g_decode) cudaGraphExecDestroy(p->g_decode);
+    if (p->g_prefill) cudaGraphExecDestroy(p->g_prefill);
+    for (void *d : p->allocs) cudaFree(d);
+    if (p->h_st) cudaFreeHost(p->h_st);
+    if (p->h_ids) cudaFreeHost(p->h_ids);
+    if (p->ev0) cudaEventDestroy(p->ev0);
+    if (p->ev1) cudaEventDestroy(p->ev1);
+    if (p->stream) cudaStreamDestroy(p->stream);
+    delete p;
+}
+
+const char *b200_last_error(b200_plan *p) { return p ? p->err.c_str() : "null plan"; }
+const char *b200_version(void) { return "b200llama 0.1 sm_100a"; }
+
+} // extern "C"

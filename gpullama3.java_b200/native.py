@@ -1,0 +1,164 @@
+"""ctypes binding of libb200llama.so (the C ABI in include/b200llama.h).
+
+There is deliberately NO fallback: if the CUDA library is missing or a call fails, this
+module raises.  Nothing here (or anywhere in the package) touches ``oracle/``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libb200llama.so")
+
+B200_OK = 0
+ERRORS = {-1: "BAD_ARG", -2: "UNSUPPORTED", -3: "OOM", -4: "CUDA", -5: "NCCL", -6: "STATE"}
+
+
+class B200Error(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"b200llama error {ERRORS.get(code, code)}: {msg}")
+        self.code = code
+
+
+class UnsupportedOperation(B200Error):
+    """Counterpart of the reference's UnsupportedOperationException (ForwardPlanFactory.java:84-87)."""
+
+
+class Config(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("arch", "dim", "hidden_dim", "n_layers", "n_heads", "n_kv_heads", "head_size",
+                                        "vocab_size", "context_length")] + \
+               [("rms_norm_eps", C.c_float), ("rope_theta", C.c_float), ("fp16_lanes", C.c_int32),
+                ("tp_rank", C.c_int32), ("tp_size", C.c_int32)]
+
+
+class Tensor(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("data", C.c_void_p), ("ggml_type", C.c_int32), ("n_dims", C.c_int32),
+                ("dims", C.c_int64 * 4)]
+
+
+EXPORTS = ["b200_plan_create", "b200_forward_decode", "b200_forward_prefill", "b200_forward_batch_prefill",
+           "b200_decode_sequence", "b200_time_kernel", "b200_kv_reset", "b200_read_buffer", "b200_launches_per_decode",
+           "b200_device_bytes", "b200_plan_free", "b200_last_error", "b200_version"]
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, i32 = C.c_void_p, C.c_int32
+    L.b200_plan_create.argtypes = [C.POINTER(Config), C.POINTER(Tensor), i32, i32, i32, C.POINTER(vp), C.c_char_p, C.c_size_t]
+    L.b200_forward_decode.argtypes = [vp, i32, i32, vp, C.POINTER(i32)]
+    L.b200_forward_prefill.argtypes = [vp, i32, i32]
+    L.b200_forward_batch_prefill.argtypes = [vp, vp, i32, i32]
+    L.b200_decode_sequence.argtypes = [vp, vp, i32, i32, i32, vp, C.POINTER(C.c_float)]
+    L.b200_kv_reset.argtypes = [vp]
+    L.b200_time_kernel.argtypes = [vp, i32, i32, C.POINTER(C.c_float), C.POINTER(C.c_int64)]
+    L.b200_read_buffer.argtypes = [vp, C.c_char_p, i32, vp, C.c_size_t]
+    L.b200_launches_per_decode.argtypes = [vp]
+    L.b200_device_bytes.argtypes = [vp]
+    L.b200_device_bytes.restype = C.c_int64
+    L.b200_plan_free.argtypes = [vp]
+    L.b200_plan_free.restype = None
+    L.b200_last_error.argtypes = [vp]
+    L.b200_last_error.restype = C.c_char_p
+    L.b200_version.restype = C.c_char_p
+    _lib = L
+    return L
+
+
+def _raise(code: int, msg: str):
+    if code == -2:
+        raise UnsupportedOperation(code, msg)
+    raise B200Error(code, msg)
+
+
+class NativePlan:
+    """Owns one ``b200_plan*``."""
+
+    def __init__(self, cfg: Config, tensors: dict, prefill_batch_size: int = 0, device: int = 0):
+        L = lib()
+        arr = (Tensor * len(tensors))()
+        self._keep = []
+        for i, (name, (tt, dims, raw)) in enumerate(tensors.items()):
+            raw = np.ascontiguousarray(raw)
+            self._keep.append(raw)
+            arr[i].name = name.encode()
+            arr[i].data = raw.ctypes.data
+            arr[i].ggml_type = int(tt)
+            arr[i].n_dims = len(dims)
+            for k, d in enumerate(dims):
+                arr[i].dims[k] = int(d)
+        out = C.c_void_p()
+        err = C.create_string_buffer(512)
+        rc = L.b200_plan_create(C.byref(cfg), arr, len(tensors), prefill_batch_size, device, C.byref(out), err, 512)
+        self._keep = None  # the library never touches the host pointers again
+        if rc != B200_OK:
+            _raise(rc, err.value.decode())
+        self._p = out
+        self.cfg = cfg
+
+    def _ck(self, rc: int):
+        if rc != B200_OK:
+            _raise(rc, lib().b200_last_error(self._p).decode())
+
+    def forward_decode(self, token: int, position: int, want_logits: bool = True, want_argmax: bool = True):
+        logits = np.empty(self.cfg.vocab_size, dtype=np.float32) if want_logits else None
+        am = C.c_int32(-1)
+        self._ck(lib().b200_forward_decode(self._p, token, position, logits.ctypes.data if want_logits else None,
+                                           C.byref(am) if want_argmax else None))
+        return logits, (am.value if want_argmax else None)
+
+    def forward_prefill(self, token: int, position: int):
+        self._ck(lib().b200_forward_prefill(self._p, token, position))
+
+    def forward_batch_prefill(self, tokens, start_pos: int):
+        t = np.ascontiguousarray(tokens, dtype=np.int32)
+        self._ck(lib().b200_forward_batch_prefill(self._p, t.ctypes.data, len(t), start_pos))
+
+    def decode_sequence(self, tokens, n: int, start_pos: int, feedback: bool = False):
+        t = np.ascontiguousarray(tokens, dtype=np.int32)
+        out = np.empty(n, dtype=np.int32)
+        ms = C.c_float(0)
+        self._ck(lib().b200_decode_sequence(self._p, t.ctypes.data, n, start_pos, 1 if feedback else 0, out.ctypes.data, C.byref(ms)))
+        return out, ms.value
+
+    def time_kernel(self, which: int, reps: int = 3):
+        ms, nbytes = C.c_float(0), C.c_int64(0)
+        self._ck(lib().b200_time_kernel(self._p, which, reps, C.byref(ms), C.byref(nbytes)))
+        return ms.value, nbytes.value
+
+    def kv_reset(self):
+        self._ck(lib().b200_kv_reset(self._p))
+
+    def read_buffer(self, name: str, n: int, dtype=np.float32, layer: int = 0) -> np.ndarray:
+        out = np.empty(n, dtype=dtype)
+        self._ck(lib().b200_read_buffer(self._p, name.encode(), layer, out.ctypes.data, out.nbytes))
+        return out
+
+    @property
+    def launches_per_decode(self) -> int:
+        return lib().b200_launches_per_decode(self._p)
+
+    @property
+    def device_bytes(self) -> int:
+        return lib().b200_device_bytes(self._p)
+
+    def free(self):
+        if self._p:
+            lib().b200_plan_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

@@ -1,0 +1,157 @@
+"""Seeded synthetic GGUF models in the BASELINE shapes (no real checkpoints are available
+offline).  Tensor names/types are exactly what the reference loaders
+expect (``model/loader/LlamaModelLoader.java:78-99``, ``Qwen3ModelLoader.java:98-124``):
+norm weights F32, matrices and the embedding table in the model quantisation, metadata keys
+per ``LlamaModelLoader.java:47-63`` / ``Qwen3ModelLoader.java:48-74``.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+from .gguf import GGMLType, write_gguf
+
+
+@dataclass(frozen=True)
+class Shape:
+    arch: str  # "llama" | "qwen3"
+    dim: int
+    hidden: int
+    n_layers: int
+    n_heads: int
+    n_kv_heads: int
+    head_size: int
+    vocab: int
+    tied: bool
+    rope_theta: float
+    eps: float
+    model_ctx: int = 8192
+
+    @property
+    def q_dim(self):
+        return self.n_heads * self.head_size
+
+    @property
+    def kv_dim(self):
+        return self.n_kv_heads * self.head_size
+
+    def matmul_elements(self) -> int:
+        """Weight elements streamed per decoded token."""
+        per_layer = 2 * self.q_dim * self.dim + 2 * self.kv_dim * self.dim + 3 * self.hidden * self.dim
+        return self.n_layers * per_layer + self.vocab * self.dim
+
+
+SHAPES = {
+    # tiny parity shapes (oracle finishes in milliseconds)
+    "tiny-llama": Shape("llama", 256, 512, 2, 4, 2, 64, 512, False, 500000.0, 1e-5),
+    "tiny-llama-tied": Shape("llama", 256, 512, 2, 4, 2, 64, 512, True, 500000.0, 1e-5),
+    "tiny-qwen3": Shape("qwen3", 256, 768, 2, 4, 2, 128, 640, True, 1000000.0, 1e-6),
+    # mid shape: exercises column tails (dim not a multiple of 512) and several row tiles
+    "small-llama": Shape("llama", 1536, 4096, 3, 12, 4, 128, 4096, False, 500000.0, 1e-5),
+    # BASELINE.json shapes
+    "llama-3.2-1b": Shape("llama", 2048, 8192, 16, 32, 8, 64, 128256, True, 500000.0, 1e-5, 131072),
+    "llama-3-8b": Shape("llama", 4096, 14336, 32, 32, 8, 128, 128256, False, 500000.0, 1e-5),
+    "qwen3-4b": Shape("qwen3", 2560, 9728, 36, 32, 8, 128, 151936, True, 1000000.0, 1e-6, 40960),
+    "llama-3-70b": Shape("llama", 8192, 28672, 80, 64, 8, 128, 128256, False, 500000.0, 1e-5),
+}
+
+
+def quantize_q8_0(x: np.ndarray) -> np.ndarray:
+    """ggml reference Q8_0 quantiser (amax/127, roundf = half away from zero, f16 scale).
+    Returns raw block bytes, 34 per 32 elements."""
+    x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1, 32)
+    amax = np.abs(x).max(axis=1)
+    d = (amax / np.float32(127.0)).astype(np.float32)
+    with np.errstate(divide="ignore"):
+        inv = np.where(d != 0, np.float32(1.0) / d, np.float32(0.0)).astype(np.float32)
+    s = x * inv[:, None]
+    q = np.trunc(s + np.copysign(np.float32(0.5), s)).astype(np.int8)
+    out = np.empty((x.shape[0], 34), dtype=np.uint8)
+    out[:, 0:2] = d.astype(np.float16).view(np.uint8).reshape(-1, 2)
+    out[:, 2:] = q.view(np.uint8)
+    return out.reshape(-1)
+
+
+def encode(x: np.ndarray, ggml_type: int) -> np.ndarray:
+    if ggml_type == GGMLType.F32:
+        return np.ascontiguousarray(x, dtype="<f4").view(np.uint8).reshape(-1)
+    if ggml_type == GGMLType.F16:
+        return np.ascontiguousarray(x, dtype=np.float32).astype("<f2").view(np.uint8).reshape(-1)
+    if ggml_type == GGMLType.Q8_0:
+        return quantize_q8_0(x)
+    raise ValueError(ggml_type)
+
+
+def metadata_for(shape: Shape, quant: int, name: str) -> dict:
+    a = shape.arch
+    md = {
+        "general.architecture": a,
+        "general.name": name,  # ModelLoader.detectModelType keys on this substring (ModelLoader.java:57-80)
+        "general.file_type": 7 if quant == GGMLType.Q8_0 else 1,  # AbstractModelLoader.java:40-50
+        f"{a}.embedding_length": shape.dim,
+        f"{a}.feed_forward_length": shape.hidden,
+        f"{a}.block_count": shape.n_layers,
+        f"{a}.attention.head_count": shape.n_heads,
+        f"{a}.attention.head_count_kv": shape.n_kv_heads,
+        f"{a}.context_length": shape.model_ctx,
+        f"{a}.attention.layer_norm_rms_epsilon": float(shape.eps),
+        f"{a}.rope.freq_base": float(shape.rope_theta),
+        f"{a}.vocab_size": shape.vocab,
+    }
+    if a == "qwen3":
+        md["qwen3.attention.key_length"] = shape.head_size
+        md["qwen3.attention.value_length"] = shape.head_size
+    return md
+
+
+def tensor_plan(shape: Shape, quant: int):
+    """[(name, ggml_type, dims(ne0 innermost), kind)] in file order."""
+    t = [("token_embd.weight", quant, (shape.dim, shape.vocab), "w")]
+    for i in range(shape.n_layers):
+        p = f"blk.{i}."
+        t += [
+            (p + "attn_norm.weight", GGMLType.F32, (shape.dim,), "n"),
+            (p + "attn_q.weight", quant, (shape.dim, shape.q_dim), "w"),
+            (p + "attn_k.weight", quant, (shape.dim, shape.kv_dim), "w"),
+            (p + "attn_v.weight", quant, (shape.dim, shape.kv_dim), "w"),
+            (p + "attn_output.weight", quant, (shape.q_dim, shape.dim), "w"),
+        ]
+        if shape.arch == "qwen3":
+            t += [(p + "attn_q_norm.weight", GGMLType.F32, (shape.head_size,), "n"),
+                  (p + "attn_k_norm.weight", GGMLType.F32, (shape.head_size,), "n")]
+        t += [
+            (p + "ffn_norm.weight", GGMLType.F32, (shape.dim,), "n"),
+            (p + "ffn_gate.weight", quant, (shape.dim, shape.hidden), "w"),
+            (p + "ffn_down.weight", quant, (shape.hidden, shape.dim), "w"),
+            (p + "ffn_up.weight", quant, (shape.dim, shape.hidden), "w"),
+        ]
+    t.append(("output_norm.weight", GGMLType.F32, (shape.dim,), "n"))
+    if not shape.tied:
+        t.append(("output.weight", quant, (shape.dim, shape.vocab), "w"))
+    return t
+
+
+def build_tensors(shape: Shape, quant: int, seed: int = 1234, w_std: float = 0.02):
+    """Seeded tensors: matrices N(0, w_std) (scaled so activations stay O(1) through the
+    stack), norm weights 1 + N(0, 0.02).  Returns [(name, type, dims, raw uint8)]."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    out = []
+    for name, tt, dims, kind in tensor_plan(shape, quant):
+        n = int(np.prod(dims))
+        if kind == "n":
+            x = (1.0 + 0.02 * rng.standard_normal(n, dtype=np.float32)).astype(np.float32)
+        else:
+            # fan-in scaled so that W.x of a unit-RMS vector is O(1): keeps logits in a sane range
+            std = w_std if w_std > 0 else 1.0 / np.sqrt(dims[0])
+            x = rng.standard_normal(n, dtype=np.float32) * np.float32(std)
+        out.append((name, tt, dims, encode(x, tt)))
+    return out
+
+
+def write_model(path: str, shape_name: str, quant: int, seed: int = 1234, w_std: float = 0.0,
+                display_name: str | None = None):
+    shape = SHAPES[shape_name]
+    name = display_name or {"llama": "Llama synthetic ", "qwen3": "Qwen3 synthetic "}[shape.arch] + shape_name
+    write_gguf(path, metadata_for(shape, quant, name), build_tensors(shape, quant, seed, w_std))
+    return shape

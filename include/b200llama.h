@@ -1,0 +1,152 @@
+/*
+ * b200llama.h -- C ABI of libb200llama.so: the B200-native replacement for the
+ * TornadoVM execution-plan layer of beehive-lab/GPULlama3.java.
+ *
+ * One `b200_plan` plays the role of one `TornadoVMMasterPlan` instance
+ * (reference: src/main/java/org/beehive/gpullama3/tornadovm/TornadoVMMasterPlan.java:30-85).
+ * It owns the device copies of the weights (repacked from GGUF block layout at
+ * creation), the FP32 KV cache ([layer][ctx][kvDim], LlamaState.java:46-47,69-70) and all
+ * activation buffers.  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Threading: a plan is single-owner (one thread at a time, like the reference where the
+ * server serialises on a lock, InferenceService.java:31,58).  Several plans may coexist;
+ * there is no process-global state.
+ *
+ * Errors: every entry point returns B200_OK (0) or a negative B200_ERR_* code;
+ * b200_last_error(plan) gives the message.  The Java shim maps B200_ERR_UNSUPPORTED to
+ * UnsupportedOperationException (ForwardPlanFactory.java:84-87) and B200_ERR_OOM to the
+ * reference's out-of-memory error (README.md:262-265).
+ */
+#ifndef B200LLAMA_H
+#define B200LLAMA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_OK 0
+#define B200_ERR_BAD_ARG (-1)
+#define B200_ERR_UNSUPPORTED (-2)
+#define B200_ERR_OOM (-3)
+#define B200_ERR_CUDA (-4)
+#define B200_ERR_NCCL (-5)
+#define B200_ERR_STATE (-6)
+
+#define B200_ARCH_LLAMA 0 /* InferenceCore.forwardJava,      InferenceCore.java:50-172  */
+#define B200_ARCH_QWEN3 1 /* InferenceCore.forwardJavaQwen3, InferenceCore.java:565-697 */
+
+/* GGML tensor type ids accepted for weights (tensor/GGMLType.java:5-20) */
+#define B200_GGML_F32 0
+#define B200_GGML_F16 1
+#define B200_GGML_Q8_0 8
+
+/* Model configuration: the fields of Configuration the forward pass reads
+ * (LlamaModelLoader.java:47-63, Qwen3ModelLoader.java:48-74). */
+typedef struct b200_config {
+    int32_t arch;           /* B200_ARCH_* */
+    int32_t dim;            /* embedding_length */
+    int32_t hidden_dim;     /* feed_forward_length */
+    int32_t n_layers;       /* block_count */
+    int32_t n_heads;        /* attention.head_count */
+    int32_t n_kv_heads;     /* attention.head_count_kv */
+    int32_t head_size;      /* dim/n_heads (Llama) or attention.key_length (Qwen3) */
+    int32_t vocab_size;
+    int32_t context_length; /* KV-cache positions to allocate (Options.maxTokens) */
+    float rms_norm_eps;
+    float rope_theta;
+    int32_t fp16_lanes;     /* FP16 weights only: lane count of the CPU path's vector species the
+                               results are pinned to (FP16FloatTensor.java:62-110, FloatTensor.java:21);
+                               8, 16 or 0 (scalar).  Ignored for Q8_0. */
+    int32_t tp_rank;        /* tensor-parallel rank of this process, 0 when tp_size == 1 */
+    int32_t tp_size;        /* 1, 2, 4 or 8 */
+} b200_config;
+
+/* One named GGUF tensor: raw host bytes exactly as mapped from the file
+ * (GGUF.loadTensorsStandard, GGUF.java:105-137).  dims[0] is the innermost dimension. */
+typedef struct b200_tensor {
+    const char *name; /* GGUF name, e.g. "blk.0.attn_q.weight" (LlamaModelLoader.java:78-99) */
+    const void *data;
+    int32_t ggml_type;
+    int32_t n_dims;
+    int64_t dims[4];
+} b200_tensor;
+
+typedef struct b200_plan b200_plan;
+
+/* TornadoVMMasterPlan.initializeTornadoVMPlan(state, model) (TornadoVMMasterPlan.java:55-70)
+ * + forceCopyInReadOnlyData (TornadoVMMasterPlanSingleToken.java:100-117): copies/repacks every
+ * tensor to `device`, allocates KV cache and activations, captures the decode CUDA graph.
+ * The host pointers are not retained.  prefill_batch_size mirrors -Dllama.prefillBatchSize
+ * (TornadoVMMasterPlan.java:41); 0/1 = no batched-prefill buffers.
+ * On failure *out is NULL and err (if non-NULL) receives the message. */
+int b200_plan_create(const b200_config *cfg, const b200_tensor *tensors, int32_t n_tensors,
+                     int32_t prefill_batch_size, int32_t device, b200_plan **out, char *err, size_t err_len);
+
+/* TornadoVMMasterPlan.tornadoVMForwardDecode(position) with the embedding gather moved
+ * device-side (replaces InferenceCore.forwardTornadoVM, InferenceCore.java:956-980, which copies
+ * the embedding row H2D every token).  Runs one single-token forward at `position`.
+ * logits (vocab_size floats, host) may be NULL: then only 4 bytes cross PCIe.
+ * argmax (host) may be NULL; otherwise receives FloatTensor.argmax semantics
+ * (first strict maximum, FloatTensor.java:138-151), computed on the device. */
+int b200_forward_decode(b200_plan *plan, int32_t token, int32_t position, float *logits, int32_t *argmax);
+
+/* TornadoVMMasterPlanPrefillDecode.tornadoVMForwardPrefill(position)
+ * (TornadoVMMasterPlanPrefillDecode.java:116): single-token forward that only fills the KV
+ * cache -- final norm, lm_head and argmax are skipped. */
+int b200_forward_prefill(b200_plan *plan, int32_t token, int32_t position);
+
+/* TornadoVMMasterPlanBatchPrefillDecode.tornadoVMForwardBatchPrefill()
+ * (TornadoVMMasterPlanBatchPrefillDecode.java:107-123) with explicit arguments instead of
+ * state.embeddingXBatch/batchStartPosHolder: tokens[b] is processed at start_pos+b,
+ * n <= prefill_batch_size.  KV cache only, no logits (InferenceCoreBatchPrefillDecode.java:166-167). */
+int b200_forward_batch_prefill(b200_plan *plan, const int32_t *tokens, int32_t n, int32_t start_pos);
+
+/* Device-resident token loop (what LlamaBench.runTest times, LlamaBench.java:234-254, and the
+ * greedy generation loop InferenceEngine.java:96-145 with the sampler on the device):
+ * runs n single-token forwards at positions start_pos..start_pos+n-1 without host round trips.
+ * feedback == 0: step i consumes tokens[i] (n entries).  feedback != 0: step 0 consumes
+ * tokens[0], step i>0 consumes the argmax of step i-1 (greedy generation).
+ * out_ids (n ints, may be NULL) receives each step's argmax.  device_ms (may be NULL)
+ * receives the CUDA-event time of the n steps on the plan's stream. */
+int b200_decode_sequence(b200_plan *plan, const int32_t *tokens, int32_t n, int32_t start_pos,
+                         int32_t feedback, int32_t *out_ids, float *device_ms);
+
+/* Zero the KV cache (a fresh State in the reference: Java arrays start zeroed,
+ * LlamaState.java:46-47; matters because the Qwen3 loop skips a position,
+ * InferenceEngine.java:175-225). */
+int b200_kv_reset(b200_plan *plan);
+
+/* Test/diagnostic read-back of a named device buffer into host memory.  Names:
+ * "x","xb","q","k","v","hb","logits","key_cache","value_cache","xq","xs".  `layer` selects the
+ * layer for the KV caches (ignored otherwise).  Copies min(bytes, buffer size). */
+int b200_read_buffer(b200_plan *plan, const char *name, int32_t layer, void *dst, size_t bytes);
+
+/* Measurement hook for bench.py's roofline line: launches ONE kernel family of the decode step
+ * stand-alone, `reps` times per layer, cycling over all layers so every launch streams weights
+ * that are not L2-resident, and returns the average duration of one launch (CUDA events on the
+ * plan's stream).  which: 0 = fused gate/up+SwiGLU, 1 = down projection (+residual),
+ * 2 = fused QKV, 3 = attention output projection (+residual), 4 = lm_head.
+ * The residual stream is restored afterwards; the KV cache is not touched. */
+int b200_time_kernel(b200_plan *plan, int32_t which, int32_t reps, float *avg_ms, int64_t *algorithmic_bytes);
+
+/* Number of kernels one decode step launches (bench.py's gpu_launches). */
+int b200_launches_per_decode(b200_plan *plan);
+
+/* Bytes of device memory held by the plan (weights + KV + activations). */
+int64_t b200_device_bytes(b200_plan *plan);
+
+/* TornadoVMMasterPlan.freeTornadoExecutionPlan() */
+void b200_plan_free(b200_plan *plan);
+
+const char *b200_last_error(b200_plan *plan);
+
+/* Library build id, e.g. "b200llama 0.1 sm_100a". */
+const char *b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200LLAMA_H */

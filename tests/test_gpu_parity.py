@@ -1,0 +1,167 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes -> libb200llama.so), against
+the CPU oracle on the same seeded synthetic GGUF models.  Bar: logits BIT-EXACT (uint32 view
+equal) and greedy token ids identical for both Q8_0 and FP16 weights -- the kernels reproduce
+the CPU path's float evaluation order (DESIGN.md "Exactness"), so no tolerance is needed."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def assert_bit_equal(a, b, what):
+    a, b = np.asarray(a, dtype=np.float32), np.asarray(b, dtype=np.float32)
+    if not np.array_equal(bits(a), bits(b)):
+        bad = np.flatnonzero(bits(a) != bits(b))
+        i = bad[0]
+        raise AssertionError(f"{what}: {len(bad)}/{a.size} elements differ; first at {i}: gpu={a[i]!r} oracle={b[i]!r} "
+                             f"max|d|={np.abs(a - b).max():.3e}")
+
+
+def run_stream(pkg, orc, model, lanes, n, check_kv=True, prefill_first=0):
+    plan = pkg.B200MasterPlan.initialize_plan(model, fp16_lanes=lanes)
+    om = orc.OracleModel(model, lanes=lanes)
+    c = model.configuration
+    stream = orc.bench_tokens(c.vocab_size, n)
+    try:
+        for pos in range(n):
+            tok = int(stream[pos])
+            if pos < prefill_first:
+                plan.forward_prefill(tok, pos)
+                om.forward(tok, pos, want_logits=False)
+                continue
+            lg, am = plan.forward_decode(tok, pos)
+            ref = om.forward(tok, pos)
+            assert_bit_equal(lg, ref, f"logits pos {pos}")
+            assert am == orc.argmax(ref), f"argmax pos {pos}"
+        if check_kv:
+            for l in range(c.n_layers):
+                nkv = c.context_length * c.kv_dim
+                assert_bit_equal(plan.read_buffer("key_cache", nkv, layer=l), om.key_cache(l), f"key cache layer {l}")
+                assert_bit_equal(plan.read_buffer("value_cache", nkv, layer=l), om.value_cache(l), f"value cache layer {l}")
+    finally:
+        plan.free()
+        om.close()
+
+
+@pytest.mark.parametrize("shape", ["tiny-llama", "tiny-llama-tied", "tiny-qwen3"])
+def test_decode_q8_bit_exact(pkg, orc, make_model, shape):
+    m = make_model(shape, pkg.gguf.GGMLType.Q8_0, 24)
+    run_stream(pkg, orc, m, 16, 20)
+
+
+@pytest.mark.parametrize("shape,lanes", [("tiny-llama", 16), ("tiny-llama-tied", 8), ("tiny-llama", 0), ("tiny-qwen3", 16)])
+def test_decode_f16_bit_exact(pkg, orc, make_model, shape, lanes):
+    m = make_model(shape, pkg.gguf.GGMLType.F16, 24)
+    run_stream(pkg, orc, m, lanes, 12)
+
+
+def test_decode_small_llama_q8(pkg, orc, make_model):
+    """dim 1536 (not a multiple of 512: exercises the column tail), 12 heads / 4 KV heads, 3 layers."""
+    m = make_model("small-llama", pkg.gguf.GGMLType.Q8_0, 40)
+    run_stream(pkg, orc, m, 16, 36, check_kv=False)
+
+
+def test_prefill_graph_then_decode(pkg, orc, make_model):
+    """forward_prefill (no logits) fills the same KV cache as a full forward."""
+    m = make_model("tiny-llama", pkg.gguf.GGMLType.Q8_0, 24)
+    run_stream(pkg, orc, m, 16, 16, prefill_first=9)
+
+
+def test_batch_prefill_matches_oracle(pkg, orc, make_model):
+    m = make_model("tiny-llama", pkg.gguf.GGMLType.Q8_0, 32)
+    c = m.configuration
+    plan = pkg.B200MasterPlan.initialize_plan(m, prefill_batch_size=8)
+    om = orc.OracleModel(m)
+    stream = orc.bench_tokens(c.vocab_size, 20)
+    for off in range(0, 16, 8):
+        plan.forward_batch_prefill(stream[off:off + 8], off)
+    for pos in range(16):
+        om.forward(int(stream[pos]), pos, want_logits=False)
+    for l in range(c.n_layers):
+        nkv = c.context_length * c.kv_dim
+        assert_bit_equal(plan.read_buffer("key_cache", nkv, layer=l), om.key_cache(l), f"key cache layer {l}")
+        assert_bit_equal(plan.read_buffer("value_cache", nkv, layer=l), om.value_cache(l), f"value cache layer {l}")
+    lg, am = plan.forward_decode(int(stream[16]), 16)
+    assert_bit_equal(lg, om.forward(int(stream[16]), 16), "decode after batched prefill")
+    plan.free()
+
+
+def test_decode_sequence_device_loop(pkg, orc, make_model):
+    """The device-resident loop (tokens and argmax never leave the GPU) equals step-by-step calls,
+    in both teacher-forced (LlamaBench) and greedy-feedback modes."""
+    m = make_model("tiny-llama", pkg.gguf.GGMLType.Q8_0, 40)
+    c = m.configuration
+    plan = pkg.B200MasterPlan.initialize_plan(m)
+    om = orc.OracleModel(m)
+    stream = orc.bench_tokens(c.vocab_size, 24)
+    ids, ms = plan.decode_sequence(stream, 24, 0, feedback=False)
+    ref = [orc.argmax(om.forward(int(stream[p]), p)) for p in range(24)]
+    assert list(ids) == ref and ms > 0
+    plan.kv_reset()
+    om.reset()
+    ids, _ = plan.decode_sequence(stream[:1], 16, 0, feedback=True)
+    tok, ref = int(stream[0]), []
+    for p in range(16):
+        tok = orc.argmax(om.forward(tok, p))
+        ref.append(tok)
+    assert list(ids) == ref
+    plan.free()
+
+
+def test_generation_loops_match_oracle(pkg, orc, make_model):
+    """The reference's loop conventions end to end: Llama (BOS at pos 0 and 1) and Qwen3 (skipped
+    position, which reads the zero-initialised KV row)."""
+    for shape, loop in (("tiny-llama", "llama"), ("tiny-qwen3", "qwen3")):
+        m = make_model(shape, pkg.gguf.GGMLType.Q8_0, 32)
+        plan = pkg.B200MasterPlan.initialize_plan(m)
+        om = orc.OracleModel(m)
+        prompt = [int(t) for t in orc.bench_tokens(m.configuration.vocab_size, 6)]
+        fn = pkg.engine.generate_tokens_llama if loop == "llama" else pkg.engine.generate_tokens_qwen3
+        got = fn(lambda t, p: plan.forward_decode(t, p, logits=False)[1], prompt[0], 0, prompt, [], 20, 32)
+        ref = fn(lambda t, p: om.forward_argmax(t, p), prompt[0], 0, prompt, [], 20, 32)
+        assert got == ref and len(got) > 8
+        plan.free()
+
+
+def test_batch_prefill_generation_loop(pkg, orc, make_model):
+    m = make_model("tiny-llama", pkg.gguf.GGMLType.Q8_0, 32)
+    plan = pkg.B200MasterPlan.initialize_plan(m, prefill_batch_size=4)
+    om = orc.OracleModel(m)
+    prompt = [int(t) for t in orc.bench_tokens(m.configuration.vocab_size, 7)]
+    got = pkg.engine.generate_tokens_llama_batch_prefill(plan, prompt[0], prompt, [], 20, 32, 4)
+    ref = pkg.engine.generate_tokens_llama(lambda t, p: om.forward_argmax(t, p), prompt[0], 0, prompt, [], 20, 32)
+    assert got == ref
+    plan.free()
+
+
+def test_kv_reset_and_determinism(pkg, orc, make_model):
+    m = make_model("tiny-qwen3", pkg.gguf.GGMLType.Q8_0, 24)
+    plan = pkg.B200MasterPlan.initialize_plan(m)
+    stream = orc.bench_tokens(m.configuration.vocab_size, 10)
+    a = [plan.forward_decode(int(stream[p]), p)[0] for p in range(10)]
+    plan.kv_reset()
+    b = [plan.forward_decode(int(stream[p]), p)[0] for p in range(10)]
+    for x, y in zip(a, b):
+        assert_bit_equal(x, y, "rerun after kv_reset")
+    plan.free()
+
+
+def test_error_conventions(pkg, make_model):
+    m = make_model("tiny-llama", pkg.gguf.GGMLType.Q8_0, 16)
+    plan = pkg.B200MasterPlan.initialize_plan(m)
+    with pytest.raises(pkg.native.B200Error):
+        plan.forward_decode(10 ** 6, 0)  # token out of range
+    with pytest.raises(pkg.native.B200Error):
+        plan.forward_decode(1, 16)  # position outside the KV cache
+    plan.free()
+    # unsupported quantisation -> UnsupportedOperation (ForwardPlanFactory.java:84-87)
+    bad = dict(m.tensors)
+    tt, dims, raw = bad["blk.0.attn_q.weight"]
+    bad["blk.0.attn_q.weight"] = (2, dims, raw)  # Q4_0
+    m.tensors = bad
+    with pytest.raises(pkg.native.UnsupportedOperation):
+        pkg.B200MasterPlan(m)
