@@ -22,6 +22,12 @@ struct StepState {
     int pad[3];
 };
 
+// Programmatic dependent launch (PDL): launch_dependents lets the next kernel of the stream become
+// resident early (it may only touch immutable weights until it executes pdl_wait, which blocks
+// until the preceding kernel has completed and flushed).  Both are no-ops without the launch attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ float warp_max_f(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));

@@ -13,6 +13,7 @@
 // but the arithmetic they implement is the CPU path's (InferenceCore.java:50-172, 565-697).
 #pragma once
 #include "common.cuh"
+#include "seqsum.cuh"
 
 enum { MODE_STORE = 0, MODE_RESID = 1 };
 
@@ -44,8 +45,10 @@ __global__ void __launch_bounds__(1024) k_rmsnorm_quant(float *__restrict__ x, c
                                                        float *__restrict__ xb) {
     extern __shared__ __align__(16) float sm[];
     float *sx = sm, *sq = sm + dim;
-    __shared__ float s_ss;
+    SeqSumScratch scratch = seqsum_carve(reinterpret_cast<unsigned char *>(sm + 2 * dim), dim);
     const int tid = threadIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
     int token = 0;
     if (EMBED) token = st->token;
     for (int i = tid; i < dim; i += blockDim.x) {
@@ -56,18 +59,11 @@ __global__ void __launch_bounds__(1024) k_rmsnorm_quant(float *__restrict__ x, c
         sq[i] = __fmul_rn(v, v);
     }
     __syncthreads();
-    if (tid == 0) {
-        float ss = 0.0f;
-        for (int i = 0; i < dim; i += 4) {
-            float4 t = *reinterpret_cast<const float4 *>(sq + i);
-            ss = __fadd_rn(ss, t.x); ss = __fadd_rn(ss, t.y); ss = __fadd_rn(ss, t.z); ss = __fadd_rn(ss, t.w);
-        }
-        ss = __fdiv_rn(ss, (float)dim);
-        ss = __fadd_rn(ss, eps);
-        s_ss = (float)(1.0 / sqrt((double)ss));
-    }
-    __syncthreads();
-    const float ss = s_ss;
+    // ss = sequential float sum of the squares (exact, parallel: seqsum.cuh)
+    float ss = block_seqsum_exact<8>(sq, dim, scratch);
+    ss = __fdiv_rn(ss, (float)dim);
+    ss = __fadd_rn(ss, eps);
+    ss = (float)(1.0 / sqrt((double)ss));
     const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     for (int b = warp; b < dim / 32; b += nwarps) {
         int i = b * 32 + lane;
@@ -80,6 +76,17 @@ __global__ void __launch_bounds__(1024) k_rmsnorm_quant(float *__restrict__ x, c
             if (lane == 0) xs[b] = as;
         }
     }
+}
+
+// Test hook: the sequential-sum emulation on arbitrary non-negative terms.
+__global__ void __launch_bounds__(1024) k_test_seqsum(const float *__restrict__ terms, int n, float *__restrict__ out) {
+    extern __shared__ __align__(16) float sm[];
+    float *sq = sm;
+    SeqSumScratch scratch = seqsum_carve(reinterpret_cast<unsigned char *>(sm + ((n + 3) & ~3)), n);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sq[i] = terms[i];
+    __syncthreads();
+    float s = block_seqsum_exact<8>(sq, n, scratch);
+    if (threadIdx.x == 0) out[0] = s;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -324,6 +331,8 @@ __global__ void k_rope_kv(float *__restrict__ qkv, const StepState *__restrict__
                           float *__restrict__ kc, float *__restrict__ vc) {
     extern __shared__ float sh[]; // hs floats
     __shared__ float s_ss;
+    pdl_launch_dependents();
+    pdl_wait();
     const int pos = st->pos, half = hs >> 1, p = threadIdx.x;
     const int slot = blockIdx.x;
     const bool is_q = slot < n_heads;
@@ -381,6 +390,8 @@ __global__ void __launch_bounds__(128) k_attention(const float *__restrict__ qkv
     __shared__ float s_val;
     float *sq = sm, *so = sm + hs, *att = sm + 2 * hs;
     const int h = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_launch_dependents();
+    pdl_wait();
     const int nt = st->pos + 1;
     const int kvh = h / kv_mul;
     for (int i = tid; i < hs; i += blockDim.x) sq[i] = qkv[h * hs + i];
@@ -449,6 +460,8 @@ __global__ void __launch_bounds__(1024) k_argmax_advance(const float *__restrict
     __shared__ float sv[32];
     __shared__ int si[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_launch_dependents();
+    pdl_wait();
     int best_i = 0;
     if (do_argmax) {
         float best = -INFINITY;

@@ -5,6 +5,7 @@
 #include "../../include/b200llama.h"
 #include "decode_kernels.cuh"
 #include "prefill.cuh"
+#include "stream_matvec.cuh"
 
 #include <math.h>
 #include <stdarg.h>
@@ -13,12 +14,14 @@
 #include <string.h>
 
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace {
 
 struct LayerW {
     DevMat qkv, wo, w1, w3, w2;
+    TileMat tqkv{}, two{}, tgu{}, tw2{}; // tile-major copies for the streaming kernel (Q8_0)
     float *attn_norm = nullptr, *ffn_norm = nullptr, *q_norm = nullptr, *k_norm = nullptr;
 };
 
@@ -36,6 +39,10 @@ struct b200_plan {
     std::string err;
 
     DevMat emb{}, out{};
+    TileMat tout{};
+    bool use_stream = false, use_pdl = false;
+    int n_sms = 148;
+    unsigned *blk_cnt = nullptr;
     float *out_norm = nullptr;
     std::vector<LayerW> layers;
     float *rope_cr = nullptr, *rope_ci = nullptr;
@@ -145,6 +152,45 @@ int upload_matrix(b200_plan *p, const b200_tensor *t, int rows, int cols, DevMat
     return B200_OK;
 }
 
+// Upload up to three stacked GGUF Q8_0 matrices (or the gate/up pair) into tile-major layout.
+int upload_tiles(b200_plan *p, const b200_tensor *t0, const b200_tensor *t1, const b200_tensor *t2, int r0, int r1, int r2, int cols,
+                 bool gateup, TileMat &out, void *stage, size_t stage_bytes) {
+    const b200_tensor *ts[3] = {t0, t1, t2};
+    int rs[3] = {r0, r1, r2};
+    RepackSrc src;
+    size_t off = 0;
+    for (int k = 0; k < 3; k++) {
+        src.raw[k] = nullptr;
+        src.rows[k] = rs[k];
+        if (rs[k] == 0) continue;
+        const b200_tensor *t = ts[k];
+        if (!t) return fail(p, B200_ERR_BAD_ARG, "missing tensor");
+        if (t->ggml_type != B200_GGML_Q8_0) return fail(p, B200_ERR_UNSUPPORTED, "tensor %s has ggml type %d, plan weight type is Q8_0", t->name, t->ggml_type);
+        if (n_elems(t) != (int64_t)rs[k] * cols) return fail(p, B200_ERR_BAD_ARG, "tensor %s has %lld elements, expected %lld", t->name, (long long)n_elems(t), (long long)rs[k] * cols);
+        size_t nbytes = (size_t)rs[k] * cols / 32 * 34;
+        if (off + nbytes > stage_bytes) return fail(p, B200_ERR_STATE, "staging buffer too small");
+        CK(cudaMemcpyAsync((unsigned char *)stage + off, t->data, nbytes, cudaMemcpyHostToDevice, p->stream));
+        src.raw[k] = (const unsigned char *)stage + off;
+        off += (nbytes + 255) & ~(size_t)255;
+    }
+    src.gateup = gateup ? 1 : 0;
+    const int rows = r0 + r1 + r2;
+    out.rows = rows;
+    out.cols = cols;
+    out.nseg = smv_pick_nseg(cols);
+    out.seg = cols / out.nseg;
+    out.unit_bytes = smv_unit_bytes(out.seg);
+    size_t total = (size_t)rows * out.nseg * out.unit_bytes;
+    unsigned char *d;
+    int rc = dalloc(p, &d, total);
+    if (rc) return rc;
+    out.base = d;
+    k_repack_tiles<<<(unsigned)((size_t)rows * out.nseg), 128, 0, p->stream>>>(src, d, rows, cols, out.seg, out.nseg, out.unit_bytes);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(p->stream));
+    return B200_OK;
+}
+
 int alloc_matrix(b200_plan *p, DevMat &m, int rows, int cols, int type) {
     m.rows = rows;
     m.cols = cols;
@@ -203,39 +249,82 @@ template <int MODE> int launch_matvec_f16(b200_plan *p, const DevMat &m, const f
     return B200_OK;
 }
 
+// Kernel launch with the programmatic-dependent-launch attribute (captured into the CUDA graph as
+// a programmatic edge): the kernel may become resident while its predecessor is still running.
+template <typename... KA, typename... A>
+int launch_k(b200_plan *p, bool pdl, void (*kern)(KA...), dim3 grid, dim3 block, size_t smem, A... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = p->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    CK(cudaLaunchKernelEx(&cfg, kern, static_cast<KA>(args)...));
+    return B200_OK;
+}
+
+const size_t SMV_SMEM_BUDGET = 100 * 1024;
+
+template <int MODE>
+int launch_stream(b200_plan *p, const TileMat &W, const int8_t *xq, const float *xs, float *out, int8_t *hq, float *hs) {
+    SmvSmem L = smv_layout(W.cols, W.seg, SMV_SMEM_BUDGET);
+    SmvArgs a;
+    a.W = W; a.xq = xq; a.xs = xs; a.out = out; a.hq = hq; a.hs = hs; a.blk_cnt = p->blk_cnt;
+    return launch_k(p, p->use_pdl, k_stream_matvec_q8<MODE>, dim3(p->n_sms), dim3(SMV_THREADS), L.total, a, L);
+}
+
+bool stream_shape_ok(int rows, int cols) {
+    if (rows % 4 || cols % 32) return false;
+    int nseg = smv_pick_nseg(cols);
+    if (!nseg) return false;
+    return smv_layout(cols, cols / nseg, SMV_SMEM_BUDGET).stages >= 3;
+}
+
 // Enqueue one single-token forward on p->stream (captured into a CUDA graph at creation).
 // with_logits=false is the prefill variant (InferenceCoreBatchPrefillDecode.java:166-167).
 int enqueue_forward(b200_plan *p, bool with_logits, int *launches) {
     const b200_config &c = p->cfg;
     const bool q8 = p->wtype == B200_GGML_Q8_0;
+    const bool st = p->use_stream, pdl = p->use_pdl;
     int n = 0;
-    const size_t norm_smem = (size_t)c.dim * 8;
+    const size_t norm_smem = (size_t)c.dim * 8 + seqsum_scratch_bytes(c.dim);
     int8_t *xq = q8 ? p->xq : nullptr;
     float *xs = q8 ? p->xs : nullptr;
     float *xbf = q8 ? nullptr : p->xb;
     const size_t ctx_kv = (size_t)c.context_length * p->kvd;
     for (int l = 0; l < c.n_layers; l++) {
         LayerW &L = p->layers[l];
-        if (l == 0) k_rmsnorm_quant<true><<<1, 1024, norm_smem, p->stream>>>(p->x, p->st, p->emb, L.attn_norm, c.rms_norm_eps, c.dim, xq, xs, xbf);
-        else k_rmsnorm_quant<false><<<1, 1024, norm_smem, p->stream>>>(p->x, p->st, p->emb, L.attn_norm, c.rms_norm_eps, c.dim, xq, xs, xbf);
-        CK(cudaGetLastError()); n++;
         int rc;
-        if (q8) rc = launch_matvec_q8<MODE_STORE>(p, L.qkv, p->xq, p->xs, p->qkv);
+        if (l == 0) rc = launch_k(p, pdl, k_rmsnorm_quant<true>, dim3(1), dim3(1024), norm_smem, p->x, (const StepState *)p->st, p->emb, (const float *)L.attn_norm, c.rms_norm_eps, c.dim, xq, xs, xbf);
+        else rc = launch_k(p, pdl, k_rmsnorm_quant<false>, dim3(1), dim3(1024), norm_smem, p->x, (const StepState *)p->st, p->emb, (const float *)L.attn_norm, c.rms_norm_eps, c.dim, xq, xs, xbf);
+        if (rc) return rc; n++;
+        if (st) rc = launch_stream<SMV_STORE>(p, L.tqkv, p->xq, p->xs, p->qkv, nullptr, nullptr);
+        else if (q8) rc = launch_matvec_q8<MODE_STORE>(p, L.qkv, p->xq, p->xs, p->qkv);
         else rc = launch_matvec_f16<MODE_STORE>(p, L.qkv, p->xb, p->qkv);
         if (rc) return rc; n++;
         float *kc = p->key_cache + (size_t)l * ctx_kv, *vc = p->value_cache + (size_t)l * ctx_kv;
-        k_rope_kv<<<c.n_heads + c.n_kv_heads, c.head_size / 2, c.head_size * 4, p->stream>>>(
-            p->qkv, p->st, p->rope_cr, p->rope_ci, c.n_heads, c.n_kv_heads, c.head_size, c.arch, L.q_norm, L.k_norm, c.rms_norm_eps, kc, vc);
-        CK(cudaGetLastError()); n++;
-        k_attention<<<c.n_heads, 128, (size_t)(2 * c.head_size + c.context_length) * 4, p->stream>>>(
-            p->qkv, kc, vc, p->st, c.head_size, p->kvd, c.n_heads / c.n_kv_heads, (float)sqrt((double)c.head_size), xq, xs, xbf);
-        CK(cudaGetLastError()); n++;
-        if (q8) rc = launch_matvec_q8<MODE_RESID>(p, L.wo, p->xq, p->xs, p->x);
+        if ((rc = launch_k(p, pdl, k_rope_kv, dim3(c.n_heads + c.n_kv_heads), dim3(c.head_size / 2), (size_t)c.head_size * 4, p->qkv, (const StepState *)p->st,
+                           (const float *)p->rope_cr, (const float *)p->rope_ci, c.n_heads, c.n_kv_heads, c.head_size, c.arch, (const float *)L.q_norm,
+                           (const float *)L.k_norm, c.rms_norm_eps, kc, vc))) return rc;
+        n++;
+        if ((rc = launch_k(p, pdl, k_attention, dim3(c.n_heads), dim3(128), (size_t)(2 * c.head_size + c.context_length) * 4, (const float *)p->qkv,
+                           (const float *)kc, (const float *)vc, (const StepState *)p->st, c.head_size, p->kvd, c.n_heads / c.n_kv_heads,
+                           (float)sqrt((double)c.head_size), xq, xs, xbf))) return rc;
+        n++;
+        if (st) rc = launch_stream<SMV_RESID>(p, L.two, p->xq, p->xs, p->x, nullptr, nullptr);
+        else if (q8) rc = launch_matvec_q8<MODE_RESID>(p, L.wo, p->xq, p->xs, p->x);
         else rc = launch_matvec_f16<MODE_RESID>(p, L.wo, p->xb, p->x);
         if (rc) return rc; n++;
-        k_rmsnorm_quant<false><<<1, 1024, norm_smem, p->stream>>>(p->x, p->st, p->emb, L.ffn_norm, c.rms_norm_eps, c.dim, xq, xs, xbf);
-        CK(cudaGetLastError()); n++;
-        if (q8) {
+        if ((rc = launch_k(p, pdl, k_rmsnorm_quant<false>, dim3(1), dim3(1024), norm_smem, p->x, (const StepState *)p->st, p->emb, (const float *)L.ffn_norm, c.rms_norm_eps, c.dim, xq, xs, xbf))) return rc;
+        n++;
+        if (st) {
+            if ((rc = launch_stream<SMV_GATEUP>(p, L.tgu, p->xq, p->xs, p->hb, p->hq, p->hs))) return rc; n++;
+            if ((rc = launch_stream<SMV_RESID>(p, L.tw2, p->hq, p->hs, p->x, nullptr, nullptr))) return rc; n++;
+        } else if (q8) {
             k_gateup_q8<<<c.hidden_dim / 32, 256, q8_smem_bytes(c.dim, 4, 8), p->stream>>>(
                 (const int8_t *)L.w1.qs, L.w1.sc, (const int8_t *)L.w3.qs, L.w3.sc, p->xq, p->xs, c.hidden_dim, c.dim, p->hq, p->hs, p->hb);
             CK(cudaGetLastError()); n++;
@@ -250,15 +339,19 @@ int enqueue_forward(b200_plan *p, bool with_logits, int *launches) {
     }
     if (with_logits) {
         // rmsnorm(x, x, rms_final_weight) then wcls.matmul (InferenceCore.java:167-169)
-        k_rmsnorm_quant<false><<<1, 1024, norm_smem, p->stream>>>(p->x, p->st, p->emb, p->out_norm, c.rms_norm_eps, c.dim, xq, xs, xbf);
-        CK(cudaGetLastError()); n++;
         int rc;
-        if (q8) rc = launch_matvec_q8<MODE_STORE>(p, p->out, p->xq, p->xs, p->logits);
+        if ((rc = launch_k(p, pdl, k_rmsnorm_quant<false>, dim3(1), dim3(1024), norm_smem, p->x, (const StepState *)p->st, p->emb, (const float *)p->out_norm, c.rms_norm_eps, c.dim, xq, xs, xbf))) return rc;
+        n++;
+        if (st) rc = launch_stream<SMV_STORE>(p, p->tout, p->xq, p->xs, p->logits, nullptr, nullptr);
+        else if (q8) rc = launch_matvec_q8<MODE_STORE>(p, p->out, p->xq, p->xs, p->logits);
         else rc = launch_matvec_f16<MODE_STORE>(p, p->out, p->xb, p->logits);
         if (rc) return rc; n++;
     }
-    k_argmax_advance<<<1, 1024, 0, p->stream>>>(p->logits, c.vocab_size, p->st, p->seq_tokens, p->out_ids, with_logits ? 1 : 0);
-    CK(cudaGetLastError()); n++;
+    {
+        int rc;
+        if ((rc = launch_k(p, pdl, k_argmax_advance, dim3(1), dim3(1024), (size_t)0, (const float *)p->logits, c.vocab_size, p->st, (const int *)p->seq_tokens, p->out_ids, with_logits ? 1 : 0))) return rc;
+        n++;
+    }
     if (launches) *launches = n;
     return B200_OK;
 }
@@ -280,7 +373,8 @@ int set_smem_attrs(b200_plan *p) {
     const b200_config &c = p->cfg;
     int maxdyn = 0;
     CK(cudaDeviceGetAttribute(&maxdyn, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device));
-    size_t need_norm = (size_t)c.dim * 8;
+    size_t need_norm = (size_t)c.dim * 8 + seqsum_scratch_bytes(c.dim);
+    if (c.dim > 8192) return fail(p, B200_ERR_UNSUPPORTED, "dim > 8192 not supported by the RMSNorm kernel");
     size_t need_att = (size_t)(2 * c.head_size + c.context_length) * 4;
     int maxcols = c.hidden_dim > c.dim ? c.hidden_dim : c.dim;
     if (p->qd > maxcols) maxcols = p->qd;
@@ -299,6 +393,9 @@ int set_smem_attrs(b200_plan *p) {
     CK(cudaFuncSetAttribute(k_matvec_q8<2, MODE_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_mv));
     CK(cudaFuncSetAttribute(k_matvec_q8<4, MODE_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_mv));
     CK(cudaFuncSetAttribute(k_gateup_q8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_mv));
+    CK(cudaFuncSetAttribute(k_stream_matvec_q8<SMV_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMV_SMEM_BUDGET));
+    CK(cudaFuncSetAttribute(k_stream_matvec_q8<SMV_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMV_SMEM_BUDGET));
+    CK(cudaFuncSetAttribute(k_stream_matvec_q8<SMV_GATEUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMV_SMEM_BUDGET));
     CK(cudaFuncSetAttribute(k_matvec_f16<MODE_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_f16));
     CK(cudaFuncSetAttribute(k_matvec_f16<MODE_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_f16));
     return B200_OK;
@@ -330,8 +427,24 @@ int build(b200_plan *p, const b200_tensor *tensors, int n_tensors) {
     CK(cudaEventCreate(&p->ev0));
     CK(cudaEventCreate(&p->ev1));
     int rc;
+    CK(cudaDeviceGetAttribute(&p->n_sms, cudaDevAttrMultiProcessorCount, p->device));
+    {
+        const char *e = getenv("B200_STREAM");
+        bool want = !(e && e[0] == '0');
+        p->use_stream = want && p->wtype == B200_GGML_Q8_0 && stream_shape_ok(p->qd + 2 * p->kvd, c.dim) && stream_shape_ok(c.dim, p->qd) &&
+                        stream_shape_ok(2 * c.hidden_dim, c.dim) && stream_shape_ok(c.dim, c.hidden_dim) && stream_shape_ok(c.vocab_size, c.dim);
+        const char *e2 = getenv("B200_PDL");
+        p->use_pdl = p->use_stream && !(e2 && e2[0] == '0');
+    }
     void *stage = nullptr;
-    const size_t stage_bytes = (size_t)34 * (8u << 20); // 8 Mi blocks = 272 MiB
+    size_t stage_bytes = (size_t)34 * (8u << 20); // 8 Mi blocks = 272 MiB
+    if (p->use_stream) {
+        size_t m1 = (size_t)c.vocab_size * c.dim, m2 = (size_t)2 * c.hidden_dim * c.dim, m3 = (size_t)(p->qd + 2 * p->kvd) * c.dim;
+        size_t mx = m1 > m2 ? m1 : m2;
+        if (m3 > mx) mx = m3;
+        size_t need = mx / 32 * 34 + 4096;
+        if (need > stage_bytes) stage_bytes = need;
+    }
     if (p->wtype == B200_GGML_Q8_0 || emb->ggml_type == B200_GGML_Q8_0) CK(cudaMalloc(&stage, stage_bytes));
     struct StageGuard { void *s; ~StageGuard() { if (s) cudaFree(s); } } guard{stage};
 
@@ -339,7 +452,13 @@ int build(b200_plan *p, const b200_tensor *tensors, int n_tensors) {
     if ((rc = alloc_matrix(p, p->emb, c.vocab_size, c.dim, emb->ggml_type))) return rc;
     if ((rc = upload_matrix(p, emb, c.vocab_size, c.dim, p->emb, 0, stage, stage_bytes))) return rc;
     const b200_tensor *outw = find(tensors, n_tensors, "output.weight");
-    if (outw) {
+    if (p->use_stream) {
+        if (!outw && emb->ggml_type != p->wtype) return fail(p, B200_ERR_UNSUPPORTED, "tied output weight type differs from the matrix type");
+        if ((rc = upload_tiles(p, outw ? outw : emb, nullptr, nullptr, c.vocab_size, 0, 0, c.dim, false, p->tout, stage, stage_bytes))) return rc;
+        p->out = p->emb;
+        if ((rc = dalloc(p, &p->blk_cnt, (size_t)(c.hidden_dim / 32) * 4))) return rc;
+        CK(cudaMemset(p->blk_cnt, 0, (size_t)(c.hidden_dim / 32) * 4));
+    } else if (outw) {
         if ((rc = alloc_matrix(p, p->out, c.vocab_size, c.dim, p->wtype))) return rc;
         if ((rc = upload_matrix(p, outw, c.vocab_size, c.dim, p->out, 0, stage, stage_bytes))) return rc;
     } else {
@@ -358,6 +477,13 @@ int build(b200_plan *p, const b200_tensor *tensors, int n_tensors) {
         if (c.arch == B200_ARCH_QWEN3) {
             if ((rc = upload_f32(p, T("attn_q_norm.weight"), c.head_size, &L.q_norm, "attn_q_norm.weight"))) return rc;
             if ((rc = upload_f32(p, T("attn_k_norm.weight"), c.head_size, &L.k_norm, "attn_k_norm.weight"))) return rc;
+        }
+        if (p->use_stream) {
+            if ((rc = upload_tiles(p, T("attn_q.weight"), T("attn_k.weight"), T("attn_v.weight"), p->qd, p->kvd, p->kvd, c.dim, false, L.tqkv, stage, stage_bytes))) return rc;
+            if ((rc = upload_tiles(p, T("attn_output.weight"), nullptr, nullptr, c.dim, 0, 0, p->qd, false, L.two, stage, stage_bytes))) return rc;
+            if ((rc = upload_tiles(p, T("ffn_gate.weight"), T("ffn_up.weight"), nullptr, c.hidden_dim, c.hidden_dim, 0, c.dim, true, L.tgu, stage, stage_bytes))) return rc;
+            if ((rc = upload_tiles(p, T("ffn_down.weight"), nullptr, nullptr, c.dim, 0, 0, c.hidden_dim, false, L.tw2, stage, stage_bytes))) return rc;
+            continue;
         }
         // fused [Wq; Wk; Wv] so one launch produces the packed q|k|v vector
         if ((rc = alloc_matrix(p, L.qkv, p->qd + 2 * p->kvd, c.dim, p->wtype))) return rc;
@@ -584,6 +710,39 @@ int b200_time_kernel(b200_plan *p, int32_t which, int32_t reps, float *avg_ms, i
     std::vector<float> save(c.dim);
     CK(cudaStreamSynchronize(p->stream));
     CK(cudaMemcpy(save.data(), p->x, (size_t)c.dim * 4, cudaMemcpyDeviceToHost));
+    if (p->use_stream) {
+        auto tb = [&](const TileMat &m) -> int64_t { return (int64_t)m.rows * m.cols / 32 * 34; };
+        int64_t bytes = 0;
+        int launches = 0, rc;
+        auto one = [&](int l) -> int {
+            LayerW &L = p->layers[l];
+            bool keep = p->use_pdl;
+            p->use_pdl = false;
+            int r;
+            switch (which) {
+            case 0: bytes = tb(L.tgu); r = launch_stream<SMV_GATEUP>(p, L.tgu, p->xq, p->xs, p->hb, p->hq, p->hs); break;
+            case 1: bytes = tb(L.tw2); r = launch_stream<SMV_RESID>(p, L.tw2, p->hq, p->hs, p->x, nullptr, nullptr); break;
+            case 2: bytes = tb(L.tqkv); r = launch_stream<SMV_STORE>(p, L.tqkv, p->xq, p->xs, p->qkv, nullptr, nullptr); break;
+            case 3: bytes = tb(L.two); r = launch_stream<SMV_RESID>(p, L.two, p->xq, p->xs, p->x, nullptr, nullptr); break;
+            default: bytes = tb(p->tout); r = launch_stream<SMV_STORE>(p, p->tout, p->xq, p->xs, p->logits, nullptr, nullptr); break;
+            }
+            p->use_pdl = keep;
+            return r;
+        };
+        if (which < 0 || which > 4) return fail(p, B200_ERR_BAD_ARG, "unknown kernel id %d", which);
+        for (int l = 0; l < c.n_layers; l++) if ((rc = one(l))) return rc;
+        CK(cudaEventRecord(p->ev0, p->stream));
+        for (int r = 0; r < reps; r++)
+            for (int l = 0; l < c.n_layers; l++) { if ((rc = one(l))) return rc; launches++; }
+        CK(cudaEventRecord(p->ev1, p->stream));
+        CK(cudaStreamSynchronize(p->stream));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, p->ev0, p->ev1));
+        *avg_ms = ms / launches;
+        if (algorithmic_bytes) *algorithmic_bytes = bytes;
+        CK(cudaMemcpy(p->x, save.data(), (size_t)c.dim * 4, cudaMemcpyHostToDevice));
+        return B200_OK;
+    }
     auto mat_bytes = [&](const DevMat &m) -> int64_t {
         int64_t e = (int64_t)m.rows * m.cols;
         return q8 ? e / 32 * 34 : e * 2;
@@ -625,6 +784,21 @@ int b200_time_kernel(b200_plan *p, int32_t which, int32_t reps, float *avg_ms, i
     if (algorithmic_bytes) *algorithmic_bytes = bytes;
     CK(cudaMemcpy(p->x, save.data(), (size_t)c.dim * 4, cudaMemcpyHostToDevice));
     return B200_OK;
+}
+
+int b200_test_seqsum(const float *terms, int32_t n, float *out) {
+    if (!terms || !out || n <= 0 || n > 8192) return B200_ERR_BAD_ARG;
+    float *d = nullptr, *o = nullptr;
+    if (cudaMalloc(&d, (size_t)n * 4) != cudaSuccess || cudaMalloc(&o, 4) != cudaSuccess) return B200_ERR_OOM;
+    size_t smem = (size_t)((n + 3) & ~3) * 4 + seqsum_scratch_bytes(n);
+    cudaFuncSetAttribute(k_test_seqsum, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaMemcpy(d, terms, (size_t)n * 4, cudaMemcpyHostToDevice);
+    k_test_seqsum<<<1, 1024, smem>>>(d, n, o);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(out, o, 4, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    cudaFree(o);
+    return e == cudaSuccess ? B200_OK : B200_ERR_CUDA;
 }
 
 int b200_launches_per_decode(b200_plan *p) { return p ? p->launches_decode : 0; }

@@ -69,17 +69,26 @@ def _quantization(metadata: dict) -> str:
 class Model:
     """Configuration + raw tensor views.  ``tensors[name] = (ggml_type, dims, uint8 ndarray)``."""
 
-    def __init__(self, gguf: GGUFFile, config: Configuration, model_type: str):
+    def __init__(self, gguf: GGUFFile | None, config: Configuration, model_type: str, tensors: dict | None = None):
         self.gguf = gguf
         self.configuration = config
         self.model_type = model_type
-        self.tensors = {}
-        for name, ti in gguf.tensor_infos.items():
-            if name == "rope_freqs.weight":  # GGUF.java:121-124
-                continue
-            self.tensors[name] = (ti.ggml_type, ti.dims, gguf.tensor_bytes(name))
+        self.tensors = dict(tensors) if tensors is not None else {}
+        if gguf is not None:
+            for name, ti in gguf.tensor_infos.items():
+                if name == "rope_freqs.weight":  # GGUF.java:121-124
+                    continue
+                self.tensors[name] = (ti.ggml_type, ti.dims, gguf.tensor_bytes(name))
         self.plan = None  # Model.setTornadoVMPlan
         self.latest_token = None
+
+
+def model_from_tensors(shape, quant: int, tensors: dict, context_length: int) -> Model:
+    """In-memory model (bench: synthetic weights never touch the disk)."""
+    cfg = Configuration(ARCH_QWEN3 if shape.arch == "qwen3" else ARCH_LLAMA, "Q8_0" if quant == GGMLType.Q8_0 else "FP16",
+                        shape.dim, shape.hidden, shape.n_layers, shape.n_heads, shape.n_kv_heads, shape.head_size,
+                        shape.vocab, context_length, float(shape.eps), float(shape.rope_theta))
+    return Model(None, cfg, "QWEN_3" if shape.arch == "qwen3" else "LLAMA_3", tensors)
 
 
 def load_model(path: str, context_length: int = -1) -> Model:

@@ -40,7 +40,7 @@ class Tensor(C.Structure):
 
 
 EXPORTS = ["b200_plan_create", "b200_forward_decode", "b200_forward_prefill", "b200_forward_batch_prefill",
-           "b200_decode_sequence", "b200_time_kernel", "b200_kv_reset", "b200_read_buffer", "b200_launches_per_decode",
+           "b200_decode_sequence", "b200_time_kernel", "b200_test_seqsum", "b200_kv_reset", "b200_read_buffer", "b200_launches_per_decode",
            "b200_device_bytes", "b200_plan_free", "b200_last_error", "b200_version"]
 
 _lib = None
@@ -61,6 +61,7 @@ def lib() -> C.CDLL:
     L.b200_forward_batch_prefill.argtypes = [vp, vp, i32, i32]
     L.b200_decode_sequence.argtypes = [vp, vp, i32, i32, i32, vp, C.POINTER(C.c_float)]
     L.b200_kv_reset.argtypes = [vp]
+    L.b200_test_seqsum.argtypes = [vp, i32, C.POINTER(C.c_float)]
     L.b200_time_kernel.argtypes = [vp, i32, i32, C.POINTER(C.c_float), C.POINTER(C.c_int64)]
     L.b200_read_buffer.argtypes = [vp, C.c_char_p, i32, vp, C.c_size_t]
     L.b200_launches_per_decode.argtypes = [vp]
@@ -79,6 +80,15 @@ def _raise(code: int, msg: str):
     if code == -2:
         raise UnsupportedOperation(code, msg)
     raise B200Error(code, msg)
+
+
+def test_seqsum(terms) -> float:
+    t = np.ascontiguousarray(terms, dtype=np.float32)
+    out = C.c_float(0)
+    rc = lib().b200_test_seqsum(t.ctypes.data, len(t), C.byref(out))
+    if rc != B200_OK:
+        _raise(rc, "b200_test_seqsum failed")
+    return out.value
 
 
 class NativePlan:

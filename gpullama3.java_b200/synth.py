@@ -155,3 +155,49 @@ def write_model(path: str, shape_name: str, quant: int, seed: int = 1234, w_std:
     name = display_name or {"llama": "Llama synthetic ", "qwen3": "Qwen3 synthetic "}[shape.arch] + shape_name
     write_gguf(path, metadata_for(shape, quant, name), build_tensors(shape, quant, seed, w_std))
     return shape
+
+
+def build_tensors_fast(shape: Shape, quant: int, seed: int = 1234, device: str | None = None):
+    """Same tensor set as build_tensors, generated with torch (on the GPU when there is one) so an
+    8B/70B-shaped model takes seconds, not minutes.  Data plumbing only -- not on the hot path.
+    Returns {name: (ggml_type, dims, uint8 ndarray in GGUF layout)} (host memory)."""
+    import torch
+
+    dev = torch.device(device or ("cuda" if torch.cuda.is_available() else "cpu"))
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed)
+    out = {}
+    chunk = 1 << 26
+    for name, tt, dims, kind in tensor_plan(shape, quant):
+        n = int(np.prod(dims))
+        if kind == "n":
+            x = 1.0 + 0.02 * torch.randn(n, device=dev, generator=gen)
+            out[name] = (tt, dims, x.float().cpu().numpy().view(np.uint8).reshape(-1))
+            continue
+        std = 1.0 / float(np.sqrt(dims[0]))
+        nbytes = GGMLType.byte_size_for(tt, n)
+        host = np.empty(nbytes, dtype=np.uint8)
+        ho = 0
+        for o in range(0, n, chunk):
+            m = min(chunk, n - o)
+            x = torch.randn(m, device=dev, generator=gen) * std
+            if tt == GGMLType.F16:
+                b = x.half().view(torch.uint8)
+            elif tt == GGMLType.Q8_0:
+                xb = x.view(-1, 32)
+                d = xb.abs().amax(dim=1) / 127.0
+                inv = torch.where(d != 0, 1.0 / d, torch.zeros_like(d))
+                s = xb * inv[:, None]
+                q = torch.trunc(s + torch.copysign(torch.full_like(s, 0.5), s)).to(torch.int8)
+                blk = torch.empty((xb.shape[0], 34), dtype=torch.uint8, device=dev)
+                blk[:, 0:2] = d.half().view(torch.uint8).view(-1, 2)
+                blk[:, 2:] = q.view(torch.uint8)
+                b = blk.view(-1)
+            else:
+                b = x.float().view(torch.uint8)
+            hb = b.cpu().numpy().reshape(-1)
+            host[ho:ho + hb.size] = hb
+            ho += hb.size
+        assert ho == nbytes
+        out[name] = (tt, dims, host)
+    return out

@@ -132,6 +132,11 @@ int b200_read_buffer(b200_plan *plan, const char *name, int32_t layer, void *dst
  * The residual stream is restored afterwards; the KV cache is not touched. */
 int b200_time_kernel(b200_plan *plan, int32_t which, int32_t reps, float *avg_ms, int64_t *algorithmic_bytes);
 
+/* Test hook for the exact parallel evaluation of the reference's sequential float sum
+ * (csrc/seqsum.cuh; the RMSNorm accumulator of InferenceCore.java:39-48): sums n <= 8192
+ * non-negative host floats on the device exactly as `for (i) s += t[i]` would. */
+int b200_test_seqsum(const float *terms, int32_t n, float *out);
+
 /* Number of kernels one decode step launches (bench.py's gpu_launches). */
 int b200_launches_per_decode(b200_plan *plan);
 

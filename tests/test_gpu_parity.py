@@ -165,3 +165,45 @@ def test_error_conventions(pkg, make_model):
     m.tensors = bad
     with pytest.raises(pkg.native.UnsupportedOperation):
         pkg.B200MasterPlan(m)
+
+
+def _seq(t):
+    return np.add.accumulate(np.asarray(t, dtype=np.float32), dtype=np.float32)[-1]
+
+
+def test_exact_parallel_sequential_sum(pkg):
+    """csrc/seqsum.cuh: the parallel emulation of `for (i) s += t[i]` in float32 must equal the
+    literal chain bit for bit, on benign and adversarial inputs (ties, binade edges, zeros,
+    huge dynamic range, sums parked next to a power of two, forced fallbacks)."""
+    rng = np.random.default_rng(0)
+    cases = []
+    for trial in range(120):
+        n = int(rng.choice([33, 64, 256, 1000, 1536, 2560, 4096, 8192]))
+        kind = trial % 10
+        if kind == 0: x = rng.standard_normal(n)
+        elif kind == 1: x = rng.standard_normal(n) * 10.0 ** rng.integers(-6, 6)
+        elif kind == 2: x = rng.standard_cauchy(n)
+        elif kind == 3: x = np.full(n, rng.standard_normal())
+        elif kind == 4: x = 2.0 ** rng.integers(-10, 10, n)
+        elif kind == 5:
+            x = rng.standard_normal(n); x[rng.integers(0, n, n // 4)] = 0
+        elif kind == 6: x = rng.standard_normal(n) * np.exp(rng.standard_normal(n) * 3)
+        elif kind == 7: x = np.round(rng.standard_normal(n) * 8) / 8
+        elif kind == 8:
+            x = np.zeros(n); x[n // 2:] = rng.standard_normal(n - n // 2)  # all-zero head -> literal path
+        else:
+            x = rng.standard_normal(n) * 1e-3; x[rng.integers(40, n)] = 1e3  # one huge term: multi-binade jump
+        cases.append((x.astype(np.float32) ** 2).astype(np.float32))
+    # sums parked right below / at / above a power of two (prediction least certain)
+    for n in (512, 4096):
+        for eps in (-3e-7, -1e-7, 0.0, 1e-7, 3e-7):
+            t = np.full(n, (1.0 + eps) / n, dtype=np.float64).astype(np.float32)
+            cases.append(t)
+            cases.append(np.concatenate([t, t]).astype(np.float32)[: min(2 * n, 8192)])
+    # more segments than the entry list holds -> sequential fallback must still be exact
+    cases.append((4.0 ** (np.arange(300) % 150 - 75)).astype(np.float32))
+    cases.append(np.array([1.0] * 40 + [np.inf] + [1.0] * 40, dtype=np.float32))
+    for t in cases:
+        got = np.float32(pkg.native.test_seqsum(t))
+        ref = _seq(t)
+        assert got.view(np.uint32) == ref.view(np.uint32) or (np.isnan(got) and np.isnan(ref)), (len(t), got, ref)
