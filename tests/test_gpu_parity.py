@@ -192,7 +192,7 @@ def test_exact_parallel_sequential_sum(pkg):
         elif kind == 8:
             x = np.zeros(n); x[n // 2:] = rng.standard_normal(n - n // 2)  # all-zero head -> literal path
         else:
-            x = rng.standard_normal(n) * 1e-3; x[rng.integers(40, n)] = 1e3  # one huge term: multi-binade jump
+            x = rng.standard_normal(n) * 1e-3; x[rng.integers(min(40, n - 1), n)] = 1e3  # one huge term: multi-binade jump
         cases.append((x.astype(np.float32) ** 2).astype(np.float32))
     # sums parked right below / at / above a power of two (prediction least certain)
     for n in (512, 4096):
