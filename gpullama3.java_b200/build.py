@@ -10,7 +10,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libb200llama.so")
 SOURCES = ["plan.cu"]
-DEPS = ["plan.cu", "common.cuh", "decode_kernels.cuh", "prefill.cuh", "../../include/b200llama.h"]
+
+
+def _deps():
+    d = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))]
+    d.append(os.path.join(HERE, "..", "include", "b200llama.h"))
+    return d
+
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -24,7 +30,7 @@ def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS) or os.path.getmtime(__file__) > t
+    return any(os.path.getmtime(d) > t for d in _deps()) or os.path.getmtime(__file__) > t
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

@@ -267,11 +267,19 @@ int launch_k(b200_plan *p, bool pdl, void (*kern)(KA...), dim3 grid, dim3 block,
     return B200_OK;
 }
 
-const size_t SMV_SMEM_BUDGET = 100 * 1024;
+const size_t SMV_SMEM_BUDGET_MAX = 100 * 1024;
+static size_t smv_budget(int cols = 0) {
+    const char *e = getenv("B200_SMV_BUDGET_KB"); // debug: force a shallow ring
+    const char *m = getenv("B200_SMV_BUDGET_COLS"); // debug: ... only for matrices with this many columns
+    size_t b = e ? (size_t)atoi(e) * 1024 : SMV_SMEM_BUDGET_MAX;
+    if (m && cols && atoi(m) != cols) b = SMV_SMEM_BUDGET_MAX;
+    return b > SMV_SMEM_BUDGET_MAX ? SMV_SMEM_BUDGET_MAX : b;
+}
+#define SMV_SMEM_BUDGET smv_budget()
 
 template <int MODE>
 int launch_stream(b200_plan *p, const TileMat &W, const int8_t *xq, const float *xs, float *out, int8_t *hq, float *hs) {
-    SmvSmem L = smv_layout(W.cols, W.seg, SMV_SMEM_BUDGET);
+    SmvSmem L = smv_layout(W.cols, W.seg, smv_budget(W.cols));
     SmvArgs a;
     a.W = W; a.xq = xq; a.xs = xs; a.out = out; a.hq = hq; a.hs = hs; a.blk_cnt = p->blk_cnt;
     return launch_k(p, p->use_pdl, k_stream_matvec_q8<MODE>, dim3(p->n_sms), dim3(SMV_THREADS), L.total, a, L);
@@ -393,9 +401,9 @@ int set_smem_attrs(b200_plan *p) {
     CK(cudaFuncSetAttribute(k_matvec_q8<2, MODE_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_mv));
     CK(cudaFuncSetAttribute(k_matvec_q8<4, MODE_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_mv));
     CK(cudaFuncSetAttribute(k_gateup_q8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_mv));
-    CK(cudaFuncSetAttribute(k_stream_matvec_q8<SMV_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMV_SMEM_BUDGET));
-    CK(cudaFuncSetAttribute(k_stream_matvec_q8<SMV_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMV_SMEM_BUDGET));
-    CK(cudaFuncSetAttribute(k_stream_matvec_q8<SMV_GATEUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMV_SMEM_BUDGET));
+    CK(cudaFuncSetAttribute(k_stream_matvec_q8<SMV_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMV_SMEM_BUDGET_MAX));
+    CK(cudaFuncSetAttribute(k_stream_matvec_q8<SMV_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMV_SMEM_BUDGET_MAX));
+    CK(cudaFuncSetAttribute(k_stream_matvec_q8<SMV_GATEUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMV_SMEM_BUDGET_MAX));
     CK(cudaFuncSetAttribute(k_matvec_f16<MODE_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_f16));
     CK(cudaFuncSetAttribute(k_matvec_f16<MODE_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_f16));
     return B200_OK;

@@ -50,7 +50,7 @@ __host__ __device__ inline SmvSmem smv_layout(int cols, int seg, size_t budget) 
     L.stage_bytes = (4 * unit + 127) & ~127;
     L.nbs_pad = (seg / 32) | 1;
     size_t o = 0;
-    L.off_bar = o; o += 2 * SMV_MAX_STAGES * 8;
+    L.off_bar = o; o += 2 * SMV_MAX_STAGES * 8 + SMV_MAX_STAGES * 4; // full[], empty[] mbarriers + release counters
     L.off_xq = o; o += (size_t)cols;
     L.off_xs = o; o += (size_t)(cols / 32) * 4;
     o = (o + 15) & ~(size_t)15;
@@ -129,10 +129,15 @@ __global__ void __launch_bounds__(SMV_THREADS, 1) k_stream_matvec_q8(SmvArgs a, 
     const int nseg = W.nseg;
     const unsigned tile_bytes = 4u * (unsigned)W.unit_bytes;
 
+    // rel[st] = number of tiles consumed from stage st so far.  The consumer warps advance
+    // independently, so a warp can reach the tile of lap k+2 of a stage while lap k+1 is still in
+    // flight; a parity wait cannot tell those apart, the counter can.
+    volatile unsigned *rel = reinterpret_cast<volatile unsigned *>(smem + L.off_bar + 2 * SMV_MAX_STAGES * 8);
     if (tid == 0) {
         for (int s = 0; s < S; s++) {
             mbar_init(bar0 + 8 * s, 1);
             mbar_init(bar0 + 8 * (SMV_MAX_STAGES + s), 1);
+            rel[s] = 0u;
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -187,7 +192,11 @@ __global__ void __launch_bounds__(SMV_THREADS, 1) k_stream_matvec_q8(SmvArgs a, 
             for (int s = 0; s < nseg; s++) {
                 const unsigned seq = seq_base + (unsigned)(s * nw + warp);
                 const int st = seq % S;
-                mbar_wait(bar0 + 8 * st, (seq / S) & 1u);
+                const unsigned lap = seq / S;
+                if (lane == 0)
+                    while (rel[st] != lap) {} // every earlier occupant of this stage has been consumed
+                __syncwarp();
+                mbar_wait(bar0 + 8 * st, lap & 1u);
                 const unsigned char *tile = smem + L.off_ring + (size_t)st * L.stage_bytes;
                 for (int b = lane; b < nbs; b += 32) {
                     const unsigned char *ab = sact + ((size_t)(s * nbs + b) << 5);
@@ -212,7 +221,10 @@ __global__ void __launch_bounds__(SMV_THREADS, 1) k_stream_matvec_q8(SmvArgs a, 
                     }
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar0 + 8 * (SMV_MAX_STAGES + st)); // weights consumed: slot back to the producer
+                if (lane == 0) { // weights consumed: slot back to the producer
+                    rel[st] = lap + 1u;
+                    mbar_arrive(bar0 + 8 * (SMV_MAX_STAGES + st));
+                }
                 if (lane < 4) {
                     const float *t = terms + lane * L.nbs_pad;
                     for (int b = 0; b < nbs; b++) acc = __fadd_rn(acc, t[b]); // strictly in block order

@@ -65,6 +65,14 @@ def test_decode_small_llama_q8(pkg, orc, make_model):
     run_stream(pkg, orc, m, 16, 36, check_kv=False)
 
 
+def test_decode_mid_llama_q8(pkg, orc):
+    """The real Llama-3-8B layer geometry (dim 4096, hidden 14336 = 7 column segments, 32/8 heads)
+    with 2 layers: the streaming kernel's ring laps many times per matvec here."""
+    sh = pkg.synth.SHAPES["mid-llama"]
+    m = pkg.loader.model_from_tensors(sh, pkg.gguf.GGMLType.Q8_0, pkg.synth.build_tensors_fast(sh, pkg.gguf.GGMLType.Q8_0, seed=5), 16)
+    run_stream(pkg, orc, m, 16, 6, check_kv=True)
+
+
 def test_prefill_graph_then_decode(pkg, orc, make_model):
     """forward_prefill (no logits) fills the same KV cache as a full forward."""
     m = make_model("tiny-llama", pkg.gguf.GGMLType.Q8_0, 24)

@@ -7,9 +7,8 @@ import __graft_entry__ as ge
 pkg = ge.import_package()
 shape = sys.argv[1] if len(sys.argv) > 1 else "small-llama"
 with tempfile.TemporaryDirectory() as d:
-    path = os.path.join(d, "m.gguf")
-    pkg.synth.write_model(path, shape, 8, seed=3)
-    m = pkg.load_model(path, 64)
+    sh = pkg.synth.SHAPES[shape]
+    m = pkg.loader.model_from_tensors(sh, 8, pkg.synth.build_tensors_fast(sh, 8, seed=3), 64)
     t0 = time.time(); plan = pkg.B200MasterPlan.initialize_plan(m); t1 = time.time()
     print(f"stream={os.environ.get('B200_STREAM','1')} pdl={os.environ.get('B200_PDL','1')} create {t1-t0:.3f}s", flush=True)
     toks = pkg.llama_bench.synthetic_tokens(m.configuration.vocab_size, 40)
