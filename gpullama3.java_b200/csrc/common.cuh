@@ -28,6 +28,25 @@ struct StepState {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// In-graph timeline tracing (diagnostic graph only; rec == nullptr in the production graphs, so the
+// branch is uniform and free).  One record per launch: {kernel id, earliest CTA entry, latest
+// dependency-wait return, latest CTA exit} in %globaltimer nanoseconds.
+struct TraceBuf {
+    unsigned long long *rec;
+    int slot, id;
+};
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void trace_entry(const TraceBuf &tr) {
+    if (tr.rec && threadIdx.x == 0) { tr.rec[tr.slot * 4] = (unsigned long long)tr.id; atomicMin(&tr.rec[tr.slot * 4 + 1], gtime()); }
+}
+__device__ __forceinline__ void trace_mark(const TraceBuf &tr, int k) {
+    if (tr.rec && threadIdx.x == 0) atomicMax(&tr.rec[tr.slot * 4 + k], gtime());
+}
+
 __device__ __forceinline__ float warp_max_f(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));

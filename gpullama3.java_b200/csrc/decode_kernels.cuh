@@ -38,55 +38,98 @@ __device__ __forceinline__ float emb_get(const DevMat &e, int token, int i) {
 // The sum is order-sensitive, so one thread walks it (squares precomputed in parallel).
 // One CTA.  Outputs: xq/xs (Q8_0 activation for the following matvec) and/or xb (float).
 // ------------------------------------------------------------------------------------------
+#define NORM_THREADS SEQSUM_THREADS
+__host__ __device__ inline size_t norm_smem_bytes(int dim) { return (size_t)dim * 4 + 16 + seqsum_scratch_bytes(dim); }
+
 template <bool EMBED>
-__global__ void __launch_bounds__(1024) k_rmsnorm_quant(float *__restrict__ x, const StepState *__restrict__ st,
-                                                       DevMat emb, const float *__restrict__ w, float eps, int dim,
-                                                       int8_t *__restrict__ xq, float *__restrict__ xs,
-                                                       float *__restrict__ xb) {
+__global__ void __launch_bounds__(NORM_THREADS, 1) k_rmsnorm_quant(float *__restrict__ x, const StepState *__restrict__ st,
+                                                               DevMat emb, const float *__restrict__ w, float eps, int dim,
+                                                               int8_t *__restrict__ xq, float *__restrict__ xs,
+                                                               float *__restrict__ xb, long long *__restrict__ prof, TraceBuf tr) {
+    // One CTA of 1024 threads: every per-group step of the exact sum is a long dependent chain, so the
+    // groups are spread over 32 warps.  Under PDL this CTA only has to fit next to ONE streaming-matvec CTA
+    // (the following matvec's CTA for this SM simply starts a little later).
     extern __shared__ __align__(16) float sm[];
-    float *sx = sm, *sq = sm + dim;
-    SeqSumScratch scratch = seqsum_carve(reinterpret_cast<unsigned char *>(sm + 2 * dim), dim);
+    float *sq = sm;
+    SeqSumScratch scratch = seqsum_carve(reinterpret_cast<unsigned char *>(sm + dim), dim);
+    __shared__ float s_ss;
     const int tid = threadIdx.x;
+    long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+    if (prof) t0 = clock64();
+    trace_entry(tr);
     pdl_launch_dependents();
     pdl_wait();
+    trace_mark(tr, 2);
+    if (prof) t1 = clock64();
     int token = 0;
     if (EMBED) token = st->token;
-    for (int i = tid; i < dim; i += blockDim.x) {
+    for (int i = tid; i < dim; i += NORM_THREADS) {
         float v;
         if (EMBED) { v = emb_get(emb, token, i); x[i] = v; }
         else v = x[i];
-        sx[i] = v;
         sq[i] = __fmul_rn(v, v);
     }
     __syncthreads();
+    if (prof) t2 = clock64();
     // ss = sequential float sum of the squares (exact, parallel: seqsum.cuh)
-    float ss = block_seqsum_exact<8>(sq, dim, scratch);
-    ss = __fdiv_rn(ss, (float)dim);
-    ss = __fadd_rn(ss, eps);
-    ss = (float)(1.0 / sqrt((double)ss));
-    const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    for (int b = warp; b < dim / 32; b += nwarps) {
-        int i = b * 32 + lane;
-        float v = __fmul_rn(w[i], __fmul_rn(ss, sx[i]));
-        if (xb) xb[i] = v;
-        if (xq) {
-            float as;
-            int q = quant_block_lane(v, as);
-            xq[i] = (int8_t)q;
-            if (lane == 0) xs[b] = as;
+    float ss = block_seqsum_exact(sq, dim, scratch, prof ? prof + 8 : nullptr);
+    if (prof) t3 = clock64();
+    if (EMBED) __threadfence_block(); // x[] written above by other threads of this block
+    if (tid == 0) {
+        ss = __fdiv_rn(ss, (float)dim);
+        ss = __fadd_rn(ss, eps);
+        s_ss = (float)(1.0 / sqrt((double)ss));
+    }
+    __syncthreads();
+    ss = s_ss;
+    const int lane = tid & 31, warp = tid >> 5;
+    constexpr int NWN = NORM_THREADS / 32;
+    const int nb = dim / 32;
+#pragma unroll 1
+    for (int b0 = warp; b0 < nb; b0 += 4 * NWN) { // 8 loads in flight per lane
+        float xv[4], wv[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int b = b0 + u * NWN;
+            xv[u] = 0.0f; wv[u] = 0.0f;
+            if (b < nb) { xv[u] = x[b * 32 + lane]; wv[u] = w[b * 32 + lane]; } // x: L1/L2 hit (or this block's own store)
         }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int b = b0 + u * NWN;
+            if (b < nb) {
+                const int i = b * 32 + lane;
+                const float v = __fmul_rn(wv[u], __fmul_rn(ss, xv[u]));
+                if (xb) xb[i] = v;
+                if (xq) {
+                    float as;
+                    int q = quant_block_lane(v, as);
+                    xq[i] = (int8_t)q;
+                    if (lane == 0) xs[b] = as;
+                }
+            }
+        }
+    }
+    trace_mark(tr, 3);
+    if (prof) {
+        __syncthreads();
+        if (tid == 0) { long long t4 = clock64(); prof[0] = t1 - t0; prof[1] = t2 - t1; prof[2] = t3 - t2; prof[3] = t4 - t3;
+                        prof[4] = scratch.info[0]; prof[5] = scratch.info[1]; prof[6] = scratch.info[2]; }
     }
 }
 
-// Test hook: the sequential-sum emulation on arbitrary non-negative terms.
-__global__ void __launch_bounds__(1024) k_test_seqsum(const float *__restrict__ terms, int n, float *__restrict__ out) {
+// Test hook: the sequential-sum emulation on arbitrary non-negative terms (padded with zeros to a
+// multiple of 32: adding +0 never changes a sum of non-negative floats).
+__global__ void __launch_bounds__(NORM_THREADS, 1) k_test_seqsum(const float *__restrict__ terms, int n, float *__restrict__ out, int *__restrict__ info) {
     extern __shared__ __align__(16) float sm[];
     float *sq = sm;
-    SeqSumScratch scratch = seqsum_carve(reinterpret_cast<unsigned char *>(sm + ((n + 3) & ~3)), n);
-    for (int i = threadIdx.x; i < n; i += blockDim.x) sq[i] = terms[i];
+    const int np = (n + 31) & ~31;
+    SeqSumScratch scratch = seqsum_carve(reinterpret_cast<unsigned char *>(sm + np), np);
+    for (int i = threadIdx.x; i < np; i += blockDim.x) sq[i] = i < n ? terms[i] : 0.0f;
+    if (threadIdx.x == 0) { scratch.info[0] = -1; scratch.info[1] = -2; }
     __syncthreads();
-    float s = block_seqsum_exact<8>(sq, n, scratch);
-    if (threadIdx.x == 0) out[0] = s;
+    float s = block_seqsum_exact(sq, np, scratch);
+    if (threadIdx.x == 0) { out[0] = s; info[0] = scratch.info[0]; info[1] = scratch.info[1]; }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -318,130 +361,167 @@ __global__ void k_swiglu(float *__restrict__ hb, const float *__restrict__ hb2, 
 }
 
 // ------------------------------------------------------------------------------------------
-// RoPE + KV-cache write (+ Qwen3 per-head q/k RMSNorm).
-// Llama: interleaved pairs (i, i+1), InferenceCore.java:75-87.  Qwen3: per-head rmsnorm
-// (InferenceCore.java:594-600) then NeoX pairs (ic, ic+half), :604-619.  KV write :92-93.
-// Grid: n_heads + n_kv_heads CTAs (q heads, then k heads which also copy their v head).
-// Block: head_size/2 threads, one rotation pair each.  cos/sin come from the table built at
-// plan creation exactly as RoPE.precomputeFreqsCis does (RoPE.java:6-37).
+// Fused RoPE + KV-cache write + attention, one query head per CTA, exact CPU-path order.
+//   prologue : (Qwen3: per-head RMSNorm of q and k, InferenceCore.java:594-600) then RoPE of this
+//              head's q and of its KV head's k (InferenceCore.java:75-87 interleaved pairs / :604-619 NeoX);
+//              every query head of a KV group rotates the same k redundantly (cheaper than a
+//              kernel boundary); the group's first head writes k,v into the cache (:92-93)
+//   scores   : score_t = scalarDot(q, k_t) / sqrt(head)   (sequential unfused mul/add, FloatTensor.java:86-92)
+//   softmax  : max, (float)Math.exp(f - max), sequential sum, divide        (FloatTensor.java:211-219)
+//   output   : xb = sum_t a_t * v_t, sequentially over t per element (saxpyInPlace, FloatTensor.java:221-227)
+// The current position's k/v come from shared memory / the packed qkv vector, older ones from the
+// FP32 cache.  Output as floats (xb) and/or quantised to Q8_0 (activation of the Wo matvec).
 // ------------------------------------------------------------------------------------------
-__global__ void k_rope_kv(float *__restrict__ qkv, const StepState *__restrict__ st, const float *__restrict__ cr,
-                          const float *__restrict__ ci, int n_heads, int n_kv_heads, int hs, int arch,
-                          const float *__restrict__ qnorm_w, const float *__restrict__ knorm_w, float eps,
-                          float *__restrict__ kc, float *__restrict__ vc) {
-    extern __shared__ float sh[]; // hs floats
-    __shared__ float s_ss;
-    pdl_launch_dependents();
-    pdl_wait();
-    const int pos = st->pos, half = hs >> 1, p = threadIdx.x;
-    const int slot = blockIdx.x;
-    const bool is_q = slot < n_heads;
-    const int head = is_q ? slot : slot - n_heads;
-    const int qd = n_heads * hs, kvd = n_kv_heads * hs;
-    float *vec = is_q ? qkv + head * hs : qkv + qd + head * hs;
-    const float fcr = cr[(size_t)pos * half + p], fci = ci[(size_t)pos * half + p];
-    int i0, i1;
-    if (arch == 1) { i0 = p; i1 = p + half; } else { i0 = 2 * p; i1 = 2 * p + 1; }
-    float v0 = vec[i0], v1 = vec[i1];
-    if (arch == 1) {
-        const float *nw = is_q ? qnorm_w : knorm_w;
-        sh[i0] = __fmul_rn(v0, v0);
-        sh[i1] = __fmul_rn(v1, v1);
-        __syncthreads();
-        if (p == 0) {
-            float ss = 0.0f;
-            for (int i = 0; i < hs; i++) ss = __fadd_rn(ss, sh[i]);
-            ss = __fdiv_rn(ss, (float)hs);
-            ss = __fadd_rn(ss, eps);
-            s_ss = (float)(1.0 / sqrt((double)ss));
-        }
-        __syncthreads();
-        float ss = s_ss;
-        v0 = __fmul_rn(nw[i0], __fmul_rn(ss, v0));
-        v1 = __fmul_rn(nw[i1], __fmul_rn(ss, v1));
-    }
-    float r0 = __fsub_rn(__fmul_rn(v0, fcr), __fmul_rn(v1, fci));
-    float r1 = __fadd_rn(__fmul_rn(v0, fci), __fmul_rn(v1, fcr));
-    vec[i0] = r0;
-    vec[i1] = r1;
-    if (!is_q) {
-        size_t o = (size_t)pos * kvd + head * hs;
-        kc[o + i0] = r0;
-        kc[o + i1] = r1;
-        const float *v = qkv + qd + kvd + head * hs;
-        vc[o + i0] = v[i0];
-        vc[o + i1] = v[i1];
-    }
-}
+#define ATT_THREADS 256
 
-// ------------------------------------------------------------------------------------------
-// Attention for one query head per CTA, exact CPU-path order (InferenceCore.java:98-137):
-//   score_t = scalarDot(q, k_t) / sqrt(head)        (sequential unfused mul/add, FloatTensor.java:86-92)
-//   softmaxInPlace: max, (float)Math.exp(f - max), sequential sum, divide   (FloatTensor.java:211-219)
-//   xb = sum_t a_t * v_t, sequentially over t per element (saxpyInPlace, FloatTensor.java:221-227)
-// Output is written as floats (xb) and/or quantised to Q8_0 (activation of the Wo matvec).
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_attention(const float *__restrict__ qkv, const float *__restrict__ kc,
-                                                   const float *__restrict__ vc, const StepState *__restrict__ st, int hs,
-                                                   int kvd, int kv_mul, float sqrt_hs, int8_t *__restrict__ xq,
-                                                   float *__restrict__ xs, float *__restrict__ xb) {
-    extern __shared__ __align__(16) float sm[]; // q[hs] | out[hs] | att[ctx]
-    __shared__ float red[4];
-    __shared__ float s_val;
-    float *sq = sm, *so = sm + hs, *att = sm + 2 * hs;
+template <int HS>
+__global__ void __launch_bounds__(ATT_THREADS) k_attention(float *__restrict__ qkv, float *__restrict__ kc, float *__restrict__ vc,
+                                                          const StepState *__restrict__ st, const float *__restrict__ cr,
+                                                          const float *__restrict__ ci, int n_heads, int n_kv_heads, int arch,
+                                                          const float *__restrict__ qnorm_w, const float *__restrict__ knorm_w,
+                                                          float eps, float sqrt_hs, int8_t *__restrict__ xq,
+                                                          float *__restrict__ xs, float *__restrict__ xb, TraceBuf tr) {
+    extern __shared__ __align__(16) float sm[]; // q[HS] | k[HS] | out[HS] | att[ctx]
+    __shared__ float red[ATT_THREADS / 32];
+    __shared__ float s_val[2];
+    float *sq = sm, *sk = sm + HS, *so = sm + 2 * HS, *att = sm + 3 * HS;
     const int h = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int HALF = HS / 2;
+    trace_entry(tr);
     pdl_launch_dependents();
     pdl_wait();
-    const int nt = st->pos + 1;
-    const int kvh = h / kv_mul;
-    for (int i = tid; i < hs; i += blockDim.x) sq[i] = qkv[h * hs + i];
-    __syncthreads();
-    float lmax = -INFINITY;
-    for (int t = tid; t < nt; t += blockDim.x) {
-        const float4 *k = reinterpret_cast<const float4 *>(kc + (size_t)t * kvd + kvh * hs);
-        float acc = 0.0f;
-        for (int j = 0; j < hs / 4; j++) {
-            float4 kk = k[j];
-            acc = __fadd_rn(acc, __fmul_rn(sq[4 * j + 0], kk.x));
-            acc = __fadd_rn(acc, __fmul_rn(sq[4 * j + 1], kk.y));
-            acc = __fadd_rn(acc, __fmul_rn(sq[4 * j + 2], kk.z));
-            acc = __fadd_rn(acc, __fmul_rn(sq[4 * j + 3], kk.w));
+    trace_mark(tr, 2);
+    const int pos = st->pos, nt = pos + 1;
+    const int kv_mul = n_heads / n_kv_heads, kvh = h / kv_mul;
+    const int qd = n_heads * HS, kvd = n_kv_heads * HS;
+    const float *qsrc = qkv + h * HS, *ksrc = qkv + qd + kvh * HS, *vsrc = qkv + qd + kvd + kvh * HS;
+    // ---- prologue: threads [0,HALF) rotate q pairs, threads [HALF,HS) rotate k pairs
+    if (tid < HS) {
+        const bool is_q = tid < HALF;
+        const int p = is_q ? tid : tid - HALF;
+        const float *src = is_q ? qsrc : ksrc;
+        int i0, i1;
+        if (arch == 1) { i0 = p; i1 = p + HALF; } else { i0 = 2 * p; i1 = 2 * p + 1; }
+        float v0 = src[i0], v1 = src[i1];
+        if (arch == 1) { // Qwen3 per-head RMSNorm: literal sequential sum over the head
+            float *sqr = is_q ? so : sk; // scratch: HS squares each
+            sqr[i0] = __fmul_rn(v0, v0);
+            sqr[i1] = __fmul_rn(v1, v1);
         }
-        float s = __fdiv_rn(acc, sqrt_hs);
+        if (arch == 1) {
+            asm volatile("bar.sync 3, %0;" ::"n"(HS) : "memory");
+            if (p == 0) {
+                const float *sqr = is_q ? so : sk;
+                float ss = 0.0f;
+                for (int i = 0; i < HS; i++) ss = __fadd_rn(ss, sqr[i]);
+                ss = __fdiv_rn(ss, (float)HS);
+                ss = __fadd_rn(ss, eps);
+                s_val[is_q ? 0 : 1] = (float)(1.0 / sqrt((double)ss));
+            }
+            asm volatile("bar.sync 3, %0;" ::"n"(HS) : "memory");
+            const float ss = s_val[is_q ? 0 : 1];
+            const float *nw = is_q ? qnorm_w : knorm_w;
+            v0 = __fmul_rn(nw[i0], __fmul_rn(ss, v0));
+            v1 = __fmul_rn(nw[i1], __fmul_rn(ss, v1));
+            asm volatile("bar.sync 3, %0;" ::"n"(HS) : "memory"); // scratch reads done before sk/so are overwritten
+        }
+        const float fcr = cr[(size_t)pos * HALF + p], fci = ci[(size_t)pos * HALF + p];
+        const float r0 = __fsub_rn(__fmul_rn(v0, fcr), __fmul_rn(v1, fci));
+        const float r1 = __fadd_rn(__fmul_rn(v0, fci), __fmul_rn(v1, fcr));
+        float *dst = is_q ? sq : sk;
+        dst[i0] = r0;
+        dst[i1] = r1;
+        if (h % kv_mul == 0) { // first query head of the KV group owns the cache / debug write-back
+            if (!is_q) {
+                const size_t o = (size_t)pos * kvd + kvh * HS;
+                kc[o + i0] = r0;
+                kc[o + i1] = r1;
+                vc[o + i0] = vsrc[i0];
+                vc[o + i1] = vsrc[i1];
+                // (the rotated k is NOT written back into qkv: the other query heads of this group read the
+                //  unrotated k from there concurrently)
+            }
+        }
+        if (is_q) { qkv[h * HS + i0] = r0; qkv[h * HS + i1] = r1; }
+    }
+    __syncthreads();
+    // ---- scores: one thread per time step, 8 x 16-byte loads in flight
+    float lmax = -INFINITY;
+    for (int t = tid; t < nt; t += ATT_THREADS) {
+        float acc = 0.0f;
+        if (t == pos) {
+#pragma unroll 8
+            for (int j = 0; j < HS; j++) acc = __fadd_rn(acc, __fmul_rn(sq[j], sk[j]));
+        } else {
+            const float4 *k = reinterpret_cast<const float4 *>(kc + (size_t)t * kvd + kvh * HS);
+#pragma unroll
+            for (int j0 = 0; j0 < HS / 4; j0 += 8) {
+                float4 kk[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) kk[u] = __ldg(k + j0 + u);
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int j = 4 * (j0 + u);
+                    acc = __fadd_rn(acc, __fmul_rn(sq[j + 0], kk[u].x));
+                    acc = __fadd_rn(acc, __fmul_rn(sq[j + 1], kk[u].y));
+                    acc = __fadd_rn(acc, __fmul_rn(sq[j + 2], kk[u].z));
+                    acc = __fadd_rn(acc, __fmul_rn(sq[j + 3], kk[u].w));
+                }
+            }
+        }
+        const float s = __fdiv_rn(acc, sqrt_hs);
         att[t] = s;
         lmax = fmaxf(lmax, s);
     }
     lmax = warp_max_f(lmax);
     if (lane == 0) red[warp] = lmax;
     __syncthreads();
-    const float mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
-    for (int t = tid; t < nt; t += blockDim.x) att[t] = (float)exp((double)__fsub_rn(att[t], mx));
+    float mx = red[0];
+#pragma unroll
+    for (int w = 1; w < ATT_THREADS / 32; w++) mx = fmaxf(mx, red[w]);
+    for (int t = tid; t < nt; t += ATT_THREADS) att[t] = (float)exp((double)__fsub_rn(att[t], mx));
     __syncthreads();
     if (tid == 0) {
         float sum = 0.0f;
-        for (int t = 0; t < nt; t++) sum = __fadd_rn(sum, att[t]);
-        s_val = sum;
+        int t = 0;
+        for (; t + 4 <= nt; t += 4) {
+            const float a0 = att[t], a1 = att[t + 1], a2 = att[t + 2], a3 = att[t + 3];
+            sum = __fadd_rn(sum, a0); sum = __fadd_rn(sum, a1); sum = __fadd_rn(sum, a2); sum = __fadd_rn(sum, a3);
+        }
+        for (; t < nt; t++) sum = __fadd_rn(sum, att[t]);
+        s_val[0] = sum;
     }
     __syncthreads();
-    const float sum = s_val;
-    for (int t = tid; t < nt; t += blockDim.x) att[t] = __fdiv_rn(att[t], sum);
+    const float sum = s_val[0];
+    for (int t = tid; t < nt; t += ATT_THREADS) att[t] = __fdiv_rn(att[t], sum);
     __syncthreads();
-    for (int i = tid; i < hs; i += blockDim.x) {
-        const float *v = vc + kvh * hs + i;
+    // ---- output: one thread per element, sequential over t, 16 loads in flight
+    if (tid < HS) {
+        const float *v = vc + kvh * HS + tid;
         float acc = 0.0f;
-        for (int t = 0; t < nt; t++) acc = __fadd_rn(__fmul_rn(att[t], v[(size_t)t * kvd]), acc);
-        so[i] = acc;
-        if (xb) xb[h * hs + i] = acc;
+        int t = 0;
+        for (; t + 16 <= pos; t += 16) {
+            float vv[16];
+#pragma unroll
+            for (int u = 0; u < 16; u++) vv[u] = __ldg(v + (size_t)(t + u) * kvd);
+#pragma unroll
+            for (int u = 0; u < 16; u++) acc = __fadd_rn(__fmul_rn(att[t + u], vv[u]), acc);
+        }
+        for (; t < pos; t++) acc = __fadd_rn(__fmul_rn(att[t], __ldg(v + (size_t)t * kvd)), acc);
+        acc = __fadd_rn(__fmul_rn(att[pos], vsrc[tid]), acc); // current position: straight from the packed qkv vector
+        so[tid] = acc;
+        if (xb) xb[h * HS + tid] = acc;
     }
     __syncthreads();
     if (xq) {
-        for (int b = warp; b < hs / 32; b += (blockDim.x >> 5)) {
+        for (int b = warp; b < HS / 32; b += ATT_THREADS / 32) {
             float as;
             int q = quant_block_lane(so[b * 32 + lane], as);
-            xq[h * hs + b * 32 + lane] = (int8_t)q;
-            if (lane == 0) xs[(h * hs) / 32 + b] = as;
+            xq[h * HS + b * 32 + lane] = (int8_t)q;
+            if (lane == 0) xs[(h * HS) / 32 + b] = as;
         }
     }
+    trace_mark(tr, 3);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -456,19 +536,30 @@ __device__ __forceinline__ void argmax_merge(float &v, int &i, float ov, int oi)
 
 __global__ void __launch_bounds__(1024) k_argmax_advance(const float *__restrict__ logits, int vocab, StepState *st,
                                                         const int *__restrict__ seq_tokens, int *__restrict__ out_ids,
-                                                        int do_argmax) {
+                                                        int do_argmax, const float *__restrict__ part_val,
+                                                        const int *__restrict__ part_idx, int n_part, TraceBuf tr) {
     __shared__ float sv[32];
     __shared__ int si[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    trace_entry(tr);
     pdl_launch_dependents();
     pdl_wait();
+    trace_mark(tr, 2);
     int best_i = 0;
     if (do_argmax) {
         float best = -INFINITY;
         best_i = 0x7fffffff;
-        for (int i = tid; i < vocab; i += blockDim.x) {
-            float v = logits[i];
-            if (v > best) { best = v; best_i = i; }
+        if (part_val) { // per-CTA (max, first index) pairs produced by the lm_head kernel
+            for (int i = tid; i < n_part; i += blockDim.x) {
+                float v = part_val[i];
+                int ix = part_idx[i];
+                argmax_merge(best, best_i, v, ix);
+            }
+        } else {
+            for (int i = tid; i < vocab; i += blockDim.x) {
+                float v = logits[i];
+                if (v > best) { best = v; best_i = i; }
+            }
         }
         // a thread that saw nothing > -inf keeps INT_MAX; index 0 wins below if all are -inf
 #pragma unroll
@@ -501,4 +592,5 @@ __global__ void __launch_bounds__(1024) k_argmax_advance(const float *__restrict
         st->step = next;
         st->pos = st->pos + 1;
     }
+    trace_mark(tr, 3);
 }

@@ -43,6 +43,8 @@ struct b200_plan {
     bool use_stream = false, use_pdl = false;
     int n_sms = 148;
     unsigned *blk_cnt = nullptr;
+    float *part_val = nullptr;
+    int *part_idx = nullptr;
     float *out_norm = nullptr;
     std::vector<LayerW> layers;
     float *rope_cr = nullptr, *rope_ci = nullptr;
@@ -58,7 +60,8 @@ struct b200_plan {
     StepState *h_st = nullptr; // pinned
     int *h_ids = nullptr;      // pinned, seq_cap
 
-    cudaGraphExec_t g_decode = nullptr, g_prefill = nullptr;
+    cudaGraphExec_t g_decode = nullptr, g_prefill = nullptr, g_trace = nullptr;
+    unsigned long long *trace_rec = nullptr;
     int launches_decode = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
@@ -267,7 +270,7 @@ int launch_k(b200_plan *p, bool pdl, void (*kern)(KA...), dim3 grid, dim3 block,
     return B200_OK;
 }
 
-const size_t SMV_SMEM_BUDGET_MAX = 100 * 1024;
+const size_t SMV_SMEM_BUDGET_MAX = 96 * 1024;
 static size_t smv_budget(int cols = 0) {
     const char *e = getenv("B200_SMV_BUDGET_KB"); // debug: force a shallow ring
     const char *m = getenv("B200_SMV_BUDGET_COLS"); // debug: ... only for matrices with this many columns
@@ -278,10 +281,18 @@ static size_t smv_budget(int cols = 0) {
 #define SMV_SMEM_BUDGET smv_budget()
 
 template <int MODE>
-int launch_stream(b200_plan *p, const TileMat &W, const int8_t *xq, const float *xs, float *out, int8_t *hq, float *hs) {
+int launch_stream(b200_plan *p, const TileMat &W, const int8_t *xq, const float *xs, float *out, int8_t *hq, float *hs, bool argmax = false,
+                  TraceBuf tr = TraceBuf{nullptr, 0, 0}) {
     SmvSmem L = smv_layout(W.cols, W.seg, smv_budget(W.cols));
     SmvArgs a;
     a.W = W; a.xq = xq; a.xs = xs; a.out = out; a.hq = hq; a.hs = hs; a.blk_cnt = p->blk_cnt;
+    a.part_val = argmax ? p->part_val : nullptr;
+    a.part_idx = argmax ? p->part_idx : nullptr;
+    a.tr = tr;
+    {
+        const char *e = getenv("B200_L2_WINDOW_KB");
+        a.l2_window = (unsigned)((e ? atoi(e) : 0) * 1024); // experimental: measured slower on B200 (profiles/), off by default
+    }
     return launch_k(p, p->use_pdl, k_stream_matvec_q8<MODE>, dim3(p->n_sms), dim3(SMV_THREADS), L.total, a, L);
 }
 
@@ -292,14 +303,19 @@ bool stream_shape_ok(int rows, int cols) {
     return smv_layout(cols, cols / nseg, SMV_SMEM_BUDGET).stages >= 3;
 }
 
+bool gateup_fits(int hidden, int n_sms) { // epilogue buffer holds this CTA's hidden units
+    return 2 * ((hidden / 2) / n_sms + 1) <= SMV_HVALS;
+}
+
 // Enqueue one single-token forward on p->stream (captured into a CUDA graph at creation).
 // with_logits=false is the prefill variant (InferenceCoreBatchPrefillDecode.java:166-167).
-int enqueue_forward(b200_plan *p, bool with_logits, int *launches) {
+int enqueue_forward(b200_plan *p, bool with_logits, int *launches, bool trace = false) {
     const b200_config &c = p->cfg;
     const bool q8 = p->wtype == B200_GGML_Q8_0;
     const bool st = p->use_stream, pdl = p->use_pdl;
     int n = 0;
-    const size_t norm_smem = (size_t)c.dim * 8 + seqsum_scratch_bytes(c.dim);
+    auto TR = [&](int id) { return TraceBuf{trace ? p->trace_rec : nullptr, n, id}; };
+    const size_t norm_smem = norm_smem_bytes(c.dim);
     int8_t *xq = q8 ? p->xq : nullptr;
     float *xs = q8 ? p->xs : nullptr;
     float *xbf = q8 ? nullptr : p->xb;
@@ -307,31 +323,37 @@ int enqueue_forward(b200_plan *p, bool with_logits, int *launches) {
     for (int l = 0; l < c.n_layers; l++) {
         LayerW &L = p->layers[l];
         int rc;
-        if (l == 0) rc = launch_k(p, pdl, k_rmsnorm_quant<true>, dim3(1), dim3(1024), norm_smem, p->x, (const StepState *)p->st, p->emb, (const float *)L.attn_norm, c.rms_norm_eps, c.dim, xq, xs, xbf);
-        else rc = launch_k(p, pdl, k_rmsnorm_quant<false>, dim3(1), dim3(1024), norm_smem, p->x, (const StepState *)p->st, p->emb, (const float *)L.attn_norm, c.rms_norm_eps, c.dim, xq, xs, xbf);
+        if (l == 0) rc = launch_k(p, pdl, k_rmsnorm_quant<true>, dim3(1), dim3(NORM_THREADS), norm_smem, p->x, (const StepState *)p->st, p->emb, (const float *)L.attn_norm, c.rms_norm_eps, c.dim, xq, xs, xbf, (long long *)nullptr, TR(1));
+        else rc = launch_k(p, pdl, k_rmsnorm_quant<false>, dim3(1), dim3(NORM_THREADS), norm_smem, p->x, (const StepState *)p->st, p->emb, (const float *)L.attn_norm, c.rms_norm_eps, c.dim, xq, xs, xbf, (long long *)nullptr, TR(1));
         if (rc) return rc; n++;
-        if (st) rc = launch_stream<SMV_STORE>(p, L.tqkv, p->xq, p->xs, p->qkv, nullptr, nullptr);
+        if (st) rc = launch_stream<SMV_STORE>(p, L.tqkv, p->xq, p->xs, p->qkv, nullptr, nullptr, false, TR(2));
         else if (q8) rc = launch_matvec_q8<MODE_STORE>(p, L.qkv, p->xq, p->xs, p->qkv);
         else rc = launch_matvec_f16<MODE_STORE>(p, L.qkv, p->xb, p->qkv);
         if (rc) return rc; n++;
         float *kc = p->key_cache + (size_t)l * ctx_kv, *vc = p->value_cache + (size_t)l * ctx_kv;
-        if ((rc = launch_k(p, pdl, k_rope_kv, dim3(c.n_heads + c.n_kv_heads), dim3(c.head_size / 2), (size_t)c.head_size * 4, p->qkv, (const StepState *)p->st,
-                           (const float *)p->rope_cr, (const float *)p->rope_ci, c.n_heads, c.n_kv_heads, c.head_size, c.arch, (const float *)L.q_norm,
-                           (const float *)L.k_norm, c.rms_norm_eps, kc, vc))) return rc;
-        n++;
-        if ((rc = launch_k(p, pdl, k_attention, dim3(c.n_heads), dim3(128), (size_t)(2 * c.head_size + c.context_length) * 4, (const float *)p->qkv,
-                           (const float *)kc, (const float *)vc, (const StepState *)p->st, c.head_size, p->kvd, c.n_heads / c.n_kv_heads,
-                           (float)sqrt((double)c.head_size), xq, xs, xbf))) return rc;
-        n++;
-        if (st) rc = launch_stream<SMV_RESID>(p, L.two, p->xq, p->xs, p->x, nullptr, nullptr);
+        {
+            const size_t att_smem = (size_t)(3 * c.head_size + c.context_length) * 4;
+            auto att = [&](auto kern) {
+                return launch_k(p, pdl, kern, dim3(c.n_heads), dim3(ATT_THREADS), att_smem, p->qkv, kc, vc, (const StepState *)p->st,
+                                (const float *)p->rope_cr, (const float *)p->rope_ci, c.n_heads, c.n_kv_heads, c.arch, (const float *)L.q_norm,
+                                (const float *)L.k_norm, c.rms_norm_eps, (float)sqrt((double)c.head_size), xq, xs, xbf, TR(4));
+            };
+            if (c.head_size == 128) rc = att(k_attention<128>);
+            else if (c.head_size == 64) rc = att(k_attention<64>);
+            else if (c.head_size == 256) rc = att(k_attention<256>);
+            else rc = att(k_attention<32>);
+            if (rc) return rc;
+            n++;
+        }
+        if (st) rc = launch_stream<SMV_RESID>(p, L.two, p->xq, p->xs, p->x, nullptr, nullptr, false, TR(5));
         else if (q8) rc = launch_matvec_q8<MODE_RESID>(p, L.wo, p->xq, p->xs, p->x);
         else rc = launch_matvec_f16<MODE_RESID>(p, L.wo, p->xb, p->x);
         if (rc) return rc; n++;
-        if ((rc = launch_k(p, pdl, k_rmsnorm_quant<false>, dim3(1), dim3(1024), norm_smem, p->x, (const StepState *)p->st, p->emb, (const float *)L.ffn_norm, c.rms_norm_eps, c.dim, xq, xs, xbf))) return rc;
+        if ((rc = launch_k(p, pdl, k_rmsnorm_quant<false>, dim3(1), dim3(NORM_THREADS), norm_smem, p->x, (const StepState *)p->st, p->emb, (const float *)L.ffn_norm, c.rms_norm_eps, c.dim, xq, xs, xbf, (long long *)nullptr, TR(1)))) return rc;
         n++;
         if (st) {
-            if ((rc = launch_stream<SMV_GATEUP>(p, L.tgu, p->xq, p->xs, p->hb, p->hq, p->hs))) return rc; n++;
-            if ((rc = launch_stream<SMV_RESID>(p, L.tw2, p->hq, p->hs, p->x, nullptr, nullptr))) return rc; n++;
+            if ((rc = launch_stream<SMV_GATEUP>(p, L.tgu, p->xq, p->xs, p->hb, p->hq, p->hs, false, TR(6)))) return rc; n++;
+            if ((rc = launch_stream<SMV_RESID>(p, L.tw2, p->hq, p->hs, p->x, nullptr, nullptr, false, TR(7)))) return rc; n++;
         } else if (q8) {
             k_gateup_q8<<<c.hidden_dim / 32, 256, q8_smem_bytes(c.dim, 4, 8), p->stream>>>(
                 (const int8_t *)L.w1.qs, L.w1.sc, (const int8_t *)L.w3.qs, L.w3.sc, p->xq, p->xs, c.hidden_dim, c.dim, p->hq, p->hs, p->hb);
@@ -348,26 +370,27 @@ int enqueue_forward(b200_plan *p, bool with_logits, int *launches) {
     if (with_logits) {
         // rmsnorm(x, x, rms_final_weight) then wcls.matmul (InferenceCore.java:167-169)
         int rc;
-        if ((rc = launch_k(p, pdl, k_rmsnorm_quant<false>, dim3(1), dim3(1024), norm_smem, p->x, (const StepState *)p->st, p->emb, (const float *)p->out_norm, c.rms_norm_eps, c.dim, xq, xs, xbf))) return rc;
+        if ((rc = launch_k(p, pdl, k_rmsnorm_quant<false>, dim3(1), dim3(NORM_THREADS), norm_smem, p->x, (const StepState *)p->st, p->emb, (const float *)p->out_norm, c.rms_norm_eps, c.dim, xq, xs, xbf, (long long *)nullptr, TR(1)))) return rc;
         n++;
-        if (st) rc = launch_stream<SMV_STORE>(p, p->tout, p->xq, p->xs, p->logits, nullptr, nullptr);
+        if (st) rc = launch_stream<SMV_STORE>(p, p->tout, p->xq, p->xs, p->logits, nullptr, nullptr, true, TR(8));
         else if (q8) rc = launch_matvec_q8<MODE_STORE>(p, p->out, p->xq, p->xs, p->logits);
         else rc = launch_matvec_f16<MODE_STORE>(p, p->out, p->xb, p->logits);
         if (rc) return rc; n++;
     }
     {
         int rc;
-        if ((rc = launch_k(p, pdl, k_argmax_advance, dim3(1), dim3(1024), (size_t)0, (const float *)p->logits, c.vocab_size, p->st, (const int *)p->seq_tokens, p->out_ids, with_logits ? 1 : 0))) return rc;
+        if ((rc = launch_k(p, pdl, k_argmax_advance, dim3(1), dim3(1024), (size_t)0, (const float *)p->logits, c.vocab_size, p->st, (const int *)p->seq_tokens, p->out_ids, with_logits ? 1 : 0,
+                           (const float *)(st ? p->part_val : nullptr), (const int *)(st ? p->part_idx : nullptr), p->n_sms, TR(9)))) return rc;
         n++;
     }
     if (launches) *launches = n;
     return B200_OK;
 }
 
-int capture(b200_plan *p, bool with_logits, cudaGraphExec_t *exec, int *launches) {
+int capture(b200_plan *p, bool with_logits, cudaGraphExec_t *exec, int *launches, bool trace = false) {
     cudaGraph_t g = nullptr;
     CK(cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal));
-    int rc = enqueue_forward(p, with_logits, launches);
+    int rc = enqueue_forward(p, with_logits, launches, trace);
     cudaError_t e = cudaStreamEndCapture(p->stream, &g);
     if (rc) { if (g) cudaGraphDestroy(g); return rc; }
     if (e != cudaSuccess) return fail(p, B200_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
@@ -381,9 +404,9 @@ int set_smem_attrs(b200_plan *p) {
     const b200_config &c = p->cfg;
     int maxdyn = 0;
     CK(cudaDeviceGetAttribute(&maxdyn, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device));
-    size_t need_norm = (size_t)c.dim * 8 + seqsum_scratch_bytes(c.dim);
+    size_t need_norm = norm_smem_bytes(c.dim);
     if (c.dim > 8192) return fail(p, B200_ERR_UNSUPPORTED, "dim > 8192 not supported by the RMSNorm kernel");
-    size_t need_att = (size_t)(2 * c.head_size + c.context_length) * 4;
+    size_t need_att = (size_t)(3 * c.head_size + c.context_length) * 4;
     int maxcols = c.hidden_dim > c.dim ? c.hidden_dim : c.dim;
     if (p->qd > maxcols) maxcols = p->qd;
     size_t need_mv = q8_smem_bytes(maxcols, 4, 8);
@@ -393,7 +416,10 @@ int set_smem_attrs(b200_plan *p) {
         return fail(p, B200_ERR_UNSUPPORTED, "shape needs more shared memory than the device offers (%d bytes)", maxdyn);
     CK(cudaFuncSetAttribute(k_rmsnorm_quant<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_norm));
     CK(cudaFuncSetAttribute(k_rmsnorm_quant<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_norm));
-    CK(cudaFuncSetAttribute(k_attention, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_att));
+    CK(cudaFuncSetAttribute(k_attention<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_att));
+    CK(cudaFuncSetAttribute(k_attention<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_att));
+    CK(cudaFuncSetAttribute(k_attention<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_att));
+    CK(cudaFuncSetAttribute(k_attention<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_att));
     CK(cudaFuncSetAttribute(k_matvec_q8<1, MODE_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_mv));
     CK(cudaFuncSetAttribute(k_matvec_q8<2, MODE_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_mv));
     CK(cudaFuncSetAttribute(k_matvec_q8<4, MODE_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_mv));
@@ -413,9 +439,9 @@ int build(b200_plan *p, const b200_tensor *tensors, int n_tensors) {
     const b200_config &c = p->cfg;
     if (c.arch != B200_ARCH_LLAMA && c.arch != B200_ARCH_QWEN3) return fail(p, B200_ERR_UNSUPPORTED, "unknown arch %d", c.arch);
     if (c.tp_size > 1) return fail(p, B200_ERR_UNSUPPORTED, "tensor parallelism is not built yet (tp_size=%d)", c.tp_size);
-    if (c.dim <= 0 || c.dim % 32 || c.hidden_dim % 32 || c.head_size % 32 || c.head_size > 256 || c.n_heads % c.n_kv_heads ||
+    if (c.dim <= 0 || c.dim % 32 || c.hidden_dim % 32 || (c.head_size != 32 && c.head_size != 64 && c.head_size != 128 && c.head_size != 256) || c.n_heads % c.n_kv_heads ||
         c.n_layers <= 0 || c.vocab_size <= 0 || c.context_length <= 0)
-        return fail(p, B200_ERR_BAD_ARG, "unsupported shape (dim/hidden/head_size must be multiples of 32, head_size <= 256)");
+        return fail(p, B200_ERR_BAD_ARG, "unsupported shape (dim/hidden must be multiples of 32, head_size one of 32/64/128/256)");
     if (c.fp16_lanes != 0 && c.fp16_lanes != 8 && c.fp16_lanes != 16 && c.fp16_lanes != 4 && c.fp16_lanes != 32)
         return fail(p, B200_ERR_BAD_ARG, "fp16_lanes must be 0, 4, 8, 16 or 32");
     p->qd = c.n_heads * c.head_size;
@@ -440,7 +466,8 @@ int build(b200_plan *p, const b200_tensor *tensors, int n_tensors) {
         const char *e = getenv("B200_STREAM");
         bool want = !(e && e[0] == '0');
         p->use_stream = want && p->wtype == B200_GGML_Q8_0 && stream_shape_ok(p->qd + 2 * p->kvd, c.dim) && stream_shape_ok(c.dim, p->qd) &&
-                        stream_shape_ok(2 * c.hidden_dim, c.dim) && stream_shape_ok(c.dim, c.hidden_dim) && stream_shape_ok(c.vocab_size, c.dim);
+                        stream_shape_ok(2 * c.hidden_dim, c.dim) && stream_shape_ok(c.dim, c.hidden_dim) && stream_shape_ok(c.vocab_size, c.dim) &&
+                        gateup_fits(c.hidden_dim, p->n_sms);
         const char *e2 = getenv("B200_PDL");
         p->use_pdl = p->use_stream && !(e2 && e2[0] == '0');
     }
@@ -464,6 +491,8 @@ int build(b200_plan *p, const b200_tensor *tensors, int n_tensors) {
         if (!outw && emb->ggml_type != p->wtype) return fail(p, B200_ERR_UNSUPPORTED, "tied output weight type differs from the matrix type");
         if ((rc = upload_tiles(p, outw ? outw : emb, nullptr, nullptr, c.vocab_size, 0, 0, c.dim, false, p->tout, stage, stage_bytes))) return rc;
         p->out = p->emb;
+        if ((rc = dalloc(p, &p->part_val, (size_t)p->n_sms * 4))) return rc;
+        if ((rc = dalloc(p, &p->part_idx, (size_t)p->n_sms * 4))) return rc;
         if ((rc = dalloc(p, &p->blk_cnt, (size_t)(c.hidden_dim / 32) * 4))) return rc;
         CK(cudaMemset(p->blk_cnt, 0, (size_t)(c.hidden_dim / 32) * 4));
     } else if (outw) {
@@ -558,6 +587,10 @@ int build(b200_plan *p, const b200_tensor *tensors, int n_tensors) {
     if ((rc = set_smem_attrs(p))) return rc;
     if ((rc = capture(p, true, &p->g_decode, &p->launches_decode))) return rc;
     if ((rc = capture(p, false, &p->g_prefill, nullptr))) return rc;
+    if (p->use_stream) {
+        if ((rc = dalloc(p, &p->trace_rec, (size_t)(p->launches_decode + 8) * 32))) return rc;
+        if ((rc = capture(p, true, &p->g_trace, nullptr, true))) return rc;
+    }
     if (p->prefill_batch > 1)
         if ((rc = prefill_init(p->prefill, p->cfg, p->prefill_batch))) return fail(p, rc, "batched prefill init failed");
     CK(cudaStreamSynchronize(p->stream));
@@ -794,16 +827,58 @@ int b200_time_kernel(b200_plan *p, int32_t which, int32_t reps, float *avg_ms, i
     return B200_OK;
 }
 
-int b200_test_seqsum(const float *terms, int32_t n, float *out) {
+int b200_trace_decode(b200_plan *p, int32_t token, int32_t position, uint64_t *records, int32_t cap, int32_t *n_out) {
+    if (!p || !records || !n_out) return B200_ERR_BAD_ARG;
+    if (!p->g_trace) return fail(p, B200_ERR_UNSUPPORTED, "tracing needs the streaming (Q8_0) path");
+    int rc;
+    if ((rc = check_pos(p, token, position))) return rc;
+    CK(cudaSetDevice(p->device));
+    int n = p->launches_decode;
+    std::vector<unsigned long long> init((size_t)n * 4);
+    for (int i = 0; i < n; i++) { init[i * 4] = 0; init[i * 4 + 1] = ~0ull; init[i * 4 + 2] = 0; init[i * 4 + 3] = 0; }
+    CK(cudaMemcpyAsync(p->trace_rec, init.data(), init.size() * 8, cudaMemcpyHostToDevice, p->stream));
+    if ((rc = set_state(p, token, position, 0, 0))) return rc;
+    CK(cudaGraphLaunch(p->g_trace, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    int m = n < cap ? n : cap;
+    CK(cudaMemcpy(records, p->trace_rec, (size_t)m * 32, cudaMemcpyDeviceToHost));
+    *n_out = m;
+    return B200_OK;
+}
+
+int b200_profile_norm(b200_plan *p, int64_t *cycles4) {
+    if (!p || !cycles4) return B200_ERR_BAD_ARG;
+    CK(cudaSetDevice(p->device));
+    long long *d = nullptr;
+    CK(cudaMalloc(&d, 128));
+    const b200_config &c = p->cfg;
+    const size_t norm_smem = norm_smem_bytes(c.dim);
+    const bool q8 = p->wtype == B200_GGML_Q8_0;
+    for (int i = 0; i < 3; i++)
+        k_rmsnorm_quant<false><<<1, NORM_THREADS, norm_smem, p->stream>>>(p->x, p->st, p->emb, p->layers[0].attn_norm, c.rms_norm_eps, c.dim,
+                                                                 q8 ? p->xq : nullptr, q8 ? p->xs : nullptr, q8 ? nullptr : p->xb, d, TraceBuf{nullptr, 0, 0});
+    cudaError_t e = cudaStreamSynchronize(p->stream);
+    long long h[16] = {0};
+    if (e == cudaSuccess) e = cudaMemcpy(h, d, 128, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    for (int i = 0; i < 7; i++) cycles4[i] = h[i];
+    for (int i = 0; i < 5; i++) cycles4[8 + i] = h[9 + i] - h[8 + i]; // seqsum phases A, B, C, barrier, resolve
+    return e == cudaSuccess ? B200_OK : B200_ERR_CUDA;
+}
+
+int b200_test_seqsum(const float *terms, int32_t n, float *out, int32_t *info) {
     if (!terms || !out || n <= 0 || n > 8192) return B200_ERR_BAD_ARG;
     float *d = nullptr, *o = nullptr;
-    if (cudaMalloc(&d, (size_t)n * 4) != cudaSuccess || cudaMalloc(&o, 4) != cudaSuccess) return B200_ERR_OOM;
-    size_t smem = (size_t)((n + 3) & ~3) * 4 + seqsum_scratch_bytes(n);
+    if (cudaMalloc(&d, (size_t)n * 4) != cudaSuccess || cudaMalloc(&o, 16) != cudaSuccess) return B200_ERR_OOM;
+    size_t smem = (size_t)((n + 31) & ~31) * 4 + seqsum_scratch_bytes((n + 31) & ~31);
     cudaFuncSetAttribute(k_test_seqsum, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaMemcpy(d, terms, (size_t)n * 4, cudaMemcpyHostToDevice);
-    k_test_seqsum<<<1, 1024, smem>>>(d, n, o);
+    k_test_seqsum<<<1, NORM_THREADS, smem>>>(d, n, o, reinterpret_cast<int *>(o) + 1);
     cudaError_t e = cudaDeviceSynchronize();
-    if (e == cudaSuccess) e = cudaMemcpy(out, o, 4, cudaMemcpyDeviceToHost);
+    int32_t host[3] = {0, 0, 0};
+    if (e == cudaSuccess) e = cudaMemcpy(host, o, 12, cudaMemcpyDeviceToHost);
+    memcpy(out, host, 4);
+    if (info) { info[0] = host[1]; info[1] = host[2]; }
     cudaFree(d);
     cudaFree(o);
     return e == cudaSuccess ? B200_OK : B200_ERR_CUDA;
@@ -819,6 +894,7 @@ void b200_plan_free(b200_plan *p) {
     prefill_free(p->prefill);
     if (p->g_decode) cudaGraphExecDestroy(p->g_decode);
     if (p->g_prefill) cudaGraphExecDestroy(p->g_prefill);
+    if (p->g_trace) cudaGraphExecDestroy(p->g_trace);
     for (void *d : p->allocs) cudaFree(d);
     if (p->h_st) cudaFreeHost(p->h_st);
     if (p->h_ids) cudaFreeHost(p->h_ids);

@@ -22,6 +22,7 @@
 #define SMV_CONSUMER_WARPS 8
 #define SMV_THREADS ((SMV_CONSUMER_WARPS + 1) * 32)
 #define SMV_MAX_STAGES 16
+#define SMV_HVALS 512 // capacity (hidden units per CTA) of the gate/up epilogue buffer
 
 enum { SMV_STORE = 0, SMV_RESID = 1, SMV_GATEUP = 2 };
 
@@ -40,7 +41,7 @@ __host__ __device__ inline int smv_pick_nseg(int cols) {
 __host__ __device__ inline int smv_unit_bytes(int seg) { return (seg + seg / 16 + 15) & ~15; }
 
 struct SmvSmem {
-    size_t off_bar, off_xq, off_xs, off_terms, off_ring, total;
+    size_t off_bar, off_xq, off_xs, off_terms, off_hvals, off_ring, total;
     int stages, stage_bytes, nbs_pad;
 };
 
@@ -55,6 +56,7 @@ __host__ __device__ inline SmvSmem smv_layout(int cols, int seg, size_t budget) 
     L.off_xs = o; o += (size_t)(cols / 32) * 4;
     o = (o + 15) & ~(size_t)15;
     L.off_terms = o; o += (size_t)SMV_CONSUMER_WARPS * 4 * L.nbs_pad * 4;
+    L.off_hvals = o; o += SMV_HVALS * 4; // GATEUP: this CTA's swiglu outputs; STORE+argmax: per-warp candidates
     o = (o + 127) & ~(size_t)127;
     L.off_ring = o;
     long room = (long)budget - (long)o;
@@ -93,6 +95,11 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned
                  "r"(bytes), "r"(bar)
                  : "memory");
 }
+// Pull a span of (immutable) weights into L2 without occupying shared memory: lets a kernel that is
+// resident but still waiting for its dependency keep HBM busy far beyond its smem ring.
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void consumer_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(SMV_CONSUMER_WARPS * 32) : "memory"); }
 
 __device__ __forceinline__ float ldcg_f32(const float *p) {
@@ -114,6 +121,10 @@ struct SmvArgs {
     int8_t *hq;         // GATEUP: quantised hb
     float *hs;          // GATEUP: hb block scales
     unsigned *blk_cnt;  // GATEUP: per-32-block arrival counters (self-resetting)
+    float *part_val;    // STORE (lm_head): per-CTA running maximum of the rows it produced ...
+    int *part_idx;      // ... and the lowest row index attaining it (FloatTensor.argmax tie-break), or NULL
+    TraceBuf tr;
+    unsigned l2_window; // bytes of this CTA's slice to keep prefetched into L2 ahead of the ring (0 = off)
 };
 
 template <int MODE>
@@ -142,18 +153,32 @@ __global__ void __launch_bounds__(SMV_THREADS, 1) k_stream_matvec_q8(SmvArgs a, 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    trace_entry(a.tr);
     pdl_launch_dependents(); // let the next kernel become resident and start prefetching its weights
 
     if (warp == SMV_CONSUMER_WARPS) {
         // ===== producer: weights are immutable, so it does not wait for the previous kernel =====
         if (lane == 0) {
             unsigned seq = 0;
+            // L2 prefetch cursor over this CTA's contiguous slice (memory order; the ring consumes the same
+            // bytes round by round), kept at most a.l2_window bytes ahead of what the ring has requested.
+            const unsigned char *slice = W.base + (size_t)g0 * nseg * tile_bytes;
+            const size_t slice_bytes = (size_t)(g1 - g0) * nseg * tile_bytes;
+            size_t pf = 0;
             for (int gb = g0; gb < g1; gb += SMV_CONSUMER_WARPS) {
                 int nw = min(SMV_CONSUMER_WARPS, g1 - gb);
                 for (int s = 0; s < nseg; s++)
                     for (int w = 0; w < nw; w++, seq++) {
                         int st = seq % S;
                         unsigned ph = (seq / S) & 1u;
+                        if (a.l2_window) {
+                            const size_t issued = (size_t)seq * tile_bytes;
+                            if (pf < issued) pf = issued;
+                            while (pf < slice_bytes && pf < issued + a.l2_window) {
+                                bulk_prefetch_l2(slice + pf, tile_bytes);
+                                pf += tile_bytes;
+                            }
+                        }
                         mbar_wait(bar0 + 8 * (SMV_MAX_STAGES + st), ph ^ 1u); // slot free (first pass returns at once)
                         unsigned full = bar0 + 8 * st;
                         mbar_expect_tx(full, tile_bytes);
@@ -167,6 +192,7 @@ __global__ void __launch_bounds__(SMV_THREADS, 1) k_stream_matvec_q8(SmvArgs a, 
 
     // ===== consumers =====
     pdl_wait(); // activations come from the previous kernel
+    trace_mark(a.tr, 2);
     {
         const int nb = W.cols >> 5;
         int4 *sxq = reinterpret_cast<int4 *>(smem + L.off_xq);
@@ -182,6 +208,10 @@ __global__ void __launch_bounds__(SMV_THREADS, 1) k_stream_matvec_q8(SmvArgs a, 
     const unsigned char *sact = smem + L.off_xq;
     const float *sxs = reinterpret_cast<const float *>(smem + L.off_xs);
     const int hsel = (lane >> 2) & 1; // half-swap: conflict-free LDS.128 over 32-byte strides
+
+    float *hvals = reinterpret_cast<float *>(smem + L.off_hvals);
+    float best = -INFINITY;
+    int best_i = 0x7fffffff;
 
     unsigned seq_base = 0;
     for (int gb = g0; gb < g1; gb += SMV_CONSUMER_WARPS) {
@@ -234,30 +264,78 @@ __global__ void __launch_bounds__(SMV_THREADS, 1) k_stream_matvec_q8(SmvArgs a, 
             // rows 4G..4G+3 are complete in lanes 0..3
             if (MODE == SMV_GATEUP) {
                 const float up = __shfl_down_sync(0xffffffffu, acc, 2);
-                const int unit = 2 * G + lane;
-                if (lane < 2) a.out[unit] = swiglu_exact(acc, up);
-                __threadfence();
-                __syncwarp();
-                unsigned old = 0;
-                const int blk = (2 * G) >> 5;
-                if (lane == 0) old = atomicAdd(&a.blk_cnt[blk], 2u);
-                old = __shfl_sync(0xffffffffu, old, 0);
-                if (old + 2u == 32u) { // this warp completed the 32-block: quantise it (Q8_0FloatTensor.java:100-117)
-                    __threadfence();
-                    float v = ldcg_f32(a.out + blk * 32 + lane);
-                    float as;
-                    int q = quant_block_lane(v, as);
-                    a.hq[blk * 32 + lane] = (int8_t)q;
-                    if (lane == 0) { a.hs[blk] = as; a.blk_cnt[blk] = 0u; }
+                if (lane < 2) {
+                    const int unit = 2 * G + lane;
+                    const float hval = swiglu_exact(acc, up);
+                    a.out[unit] = hval;
+                    hvals[unit - 2 * g0] = hval;
                 }
             } else if (lane < 4) {
                 const size_t row = (size_t)4 * G + lane;
                 if (MODE == SMV_RESID) a.out[row] = __fadd_rn(a.out[row], acc); // x[i] = x[i] + xb2[i]
-                else a.out[row] = acc;
+                else {
+                    a.out[row] = acc;
+                    if (acc > best) { best = acc; best_i = (int)row; } // rows ascend per lane: first maximum kept
+                }
             }
         }
         seq_base += (unsigned)(nseg * nw);
     }
+
+    if (MODE == SMV_GATEUP) {
+        // Quantise hb = silu(gate)*up to Q8_0 (the activation of the down projection,
+        // Q8_0FloatTensor.java:100-117).  Blocks of 32 units that lie wholly inside this CTA's range are
+        // quantised from shared memory; the (at most two) blocks shared with a neighbouring CTA are finished
+        // by whichever CTA arrives last (fence + counter), so no warp ever fences inside the streaming loop.
+        consumer_bar_sync();
+        const int u0 = 2 * g0, u1 = 2 * g1;
+        if (u1 > u0) {
+            for (int blk = (u0 >> 5) + warp; blk <= ((u1 - 1) >> 5); blk += SMV_CONSUMER_WARPS) {
+                const int lo = max(blk << 5, u0), hi = min((blk << 5) + 32, u1);
+                float v = 0.0f;
+                bool mine = true;
+                if (hi - lo == 32) v = hvals[(blk << 5) + lane - u0];
+                else {
+                    unsigned old = 0;
+                    if (lane == 0) {
+                        __threadfence(); // cumulative: publishes the hb stores of the whole CTA (ordered by the barrier above)
+                        old = atomicAdd(&a.blk_cnt[blk], (unsigned)(hi - lo));
+                    }
+                    old = __shfl_sync(0xffffffffu, old, 0);
+                    mine = (old + (unsigned)(hi - lo) == 32u);
+                    if (mine) {
+                        __threadfence();
+                        v = ldcg_f32(a.out + (blk << 5) + lane);
+                        if (lane == 0) a.blk_cnt[blk] = 0u;
+                    }
+                }
+                if (mine) {
+                    float as;
+                    int q = quant_block_lane(v, as);
+                    a.hq[(blk << 5) + lane] = (int8_t)q;
+                    if (lane == 0) a.hs[blk] = as;
+                }
+            }
+        }
+    } else if (MODE == SMV_STORE) {
+        if (a.part_val) { // on-device greedy sampler, stage 1: this CTA's (max, first index)
+            int *cand_i = reinterpret_cast<int *>(hvals + 64);
+            if (lane < 4) { hvals[warp * 4 + lane] = best; cand_i[warp * 4 + lane] = best_i; }
+            consumer_bar_sync();
+            if (tid == 0) {
+                float bv = -INFINITY;
+                int bi = 0x7fffffff;
+                for (int k = 0; k < SMV_CONSUMER_WARPS * 4; k++) {
+                    float v = hvals[k];
+                    int ix = cand_i[k];
+                    if (v > bv || (v == bv && ix < bi)) { bv = v; bi = ix; }
+                }
+                a.part_val[blockIdx.x] = bv;
+                a.part_idx[blockIdx.x] = bi;
+            }
+        }
+    }
+    trace_mark(a.tr, 3);
 }
 
 // ---- upload-time repack: GGUF Q8_0 blocks (34 B: f16 scale + 32 int8) -> tile-major -----------

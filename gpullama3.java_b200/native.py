@@ -40,7 +40,7 @@ class Tensor(C.Structure):
 
 
 EXPORTS = ["b200_plan_create", "b200_forward_decode", "b200_forward_prefill", "b200_forward_batch_prefill",
-           "b200_decode_sequence", "b200_time_kernel", "b200_test_seqsum", "b200_kv_reset", "b200_read_buffer", "b200_launches_per_decode",
+           "b200_decode_sequence", "b200_time_kernel", "b200_trace_decode", "b200_profile_norm", "b200_test_seqsum", "b200_kv_reset", "b200_read_buffer", "b200_launches_per_decode",
            "b200_device_bytes", "b200_plan_free", "b200_last_error", "b200_version"]
 
 _lib = None
@@ -61,7 +61,9 @@ def lib() -> C.CDLL:
     L.b200_forward_batch_prefill.argtypes = [vp, vp, i32, i32]
     L.b200_decode_sequence.argtypes = [vp, vp, i32, i32, i32, vp, C.POINTER(C.c_float)]
     L.b200_kv_reset.argtypes = [vp]
-    L.b200_test_seqsum.argtypes = [vp, i32, C.POINTER(C.c_float)]
+    L.b200_profile_norm.argtypes = [vp, C.POINTER(C.c_int64)]
+    L.b200_trace_decode.argtypes = [vp, i32, i32, vp, i32, C.POINTER(i32)]
+    L.b200_test_seqsum.argtypes = [vp, i32, C.POINTER(C.c_float), C.POINTER(i32)]
     L.b200_time_kernel.argtypes = [vp, i32, i32, C.POINTER(C.c_float), C.POINTER(C.c_int64)]
     L.b200_read_buffer.argtypes = [vp, C.c_char_p, i32, vp, C.c_size_t]
     L.b200_launches_per_decode.argtypes = [vp]
@@ -82,13 +84,14 @@ def _raise(code: int, msg: str):
     raise B200Error(code, msg)
 
 
-def test_seqsum(terms) -> float:
+def test_seqsum(terms, want_info: bool = False):
     t = np.ascontiguousarray(terms, dtype=np.float32)
     out = C.c_float(0)
-    rc = lib().b200_test_seqsum(t.ctypes.data, len(t), C.byref(out))
+    info = (C.c_int32 * 2)()
+    rc = lib().b200_test_seqsum(t.ctypes.data, len(t), C.byref(out), info)
     if rc != B200_OK:
         _raise(rc, "b200_test_seqsum failed")
-    return out.value
+    return (out.value, info[0], info[1]) if want_info else out.value
 
 
 class NativePlan:
@@ -145,6 +148,18 @@ class NativePlan:
         ms, nbytes = C.c_float(0), C.c_int64(0)
         self._ck(lib().b200_time_kernel(self._p, which, reps, C.byref(ms), C.byref(nbytes)))
         return ms.value, nbytes.value
+
+    def trace_decode(self, token: int, position: int):
+        cap = self.launches_per_decode + 8
+        rec = np.zeros((cap, 4), dtype=np.uint64)
+        n = C.c_int32(0)
+        self._ck(lib().b200_trace_decode(self._p, token, position, rec.ctypes.data, cap, C.byref(n)))
+        return rec[: n.value]
+
+    def profile_norm(self):
+        a = (C.c_int64 * 16)()
+        self._ck(lib().b200_profile_norm(self._p, a))
+        return list(a)
 
     def kv_reset(self):
         self._ck(lib().b200_kv_reset(self._p))

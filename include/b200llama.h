@@ -132,10 +132,23 @@ int b200_read_buffer(b200_plan *plan, const char *name, int32_t layer, void *dst
  * The residual stream is restored afterwards; the KV cache is not touched. */
 int b200_time_kernel(b200_plan *plan, int32_t which, int32_t reps, float *avg_ms, int64_t *algorithmic_bytes);
 
+/* Diagnostic: runs ONE decode step through a traced copy of the decode graph (same kernels, same
+ * programmatic-dependent-launch edges) and returns one record per kernel launch, in launch order:
+ * {kernel id, earliest CTA entry, latest dependency-wait return, latest CTA exit}, the times in
+ * %globaltimer nanoseconds.  ids: 1 rmsnorm, 2 qkv, 3 rope+kv, 4 attention, 5 attn-out, 6 gate/up,
+ * 7 down, 8 lm_head, 9 argmax/advance.  records holds 4*cap uint64. */
+int b200_trace_decode(b200_plan *plan, int32_t token, int32_t position, uint64_t *records, int32_t cap, int32_t *n_out);
+
+/* Diagnostic: SM-clock cycles of the RMSNorm kernel's phases {launch->dependency wait, load+square,
+ * exact sequential sum, normalise+quantise+store} followed by {entries, first fallback element or -1,
+ * overflow flag} of the sequential-sum emulation, then at [8..12] the cycles of its phases
+ * {group sums, head+prefix, group composition, barrier, resolve}.  cycles holds 16 int64. */
+int b200_profile_norm(b200_plan *plan, int64_t *cycles);
+
 /* Test hook for the exact parallel evaluation of the reference's sequential float sum
  * (csrc/seqsum.cuh; the RMSNorm accumulator of InferenceCore.java:39-48): sums n <= 8192
  * non-negative host floats on the device exactly as `for (i) s += t[i]` would. */
-int b200_test_seqsum(const float *terms, int32_t n, float *out);
+int b200_test_seqsum(const float *terms, int32_t n, float *out, int32_t *info /* nullable: {entries, first fallback element or -1} */);
 
 /* Number of kernels one decode step launches (bench.py's gpu_launches). */
 int b200_launches_per_decode(b200_plan *plan);

@@ -16,4 +16,5 @@ with tempfile.TemporaryDirectory() as d:
         t0 = time.time(); plan.forward_decode(toks[i], i); print(f"  decode {i}: {(time.time()-t0)*1e3:.2f} ms", flush=True)
     t0 = time.time(); ids, ms = plan.decode_sequence(toks[3:35], 32, 3); t1 = time.time()
     print(f"  decode_sequence 32: device {ms:.3f} ms wall {(t1-t0)*1e3:.2f} ms -> {ms/32*1e3:.1f} us/token", flush=True)
+    print('  norm phase cycles [wait, load, seqsum, norm+quant]:', plan._native.profile_norm(), flush=True)
     plan.free()
