@@ -28,6 +28,57 @@ struct StepState {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// ---- tensor parallelism over NVLink peer memory ------------------------------------------------
+// Every rank owns ROWS of every matrix, so each dot product keeps its full sequential order and the
+// results stay bit-identical to the single-GPU (and CPU) path; what would be an all-reduce becomes an
+// all-gather: the producing kernel's epilogue stores its slice straight into every rank's
+// communication buffer (peer-mapped via CUDA IPC) and then raises a monotonically increasing flag;
+// the consuming kernel spins on the flags of all ranks.  n == 1 turns every helper into a no-op.
+#define TP_MAX 8
+enum { TP_SLOT_X = 0, TP_SLOT_ATT = 1, TP_SLOT_HQ = 2, TP_SLOT_ARG = 3, TP_SLOTS = 4 };
+struct TpCtx {
+    int rank, n;
+    unsigned ops_per_fwd;          // 4 * layers + 1
+    unsigned char *peer[TP_MAX];   // base of each rank's communication buffer (peer[rank] = own)
+    unsigned off_x, off_attq, off_atts, off_hq, off_hs, off_pv, off_pi, off_flags, off_tick, off_done;
+};
+template <typename T> __device__ __forceinline__ T *tp_ptr(const TpCtx &t, int k, unsigned off) {
+    return reinterpret_cast<T *>(t.peer[k] + off);
+}
+__device__ __forceinline__ unsigned tp_seq(const TpCtx &t, unsigned op) {
+    const unsigned tick = *reinterpret_cast<volatile unsigned *>(t.peer[t.rank] + t.off_tick);
+    return tick * t.ops_per_fwd + op + 1u;
+}
+__device__ __forceinline__ void tp_wait(const TpCtx &t, int slot, unsigned seq) { // one thread
+    const unsigned *f = reinterpret_cast<const unsigned *>(t.peer[t.rank] + t.off_flags) + slot * TP_MAX;
+    for (int k = 0; k < t.n; k++) {
+        unsigned v;
+        do { asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f + k) : "memory"); } while ((int)(v - seq) < 0);
+    }
+}
+__device__ __forceinline__ void tp_signal(const TpCtx &t, int slot, unsigned seq) { // one thread, after the data stores
+    __threadfence_system();
+    for (int k = 0; k < t.n; k++) {
+        unsigned *f = reinterpret_cast<unsigned *>(t.peer[k] + t.off_flags) + slot * TP_MAX + t.rank;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(seq) : "memory");
+    }
+}
+// Grid-wide "last CTA signals": every CTA calls this (one thread, after a CTA barrier that follows the
+// CTA's peer stores + __threadfence_system()); the last one to arrive raises the flag on every rank.
+__device__ __forceinline__ void tp_cta_done(const TpCtx &t, int slot, unsigned seq, unsigned n_ctas) {
+    unsigned *cnt = reinterpret_cast<unsigned *>(t.peer[t.rank] + t.off_done) + slot;
+    __threadfence();
+    if (atomicAdd(cnt, 1u) == n_ctas - 1u) {
+        *cnt = 0u;
+        tp_signal(t, slot, seq);
+    }
+}
+__device__ __forceinline__ float ldcg_f32c(const float *p) {
+    float v;
+    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
 // In-graph timeline tracing (diagnostic graph only; rec == nullptr in the production graphs, so the
 // branch is uniform and free).  One record per launch: {kernel id, earliest CTA entry, latest
 // dependency-wait return, latest CTA exit} in %globaltimer nanoseconds.

@@ -45,7 +45,7 @@ template <bool EMBED>
 __global__ void __launch_bounds__(NORM_THREADS, 1) k_rmsnorm_quant(float *__restrict__ x, const StepState *__restrict__ st,
                                                                DevMat emb, const float *__restrict__ w, float eps, int dim,
                                                                int8_t *__restrict__ xq, float *__restrict__ xs,
-                                                               float *__restrict__ xb, long long *__restrict__ prof, TraceBuf tr) {
+                                                               float *__restrict__ xb, long long *__restrict__ prof, TraceBuf tr, TpCtx tp, int tp_wait_op) {
     // One CTA of 1024 threads: every per-group step of the exact sum is a long dependent chain, so the
     // groups are spread over 32 warps.  Under PDL this CTA only has to fit next to ONE streaming-matvec CTA
     // (the following matvec's CTA for this SM simply starts a little later).
@@ -61,12 +61,16 @@ __global__ void __launch_bounds__(NORM_THREADS, 1) k_rmsnorm_quant(float *__rest
     pdl_wait();
     trace_mark(tr, 2);
     if (prof) t1 = clock64();
+    if (tp.n > 1 && tp_wait_op >= 0) { // x is gathered from all ranks: wait for their slices
+        if (tid == 0) tp_wait(tp, TP_SLOT_X, tp_seq(tp, (unsigned)tp_wait_op));
+        __syncthreads();
+    }
     int token = 0;
     if (EMBED) token = st->token;
     for (int i = tid; i < dim; i += NORM_THREADS) {
         float v;
         if (EMBED) { v = emb_get(emb, token, i); x[i] = v; }
-        else v = x[i];
+        else v = ldcg_f32c(x + i);
         sq[i] = __fmul_rn(v, v);
     }
     __syncthreads();
@@ -92,7 +96,7 @@ __global__ void __launch_bounds__(NORM_THREADS, 1) k_rmsnorm_quant(float *__rest
         for (int u = 0; u < 4; u++) {
             const int b = b0 + u * NWN;
             xv[u] = 0.0f; wv[u] = 0.0f;
-            if (b < nb) { xv[u] = x[b * 32 + lane]; wv[u] = w[b * 32 + lane]; } // x: L1/L2 hit (or this block's own store)
+            if (b < nb) { xv[u] = ldcg_f32c(x + b * 32 + lane); wv[u] = w[b * 32 + lane]; } // x: L2 hit (or this block's own store)
         }
 #pragma unroll
         for (int u = 0; u < 4; u++) {
@@ -380,7 +384,8 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attention(float *__restrict__ q
                                                           const float *__restrict__ ci, int n_heads, int n_kv_heads, int arch,
                                                           const float *__restrict__ qnorm_w, const float *__restrict__ knorm_w,
                                                           float eps, float sqrt_hs, int8_t *__restrict__ xq,
-                                                          float *__restrict__ xs, float *__restrict__ xb, TraceBuf tr) {
+                                                          float *__restrict__ xs, float *__restrict__ xb, TraceBuf tr, TpCtx tp,
+                                                          unsigned tp_out_op, int head_base) {
     extern __shared__ __align__(16) float sm[]; // q[HS] | k[HS] | out[HS] | att[ctx]
     __shared__ float red[ATT_THREADS / 32];
     __shared__ float s_val[2];
@@ -517,9 +522,22 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attention(float *__restrict__ q
         for (int b = warp; b < HS / 32; b += ATT_THREADS / 32) {
             float as;
             int q = quant_block_lane(so[b * 32 + lane], as);
-            xq[h * HS + b * 32 + lane] = (int8_t)q;
-            if (lane == 0) xs[(h * HS) / 32 + b] = as;
+            if (tp.n > 1) { // all-gather: this head's quantised output goes straight into every rank's buffer
+                const int gh = head_base + h;
+                for (int k = 0; k < tp.n; k++) {
+                    tp_ptr<int8_t>(tp, k, tp.off_attq)[gh * HS + b * 32 + lane] = (int8_t)q;
+                    if (lane == 0) tp_ptr<float>(tp, k, tp.off_atts)[(gh * HS) / 32 + b] = as;
+                }
+            } else {
+                xq[h * HS + b * 32 + lane] = (int8_t)q;
+                if (lane == 0) xs[(h * HS) / 32 + b] = as;
+            }
         }
+    }
+    if (tp.n > 1) {
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) tp_cta_done(tp, TP_SLOT_ATT, tp_seq(tp, tp_out_op), gridDim.x);
     }
     trace_mark(tr, 3);
 }
@@ -537,7 +555,7 @@ __device__ __forceinline__ void argmax_merge(float &v, int &i, float ov, int oi)
 __global__ void __launch_bounds__(1024) k_argmax_advance(const float *__restrict__ logits, int vocab, StepState *st,
                                                         const int *__restrict__ seq_tokens, int *__restrict__ out_ids,
                                                         int do_argmax, const float *__restrict__ part_val,
-                                                        const int *__restrict__ part_idx, int n_part, TraceBuf tr) {
+                                                        const int *__restrict__ part_idx, int n_part, TraceBuf tr, TpCtx tp, int tp_wait_x_op) {
     __shared__ float sv[32];
     __shared__ int si[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -580,8 +598,33 @@ __global__ void __launch_bounds__(1024) k_argmax_advance(const float *__restrict
                 int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
                 argmax_merge(best, best_i, ov, oi);
             }
+            if (tp.n > 1) { // exchange every rank's (max, lowest global index) and merge identically everywhere
+                const unsigned seq = tp_seq(tp, tp.ops_per_fwd - 1u);
+                if (lane == 0) {
+                    for (int k = 0; k < tp.n; k++) {
+                        tp_ptr<float>(tp, k, tp.off_pv)[tp.rank] = best;
+                        tp_ptr<int>(tp, k, tp.off_pi)[tp.rank] = best_i;
+                    }
+                    tp_signal(tp, TP_SLOT_ARG, seq);
+                    tp_wait(tp, TP_SLOT_ARG, seq);
+                }
+                __syncwarp();
+                best = lane < tp.n ? ldcg_f32c(tp_ptr<float>(tp, tp.rank, tp.off_pv) + lane) : -INFINITY;
+                best_i = lane < tp.n ? (int)__float_as_int(ldcg_f32c(reinterpret_cast<const float *>(tp_ptr<int>(tp, tp.rank, tp.off_pi)) + lane)) : 0x7fffffff;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    float ov = __shfl_xor_sync(0xffffffffu, best, o);
+                    int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+                    argmax_merge(best, best_i, ov, oi);
+                }
+            }
             if (best_i == 0x7fffffff) best_i = 0;
         }
+    } else if (tp.n > 1 && tp_wait_x_op >= 0) {
+        // prefill graph: no argmax exchange, but the next forward's embedding write must not race the peers'
+        // last residual-stream pushes of this forward
+        if (tid == 0) tp_wait(tp, TP_SLOT_X, tp_seq(tp, (unsigned)tp_wait_x_op));
+        __syncthreads();
     }
     if (tid == 0) {
         int step = st->step;
@@ -591,6 +634,7 @@ __global__ void __launch_bounds__(1024) k_argmax_advance(const float *__restrict
         else if (next < st->n_seq) st->token = seq_tokens[next];
         st->step = next;
         st->pos = st->pos + 1;
+        if (tp.n > 1) *reinterpret_cast<volatile unsigned *>(tp.peer[tp.rank] + tp.off_tick) += 1u; // next forward's flag epoch
     }
     trace_mark(tr, 3);
 }

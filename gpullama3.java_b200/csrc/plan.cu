@@ -62,6 +62,16 @@ struct b200_plan {
 
     cudaGraphExec_t g_decode = nullptr, g_prefill = nullptr, g_trace = nullptr;
     unsigned long long *trace_rec = nullptr;
+
+    // tensor parallelism (tp.n == 1: single GPU).  *_l = this rank's share.
+    TpCtx tp{};
+    unsigned char *comm = nullptr; // IPC-exported communication buffer (x, gathered activations, flags)
+    size_t comm_bytes = 0;
+    bool attached = false;
+    int nh_l = 0, nkv_l = 0, qd_l = 0, kvd_l = 0, hid_l = 0, dim_l = 0, voc_l = 0;
+    int8_t *attq = nullptr; // gathered attention output (quantised) feeding the Wo matvec
+    float *atts = nullptr;
+    void *peer_open[TP_MAX] = {nullptr};
     int launches_decode = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
@@ -157,7 +167,7 @@ int upload_matrix(b200_plan *p, const b200_tensor *t, int rows, int cols, DevMat
 
 // Upload up to three stacked GGUF Q8_0 matrices (or the gate/up pair) into tile-major layout.
 int upload_tiles(b200_plan *p, const b200_tensor *t0, const b200_tensor *t1, const b200_tensor *t2, int r0, int r1, int r2, int cols,
-                 bool gateup, TileMat &out, void *stage, size_t stage_bytes) {
+                 bool gateup, TileMat &out, void *stage, size_t stage_bytes, const int *row0 = nullptr, const int *full = nullptr) {
     const b200_tensor *ts[3] = {t0, t1, t2};
     int rs[3] = {r0, r1, r2};
     RepackSrc src;
@@ -165,19 +175,21 @@ int upload_tiles(b200_plan *p, const b200_tensor *t0, const b200_tensor *t1, con
     for (int k = 0; k < 3; k++) {
         src.raw[k] = nullptr;
         src.rows[k] = rs[k];
+        src.row0[k] = row0 ? row0[k] : 0;
         if (rs[k] == 0) continue;
+        const int full_rows = full ? full[k] : rs[k];
         const b200_tensor *t = ts[k];
         if (!t) return fail(p, B200_ERR_BAD_ARG, "missing tensor");
         if (t->ggml_type != B200_GGML_Q8_0) return fail(p, B200_ERR_UNSUPPORTED, "tensor %s has ggml type %d, plan weight type is Q8_0", t->name, t->ggml_type);
-        if (n_elems(t) != (int64_t)rs[k] * cols) return fail(p, B200_ERR_BAD_ARG, "tensor %s has %lld elements, expected %lld", t->name, (long long)n_elems(t), (long long)rs[k] * cols);
-        size_t nbytes = (size_t)rs[k] * cols / 32 * 34;
+        if (n_elems(t) != (int64_t)full_rows * cols) return fail(p, B200_ERR_BAD_ARG, "tensor %s has %lld elements, expected %lld", t->name, (long long)n_elems(t), (long long)full_rows * cols);
+        size_t nbytes = (size_t)full_rows * cols / 32 * 34;
         if (off + nbytes > stage_bytes) return fail(p, B200_ERR_STATE, "staging buffer too small");
         CK(cudaMemcpyAsync((unsigned char *)stage + off, t->data, nbytes, cudaMemcpyHostToDevice, p->stream));
         src.raw[k] = (const unsigned char *)stage + off;
         off += (nbytes + 255) & ~(size_t)255;
     }
     src.gateup = gateup ? 1 : 0;
-    const int rows = r0 + r1 + r2;
+    const int rows = gateup ? r0 + r1 : r0 + r1 + r2;
     out.rows = rows;
     out.cols = cols;
     out.nseg = smv_pick_nseg(cols);
@@ -282,13 +294,16 @@ static size_t smv_budget(int cols = 0) {
 
 template <int MODE>
 int launch_stream(b200_plan *p, const TileMat &W, const int8_t *xq, const float *xs, float *out, int8_t *hq, float *hs, bool argmax = false,
-                  TraceBuf tr = TraceBuf{nullptr, 0, 0}) {
+                  TraceBuf tr = TraceBuf{nullptr, 0, 0}, int wait_slot = -1, unsigned wait_op = 0, int out_slot = -1, unsigned out_op = 0,
+                  int row_base = 0) {
     SmvSmem L = smv_layout(W.cols, W.seg, smv_budget(W.cols));
     SmvArgs a;
     a.W = W; a.xq = xq; a.xs = xs; a.out = out; a.hq = hq; a.hs = hs; a.blk_cnt = p->blk_cnt;
     a.part_val = argmax ? p->part_val : nullptr;
     a.part_idx = argmax ? p->part_idx : nullptr;
     a.tr = tr;
+    a.tp = p->tp;
+    a.wait_slot = wait_slot; a.wait_op = wait_op; a.out_slot = out_slot; a.out_op = out_op; a.row_base = row_base;
     {
         const char *e = getenv("B200_L2_WINDOW_KB");
         a.l2_window = (unsigned)((e ? atoi(e) : 0) * 1024); // experimental: measured slower on B200 (profiles/), off by default
@@ -313,19 +328,25 @@ int enqueue_forward(b200_plan *p, bool with_logits, int *launches, bool trace = 
     const b200_config &c = p->cfg;
     const bool q8 = p->wtype == B200_GGML_Q8_0;
     const bool st = p->use_stream, pdl = p->use_pdl;
+    const bool tpar = p->tp.n > 1;
     int n = 0;
     auto TR = [&](int id) { return TraceBuf{trace ? p->trace_rec : nullptr, n, id}; };
     const size_t norm_smem = norm_smem_bytes(c.dim);
     int8_t *xq = q8 ? p->xq : nullptr;
     float *xs = q8 ? p->xs : nullptr;
     float *xbf = q8 ? nullptr : p->xb;
-    const size_t ctx_kv = (size_t)c.context_length * p->kvd;
+    const size_t ctx_kv = (size_t)c.context_length * p->kvd_l;
+    const int rank = p->tp.rank;
+    auto norm = [&](bool embed, const float *w, int wait_op) {
+        if (embed) return launch_k(p, pdl, k_rmsnorm_quant<true>, dim3(1), dim3(NORM_THREADS), norm_smem, p->x, (const StepState *)p->st, p->emb, w, c.rms_norm_eps, c.dim, xq, xs, xbf, (long long *)nullptr, TR(1), p->tp, wait_op);
+        return launch_k(p, pdl, k_rmsnorm_quant<false>, dim3(1), dim3(NORM_THREADS), norm_smem, p->x, (const StepState *)p->st, p->emb, w, c.rms_norm_eps, c.dim, xq, xs, xbf, (long long *)nullptr, TR(1), p->tp, wait_op);
+    };
     for (int l = 0; l < c.n_layers; l++) {
         LayerW &L = p->layers[l];
         int rc;
-        if (l == 0) rc = launch_k(p, pdl, k_rmsnorm_quant<true>, dim3(1), dim3(NORM_THREADS), norm_smem, p->x, (const StepState *)p->st, p->emb, (const float *)L.attn_norm, c.rms_norm_eps, c.dim, xq, xs, xbf, (long long *)nullptr, TR(1));
-        else rc = launch_k(p, pdl, k_rmsnorm_quant<false>, dim3(1), dim3(NORM_THREADS), norm_smem, p->x, (const StepState *)p->st, p->emb, (const float *)L.attn_norm, c.rms_norm_eps, c.dim, xq, xs, xbf, (long long *)nullptr, TR(1));
-        if (rc) return rc; n++;
+        // TP flag epochs inside one forward: op = 4*l + {0: attention out, 1: x after Wo, 2: hb, 3: x after W2}
+        if ((rc = norm(l == 0, L.attn_norm, l == 0 ? -1 : 4 * (l - 1) + 3))) return rc;
+        n++;
         if (st) rc = launch_stream<SMV_STORE>(p, L.tqkv, p->xq, p->xs, p->qkv, nullptr, nullptr, false, TR(2));
         else if (q8) rc = launch_matvec_q8<MODE_STORE>(p, L.qkv, p->xq, p->xs, p->qkv);
         else rc = launch_matvec_f16<MODE_STORE>(p, L.qkv, p->xb, p->qkv);
@@ -334,9 +355,10 @@ int enqueue_forward(b200_plan *p, bool with_logits, int *launches, bool trace = 
         {
             const size_t att_smem = (size_t)(3 * c.head_size + c.context_length) * 4;
             auto att = [&](auto kern) {
-                return launch_k(p, pdl, kern, dim3(c.n_heads), dim3(ATT_THREADS), att_smem, p->qkv, kc, vc, (const StepState *)p->st,
-                                (const float *)p->rope_cr, (const float *)p->rope_ci, c.n_heads, c.n_kv_heads, c.arch, (const float *)L.q_norm,
-                                (const float *)L.k_norm, c.rms_norm_eps, (float)sqrt((double)c.head_size), xq, xs, xbf, TR(4));
+                return launch_k(p, pdl, kern, dim3(p->nh_l), dim3(ATT_THREADS), att_smem, p->qkv, kc, vc, (const StepState *)p->st,
+                                (const float *)p->rope_cr, (const float *)p->rope_ci, p->nh_l, p->nkv_l, c.arch, (const float *)L.q_norm,
+                                (const float *)L.k_norm, c.rms_norm_eps, (float)sqrt((double)c.head_size), q8 ? p->attq : nullptr, q8 ? p->atts : nullptr, xbf, TR(4),
+                                p->tp, (unsigned)(4 * l + 0), rank * p->nh_l);
             };
             if (c.head_size == 128) rc = att(k_attention<128>);
             else if (c.head_size == 64) rc = att(k_attention<64>);
@@ -345,15 +367,15 @@ int enqueue_forward(b200_plan *p, bool with_logits, int *launches, bool trace = 
             if (rc) return rc;
             n++;
         }
-        if (st) rc = launch_stream<SMV_RESID>(p, L.two, p->xq, p->xs, p->x, nullptr, nullptr, false, TR(5));
+        if (st) rc = launch_stream<SMV_RESID>(p, L.two, p->attq, p->atts, p->x, nullptr, nullptr, false, TR(5), tpar ? TP_SLOT_ATT : -1, 4 * l + 0, tpar ? TP_SLOT_X : -1, 4 * l + 1, rank * p->dim_l);
         else if (q8) rc = launch_matvec_q8<MODE_RESID>(p, L.wo, p->xq, p->xs, p->x);
         else rc = launch_matvec_f16<MODE_RESID>(p, L.wo, p->xb, p->x);
         if (rc) return rc; n++;
-        if ((rc = launch_k(p, pdl, k_rmsnorm_quant<false>, dim3(1), dim3(NORM_THREADS), norm_smem, p->x, (const StepState *)p->st, p->emb, (const float *)L.ffn_norm, c.rms_norm_eps, c.dim, xq, xs, xbf, (long long *)nullptr, TR(1)))) return rc;
+        if ((rc = norm(false, L.ffn_norm, 4 * l + 1))) return rc;
         n++;
         if (st) {
-            if ((rc = launch_stream<SMV_GATEUP>(p, L.tgu, p->xq, p->xs, p->hb, p->hq, p->hs, false, TR(6)))) return rc; n++;
-            if ((rc = launch_stream<SMV_RESID>(p, L.tw2, p->hq, p->hs, p->x, nullptr, nullptr, false, TR(7)))) return rc; n++;
+            if ((rc = launch_stream<SMV_GATEUP>(p, L.tgu, p->xq, p->xs, p->hb, p->hq, p->hs, false, TR(6), -1, 0, tpar ? TP_SLOT_HQ : -1, 4 * l + 2, rank * p->hid_l))) return rc; n++;
+            if ((rc = launch_stream<SMV_RESID>(p, L.tw2, p->hq, p->hs, p->x, nullptr, nullptr, false, TR(7), tpar ? TP_SLOT_HQ : -1, 4 * l + 2, tpar ? TP_SLOT_X : -1, 4 * l + 3, rank * p->dim_l))) return rc; n++;
         } else if (q8) {
             k_gateup_q8<<<c.hidden_dim / 32, 256, q8_smem_bytes(c.dim, 4, 8), p->stream>>>(
                 (const int8_t *)L.w1.qs, L.w1.sc, (const int8_t *)L.w3.qs, L.w3.sc, p->xq, p->xs, c.hidden_dim, c.dim, p->hq, p->hs, p->hb);
@@ -367,12 +389,13 @@ int enqueue_forward(b200_plan *p, bool with_logits, int *launches, bool trace = 
             if ((rc = launch_matvec_f16<MODE_RESID>(p, L.w2, p->hb, p->x))) return rc; n++;
         }
     }
+    const int last_x_op = 4 * (c.n_layers - 1) + 3;
     if (with_logits) {
         // rmsnorm(x, x, rms_final_weight) then wcls.matmul (InferenceCore.java:167-169)
         int rc;
-        if ((rc = launch_k(p, pdl, k_rmsnorm_quant<false>, dim3(1), dim3(NORM_THREADS), norm_smem, p->x, (const StepState *)p->st, p->emb, (const float *)p->out_norm, c.rms_norm_eps, c.dim, xq, xs, xbf, (long long *)nullptr, TR(1)))) return rc;
+        if ((rc = norm(false, p->out_norm, last_x_op))) return rc;
         n++;
-        if (st) rc = launch_stream<SMV_STORE>(p, p->tout, p->xq, p->xs, p->logits, nullptr, nullptr, true, TR(8));
+        if (st) rc = launch_stream<SMV_STORE>(p, p->tout, p->xq, p->xs, p->logits, nullptr, nullptr, true, TR(8), -1, 0, -1, 0, rank * p->voc_l);
         else if (q8) rc = launch_matvec_q8<MODE_STORE>(p, p->out, p->xq, p->xs, p->logits);
         else rc = launch_matvec_f16<MODE_STORE>(p, p->out, p->xb, p->logits);
         if (rc) return rc; n++;
@@ -380,7 +403,7 @@ int enqueue_forward(b200_plan *p, bool with_logits, int *launches, bool trace = 
     {
         int rc;
         if ((rc = launch_k(p, pdl, k_argmax_advance, dim3(1), dim3(1024), (size_t)0, (const float *)p->logits, c.vocab_size, p->st, (const int *)p->seq_tokens, p->out_ids, with_logits ? 1 : 0,
-                           (const float *)(st ? p->part_val : nullptr), (const int *)(st ? p->part_idx : nullptr), p->n_sms, TR(9)))) return rc;
+                           (const float *)(st ? p->part_val : nullptr), (const int *)(st ? p->part_idx : nullptr), p->n_sms, TR(9), p->tp, with_logits ? -1 : last_x_op))) return rc;
         n++;
     }
     if (launches) *launches = n;
@@ -438,7 +461,6 @@ int set_smem_attrs(b200_plan *p) {
 int build(b200_plan *p, const b200_tensor *tensors, int n_tensors) {
     const b200_config &c = p->cfg;
     if (c.arch != B200_ARCH_LLAMA && c.arch != B200_ARCH_QWEN3) return fail(p, B200_ERR_UNSUPPORTED, "unknown arch %d", c.arch);
-    if (c.tp_size > 1) return fail(p, B200_ERR_UNSUPPORTED, "tensor parallelism is not built yet (tp_size=%d)", c.tp_size);
     if (c.dim <= 0 || c.dim % 32 || c.hidden_dim % 32 || (c.head_size != 32 && c.head_size != 64 && c.head_size != 128 && c.head_size != 256) || c.n_heads % c.n_kv_heads ||
         c.n_layers <= 0 || c.vocab_size <= 0 || c.context_length <= 0)
         return fail(p, B200_ERR_BAD_ARG, "unsupported shape (dim/hidden must be multiples of 32, head_size one of 32/64/128/256)");
@@ -447,6 +469,17 @@ int build(b200_plan *p, const b200_tensor *tensors, int n_tensors) {
     p->qd = c.n_heads * c.head_size;
     p->kvd = c.n_kv_heads * c.head_size;
     if (c.arch == B200_ARCH_LLAMA && p->qd != c.dim) return fail(p, B200_ERR_BAD_ARG, "llama: n_heads*head_size must equal dim");
+    {
+        const int tn = c.tp_size;
+        if (tn < 1 || tn > TP_MAX || c.tp_rank < 0 || c.tp_rank >= tn) return fail(p, B200_ERR_BAD_ARG, "bad tp_rank/tp_size %d/%d", c.tp_rank, tn);
+        if (tn > 1 && (c.n_heads % tn || c.n_kv_heads % tn || c.dim % (4 * tn) || c.hidden_dim % (32 * tn) || c.vocab_size % (4 * tn)))
+            return fail(p, B200_ERR_UNSUPPORTED, "shape does not split %d ways (heads, kv heads, dim/4, hidden/32 and vocab/4 must be divisible)", tn);
+        p->nh_l = c.n_heads / tn; p->nkv_l = c.n_kv_heads / tn;
+        p->qd_l = p->nh_l * c.head_size; p->kvd_l = p->nkv_l * c.head_size;
+        p->hid_l = c.hidden_dim / tn; p->dim_l = c.dim / tn; p->voc_l = c.vocab_size / tn;
+        p->tp.rank = c.tp_rank; p->tp.n = 1; // n becomes tp_size once the peers are attached
+        p->tp.ops_per_fwd = 4u * (unsigned)c.n_layers + 1u;
+    }
 
     const b200_tensor *emb = find(tensors, n_tensors, "token_embd.weight");
     if (!emb) return fail(p, B200_ERR_BAD_ARG, "missing tensor token_embd.weight");
@@ -465,11 +498,12 @@ int build(b200_plan *p, const b200_tensor *tensors, int n_tensors) {
     {
         const char *e = getenv("B200_STREAM");
         bool want = !(e && e[0] == '0');
-        p->use_stream = want && p->wtype == B200_GGML_Q8_0 && stream_shape_ok(p->qd + 2 * p->kvd, c.dim) && stream_shape_ok(c.dim, p->qd) &&
-                        stream_shape_ok(2 * c.hidden_dim, c.dim) && stream_shape_ok(c.dim, c.hidden_dim) && stream_shape_ok(c.vocab_size, c.dim) &&
-                        gateup_fits(c.hidden_dim, p->n_sms);
+        p->use_stream = want && p->wtype == B200_GGML_Q8_0 && stream_shape_ok(p->qd_l + 2 * p->kvd_l, c.dim) && stream_shape_ok(p->dim_l, p->qd) &&
+                        stream_shape_ok(2 * p->hid_l, c.dim) && stream_shape_ok(p->dim_l, c.hidden_dim) && stream_shape_ok(p->voc_l, c.dim) &&
+                        gateup_fits(p->hid_l, p->n_sms);
         const char *e2 = getenv("B200_PDL");
         p->use_pdl = p->use_stream && !(e2 && e2[0] == '0');
+        if (c.tp_size > 1 && !p->use_stream) return fail(p, B200_ERR_UNSUPPORTED, "tensor parallelism needs the Q8_0 streaming path");
     }
     void *stage = nullptr;
     size_t stage_bytes = (size_t)34 * (8u << 20); // 8 Mi blocks = 272 MiB
@@ -489,7 +523,10 @@ int build(b200_plan *p, const b200_tensor *tensors, int n_tensors) {
     const b200_tensor *outw = find(tensors, n_tensors, "output.weight");
     if (p->use_stream) {
         if (!outw && emb->ggml_type != p->wtype) return fail(p, B200_ERR_UNSUPPORTED, "tied output weight type differs from the matrix type");
-        if ((rc = upload_tiles(p, outw ? outw : emb, nullptr, nullptr, c.vocab_size, 0, 0, c.dim, false, p->tout, stage, stage_bytes))) return rc;
+        {
+            const int r0[3] = {c.tp_rank * p->voc_l, 0, 0}, fu[3] = {c.vocab_size, 0, 0};
+            if ((rc = upload_tiles(p, outw ? outw : emb, nullptr, nullptr, p->voc_l, 0, 0, c.dim, false, p->tout, stage, stage_bytes, r0, fu))) return rc;
+        }
         p->out = p->emb;
         if ((rc = dalloc(p, &p->part_val, (size_t)p->n_sms * 4))) return rc;
         if ((rc = dalloc(p, &p->part_idx, (size_t)p->n_sms * 4))) return rc;
@@ -516,10 +553,14 @@ int build(b200_plan *p, const b200_tensor *tensors, int n_tensors) {
             if ((rc = upload_f32(p, T("attn_k_norm.weight"), c.head_size, &L.k_norm, "attn_k_norm.weight"))) return rc;
         }
         if (p->use_stream) {
-            if ((rc = upload_tiles(p, T("attn_q.weight"), T("attn_k.weight"), T("attn_v.weight"), p->qd, p->kvd, p->kvd, c.dim, false, L.tqkv, stage, stage_bytes))) return rc;
-            if ((rc = upload_tiles(p, T("attn_output.weight"), nullptr, nullptr, c.dim, 0, 0, p->qd, false, L.two, stage, stage_bytes))) return rc;
-            if ((rc = upload_tiles(p, T("ffn_gate.weight"), T("ffn_up.weight"), nullptr, c.hidden_dim, c.hidden_dim, 0, c.dim, true, L.tgu, stage, stage_bytes))) return rc;
-            if ((rc = upload_tiles(p, T("ffn_down.weight"), nullptr, nullptr, c.dim, 0, 0, c.hidden_dim, false, L.tw2, stage, stage_bytes))) return rc;
+            const int rk = c.tp_rank;
+            const int qr0[3] = {rk * p->qd_l, rk * p->kvd_l, rk * p->kvd_l}, qfu[3] = {p->qd, p->kvd, p->kvd};
+            if ((rc = upload_tiles(p, T("attn_q.weight"), T("attn_k.weight"), T("attn_v.weight"), p->qd_l, p->kvd_l, p->kvd_l, c.dim, false, L.tqkv, stage, stage_bytes, qr0, qfu))) return rc;
+            const int dr0[3] = {rk * p->dim_l, 0, 0}, dfu[3] = {c.dim, 0, 0};
+            if ((rc = upload_tiles(p, T("attn_output.weight"), nullptr, nullptr, p->dim_l, 0, 0, p->qd, false, L.two, stage, stage_bytes, dr0, dfu))) return rc;
+            const int gr0[3] = {rk * p->hid_l, rk * p->hid_l, 0}, gfu[3] = {c.hidden_dim, c.hidden_dim, 0};
+            if ((rc = upload_tiles(p, T("ffn_gate.weight"), T("ffn_up.weight"), nullptr, p->hid_l, p->hid_l, 0, c.dim, true, L.tgu, stage, stage_bytes, gr0, gfu))) return rc;
+            if ((rc = upload_tiles(p, T("ffn_down.weight"), nullptr, nullptr, p->dim_l, 0, 0, c.hidden_dim, false, L.tw2, stage, stage_bytes, dr0, dfu))) return rc;
             continue;
         }
         // fused [Wq; Wk; Wv] so one launch produces the packed q|k|v vector
@@ -559,17 +600,44 @@ int build(b200_plan *p, const b200_tensor *tensors, int n_tensors) {
     }
 
     int big = c.dim > p->qd ? c.dim : p->qd;
-    if ((rc = dalloc(p, &p->x, (size_t)c.dim * 4))) return rc;
+    if (c.tp_size > 1) {
+        // one IPC-exportable allocation: x | attq | atts | hq | hs | argmax partials | flags | tick | done counters
+        auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+        size_t o = 0;
+        p->tp.off_x = (unsigned)o; o = al(o + (size_t)c.dim * 4);
+        p->tp.off_attq = (unsigned)o; o = al(o + (size_t)p->qd);
+        p->tp.off_atts = (unsigned)o; o = al(o + (size_t)(p->qd / 32) * 4);
+        p->tp.off_hq = (unsigned)o; o = al(o + (size_t)c.hidden_dim);
+        p->tp.off_hs = (unsigned)o; o = al(o + (size_t)(c.hidden_dim / 32) * 4);
+        p->tp.off_pv = (unsigned)o; o = al(o + TP_MAX * 4);
+        p->tp.off_pi = (unsigned)o; o = al(o + TP_MAX * 4);
+        p->tp.off_flags = (unsigned)o; o = al(o + TP_SLOTS * TP_MAX * 4);
+        p->tp.off_tick = (unsigned)o; o = al(o + 4);
+        p->tp.off_done = (unsigned)o; o = al(o + TP_SLOTS * 4);
+        p->comm_bytes = o;
+        if ((rc = dalloc(p, &p->comm, o))) return rc;
+        CK(cudaMemset(p->comm, 0, o));
+        p->x = reinterpret_cast<float *>(p->comm + p->tp.off_x);
+    } else if ((rc = dalloc(p, &p->x, (size_t)c.dim * 4))) return rc;
     if ((rc = dalloc(p, &p->xb, (size_t)big * 4))) return rc;
-    if ((rc = dalloc(p, &p->qkv, (size_t)(p->qd + 2 * p->kvd) * 4))) return rc;
+    if ((rc = dalloc(p, &p->qkv, (size_t)(p->qd_l + 2 * p->kvd_l) * 4))) return rc;
     if ((rc = dalloc(p, &p->hb, (size_t)c.hidden_dim * 4))) return rc;
     if ((rc = dalloc(p, &p->hb2, (size_t)c.hidden_dim * 4))) return rc;
     if ((rc = dalloc(p, &p->logits, (size_t)c.vocab_size * 4))) return rc;
     if ((rc = dalloc(p, &p->xq, (size_t)big))) return rc;
     if ((rc = dalloc(p, &p->xs, (size_t)(big / 32) * 4))) return rc;
-    if ((rc = dalloc(p, &p->hq, (size_t)c.hidden_dim))) return rc;
-    if ((rc = dalloc(p, &p->hs, (size_t)(c.hidden_dim / 32) * 4))) return rc;
-    size_t kv_bytes = (size_t)c.n_layers * c.context_length * p->kvd * 4;
+    if (c.tp_size > 1) {
+        p->hq = reinterpret_cast<int8_t *>(p->comm + p->tp.off_hq);
+        p->hs = reinterpret_cast<float *>(p->comm + p->tp.off_hs);
+        p->attq = reinterpret_cast<int8_t *>(p->comm + p->tp.off_attq);
+        p->atts = reinterpret_cast<float *>(p->comm + p->tp.off_atts);
+    } else {
+        if ((rc = dalloc(p, &p->hq, (size_t)c.hidden_dim))) return rc;
+        if ((rc = dalloc(p, &p->hs, (size_t)(c.hidden_dim / 32) * 4))) return rc;
+        p->attq = p->xq; // the attention output is the activation of the Wo matvec
+        p->atts = p->xs;
+    }
+    size_t kv_bytes = (size_t)c.n_layers * c.context_length * p->kvd_l * 4;
     if ((rc = dalloc(p, &p->key_cache, kv_bytes))) return rc;
     if ((rc = dalloc(p, &p->value_cache, kv_bytes))) return rc;
     CK(cudaMemset(p->key_cache, 0, kv_bytes));
@@ -585,6 +653,7 @@ int build(b200_plan *p, const b200_tensor *tensors, int n_tensors) {
     CK(cudaMallocHost(&p->h_ids, (size_t)p->seq_cap * 4));
 
     if ((rc = set_smem_attrs(p))) return rc;
+    if (c.tp_size > 1) { CK(cudaStreamSynchronize(p->stream)); return B200_OK; } // graphs are captured by b200_tp_attach
     if ((rc = capture(p, true, &p->g_decode, &p->launches_decode))) return rc;
     if ((rc = capture(p, false, &p->g_prefill, nullptr))) return rc;
     if (p->use_stream) {
@@ -638,6 +707,8 @@ int b200_plan_create(const b200_config *cfg, const b200_tensor *tensors, int32_t
 
 int b200_forward_decode(b200_plan *p, int32_t token, int32_t position, float *logits, int32_t *argmax) {
     if (!p) return B200_ERR_BAD_ARG;
+    if (!p->g_decode) return fail(p, B200_ERR_STATE, "tensor-parallel plan: call b200_tp_attach on every rank first");
+    if (logits && p->tp.n > 1) return fail(p, B200_ERR_UNSUPPORTED, "full logits are not gathered under tensor parallelism (argmax is)");
     int rc;
     if ((rc = check_pos(p, token, position))) return rc;
     CK(cudaSetDevice(p->device));
@@ -652,6 +723,7 @@ int b200_forward_decode(b200_plan *p, int32_t token, int32_t position, float *lo
 
 int b200_forward_prefill(b200_plan *p, int32_t token, int32_t position) {
     if (!p) return B200_ERR_BAD_ARG;
+    if (!p->g_prefill) return fail(p, B200_ERR_STATE, "tensor-parallel plan: call b200_tp_attach on every rank first");
     int rc;
     if ((rc = check_pos(p, token, position))) return rc;
     CK(cudaSetDevice(p->device));
@@ -664,6 +736,7 @@ int b200_forward_prefill(b200_plan *p, int32_t token, int32_t position) {
 int b200_forward_batch_prefill(b200_plan *p, const int32_t *tokens, int32_t n, int32_t start_pos) {
     if (!p || !tokens) return B200_ERR_BAD_ARG;
     if (n <= 0) return B200_OK;
+    if (!p->g_prefill) return fail(p, B200_ERR_STATE, "tensor-parallel plan: call b200_tp_attach on every rank first");
     if (p->prefill_batch > 1 && n > p->prefill_batch) return fail(p, B200_ERR_BAD_ARG, "chunk of %d tokens exceeds prefill_batch_size %d", n, p->prefill_batch);
     if (start_pos < 0 || start_pos + n > p->cfg.context_length) return fail(p, B200_ERR_BAD_ARG, "positions %d..%d outside the KV cache", start_pos, start_pos + n - 1);
     for (int i = 0; i < n; i++)
@@ -685,6 +758,7 @@ int b200_decode_sequence(b200_plan *p, const int32_t *tokens, int32_t n, int32_t
                          int32_t *out_ids, float *device_ms) {
     if (!p || !tokens) return B200_ERR_BAD_ARG;
     if (n <= 0) return B200_OK;
+    if (!p->g_decode) return fail(p, B200_ERR_STATE, "tensor-parallel plan: call b200_tp_attach on every rank first");
     if (n > p->seq_cap) return fail(p, B200_ERR_BAD_ARG, "sequence of %d steps exceeds capacity %d", n, p->seq_cap);
     if (start_pos < 0 || start_pos + n > p->cfg.context_length) return fail(p, B200_ERR_BAD_ARG, "positions %d..%d outside the KV cache (%d)", start_pos, start_pos + n - 1, p->cfg.context_length);
     int nt = feedback ? 1 : n;
@@ -708,7 +782,7 @@ int b200_decode_sequence(b200_plan *p, const int32_t *tokens, int32_t n, int32_t
 int b200_kv_reset(b200_plan *p) {
     if (!p) return B200_ERR_BAD_ARG;
     CK(cudaSetDevice(p->device));
-    size_t kv_bytes = (size_t)p->cfg.n_layers * p->cfg.context_length * p->kvd * 4;
+    size_t kv_bytes = (size_t)p->cfg.n_layers * p->cfg.context_length * p->kvd_l * 4;
     CK(cudaMemsetAsync(p->key_cache, 0, kv_bytes, p->stream));
     CK(cudaMemsetAsync(p->value_cache, 0, kv_bytes, p->stream));
     CK(cudaStreamSynchronize(p->stream));
@@ -721,10 +795,10 @@ int b200_read_buffer(b200_plan *p, const char *name, int32_t layer, void *dst, s
     const void *src = nullptr;
     size_t sz = 0;
     std::string s = name;
-    size_t ctx_kv = (size_t)c.context_length * p->kvd;
+    size_t ctx_kv = (size_t)c.context_length * p->kvd_l;
     if (s == "x") { src = p->x; sz = (size_t)c.dim * 4; }
     else if (s == "xb") { src = p->xb; sz = (size_t)(c.dim > p->qd ? c.dim : p->qd) * 4; }
-    else if (s == "q" || s == "qkv") { src = p->qkv; sz = (size_t)(p->qd + 2 * p->kvd) * 4; }
+    else if (s == "q" || s == "qkv") { src = p->qkv; sz = (size_t)(p->qd_l + 2 * p->kvd_l) * 4; }
     else if (s == "hb") { src = p->hb; sz = (size_t)c.hidden_dim * 4; }
     else if (s == "logits") { src = p->logits; sz = (size_t)c.vocab_size * 4; }
     else if (s == "xq") { src = p->xq; sz = (size_t)(c.dim > p->qd ? c.dim : p->qd); }
@@ -745,6 +819,7 @@ int b200_read_buffer(b200_plan *p, const char *name, int32_t layer, void *dst, s
 
 int b200_time_kernel(b200_plan *p, int32_t which, int32_t reps, float *avg_ms, int64_t *algorithmic_bytes) {
     if (!p || !avg_ms || reps <= 0) return B200_ERR_BAD_ARG;
+    if (p->cfg.tp_size > 1) return fail(p, B200_ERR_UNSUPPORTED, "b200_time_kernel is single-GPU only");
     const b200_config &c = p->cfg;
     const bool q8 = p->wtype == B200_GGML_Q8_0;
     CK(cudaSetDevice(p->device));
@@ -827,6 +902,41 @@ int b200_time_kernel(b200_plan *p, int32_t which, int32_t reps, float *avg_ms, i
     return B200_OK;
 }
 
+int b200_tp_handle(b200_plan *p, void *handle64) {
+    if (!p || !handle64) return B200_ERR_BAD_ARG;
+    if (p->cfg.tp_size <= 1 || !p->comm) return fail(p, B200_ERR_STATE, "not a tensor-parallel plan");
+    CK(cudaSetDevice(p->device));
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, p->comm));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(handle64, &h, 64);
+    return B200_OK;
+}
+
+int b200_tp_attach(b200_plan *p, const void *handles, int32_t n) {
+    if (!p || !handles) return B200_ERR_BAD_ARG;
+    if (p->cfg.tp_size <= 1 || !p->comm) return fail(p, B200_ERR_STATE, "not a tensor-parallel plan");
+    if (n != p->cfg.tp_size) return fail(p, B200_ERR_BAD_ARG, "expected %d handles, got %d", p->cfg.tp_size, n);
+    if (p->attached) return fail(p, B200_ERR_STATE, "already attached");
+    CK(cudaSetDevice(p->device));
+    for (int k = 0; k < n; k++) {
+        if (k == p->cfg.tp_rank) { p->tp.peer[k] = p->comm; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const unsigned char *)handles + (size_t)k * 64, 64);
+        void *ptr = nullptr;
+        CK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        p->peer_open[k] = ptr;
+        p->tp.peer[k] = (unsigned char *)ptr;
+    }
+    p->tp.n = n;
+    p->attached = true;
+    int rc;
+    if ((rc = capture(p, true, &p->g_decode, &p->launches_decode))) return rc;
+    if ((rc = capture(p, false, &p->g_prefill, nullptr))) return rc;
+    CK(cudaStreamSynchronize(p->stream));
+    return B200_OK;
+}
+
 int b200_trace_decode(b200_plan *p, int32_t token, int32_t position, uint64_t *records, int32_t cap, int32_t *n_out) {
     if (!p || !records || !n_out) return B200_ERR_BAD_ARG;
     if (!p->g_trace) return fail(p, B200_ERR_UNSUPPORTED, "tracing needs the streaming (Q8_0) path");
@@ -856,7 +966,7 @@ int b200_profile_norm(b200_plan *p, int64_t *cycles4) {
     const bool q8 = p->wtype == B200_GGML_Q8_0;
     for (int i = 0; i < 3; i++)
         k_rmsnorm_quant<false><<<1, NORM_THREADS, norm_smem, p->stream>>>(p->x, p->st, p->emb, p->layers[0].attn_norm, c.rms_norm_eps, c.dim,
-                                                                 q8 ? p->xq : nullptr, q8 ? p->xs : nullptr, q8 ? nullptr : p->xb, d, TraceBuf{nullptr, 0, 0});
+                                                                 q8 ? p->xq : nullptr, q8 ? p->xs : nullptr, q8 ? nullptr : p->xb, d, TraceBuf{nullptr, 0, 0}, p->tp, -1);
     cudaError_t e = cudaStreamSynchronize(p->stream);
     long long h[16] = {0};
     if (e == cudaSuccess) e = cudaMemcpy(h, d, 128, cudaMemcpyDeviceToHost);
@@ -895,6 +1005,7 @@ void b200_plan_free(b200_plan *p) {
     if (p->g_decode) cudaGraphExecDestroy(p->g_decode);
     if (p->g_prefill) cudaGraphExecDestroy(p->g_prefill);
     if (p->g_trace) cudaGraphExecDestroy(p->g_trace);
+    for (int k = 0; k < TP_MAX; k++) if (p->peer_open[k]) cudaIpcCloseMemHandle(p->peer_open[k]);
     for (void *d : p->allocs) cudaFree(d);
     if (p->h_st) cudaFreeHost(p->h_st);
     if (p->h_ids) cudaFreeHost(p->h_ids);

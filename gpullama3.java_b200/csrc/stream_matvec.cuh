@@ -125,6 +125,13 @@ struct SmvArgs {
     int *part_idx;      // ... and the lowest row index attaining it (FloatTensor.argmax tie-break), or NULL
     TraceBuf tr;
     unsigned l2_window; // bytes of this CTA's slice to keep prefetched into L2 ahead of the ring (0 = off)
+    // tensor parallelism (tp.n == 1: unused)
+    TpCtx tp;
+    int wait_slot;      // slot whose flags gate the activation (-1: none)
+    unsigned wait_op;
+    int out_slot;       // slot to raise after this kernel's peer stores (-1: outputs stay local)
+    unsigned out_op;
+    int row_base;       // global index of this rank's first output row (RESID/STORE) or hidden unit (GATEUP)
 };
 
 template <int MODE>
@@ -193,13 +200,17 @@ __global__ void __launch_bounds__(SMV_THREADS, 1) k_stream_matvec_q8(SmvArgs a, 
     // ===== consumers =====
     pdl_wait(); // activations come from the previous kernel
     trace_mark(a.tr, 2);
+    if (a.tp.n > 1 && a.wait_slot >= 0) { // ... and, under TP, from every rank
+        if (tid == 0) tp_wait(a.tp, a.wait_slot, tp_seq(a.tp, a.wait_op));
+        consumer_bar_sync();
+    }
     {
         const int nb = W.cols >> 5;
         int4 *sxq = reinterpret_cast<int4 *>(smem + L.off_xq);
         float *sxs = reinterpret_cast<float *>(smem + L.off_xs);
         const int4 *src = reinterpret_cast<const int4 *>(a.xq);
-        for (int c = tid; c < W.cols / 16; c += SMV_CONSUMER_WARPS * 32) sxq[c] = src[c];
-        for (int b = tid; b < nb; b += SMV_CONSUMER_WARPS * 32) sxs[b] = a.xs[b];
+        for (int c = tid; c < W.cols / 16; c += SMV_CONSUMER_WARPS * 32) sxq[c] = __ldcg(src + c);
+        for (int b = tid; b < nb; b += SMV_CONSUMER_WARPS * 32) sxs[b] = __ldcg(a.xs + b);
     }
     consumer_bar_sync();
 
@@ -272,10 +283,16 @@ __global__ void __launch_bounds__(SMV_THREADS, 1) k_stream_matvec_q8(SmvArgs a, 
                 }
             } else if (lane < 4) {
                 const size_t row = (size_t)4 * G + lane;
-                if (MODE == SMV_RESID) a.out[row] = __fadd_rn(a.out[row], acc); // x[i] = x[i] + xb2[i]
-                else {
+                if (MODE == SMV_RESID) {
+                    if (a.tp.n > 1) { // all-gather of the residual stream: this rank's rows go to every rank
+                        const size_t grow = (size_t)a.row_base + row;
+                        const float v = __fadd_rn(ldcg_f32c(a.out + grow), acc);
+                        for (int k = 0; k < a.tp.n; k++) tp_ptr<float>(a.tp, k, a.tp.off_x)[grow] = v;
+                    } else a.out[row] = __fadd_rn(a.out[row], acc); // x[i] = x[i] + xb2[i]
+                } else {
                     a.out[row] = acc;
-                    if (acc > best) { best = acc; best_i = (int)row; } // rows ascend per lane: first maximum kept
+                    const int grow = a.row_base + (int)row;
+                    if (acc > best) { best = acc; best_i = grow; } // rows ascend per lane: first maximum kept
                 }
             }
         }
@@ -312,8 +329,16 @@ __global__ void __launch_bounds__(SMV_THREADS, 1) k_stream_matvec_q8(SmvArgs a, 
                 if (mine) {
                     float as;
                     int q = quant_block_lane(v, as);
-                    a.hq[(blk << 5) + lane] = (int8_t)q;
-                    if (lane == 0) a.hs[blk] = as;
+                    if (a.tp.n > 1) {
+                        const int gblk = (a.row_base >> 5) + blk;
+                        for (int k = 0; k < a.tp.n; k++) {
+                            tp_ptr<int8_t>(a.tp, k, a.tp.off_hq)[(gblk << 5) + lane] = (int8_t)q;
+                            if (lane == 0) tp_ptr<float>(a.tp, k, a.tp.off_hs)[gblk] = as;
+                        }
+                    } else {
+                        a.hq[(blk << 5) + lane] = (int8_t)q;
+                        if (lane == 0) a.hs[blk] = as;
+                    }
                 }
             }
         }
@@ -335,6 +360,11 @@ __global__ void __launch_bounds__(SMV_THREADS, 1) k_stream_matvec_q8(SmvArgs a, 
             }
         }
     }
+    if (a.tp.n > 1 && a.out_slot >= 0) { // publish: all peer stores of this CTA, then (last CTA) the flag
+        __threadfence_system();
+        consumer_bar_sync();
+        if (tid == 0) tp_cta_done(a.tp, a.out_slot, tp_seq(a.tp, a.out_op), gridDim.x);
+    }
     trace_mark(a.tr, 3);
 }
 
@@ -344,6 +374,7 @@ __global__ void __launch_bounds__(SMV_THREADS, 1) k_stream_matvec_q8(SmvArgs a, 
 struct RepackSrc {
     const unsigned char *raw[3]; // up to three source tensors stacked by rows (q|k|v), or gate/up
     int rows[3];
+    int row0[3];                 // first source row of each part (tensor-parallel slices)
     int gateup;                  // 1: raw[0] = gate, raw[1] = up, group G = {g 2G, g 2G+1, u 2G, u 2G+1}
 };
 
@@ -357,12 +388,13 @@ __global__ void k_repack_tiles(RepackSrc src, unsigned char *dst, int rows, int 
     const unsigned char *raw;
     if (src.gateup) {
         raw = src.raw[r >> 1];
-        row = 2 * G + (r & 1);
+        row = src.row0[r >> 1] + 2 * G + (r & 1);
     } else {
         row = 4 * G + r;
         int k = 0;
         while (k < 2 && row >= src.rows[k]) { row -= src.rows[k]; k++; }
         raw = src.raw[k];
+        row += src.row0[k];
     }
     const int nbs = seg / 32;
     const unsigned char *blocks = raw + ((size_t)row * (cols / 32) + (size_t)s * nbs) * 34; // first source block of this unit

@@ -40,7 +40,7 @@ class Tensor(C.Structure):
 
 
 EXPORTS = ["b200_plan_create", "b200_forward_decode", "b200_forward_prefill", "b200_forward_batch_prefill",
-           "b200_decode_sequence", "b200_time_kernel", "b200_trace_decode", "b200_profile_norm", "b200_test_seqsum", "b200_kv_reset", "b200_read_buffer", "b200_launches_per_decode",
+           "b200_decode_sequence", "b200_time_kernel", "b200_tp_handle", "b200_tp_attach", "b200_trace_decode", "b200_profile_norm", "b200_test_seqsum", "b200_kv_reset", "b200_read_buffer", "b200_launches_per_decode",
            "b200_device_bytes", "b200_plan_free", "b200_last_error", "b200_version"]
 
 _lib = None
@@ -63,6 +63,8 @@ def lib() -> C.CDLL:
     L.b200_kv_reset.argtypes = [vp]
     L.b200_profile_norm.argtypes = [vp, C.POINTER(C.c_int64)]
     L.b200_trace_decode.argtypes = [vp, i32, i32, vp, i32, C.POINTER(i32)]
+    L.b200_tp_handle.argtypes = [vp, vp]
+    L.b200_tp_attach.argtypes = [vp, vp, i32]
     L.b200_test_seqsum.argtypes = [vp, i32, C.POINTER(C.c_float), C.POINTER(i32)]
     L.b200_time_kernel.argtypes = [vp, i32, i32, C.POINTER(C.c_float), C.POINTER(C.c_int64)]
     L.b200_read_buffer.argtypes = [vp, C.c_char_p, i32, vp, C.c_size_t]
@@ -148,6 +150,15 @@ class NativePlan:
         ms, nbytes = C.c_float(0), C.c_int64(0)
         self._ck(lib().b200_time_kernel(self._p, which, reps, C.byref(ms), C.byref(nbytes)))
         return ms.value, nbytes.value
+
+    def tp_handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._ck(lib().b200_tp_handle(self._p, buf))
+        return buf.raw
+
+    def tp_attach(self, handles: list):
+        blob = b"".join(handles)
+        self._ck(lib().b200_tp_attach(self._p, blob, len(handles)))
 
     def trace_decode(self, token: int, position: int):
         cap = self.launches_per_decode + 8

@@ -26,6 +26,37 @@ PREFILL_BATCH_SIZE = int(_flag("llama.prefillBatchSize", "1"))
 FP16_LANES = int(_flag("llama.VectorBitSize", "512")) // 32  # FloatTensor.java:21 (species width / 32-bit lanes)
 
 
+def tp_shard_plan(c, n: int) -> list[dict]:
+    """Row ranges every rank owns under n-way tensor parallelism (mirrors csrc/plan.cu).  Every matrix is
+    split by OUTPUT rows -- query/KV heads, FFN hidden units, residual rows, vocabulary rows -- so each dot
+    product keeps its full column range and therefore the reference's summation order; what the usual
+    column split turns into an all-reduce is an all-gather of the output slices here."""
+    if n < 1 or n > 8 or c.n_heads % n or c.n_kv_heads % n or c.dim % (4 * n) or c.hidden_dim % (32 * n) or c.vocab_size % (4 * n):
+        raise native.UnsupportedOperation(-2, f"shape does not split {n} ways")
+    hs = c.head_size
+    out = []
+    for r in range(n):
+        nh, nkv = c.n_heads // n, c.n_kv_heads // n
+        out.append({
+            "q_rows": (r * nh * hs, (r + 1) * nh * hs), "kv_rows": (r * nkv * hs, (r + 1) * nkv * hs),
+            "heads": (r * nh, (r + 1) * nh), "kv_heads": (r * nkv, (r + 1) * nkv),
+            "residual_rows": (r * c.dim // n, (r + 1) * c.dim // n),          # rows of Wo and W2
+            "hidden_units": (r * c.hidden_dim // n, (r + 1) * c.hidden_dim // n),  # rows of gate/up
+            "vocab_rows": (r * c.vocab_size // n, (r + 1) * c.vocab_size // n),
+        })
+    return out
+
+
+def exchange_handles(handle: bytes, group=None) -> list[bytes]:
+    """All-gather the 64-byte CUDA IPC handles in rank order (any torch.distributed backend)."""
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    out = [None] * world
+    dist.all_gather_object(out, handle, group=group)
+    return out
+
+
 def make_config(model: Model, fp16_lanes: int | None = None) -> native.Config:
     c = model.configuration
     cfg = native.Config()
@@ -42,10 +73,23 @@ def make_config(model: Model, fp16_lanes: int | None = None) -> native.Config:
 class B200MasterPlan:
     """One plan per model, used from one thread at a time (InferenceService.java:31,58)."""
 
-    def __init__(self, model: Model, prefill_batch_size: int | None = None, device: int = 0, fp16_lanes: int | None = None):
+    def __init__(self, model: Model, prefill_batch_size: int | None = None, device: int = 0, fp16_lanes: int | None = None,
+                 tp_rank: int = 0, tp_size: int = 1, tp_group=None):
         self.model = model
         self.prefill_batch_size = PREFILL_BATCH_SIZE if prefill_batch_size is None else prefill_batch_size
-        self._native = native.NativePlan(make_config(model, fp16_lanes), model.tensors, self.prefill_batch_size, device)
+        cfg = make_config(model, fp16_lanes)
+        cfg.tp_rank, cfg.tp_size = tp_rank, tp_size
+        if tp_size > 1:
+            tp_shard_plan(model.configuration, tp_size)  # raises early on shapes that do not split
+        self._native = native.NativePlan(cfg, model.tensors, self.prefill_batch_size, device)
+        self.tp_rank, self.tp_size = tp_rank, tp_size
+        if tp_size > 1:
+            # one process per GPU: swap IPC handles of the communication buffers, then wire the peers
+            import torch.distributed as dist
+
+            handles = exchange_handles(self._native.tp_handle(), tp_group)
+            self._native.tp_attach(handles)
+            dist.barrier(group=tp_group)
 
     # TornadoVMMasterPlan.initializeTornadoVMPlan(state, model)  (TornadoVMMasterPlan.java:55-70)
     @staticmethod

@@ -132,6 +132,19 @@ int b200_read_buffer(b200_plan *plan, const char *name, int32_t layer, void *dst
  * The residual stream is restored afterwards; the KV cache is not touched. */
 int b200_time_kernel(b200_plan *plan, int32_t which, int32_t reps, float *avg_ms, int64_t *algorithmic_bytes);
 
+/* ---- tensor parallelism (one process per GPU; cfg.tp_size in {2,4,8}) ----------------------------
+ * Nothing like this exists in the reference (docs/GPULlama3_ROADMAP.md:21 lists multi-GPU as open).
+ * Every rank holds ROWS of every matrix (its query/KV heads, its slice of the FFN and of the
+ * vocabulary), so each dot product keeps the reference's summation order and the tokens stay
+ * bit-identical to the single-GPU path; slices are all-gathered by the kernels themselves through
+ * peer-mapped buffers.  Protocol: every rank calls b200_plan_create (with the FULL tensors; the
+ * library uploads only its share), then b200_tp_handle; the 64-byte handles are exchanged by the
+ * host (torch.distributed / MPI / anything), then every rank calls b200_tp_attach with the n handles
+ * in rank order.  After that all ranks must issue the same forward calls with the same arguments.
+ * Under TP b200_forward_decode returns the argmax only (logits must be NULL). */
+int b200_tp_handle(b200_plan *plan, void *handle64);
+int b200_tp_attach(b200_plan *plan, const void *handles, int32_t n);
+
 /* Diagnostic: runs ONE decode step through a traced copy of the decode graph (same kernels, same
  * programmatic-dependent-launch edges) and returns one record per kernel launch, in launch order:
  * {kernel id, earliest CTA entry, latest dependency-wait return, latest CTA exit}, the times in
