@@ -60,7 +60,7 @@ __device__ __forceinline__ void tp_signal(const TpCtx &t, int slot, unsigned seq
     __threadfence_system();
     for (int k = 0; k < t.n; k++) {
         unsigned *f = reinterpret_cast<unsigned *>(t.peer[k] + t.off_flags) + slot * TP_MAX + t.rank;
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(seq) : "memory");
+        asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(f), "r"(seq) : "memory"); // ordered by the fence above
     }
 }
 // Grid-wide "last CTA signals": every CTA calls this (one thread, after a CTA barrier that follows the

@@ -535,7 +535,6 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attention(float *__restrict__ q
         }
     }
     if (tp.n > 1) {
-        __threadfence_system();
         __syncthreads();
         if (tid == 0) tp_cta_done(tp, TP_SLOT_ATT, tp_seq(tp, tp_out_op), gridDim.x);
     }

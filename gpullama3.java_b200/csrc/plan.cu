@@ -933,6 +933,8 @@ int b200_tp_attach(b200_plan *p, const void *handles, int32_t n) {
     int rc;
     if ((rc = capture(p, true, &p->g_decode, &p->launches_decode))) return rc;
     if ((rc = capture(p, false, &p->g_prefill, nullptr))) return rc;
+    if ((rc = dalloc(p, &p->trace_rec, (size_t)(p->launches_decode + 8) * 32))) return rc;
+    if ((rc = capture(p, true, &p->g_trace, nullptr, true))) return rc;
     CK(cudaStreamSynchronize(p->stream));
     return B200_OK;
 }

@@ -361,9 +361,8 @@ __global__ void __launch_bounds__(SMV_THREADS, 1) k_stream_matvec_q8(SmvArgs a, 
         }
     }
     if (a.tp.n > 1 && a.out_slot >= 0) { // publish: all peer stores of this CTA, then (last CTA) the flag
-        __threadfence_system();
-        consumer_bar_sync();
-        if (tid == 0) tp_cta_done(a.tp, a.out_slot, tp_seq(a.tp, a.out_op), gridDim.x);
+        consumer_bar_sync(); // the CTA's stores are ordered before thread 0's device-scope fence + counter (tp_cta_done);
+        if (tid == 0) tp_cta_done(a.tp, a.out_slot, tp_seq(a.tp, a.out_op), gridDim.x); // only the LAST CTA pays the system-scope fence
     }
     trace_mark(a.tr, 3);
 }
