@@ -5,6 +5,7 @@
 #include "../../include/b200llama.h"
 #include "decode_kernels.cuh"
 #include "prefill.cuh"
+#include "prefill_gemm.cuh"
 #include "stream_matvec.cuh"
 
 #include <math.h>
@@ -993,6 +994,38 @@ int b200_test_seqsum(const float *terms, int32_t n, float *out, int32_t *info) {
     if (info) { info[0] = host[1]; info[1] = host[2]; }
     cudaFree(d);
     cudaFree(o);
+    return e == cudaSuccess ? B200_OK : B200_ERR_CUDA;
+}
+
+int b200_gemm_f16(const uint16_t *a, const uint16_t *b, float *c, int32_t m, int32_t n, int32_t k, int32_t iters, float *ms) {
+    if (!a || !b || !c || m <= 0 || n <= 0 || k <= 0 || m % 128 || n % 128 || k % 64) return B200_ERR_BAD_ARG;
+    __half *da = nullptr, *db = nullptr;
+    float *dc = nullptr;
+    if (cudaMalloc(&da, (size_t)m * k * 2) != cudaSuccess || cudaMalloc(&db, (size_t)n * k * 2) != cudaSuccess ||
+        cudaMalloc(&dc, (size_t)m * n * 4) != cudaSuccess) {
+        cudaFree(da); cudaFree(db); cudaFree(dc);
+        return B200_ERR_OOM;
+    }
+    cudaMemcpy(da, a, (size_t)m * k * 2, cudaMemcpyHostToDevice);
+    cudaMemcpy(db, b, (size_t)n * k * 2, cudaMemcpyHostToDevice);
+    cudaMemset(dc, 0xFF, (size_t)m * n * 4);
+    int rc = pg::gemm_f16(da, db, dc, m, n, k, 0);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (rc == 0 && e == cudaSuccess && iters > 0 && ms) {
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0, 0);
+        for (int i = 0; i < iters; i++) pg::gemm_f16(da, db, dc, m, n, k, 0);
+        cudaEventRecord(e1, 0);
+        e = cudaEventSynchronize(e1);
+        float t = 0.f;
+        cudaEventElapsedTime(&t, e0, e1);
+        *ms = t / iters;
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
+    if (rc == 0 && e == cudaSuccess) e = cudaMemcpy(c, dc, (size_t)m * n * 4, cudaMemcpyDeviceToHost);
+    cudaFree(da); cudaFree(db); cudaFree(dc);
+    if (rc) return B200_ERR_CUDA;
     return e == cudaSuccess ? B200_OK : B200_ERR_CUDA;
 }
 

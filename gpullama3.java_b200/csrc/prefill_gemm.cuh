@@ -1,0 +1,193 @@
+// prefill_gemm.cuh -- the batched-prefill building block: C[M,N] (fp32) = A[M,K] (fp16) * B[N,K]^T (fp16)
+// on the 5th-generation tensor cores (sm_100a): TMA (cp.async.bulk.tensor, SWIZZLE_128B) -> shared
+// memory ring -> tcgen05.mma (kind::f16, cta_group::1, 128 x BN x 16 per instruction, accumulator in
+// TMEM) -> tcgen05.ld epilogue.  Replaces the reference's mma.sync m16n8k16 GEMMs gemmMMA / gemmMMAQKV /
+// gemmMMAGateUp (TransformerBatchPrefillKernels.java:792-915, 971, 1132), which stage BK=16 through a
+// single shared-memory buffer.  A = activations rounded to FP16 (batchedRmsApplyFP16, :61), B = the FP16
+// weight matrix exactly as stored in GGUF ([N][K], K contiguous = "K-major" for both operands).
+//
+// Warp roles (256 threads): warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer, warp 2 = TMEM
+// allocator, warps 4-7 = epilogue (warp w owns TMEM lanes 32*(w%4) .. +31, i.e. 32 rows of the tile).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pg {
+
+constexpr int BM = 128, BK = 64, STAGES = 4;
+
+__device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t cnt) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(cnt)); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "PG_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra PG_DONE;\n"
+        "bra PG_WAIT;\n"
+        "PG_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+                 "l"(map), "r"(c0), "r"(c1), "r"(bar)
+                 : "memory");
+}
+// UMMA shared-memory matrix descriptor, K-major operand, 128-byte swizzle (cute/arch/mma_sm100_desc.hpp
+// SmemDescriptor): start address >> 4 | LBO (unused for swizzled K-major, 1) << 16 | SBO = 8 rows * 128 B >> 4
+// << 32 | version 1 << 46 | layout SWIZZLE_128B (2) << 61.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// Instruction descriptor for kind::f16: D = f32 (bit 4), A = B = f16 (0), both K-major, N >> 3 at bit 17, M >> 4 at bit 24.
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int m, int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24); }
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_c),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+template <int BN> constexpr size_t smem_bytes() { return (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + (2 * STAGES + 1) * 8 + 16 + 1024; }
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1) k_gemm_f16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                                                            float *__restrict__ C, int M, int N, int K) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023); // SWIZZLE_128B tiles need 1024-byte alignment
+    constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
+    uint8_t *sA = smem, *sB = smem + STAGES * A_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + STAGES * B_BYTES);
+    const uint32_t full0 = s32(bars), empty0 = s32(bars + STAGES), tmem_full = s32(bars + 2 * STAGES);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) { // TMEM: BN fp32 accumulator columns x 128 lanes
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)), "r"((uint32_t)BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    const int nk = K / BK, m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+
+    if (warp == 0 && lane == 0) {
+        // ===== TMA producer =====
+        for (int kb = 0; kb < nk; kb++) {
+            const int st = kb % STAGES;
+            mbar_wait(empty0 + 8 * st, ((kb / STAGES) & 1) ^ 1);
+            mbar_expect_tx(full0 + 8 * st, A_BYTES + B_BYTES);
+            tma_load_2d(s32(sA + st * A_BYTES), &tma_a, kb * BK, m0, full0 + 8 * st);
+            tma_load_2d(s32(sB + st * B_BYTES), &tma_b, kb * BK, n0, full0 + 8 * st);
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===== MMA issuer: one thread issues tcgen05.mma for the whole CTA =====
+        constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
+        for (int kb = 0; kb < nk; kb++) {
+            const int st = kb % STAGES;
+            mbar_wait(full0 + 8 * st, (kb / STAGES) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint64_t da = umma_desc_sw128(s32(sA + st * A_BYTES)), db = umma_desc_sw128(s32(sB + st * B_BYTES));
+#pragma unroll
+            for (int k = 0; k < BK / 16; k++) // UMMA_K = 16 fp16 = 32 bytes = +2 in the (addr >> 4) field
+                umma_f16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit(empty0 + 8 * st); // smem slot free once these MMAs have read it
+        }
+        umma_commit(tmem_full); // accumulator complete
+    } else if (warp >= 4) {
+        // ===== epilogue: TMEM -> registers -> global (fp32) =====
+        mbar_wait(tmem_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int q = warp & 3; // TMEM lane quarter this warp may touch
+        const int row = m0 + q * 32 + lane;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t r[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+                  "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+                  "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (row < M) {
+                float4 *dst = reinterpret_cast<float4 *>(C + (size_t)row * N + n0 + c0);
+#pragma unroll
+                for (int v = 0; v < 8; v++)
+                    dst[v] = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]), __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+}
+
+// ---- host side ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// [rows][K] fp16 row-major, box = {BK (inner, 128 bytes), box_rows}, 128-byte swizzle
+inline int make_map(CUtensorMap *map, const void *base, uint64_t rows, uint64_t K, uint32_t box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return -1;
+    cuuint64_t dims[2] = {K, rows};
+    cuuint64_t strides[1] = {K * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -2;
+}
+
+// C[M,N] = A[M,K] * B[N,K]^T ; M multiple of 128 (pad), N multiple of 128, K multiple of 64.  Device pointers.
+inline int gemm_f16(const __half *A, const __half *B, float *C, int M, int N, int K, cudaStream_t stream) {
+    constexpr int BN = 128;
+    if (M % BM || N % BN || K % BK) return -3;
+    CUtensorMap ma, mb;
+    int rc;
+    if ((rc = make_map(&ma, A, (uint64_t)M, (uint64_t)K, BM))) return rc;
+    if ((rc = make_map(&mb, B, (uint64_t)N, (uint64_t)K, BN))) return rc;
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(k_gemm_f16_tcgen05<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<BN>()) != cudaSuccess) return -4;
+        attr = true;
+    }
+    k_gemm_f16_tcgen05<BN><<<dim3(N / BN, M / BM), 256, smem_bytes<BN>(), stream>>>(ma, mb, C, M, N, K);
+    return cudaGetLastError() == cudaSuccess ? 0 : -5;
+}
+
+} // namespace pg

@@ -40,7 +40,7 @@ class Tensor(C.Structure):
 
 
 EXPORTS = ["b200_plan_create", "b200_forward_decode", "b200_forward_prefill", "b200_forward_batch_prefill",
-           "b200_decode_sequence", "b200_time_kernel", "b200_tp_handle", "b200_tp_attach", "b200_trace_decode", "b200_profile_norm", "b200_test_seqsum", "b200_kv_reset", "b200_read_buffer", "b200_launches_per_decode",
+           "b200_decode_sequence", "b200_time_kernel", "b200_tp_handle", "b200_tp_attach", "b200_trace_decode", "b200_profile_norm", "b200_test_seqsum", "b200_gemm_f16", "b200_kv_reset", "b200_read_buffer", "b200_launches_per_decode",
            "b200_device_bytes", "b200_plan_free", "b200_last_error", "b200_version"]
 
 _lib = None
@@ -66,6 +66,7 @@ def lib() -> C.CDLL:
     L.b200_tp_handle.argtypes = [vp, vp]
     L.b200_tp_attach.argtypes = [vp, vp, i32]
     L.b200_test_seqsum.argtypes = [vp, i32, C.POINTER(C.c_float), C.POINTER(i32)]
+    L.b200_gemm_f16.argtypes = [vp, vp, vp, i32, i32, i32, i32, C.POINTER(C.c_float)]
     L.b200_time_kernel.argtypes = [vp, i32, i32, C.POINTER(C.c_float), C.POINTER(C.c_int64)]
     L.b200_read_buffer.argtypes = [vp, C.c_char_p, i32, vp, C.c_size_t]
     L.b200_launches_per_decode.argtypes = [vp]
@@ -94,6 +95,22 @@ def test_seqsum(terms, want_info: bool = False):
     if rc != B200_OK:
         _raise(rc, "b200_test_seqsum failed")
     return (out.value, info[0], info[1]) if want_info else out.value
+
+
+def gemm_f16(a, b, iters: int = 0):
+    """C = A @ B.T on the tcgen05 prefill GEMM (A [m,k], B [n,k] float16) -> (C float32, ms per launch or None)."""
+    a = np.ascontiguousarray(a, dtype=np.float16)
+    b = np.ascontiguousarray(b, dtype=np.float16)
+    m, k = a.shape
+    n, k2 = b.shape
+    if k != k2:
+        raise ValueError("inner dimensions differ")
+    c = np.empty((m, n), dtype=np.float32)
+    ms = C.c_float(0)
+    rc = lib().b200_gemm_f16(a.ctypes.data, b.ctypes.data, c.ctypes.data, m, n, k, iters, C.byref(ms))
+    if rc != B200_OK:
+        _raise(rc, "b200_gemm_f16 failed")
+    return c, (ms.value if iters > 0 else None)
 
 
 class NativePlan:

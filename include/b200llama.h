@@ -163,6 +163,13 @@ int b200_profile_norm(b200_plan *plan, int64_t *cycles);
  * non-negative host floats on the device exactly as `for (i) s += t[i]` would. */
 int b200_test_seqsum(const float *terms, int32_t n, float *out, int32_t *info /* nullable: {entries, first fallback element or -1} */);
 
+/* Batched-prefill GEMM building block (csrc/prefill_gemm.cuh; replaces the reference's mma.sync GEMMs
+ * gemmMMA / gemmMMAQKV / gemmMMAGateUp, TransformerBatchPrefillKernels.java:792-1132) exposed for
+ * tests and measurement: C[m][n] (f32) = A[m][k] (f16 bits) x B[n][k]^T (f16 bits) on tcgen05 tensor
+ * cores, FP32 accumulation in TMEM.  Host pointers; m % 128 == n % 128 == k % 64 == 0.
+ * iters > 0 additionally times `iters` back-to-back launches (device events) into *ms. */
+int b200_gemm_f16(const uint16_t *a, const uint16_t *b, float *c, int32_t m, int32_t n, int32_t k, int32_t iters, float *ms /* nullable */);
+
 /* Number of kernels one decode step launches (bench.py's gpu_launches). */
 int b200_launches_per_decode(b200_plan *plan);
 
