@@ -5,7 +5,6 @@
 #include "../../include/b200llama.h"
 #include "decode_kernels.cuh"
 #include "prefill.cuh"
-#include "prefill_gemm.cuh"
 #include "stream_matvec.cuh"
 
 #include <math.h>
@@ -73,7 +72,8 @@ struct b200_plan {
     int8_t *attq = nullptr; // gathered attention output (quantised) feeding the Wo matvec
     float *atts = nullptr;
     void *peer_open[TP_MAX] = {nullptr};
-    int launches_decode = 0;
+    int launches_decode = 0, launches_prefill = 0;
+    float prefill_ms = 0.f; // device time of the last tensor-core prefill chunk
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
     PrefillCtx prefill;
@@ -459,6 +459,8 @@ int set_smem_attrs(b200_plan *p) {
     return B200_OK;
 }
 
+int prefill_init(b200_plan *p);
+
 int build(b200_plan *p, const b200_tensor *tensors, int n_tensors) {
     const b200_config &c = p->cfg;
     if (c.arch != B200_ARCH_LLAMA && c.arch != B200_ARCH_QWEN3) return fail(p, B200_ERR_UNSUPPORTED, "unknown arch %d", c.arch);
@@ -662,8 +664,109 @@ int build(b200_plan *p, const b200_tensor *tensors, int n_tensors) {
         if ((rc = capture(p, true, &p->g_trace, nullptr, true))) return rc;
     }
     if (p->prefill_batch > 1)
-        if ((rc = prefill_init(p->prefill, p->cfg, p->prefill_batch))) return fail(p, rc, "batched prefill init failed");
+        if ((rc = prefill_init(p))) return rc;
     CK(cudaStreamSynchronize(p->stream));
+    return B200_OK;
+}
+
+// ---- batched prefill on the tensor cores (prefill.cuh) -------------------------------------------
+int prefill_init(b200_plan *p) {
+    PrefillCtx &c = p->prefill;
+    const b200_config &g = p->cfg;
+    c.batch = p->prefill_batch;
+    c.ready = false;
+    c.mode = 0;
+    const int kv_mul = g.n_heads / g.n_kv_heads, nqkv = p->qd + 2 * p->kvd;
+    if (p->wtype != B200_GGML_F16) { c.why = "tensor-core prefill needs FP16 weight matrices (Q8_0 plans use the exact token-by-token path)"; return B200_OK; }
+    if (g.tp_size > 1) { c.why = "tensor-core prefill is single-GPU"; return B200_OK; }
+    if (g.head_size != 64 && g.head_size != 128) { c.why = "tensor-core prefill supports head sizes 64 and 128"; return B200_OK; }
+    if (kv_mul > 64 || (kv_mul & (kv_mul - 1))) { c.why = "tensor-core prefill needs a power-of-two GQA ratio <= 64"; return B200_OK; }
+    if (g.dim % 128 || p->qd % 128 || nqkv % 128 || g.hidden_dim % 64) { c.why = "tensor-core prefill needs dim, q width and q+k+v width multiples of 128, hidden a multiple of 64"; return B200_OK; }
+    if (!pg::encode_fn()) { c.why = "cuTensorMapEncodeTiled not available from the driver"; return B200_OK; }
+    c.bpad = (c.batch + pg::BM - 1) / pg::BM * pg::BM;
+    int rc;
+    if ((rc = dalloc(p, &c.X, (size_t)c.bpad * g.dim * 4))) return rc;
+    if ((rc = dalloc(p, &c.QKV, (size_t)c.bpad * nqkv * 4))) return rc;
+    if ((rc = dalloc(p, &c.A16, (size_t)c.bpad * g.dim * 2))) return rc;
+    if ((rc = dalloc(p, &c.ATT16, (size_t)c.bpad * p->qd * 2))) return rc;
+    if ((rc = dalloc(p, &c.H16, (size_t)c.bpad * g.hidden_dim * 2))) return rc;
+    if ((rc = dalloc(p, &c.tok, (size_t)c.bpad * 4))) return rc;
+    CK(cudaMemset(c.X, 0, (size_t)c.bpad * g.dim * 4));
+    CK(cudaMemset(c.QKV, 0, (size_t)c.bpad * nqkv * 4));
+    CK(cudaMemset(c.A16, 0, (size_t)c.bpad * g.dim * 2));
+    CK(cudaMemset(c.ATT16, 0, (size_t)c.bpad * p->qd * 2));
+    CK(cudaMemset(c.H16, 0, (size_t)c.bpad * g.hidden_dim * 2));
+    CK(cudaMemset(c.tok, 0, (size_t)c.bpad * 4));
+    bool ok = pg::make_map(&c.mA, c.A16, c.bpad, g.dim, pg::BM) == 0 && pg::make_map(&c.mATT, c.ATT16, c.bpad, p->qd, pg::BM) == 0 &&
+              pg::make_map(&c.mH, c.H16, c.bpad, g.hidden_dim, pg::BM) == 0 && pg::make_map_c(&c.mX, c.X, c.bpad, g.dim) == 0 &&
+              pg::make_map_c(&c.mQKV, c.QKV, c.bpad, nqkv) == 0;
+    c.maps.resize(g.n_layers);
+    for (int l = 0; ok && l < g.n_layers; l++) {
+        const LayerW &L = p->layers[l];
+        PrefillLayerMaps &m = c.maps[l];
+        ok = pg::make_map(&m.qkv, L.qkv.qs, nqkv, g.dim, pg::BN) == 0 && pg::make_map(&m.wo, L.wo.qs, g.dim, p->qd, pg::BN) == 0 &&
+             pg::make_map(&m.w1, L.w1.qs, g.hidden_dim, g.dim, pg::BN / 2) == 0 && pg::make_map(&m.w3, L.w3.qs, g.hidden_dim, g.dim, pg::BN / 2) == 0 &&
+             pg::make_map(&m.w2, L.w2.qs, g.dim, g.hidden_dim, pg::BN) == 0;
+    }
+    if (!ok) { c.why = "cuTensorMapEncodeTiled rejected a tensor map"; return B200_OK; }
+    if (g.head_size == 128) {
+        CK(cudaFuncSetAttribute(k_pf_attention<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pa_smem_bytes<128>()));
+        CK(cudaFuncSetAttribute(k_pf_attention_mma<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pm_smem_bytes<128>()));
+    } else {
+        CK(cudaFuncSetAttribute(k_pf_attention<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pa_smem_bytes<64>()));
+        CK(cudaFuncSetAttribute(k_pf_attention_mma<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pm_smem_bytes<64>()));
+    }
+    {
+        const char *e = getenv("B200_PF_ATT");
+        c.att_simt = e && !strcmp(e, "simt");
+    }
+    c.ready = true;
+    c.mode = 1;
+    c.why = "";
+    return B200_OK;
+}
+
+// n tokens already in c.tok (device), positions start_pos .. start_pos + n - 1
+int prefill_forward(b200_plan *p, int n, int start_pos, int *launches) {
+    PrefillCtx &c = p->prefill;
+    const b200_config &g = p->cfg;
+    cudaStream_t s = p->stream;
+    const int nqkv = p->qd + 2 * p->kvd, mt = (n + pg::BM - 1) / pg::BM, kv_mul = g.n_heads / g.n_kv_heads;
+    const size_t ctx_kv = (size_t)g.context_length * p->kvd;
+    const float inv_sqrt_hs = (float)(1.0 / sqrt((double)g.head_size));
+    int nl = 0;
+    constexpr int ST = pg::GEMM_STAGES;
+    k_pf_embed<<<n, 256, 0, s>>>(c.tok, p->emb, c.X, g.dim); nl++;
+    for (int l = 0; l < g.n_layers; l++) {
+        const LayerW &L = p->layers[l];
+        const PrefillLayerMaps &m = c.maps[l];
+        float *kc = p->key_cache + (size_t)l * ctx_kv, *vc = p->value_cache + (size_t)l * ctx_kv;
+        k_pf_rmsnorm_f16<<<n, 256, 0, s>>>(c.X, L.attn_norm, g.rms_norm_eps, g.dim, c.A16); nl++;
+        if (pg::gemm_launch<pg::GEMM_F32, ST>(c.mA, m.qkv, m.qkv, c.mQKV, c.QKV, nqkv, n, mt, nqkv / pg::BN, g.dim, s)) return fail(p, B200_ERR_CUDA, "QKV GEMM launch failed");
+        nl++;
+        const dim3 rg(n, g.n_heads + g.n_kv_heads);
+        const int qt = PA_ROWS / kv_mul;
+        const dim3 ag((n + qt - 1) / qt, g.n_kv_heads);
+        if (g.head_size == 128) {
+            k_pf_rope_kv<128><<<rg, 64, 0, s>>>(c.QKV, nqkv, kc, vc, p->kvd, g.n_heads, g.arch, L.q_norm, L.k_norm, g.rms_norm_eps, p->rope_cr, p->rope_ci, start_pos);
+            if (c.att_simt) k_pf_attention<128><<<ag, PA_THREADS, pa_smem_bytes<128>(), s>>>(c.QKV, nqkv, kc, vc, p->kvd, kv_mul, n, start_pos, inv_sqrt_hs, c.ATT16, p->qd);
+            else k_pf_attention_mma<128><<<ag, PM_THREADS, pm_smem_bytes<128>(), s>>>(c.QKV, nqkv, kc, vc, p->kvd, kv_mul, n, start_pos, inv_sqrt_hs, c.ATT16, p->qd);
+        } else {
+            k_pf_rope_kv<64><<<rg, 32, 0, s>>>(c.QKV, nqkv, kc, vc, p->kvd, g.n_heads, g.arch, L.q_norm, L.k_norm, g.rms_norm_eps, p->rope_cr, p->rope_ci, start_pos);
+            if (c.att_simt) k_pf_attention<64><<<ag, PA_THREADS, pa_smem_bytes<64>(), s>>>(c.QKV, nqkv, kc, vc, p->kvd, kv_mul, n, start_pos, inv_sqrt_hs, c.ATT16, p->qd);
+            else k_pf_attention_mma<64><<<ag, PM_THREADS, pm_smem_bytes<64>(), s>>>(c.QKV, nqkv, kc, vc, p->kvd, kv_mul, n, start_pos, inv_sqrt_hs, c.ATT16, p->qd);
+        }
+        nl += 2;
+        if (pg::gemm_launch<pg::GEMM_RESID, ST>(c.mATT, m.wo, m.wo, c.mX, c.X, g.dim, n, mt, g.dim / pg::BN, p->qd, s)) return fail(p, B200_ERR_CUDA, "Wo GEMM launch failed");
+        nl++;
+        k_pf_rmsnorm_f16<<<n, 256, 0, s>>>(c.X, L.ffn_norm, g.rms_norm_eps, g.dim, c.A16); nl++;
+        if (pg::gemm_launch<pg::GEMM_GATEUP, ST>(c.mA, m.w1, m.w3, c.mX, c.H16, g.hidden_dim, n, mt, g.hidden_dim / (pg::BN / 2), g.dim, s)) return fail(p, B200_ERR_CUDA, "gate/up GEMM launch failed");
+        nl++;
+        if (pg::gemm_launch<pg::GEMM_RESID, ST>(c.mH, m.w2, m.w2, c.mX, c.X, g.dim, n, mt, g.dim / pg::BN, g.hidden_dim, s)) return fail(p, B200_ERR_CUDA, "W2 GEMM launch failed");
+        nl++;
+    }
+    CK(cudaGetLastError());
+    if (launches) *launches = nl;
     return B200_OK;
 }
 
@@ -743,6 +846,17 @@ int b200_forward_batch_prefill(b200_plan *p, const int32_t *tokens, int32_t n, i
     for (int i = 0; i < n; i++)
         if (tokens[i] < 0 || tokens[i] >= p->cfg.vocab_size) return fail(p, B200_ERR_BAD_ARG, "token %d out of range", tokens[i]);
     CK(cudaSetDevice(p->device));
+    if (p->prefill.ready && p->prefill.mode == 1) { // tensor-core GEMM path (prefill.cuh)
+        memcpy(p->h_ids, tokens, (size_t)n * 4);
+        CK(cudaMemcpyAsync(p->prefill.tok, p->h_ids, (size_t)n * 4, cudaMemcpyHostToDevice, p->stream));
+        CK(cudaEventRecord(p->ev0, p->stream));
+        int rc2 = prefill_forward(p, n, start_pos, &p->launches_prefill);
+        if (rc2) return rc2;
+        CK(cudaEventRecord(p->ev1, p->stream));
+        CK(cudaStreamSynchronize(p->stream));
+        CK(cudaEventElapsedTime(&p->prefill_ms, p->ev0, p->ev1));
+        return B200_OK;
+    }
     // Exact path: the prefill graph token by token (bit-identical KV cache to the CPU
     // batchForwardJavaPrefill, InferenceCoreBatchPrefillDecode.java:62-168).
     if (n > p->seq_cap) return fail(p, B200_ERR_BAD_ARG, "chunk too long");
@@ -777,6 +891,21 @@ int b200_decode_sequence(b200_plan *p, const int32_t *tokens, int32_t n, int32_t
     CK(cudaStreamSynchronize(p->stream));
     if (out_ids) memcpy(out_ids, p->h_ids, (size_t)n * 4);
     if (device_ms) CK(cudaEventElapsedTime(device_ms, p->ev0, p->ev1));
+    return B200_OK;
+}
+
+int b200_set_prefill_mode(b200_plan *p, int32_t mode) {
+    if (!p || (mode != B200_PREFILL_EXACT && mode != B200_PREFILL_TENSOR_CORE)) return B200_ERR_BAD_ARG;
+    if (mode == B200_PREFILL_TENSOR_CORE && !p->prefill.ready) return fail(p, B200_ERR_UNSUPPORTED, "%s", p->prefill.why);
+    p->prefill.mode = mode;
+    return B200_OK;
+}
+
+int b200_prefill_info(b200_plan *p, int32_t *mode, int32_t *launches, float *device_ms) {
+    if (!p) return B200_ERR_BAD_ARG;
+    if (mode) *mode = p->prefill.ready ? p->prefill.mode : B200_PREFILL_EXACT;
+    if (launches) *launches = p->launches_prefill;
+    if (device_ms) *device_ms = p->prefill_ms;
     return B200_OK;
 }
 
@@ -998,6 +1127,8 @@ int b200_test_seqsum(const float *terms, int32_t n, float *out, int32_t *info) {
 }
 
 int b200_gemm_f16(const uint16_t *a, const uint16_t *b, float *c, int32_t m, int32_t n, int32_t k, int32_t iters, float *ms) {
+    const int stages = getenv("B200_GEMM_STAGES") ? atoi(getenv("B200_GEMM_STAGES")) : 0;
+    const int resid = getenv("B200_GEMM_RESID") ? atoi(getenv("B200_GEMM_RESID")) : 0; // C starts at 0 and accumulates over the timed launches
     if (!a || !b || !c || m <= 0 || n <= 0 || k <= 0 || m % 128 || n % 128 || k % 64) return B200_ERR_BAD_ARG;
     __half *da = nullptr, *db = nullptr;
     float *dc = nullptr;
@@ -1008,20 +1139,25 @@ int b200_gemm_f16(const uint16_t *a, const uint16_t *b, float *c, int32_t m, int
     }
     cudaMemcpy(da, a, (size_t)m * k * 2, cudaMemcpyHostToDevice);
     cudaMemcpy(db, b, (size_t)n * k * 2, cudaMemcpyHostToDevice);
-    cudaMemset(dc, 0xFF, (size_t)m * n * 4);
-    int rc = pg::gemm_f16(da, db, dc, m, n, k, 0);
+    cudaMemset(dc, resid ? 0 : 0xFF, (size_t)m * n * 4);
+    int rc = pg::gemm_f16(da, db, dc, m, n, k, stages, resid, 0);
     cudaError_t e = cudaDeviceSynchronize();
     if (rc == 0 && e == cudaSuccess && iters > 0 && ms) {
         cudaEvent_t e0, e1;
         cudaEventCreate(&e0); cudaEventCreate(&e1);
         cudaEventRecord(e0, 0);
-        for (int i = 0; i < iters; i++) pg::gemm_f16(da, db, dc, m, n, k, 0);
+        for (int i = 0; i < iters; i++) pg::gemm_f16(da, db, dc, m, n, k, stages, resid, 0);
         cudaEventRecord(e1, 0);
         e = cudaEventSynchronize(e1);
         float t = 0.f;
         cudaEventElapsedTime(&t, e0, e1);
         *ms = t / iters;
         cudaEventDestroy(e0); cudaEventDestroy(e1);
+        if (resid) { // C accumulated 1 + iters products: return exactly one
+            cudaMemset(dc, 0, (size_t)m * n * 4);
+            pg::gemm_f16(da, db, dc, m, n, k, stages, resid, 0);
+            e = cudaDeviceSynchronize();
+        }
     }
     if (rc == 0 && e == cudaSuccess) e = cudaMemcpy(c, dc, (size_t)m * n * 4, cudaMemcpyDeviceToHost);
     cudaFree(da); cudaFree(db); cudaFree(dc);

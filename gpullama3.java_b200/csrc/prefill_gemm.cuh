@@ -16,7 +16,11 @@
 
 namespace pg {
 
-constexpr int BM = 128, BK = 64, STAGES = 4;
+constexpr int BM = 128, BK = 64, BN = 128;
+// Epilogue modes: F32 store (QKV), F32 read-add-store (x += A*W^T: Wo and W2), and the gate/up pair:
+// the B tile is 64 rows of W1 and 64 rows of W3 for the same 64 hidden units, so accumulator columns
+// [0,64) = gate, [64,128) = up, and the epilogue emits f16(silu(gate)*up) (InferenceCore.java:150-158).
+enum { GEMM_F32 = 0, GEMM_RESID = 1, GEMM_GATEUP = 2 };
 
 __device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t cnt) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(cnt)); }
@@ -63,14 +67,29 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-template <int BN> constexpr size_t smem_bytes() { return (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + (2 * STAGES + 1) * 8 + 16 + 1024; }
+// 32 lanes x 32 consecutive fp32 accumulator columns: thread `lane` of the warp gets row (lane quarter base + lane)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
 
-template <int BN>
-__global__ void __launch_bounds__(256, 1) k_gemm_f16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                                                            float *__restrict__ C, int M, int N, int K) {
+template <int STAGES> constexpr size_t smem_bytes() { return (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + (2 * STAGES + 1) * 8 + 16 + 1024; }
+
+// grid = (M tiles, N tiles): the CTAs that share a weight (B) tile are adjacent in launch order, so the
+// tile comes from HBM once and from L2 for the others; A (activations, a few MB) lives in L2.
+// C: row stride ldc (elements); rows >= m_valid are not stored.  GEMM_GATEUP: N tiles index 64 hidden units.
+template <int MODE, int STAGES>
+__global__ void __launch_bounds__(256) k_gemm_f16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                                                         const __grid_constant__ CUtensorMap tma_b2, const __grid_constant__ CUtensorMap tma_c,
+                                                         void *__restrict__ Cv, int ldc, int m_valid, int K) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023); // SWIZZLE_128B tiles need 1024-byte alignment
     constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
+    static_assert(STAGES * (A_BYTES + B_BYTES) >= BM * BN * 4, "the C tile is staged in the operand ring");
     uint8_t *sA = smem, *sB = smem + STAGES * A_BYTES;
     uint64_t *bars = reinterpret_cast<uint64_t *>(sB + STAGES * B_BYTES);
     const uint32_t full0 = s32(bars), empty0 = s32(bars + STAGES), tmem_full = s32(bars + 2 * STAGES);
@@ -90,7 +109,8 @@ __global__ void __launch_bounds__(256, 1) k_gemm_f16_tcgen05(const __grid_consta
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
-    const int nk = K / BK, m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int nk = (K + BK - 1) / BK, m0 = blockIdx.x * BM;
+    const int n0 = blockIdx.y * (MODE == GEMM_GATEUP ? BN / 2 : BN);
 
     if (warp == 0 && lane == 0) {
         // ===== TMA producer =====
@@ -99,7 +119,12 @@ __global__ void __launch_bounds__(256, 1) k_gemm_f16_tcgen05(const __grid_consta
             mbar_wait(empty0 + 8 * st, ((kb / STAGES) & 1) ^ 1);
             mbar_expect_tx(full0 + 8 * st, A_BYTES + B_BYTES);
             tma_load_2d(s32(sA + st * A_BYTES), &tma_a, kb * BK, m0, full0 + 8 * st);
-            tma_load_2d(s32(sB + st * B_BYTES), &tma_b, kb * BK, n0, full0 + 8 * st);
+            if (MODE == GEMM_GATEUP) {
+                tma_load_2d(s32(sB + st * B_BYTES), &tma_b, kb * BK, n0, full0 + 8 * st);
+                tma_load_2d(s32(sB + st * B_BYTES + B_BYTES / 2), &tma_b2, kb * BK, n0, full0 + 8 * st);
+            } else {
+                tma_load_2d(s32(sB + st * B_BYTES), &tma_b, kb * BK, n0, full0 + 8 * st);
+            }
         }
     } else if (warp == 1 && lane == 0) {
         // ===== MMA issuer: one thread issues tcgen05.mma for the whole CTA =====
@@ -121,22 +146,68 @@ __global__ void __launch_bounds__(256, 1) k_gemm_f16_tcgen05(const __grid_consta
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int q = warp & 3; // TMEM lane quarter this warp may touch
         const int row = m0 + q * 32 + lane;
+        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+        if (MODE == GEMM_GATEUP) {
+            __half *C = reinterpret_cast<__half *>(Cv);
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t r[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
-                  "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
-                  "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (row < M) {
-                float4 *dst = reinterpret_cast<float4 *>(C + (size_t)row * N + n0 + c0);
+            for (int c0 = 0; c0 < BN / 2; c0 += 32) {
+                uint32_t g[32], u[32];
+                tmem_ld32(tlane + (uint32_t)c0, g);
+                tmem_ld32(tlane + (uint32_t)(BN / 2 + c0), u);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (row < m_valid) {
+                    uint4 *dst = reinterpret_cast<uint4 *>(C + (size_t)row * ldc + n0 + c0);
 #pragma unroll
-                for (int v = 0; v < 8; v++)
-                    dst[v] = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]), __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
+                    for (int v = 0; v < 4; v++) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            const float g0 = __uint_as_float(g[8 * v + 2 * e]), g1 = __uint_as_float(g[8 * v + 2 * e + 1]);
+                            const float h0 = (g0 / (1.0f + expf(-g0))) * __uint_as_float(u[8 * v + 2 * e]);
+                            const float h1 = (g1 / (1.0f + expf(-g1))) * __uint_as_float(u[8 * v + 2 * e + 1]);
+                            const __half2 hh = __floats2half2_rn(h0, h1);
+                            w[e] = *reinterpret_cast<const uint32_t *>(&hh);
+                        }
+                        dst[v] = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                }
+            }
+        } else {
+            // FP32 tile -> shared memory (the ring is idle now: every TMA load has landed and every MMA has
+            // read it) in the SWIZZLE_128B layout of the C tensor map, then ONE thread hands the four
+            // 128 x 32 boxes to TMA: a plain tensor store (QKV) or an f32 reduce-add performed by the memory
+            // system (x += A W^T for Wo / W2 -- no read-modify-write through the SM).  Rows past m_valid add 0.
+            const int rloc = q * 32 + lane;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; c++) {
+                uint32_t r[32];
+                tmem_ld32(tlane + (uint32_t)(c * 32), r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                uint8_t *buf = smem + c * (BM * 32 * 4) + rloc * 128;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    uint4 o = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                    if (row >= m_valid) o = make_uint4(0u, 0u, 0u, 0u);
+                    *reinterpret_cast<uint4 *>(buf + ((j ^ (rloc & 7)) << 4)) = o;
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("bar.sync 1, 128;" ::: "memory"); // the four epilogue warps
+            if (warp == 4 && lane == 0) {
+#pragma unroll
+                for (int c = 0; c < BN / 32; c++) {
+                    const uint32_t src = s32(smem + c * (BM * 32 * 4));
+                    if (MODE == GEMM_RESID)
+                        asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tma_c), "r"(src),
+                                     "r"(n0 + c * 32), "r"(m0)
+                                     : "memory");
+                    else
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tma_c), "r"(src), "r"(n0 + c * 32),
+                                     "r"(m0)
+                                     : "memory");
+                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
             }
         }
     }
@@ -173,21 +244,47 @@ inline int make_map(CUtensorMap *map, const void *base, uint64_t rows, uint64_t 
     return r == CUDA_SUCCESS ? 0 : -2;
 }
 
-// C[M,N] = A[M,K] * B[N,K]^T ; M multiple of 128 (pad), N multiple of 128, K multiple of 64.  Device pointers.
-inline int gemm_f16(const __half *A, const __half *B, float *C, int M, int N, int K, cudaStream_t stream) {
-    constexpr int BN = 128;
+// C / x as [rows][cols] fp32 row-major, box = 32 columns (128 bytes) x 128 rows, 128-byte swizzle (matches the epilogue's staging)
+inline int make_map_c(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return -1;
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * 4};
+    cuuint32_t box[2] = {32, (cuuint32_t)BM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -2;
+}
+
+template <int MODE, int STAGES>
+inline int gemm_launch(const CUtensorMap &a, const CUtensorMap &b, const CUtensorMap &b2, const CUtensorMap &c, void *C, int ldc, int m_valid, int m_tiles,
+                       int n_tiles, int K, cudaStream_t stream) {
+    static bool attr = false; // one flag per instantiation
+    if (!attr) {
+        if (cudaFuncSetAttribute(k_gemm_f16_tcgen05<MODE, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<STAGES>()) != cudaSuccess) return -4;
+        attr = true;
+    }
+    k_gemm_f16_tcgen05<MODE, STAGES><<<dim3(m_tiles, n_tiles), 256, smem_bytes<STAGES>(), stream>>>(a, b, b2, c, C, ldc, m_valid, K);
+    return cudaGetLastError() == cudaSuccess ? 0 : -5;
+}
+
+// 3 stages of 32 KB: two CTAs fit one SM (2 x 99 KB shared memory, 2 x 128 TMEM columns), so one CTA's
+// epilogue overlaps the other's main loop.
+constexpr int GEMM_STAGES = 3;
+
+// Test/measurement entry: C[M,N] (+)= A[M,K] * B[N,K]^T ; M, N multiples of 128, K multiple of 64.  Device pointers.
+inline int gemm_f16(const __half *A, const __half *B, float *C, int M, int N, int K, int stages, int resid, cudaStream_t stream) {
     if (M % BM || N % BN || K % BK) return -3;
-    CUtensorMap ma, mb;
+    CUtensorMap ma, mb, mc;
     int rc;
     if ((rc = make_map(&ma, A, (uint64_t)M, (uint64_t)K, BM))) return rc;
     if ((rc = make_map(&mb, B, (uint64_t)N, (uint64_t)K, BN))) return rc;
-    static bool attr = false;
-    if (!attr) {
-        if (cudaFuncSetAttribute(k_gemm_f16_tcgen05<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<BN>()) != cudaSuccess) return -4;
-        attr = true;
-    }
-    k_gemm_f16_tcgen05<BN><<<dim3(N / BN, M / BM), 256, smem_bytes<BN>(), stream>>>(ma, mb, C, M, N, K);
-    return cudaGetLastError() == cudaSuccess ? 0 : -5;
+    if ((rc = make_map_c(&mc, C, (uint64_t)M, (uint64_t)N))) return rc;
+    if (resid) return gemm_launch<GEMM_RESID, GEMM_STAGES>(ma, mb, mb, mc, C, N, M, M / BM, N / BN, K, stream);
+    if (stages == 4) return gemm_launch<GEMM_F32, 4>(ma, mb, mb, mc, C, N, M, M / BM, N / BN, K, stream);
+    if (stages == 6) return gemm_launch<GEMM_F32, 6>(ma, mb, mb, mc, C, N, M, M / BM, N / BN, K, stream);
+    return gemm_launch<GEMM_F32, GEMM_STAGES>(ma, mb, mb, mc, C, N, M, M / BM, N / BN, K, stream);
 }
 
 } // namespace pg

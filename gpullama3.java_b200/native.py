@@ -39,7 +39,7 @@ class Tensor(C.Structure):
                 ("dims", C.c_int64 * 4)]
 
 
-EXPORTS = ["b200_plan_create", "b200_forward_decode", "b200_forward_prefill", "b200_forward_batch_prefill",
+EXPORTS = ["b200_plan_create", "b200_forward_decode", "b200_forward_prefill", "b200_forward_batch_prefill", "b200_set_prefill_mode", "b200_prefill_info",
            "b200_decode_sequence", "b200_time_kernel", "b200_tp_handle", "b200_tp_attach", "b200_trace_decode", "b200_profile_norm", "b200_test_seqsum", "b200_gemm_f16", "b200_kv_reset", "b200_read_buffer", "b200_launches_per_decode",
            "b200_device_bytes", "b200_plan_free", "b200_last_error", "b200_version"]
 
@@ -66,6 +66,8 @@ def lib() -> C.CDLL:
     L.b200_tp_handle.argtypes = [vp, vp]
     L.b200_tp_attach.argtypes = [vp, vp, i32]
     L.b200_test_seqsum.argtypes = [vp, i32, C.POINTER(C.c_float), C.POINTER(i32)]
+    L.b200_set_prefill_mode.argtypes = [vp, i32]
+    L.b200_prefill_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_float)]
     L.b200_gemm_f16.argtypes = [vp, vp, vp, i32, i32, i32, i32, C.POINTER(C.c_float)]
     L.b200_time_kernel.argtypes = [vp, i32, i32, C.POINTER(C.c_float), C.POINTER(C.c_int64)]
     L.b200_read_buffer.argtypes = [vp, C.c_char_p, i32, vp, C.c_size_t]
@@ -151,6 +153,14 @@ class NativePlan:
 
     def forward_prefill(self, token: int, position: int):
         self._ck(lib().b200_forward_prefill(self._p, token, position))
+
+    def set_prefill_mode(self, mode: int):
+        self._ck(lib().b200_set_prefill_mode(self._p, mode))
+
+    def prefill_info(self):
+        mode, launches, ms = C.c_int32(0), C.c_int32(0), C.c_float(0)
+        self._ck(lib().b200_prefill_info(self._p, C.byref(mode), C.byref(launches), C.byref(ms)))
+        return mode.value, launches.value, ms.value
 
     def forward_batch_prefill(self, tokens, start_pos: int):
         t = np.ascontiguousarray(tokens, dtype=np.int32)

@@ -112,6 +112,19 @@ class B200MasterPlan:
     def forward_batch_prefill(self, tokens, start_pos: int):
         self._native.forward_batch_prefill(np.asarray(tokens, dtype=np.int32), start_pos)
 
+    # TensorCoreSupport.java's switch between the MMA and the plain batch-prefill layer families
+    PREFILL_EXACT, PREFILL_TENSOR_CORE = 0, 1
+
+    def set_prefill_mode(self, mode):
+        """"exact" (token-by-token graph, bit-identical KV cache) or "tensor_core" (tcgen05 GEMMs, FP16 tolerance)."""
+        if isinstance(mode, str):
+            mode = {"exact": 0, "tensor_core": 1}[mode]
+        self._native.set_prefill_mode(int(mode))
+
+    def prefill_info(self):
+        """(active mode, kernels launched, device ms) of the last tensor-core prefill chunk."""
+        return self._native.prefill_info()
+
     def decode_sequence(self, tokens, n: int, start_pos: int, feedback: bool = False):
         return self._native.decode_sequence(tokens, n, start_pos, feedback)
 

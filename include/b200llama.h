@@ -104,6 +104,21 @@ int b200_forward_prefill(b200_plan *plan, int32_t token, int32_t position);
  * n <= prefill_batch_size.  KV cache only, no logits (InferenceCoreBatchPrefillDecode.java:166-167). */
 int b200_forward_batch_prefill(b200_plan *plan, const int32_t *tokens, int32_t n, int32_t start_pos);
 
+/* How b200_forward_batch_prefill computes (the reference has the same two families:
+ * LlamaFP16LayersBatchPrefill vs ...BatchPrefillMMA, selected by TensorCoreSupport.java):
+ *   B200_PREFILL_EXACT       the single-token prefill graph per token: KV cache bit-identical to the CPU path;
+ *   B200_PREFILL_TENSOR_CORE TMA + tcgen05 GEMMs over the whole chunk, FP16 operands / FP32 accumulation:
+ *                            KV cache within FP16 tolerance of the CPU path.  Default when the plan was
+ *                            created with prefill_batch_size > 1 and supports it (FP16 weight matrices,
+ *                            single GPU); otherwise returns B200_ERR_UNSUPPORTED with the reason in
+ *                            b200_last_error. */
+#define B200_PREFILL_EXACT 0
+#define B200_PREFILL_TENSOR_CORE 1
+int b200_set_prefill_mode(b200_plan *plan, int32_t mode);
+
+/* Active mode, kernels launched and device milliseconds of the last tensor-core chunk (any pointer may be NULL). */
+int b200_prefill_info(b200_plan *plan, int32_t *mode, int32_t *launches, float *device_ms);
+
 /* Device-resident token loop (what LlamaBench.runTest times, LlamaBench.java:234-254, and the
  * greedy generation loop InferenceEngine.java:96-145 with the sampler on the device):
  * runs n single-token forwards at positions start_pos..start_pos+n-1 without host round trips.
