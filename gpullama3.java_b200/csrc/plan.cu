@@ -691,6 +691,8 @@ int prefill_init(b200_plan *p) {
     if ((rc = dalloc(p, &c.ATT16, (size_t)c.bpad * p->qd * 2))) return rc;
     if ((rc = dalloc(p, &c.H16, (size_t)c.bpad * g.hidden_dim * 2))) return rc;
     if ((rc = dalloc(p, &c.tok, (size_t)c.bpad * 4))) return rc;
+    if ((rc = dalloc(p, &c.KH, (size_t)g.context_length * p->kvd * 2))) return rc; // f16 K / V of the layer being processed
+    if ((rc = dalloc(p, &c.VH, (size_t)g.context_length * p->kvd * 2))) return rc;
     CK(cudaMemset(c.X, 0, (size_t)c.bpad * g.dim * 4));
     CK(cudaMemset(c.QKV, 0, (size_t)c.bpad * nqkv * 4));
     CK(cudaMemset(c.A16, 0, (size_t)c.bpad * g.dim * 2));
@@ -735,34 +737,48 @@ int prefill_forward(b200_plan *p, int n, int start_pos, int *launches) {
     const size_t ctx_kv = (size_t)g.context_length * p->kvd;
     const float inv_sqrt_hs = (float)(1.0 / sqrt((double)g.head_size));
     int nl = 0;
-    constexpr int ST = pg::GEMM_STAGES;
+    constexpr int ST = pg::GEMM_STAGES, DEEP = pg::GEMM_STAGES_DEEP;
+    // a GEMM that fits one wave has one CTA per SM anyway: give it the deep ring; otherwise two CTAs share an SM
+    auto one_wave = [&](int n_tiles) { return mt * n_tiles <= p->n_sms; };
     k_pf_embed<<<n, 256, 0, s>>>(c.tok, p->emb, c.X, g.dim); nl++;
     for (int l = 0; l < g.n_layers; l++) {
         const LayerW &L = p->layers[l];
         const PrefillLayerMaps &m = c.maps[l];
         float *kc = p->key_cache + (size_t)l * ctx_kv, *vc = p->value_cache + (size_t)l * ctx_kv;
         k_pf_rmsnorm_f16<<<n, 256, 0, s>>>(c.X, L.attn_norm, g.rms_norm_eps, g.dim, c.A16); nl++;
-        if (pg::gemm_launch<pg::GEMM_F32, ST>(c.mA, m.qkv, m.qkv, c.mQKV, c.QKV, nqkv, n, mt, nqkv / pg::BN, g.dim, s)) return fail(p, B200_ERR_CUDA, "QKV GEMM launch failed");
+        if (one_wave(nqkv / pg::BN) ? pg::gemm_launch<pg::GEMM_F32, DEEP>(c.mA, m.qkv, m.qkv, c.mQKV, c.QKV, nqkv, n, mt, nqkv / pg::BN, g.dim, s)
+                                    : pg::gemm_launch<pg::GEMM_F32, ST>(c.mA, m.qkv, m.qkv, c.mQKV, c.QKV, nqkv, n, mt, nqkv / pg::BN, g.dim, s))
+            return fail(p, B200_ERR_CUDA, "QKV GEMM launch failed");
         nl++;
-        const dim3 rg(n, g.n_heads + g.n_kv_heads);
         const int qt = PA_ROWS / kv_mul;
         const dim3 ag((n + qt - 1) / qt, g.n_kv_heads);
+        if (start_pos > 0 && !c.att_simt) { // rows written by earlier chunks / decode steps
+            const size_t n4 = (size_t)start_pos * p->kvd / 4;
+            k_pf_kv_to_f16<<<(unsigned)((n4 + 255) / 256 < 1184 ? (n4 + 255) / 256 : 1184), 256, 0, s>>>(kc, vc, c.KH, c.VH, n4);
+            nl++;
+        }
         if (g.head_size == 128) {
-            k_pf_rope_kv<128><<<rg, 64, 0, s>>>(c.QKV, nqkv, kc, vc, p->kvd, g.n_heads, g.arch, L.q_norm, L.k_norm, g.rms_norm_eps, p->rope_cr, p->rope_ci, start_pos);
+            k_pf_rope_kv<128><<<n, 256, 0, s>>>(c.QKV, nqkv, kc, vc, c.KH, c.VH, p->kvd, g.n_heads, g.n_kv_heads, g.arch, L.q_norm, L.k_norm, g.rms_norm_eps, p->rope_cr, p->rope_ci, start_pos);
             if (c.att_simt) k_pf_attention<128><<<ag, PA_THREADS, pa_smem_bytes<128>(), s>>>(c.QKV, nqkv, kc, vc, p->kvd, kv_mul, n, start_pos, inv_sqrt_hs, c.ATT16, p->qd);
-            else k_pf_attention_mma<128><<<ag, PM_THREADS, pm_smem_bytes<128>(), s>>>(c.QKV, nqkv, kc, vc, p->kvd, kv_mul, n, start_pos, inv_sqrt_hs, c.ATT16, p->qd);
+            else k_pf_attention_mma<128><<<ag, PM_THREADS, pm_smem_bytes<128>(), s>>>(c.QKV, nqkv, c.KH, c.VH, p->kvd, kv_mul, n, start_pos, inv_sqrt_hs, c.ATT16, p->qd);
         } else {
-            k_pf_rope_kv<64><<<rg, 32, 0, s>>>(c.QKV, nqkv, kc, vc, p->kvd, g.n_heads, g.arch, L.q_norm, L.k_norm, g.rms_norm_eps, p->rope_cr, p->rope_ci, start_pos);
+            k_pf_rope_kv<64><<<n, 256, 0, s>>>(c.QKV, nqkv, kc, vc, c.KH, c.VH, p->kvd, g.n_heads, g.n_kv_heads, g.arch, L.q_norm, L.k_norm, g.rms_norm_eps, p->rope_cr, p->rope_ci, start_pos);
             if (c.att_simt) k_pf_attention<64><<<ag, PA_THREADS, pa_smem_bytes<64>(), s>>>(c.QKV, nqkv, kc, vc, p->kvd, kv_mul, n, start_pos, inv_sqrt_hs, c.ATT16, p->qd);
-            else k_pf_attention_mma<64><<<ag, PM_THREADS, pm_smem_bytes<64>(), s>>>(c.QKV, nqkv, kc, vc, p->kvd, kv_mul, n, start_pos, inv_sqrt_hs, c.ATT16, p->qd);
+            else k_pf_attention_mma<64><<<ag, PM_THREADS, pm_smem_bytes<64>(), s>>>(c.QKV, nqkv, c.KH, c.VH, p->kvd, kv_mul, n, start_pos, inv_sqrt_hs, c.ATT16, p->qd);
         }
         nl += 2;
-        if (pg::gemm_launch<pg::GEMM_RESID, ST>(c.mATT, m.wo, m.wo, c.mX, c.X, g.dim, n, mt, g.dim / pg::BN, p->qd, s)) return fail(p, B200_ERR_CUDA, "Wo GEMM launch failed");
+        if (one_wave(g.dim / pg::BN) ? pg::gemm_launch<pg::GEMM_RESID, DEEP>(c.mATT, m.wo, m.wo, c.mX, c.X, g.dim, n, mt, g.dim / pg::BN, p->qd, s)
+                                     : pg::gemm_launch<pg::GEMM_RESID, ST>(c.mATT, m.wo, m.wo, c.mX, c.X, g.dim, n, mt, g.dim / pg::BN, p->qd, s))
+            return fail(p, B200_ERR_CUDA, "Wo GEMM launch failed");
         nl++;
         k_pf_rmsnorm_f16<<<n, 256, 0, s>>>(c.X, L.ffn_norm, g.rms_norm_eps, g.dim, c.A16); nl++;
-        if (pg::gemm_launch<pg::GEMM_GATEUP, ST>(c.mA, m.w1, m.w3, c.mX, c.H16, g.hidden_dim, n, mt, g.hidden_dim / (pg::BN / 2), g.dim, s)) return fail(p, B200_ERR_CUDA, "gate/up GEMM launch failed");
+        if (one_wave(g.hidden_dim / (pg::BN / 2)) ? pg::gemm_launch<pg::GEMM_GATEUP, DEEP>(c.mA, m.w1, m.w3, c.mX, c.H16, g.hidden_dim, n, mt, g.hidden_dim / (pg::BN / 2), g.dim, s)
+                                                  : pg::gemm_launch<pg::GEMM_GATEUP, ST>(c.mA, m.w1, m.w3, c.mX, c.H16, g.hidden_dim, n, mt, g.hidden_dim / (pg::BN / 2), g.dim, s))
+            return fail(p, B200_ERR_CUDA, "gate/up GEMM launch failed");
         nl++;
-        if (pg::gemm_launch<pg::GEMM_RESID, ST>(c.mH, m.w2, m.w2, c.mX, c.X, g.dim, n, mt, g.dim / pg::BN, g.hidden_dim, s)) return fail(p, B200_ERR_CUDA, "W2 GEMM launch failed");
+        if (one_wave(g.dim / pg::BN) ? pg::gemm_launch<pg::GEMM_RESID, DEEP>(c.mH, m.w2, m.w2, c.mX, c.X, g.dim, n, mt, g.dim / pg::BN, g.hidden_dim, s)
+                                     : pg::gemm_launch<pg::GEMM_RESID, ST>(c.mH, m.w2, m.w2, c.mX, c.X, g.dim, n, mt, g.dim / pg::BN, g.hidden_dim, s))
+            return fail(p, B200_ERR_CUDA, "W2 GEMM launch failed");
         nl++;
     }
     CK(cudaGetLastError());

@@ -36,6 +36,7 @@ struct PrefillCtx {
     float *X = nullptr, *QKV = nullptr;
     __half *A16 = nullptr, *ATT16 = nullptr, *H16 = nullptr;
     int *tok = nullptr;
+    __half *KH = nullptr, *VH = nullptr; // f16 K / V rows [0, start+n) of the layer in flight
     CUtensorMap mA, mATT, mH; // GEMM A operands (f16 activations)
     CUtensorMap mX, mQKV;     // GEMM outputs written by TMA (f32)
     std::vector<PrefillLayerMaps> maps;
@@ -83,40 +84,72 @@ __global__ void __launch_bounds__(256) k_pf_rmsnorm_f16(const float *__restrict_
     }
 }
 
-// grid (n, n_heads + n_kv_heads), HS/2 threads: one head of one token.  Llama rotates interleaved pairs
-// (InferenceCore.java:75-87), Qwen3 normalises the head then rotates NeoX pairs (:594-619).
+// One CTA per token, one warp per head at a time.  Llama rotates interleaved pairs (InferenceCore.java:75-87);
+// Qwen3 normalises the head, then rotates NeoX pairs (:594-619).  q is rotated in place; k and v go to the
+// FP32 KV cache (what decode reads) and, as f16, to the per-layer scratch the attention kernel streams.
 template <int HS>
-__global__ void __launch_bounds__(HS / 2) k_pf_rope_kv(float *__restrict__ qkv, int ldq, float *__restrict__ kc, float *__restrict__ vc, int kvd, int n_heads,
-                                                      int arch, const float *__restrict__ qnw, const float *__restrict__ knw, float eps,
-                                                      const float *__restrict__ cr, const float *__restrict__ ci, int start_pos) {
-    __shared__ float red[8];
-    constexpr int HALF = HS / 2;
-    const int b = blockIdx.x, hh = blockIdx.y, p = threadIdx.x, pos = start_pos + b;
-    const bool is_q = hh < n_heads;
-    const int qd = n_heads * HS, kvh = hh - n_heads;
-    float *src = qkv + (size_t)b * ldq + (is_q ? hh * HS : qd + kvh * HS);
-    int i0, i1;
-    if (arch == 1) { i0 = p; i1 = p + HALF; } else { i0 = 2 * p; i1 = 2 * p + 1; }
-    float v0 = src[i0], v1 = src[i1];
-    if (arch == 1) {
-        const float ss = pf_block_sum(v0 * v0 + v1 * v1, red);
-        const float sc = (float)(1.0 / sqrt((double)(ss / (float)HS + eps)));
-        const float *nw = is_q ? qnw : knw;
-        v0 = nw[i0] * (sc * v0);
-        v1 = nw[i1] * (sc * v1);
+__global__ void __launch_bounds__(256) k_pf_rope_kv(float *__restrict__ qkv, int ldq, float *__restrict__ kc, float *__restrict__ vc, __half *__restrict__ kh,
+                                                   __half *__restrict__ vh, int kvd, int n_heads, int n_kv_heads, int arch, const float *__restrict__ qnw,
+                                                   const float *__restrict__ knw, float eps, const float *__restrict__ cr, const float *__restrict__ ci,
+                                                   int start_pos) {
+    constexpr int HALF = HS / 2, PPL = HALF / 32; // pairs per lane
+    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, pos = start_pos + b;
+    const int qd = n_heads * HS;
+    for (int hh = warp; hh < n_heads + n_kv_heads; hh += 8) {
+        const bool is_q = hh < n_heads;
+        const int kvh = hh - n_heads;
+        float *src = qkv + (size_t)b * ldq + (is_q ? hh * HS : qd + kvh * HS);
+        float v0[PPL], v1[PPL];
+        int i0[PPL], i1[PPL];
+        float ss = 0.0f;
+#pragma unroll
+        for (int u = 0; u < PPL; u++) {
+            const int p = lane + 32 * u;
+            if (arch == 1) { i0[u] = p; i1[u] = p + HALF; } else { i0[u] = 2 * p; i1[u] = 2 * p + 1; }
+            v0[u] = src[i0[u]];
+            v1[u] = src[i1[u]];
+            ss += v0[u] * v0[u] + v1[u] * v1[u];
+        }
+        if (arch == 1) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            const float sc = (float)(1.0 / sqrt((double)(ss / (float)HS + eps)));
+            const float *nw = is_q ? qnw : knw;
+#pragma unroll
+            for (int u = 0; u < PPL; u++) { v0[u] = nw[i0[u]] * (sc * v0[u]); v1[u] = nw[i1[u]] * (sc * v1[u]); }
+        }
+#pragma unroll
+        for (int u = 0; u < PPL; u++) {
+            const int p = lane + 32 * u;
+            const float fcr = cr[(size_t)pos * HALF + p], fci = ci[(size_t)pos * HALF + p];
+            const float r0 = v0[u] * fcr - v1[u] * fci, r1 = v0[u] * fci + v1[u] * fcr;
+            if (is_q) {
+                src[i0[u]] = r0;
+                src[i1[u]] = r1;
+            } else {
+                const size_t o = (size_t)pos * kvd + kvh * HS;
+                const float *vsrc = qkv + (size_t)b * ldq + qd + kvd + kvh * HS;
+                const float w0 = vsrc[i0[u]], w1 = vsrc[i1[u]];
+                kc[o + i0[u]] = r0; kc[o + i1[u]] = r1;
+                vc[o + i0[u]] = w0; vc[o + i1[u]] = w1;
+                kh[o + i0[u]] = __float2half_rn(r0); kh[o + i1[u]] = __float2half_rn(r1);
+                vh[o + i0[u]] = __float2half_rn(w0); vh[o + i1[u]] = __float2half_rn(w1);
+            }
+        }
     }
-    const float fcr = cr[(size_t)pos * HALF + p], fci = ci[(size_t)pos * HALF + p];
-    const float r0 = v0 * fcr - v1 * fci, r1 = v0 * fci + v1 * fcr;
-    if (is_q) {
-        src[i0] = r0;
-        src[i1] = r1;
-    } else {
-        const size_t o = (size_t)pos * kvd + kvh * HS;
-        const float *vsrc = qkv + (size_t)b * ldq + qd + kvd + kvh * HS;
-        kc[o + i0] = r0;
-        kc[o + i1] = r1;
-        vc[o + i0] = vsrc[i0];
-        vc[o + i1] = vsrc[i1];
+}
+
+// f16 copies of cache rows written before this chunk (start_pos > 0): rows [0, rows) of one layer
+__global__ void __launch_bounds__(256) k_pf_kv_to_f16(const float *__restrict__ kc, const float *__restrict__ vc, __half *__restrict__ kh, __half *__restrict__ vh,
+                                                     size_t n4) {
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) {
+        const float4 a = reinterpret_cast<const float4 *>(kc)[i], c = reinterpret_cast<const float4 *>(vc)[i];
+        const __half2 a0 = __floats2half2_rn(a.x, a.y), a1 = __floats2half2_rn(a.z, a.w), c0 = __floats2half2_rn(c.x, c.y), c1 = __floats2half2_rn(c.z, c.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t *>(&a0); pk.y = *reinterpret_cast<const uint32_t *>(&a1);
+        reinterpret_cast<uint2 *>(kh)[i] = pk;
+        pk.x = *reinterpret_cast<const uint32_t *>(&c0); pk.y = *reinterpret_cast<const uint32_t *>(&c1);
+        reinterpret_cast<uint2 *>(vh)[i] = pk;
     }
 }
 
@@ -260,7 +293,7 @@ __global__ void __launch_bounds__(PA_THREADS) k_pf_attention(const float *__rest
 // A operand of P V, and V's B fragments come from ldmatrix.trans.  This op is 1 % of the prefill FLOPs
 // (0.07 of 7.2 TFLOP at pp512); the GEMMs that carry the rest run on tcgen05.
 constexpr int PM_THREADS = 128, PM_ROWS = 64, PM_KT = 64;
-template <int HS> constexpr size_t pm_smem_bytes() { return (size_t)3 * PM_ROWS * (HS + 8) * 2; }
+template <int HS> constexpr size_t pm_smem_bytes() { return (size_t)5 * PM_ROWS * (HS + 8) * 2; } // Q + 2 x (K, V)
 
 __device__ __forceinline__ void mma_f16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -273,13 +306,30 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
 }
 
 template <int HS>
-__global__ void __launch_bounds__(PM_THREADS) k_pf_attention_mma(const float *__restrict__ qkv, int ldq, const float *__restrict__ kc, const float *__restrict__ vc,
+__global__ void __launch_bounds__(PM_THREADS) k_pf_attention_mma(const float *__restrict__ qkv, int ldq, const __half *__restrict__ kh, const __half *__restrict__ vh,
                                                                 int kvd, int kv_mul, int n, int start_pos, float inv_sqrt_hs, __half *__restrict__ out, int ldo) {
     extern __shared__ __align__(16) unsigned char pm_sm[];
     constexpr int RP = HS + 8, H4 = HS / 4, KS = HS / 16, NB = HS / 8; // row pitch (halves): 16 B of padding keeps fragment loads conflict-free
-    __half *sQ = reinterpret_cast<__half *>(pm_sm), *sK = sQ + PM_ROWS * RP, *sV = sK + PM_KT * RP;
+    __half *sQ = reinterpret_cast<__half *>(pm_sm), *sKV = sQ + PM_ROWS * RP; // stage s: K at sKV + s*2*64*RP, V right after it
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
     const int QT = PM_ROWS / kv_mul, q0 = ((int)gridDim.x - 1 - (int)blockIdx.x) * QT, grp = blockIdx.y; // longest (latest) query tiles first
+    const int q_end = (q0 + QT < n ? q0 + QT : n), nkeys = start_pos + q_end, ntiles = (nkeys + PM_KT - 1) / PM_KT;
+    const uint32_t sKV_addr = (uint32_t)__cvta_generic_to_shared(sKV);
+    // K/V tile -> shared memory with cp.async (16 bytes per request, rows past nkeys zero-filled), double buffered
+    auto load_tile = [&](int it) {
+        const uint32_t base = sKV_addr + (uint32_t)((it & 1) * 2 * PM_KT * RP * 2);
+        constexpr int C8 = HS / 8; // 16-byte chunks per row
+        for (int idx = tid; idx < PM_KT * C8; idx += PM_THREADS) {
+            const int j = idx / C8, c8 = idx % C8, tk = it * PM_KT + j;
+            const int ok = tk < nkeys ? 16 : 0;
+            const size_t goff = (size_t)(ok ? tk : 0) * kvd + grp * HS + c8 * 8;
+            const uint32_t d = base + (uint32_t)((j * RP + c8 * 8) * 2);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(kh + goff), "r"(ok) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d + (uint32_t)(PM_KT * RP * 2)), "l"(vh + goff), "r"(ok) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (ntiles > 0) load_tile(0);
 
     for (int idx = tid; idx < PM_ROWS * H4; idx += PM_THREADS) {
         const int r = idx / H4, d4 = idx % H4, b = q0 + r / kv_mul, h = grp * kv_mul + r % kv_mul;
@@ -309,26 +359,19 @@ __global__ void __launch_bounds__(PM_THREADS) k_pf_attention_mma(const float *__
     const int row0 = warp * 16 + g, row1 = row0 + 8;
     const int tb0 = q0 + row0 / kv_mul, tb1 = q0 + row1 / kv_mul;
     const int qpos0 = tb0 < n ? start_pos + tb0 : -1, qpos1 = tb1 < n ? start_pos + tb1 : -1; // -1: every key masked
-    const int q_end = (q0 + QT < n ? q0 + QT : n), nkeys = start_pos + q_end;
-    const uint32_t sV_addr = (uint32_t)__cvta_generic_to_shared(sV);
 
 #pragma unroll 1
-    for (int k0 = 0; k0 < nkeys; k0 += PM_KT) {
-        __syncthreads();
-        for (int idx = tid; idx < PM_KT * H4; idx += PM_THREADS) {
-            const int j = idx / H4, d4 = idx % H4, tk = k0 + j;
-            float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
-            if (tk < nkeys) {
-                kv = *reinterpret_cast<const float4 *>(kc + (size_t)tk * kvd + grp * HS + d4 * 4);
-                vv = *reinterpret_cast<const float4 *>(vc + (size_t)tk * kvd + grp * HS + d4 * 4);
-            }
-            uint2 pk;
-            pk.x = pack_h2(kv.x, kv.y); pk.y = pack_h2(kv.z, kv.w);
-            *reinterpret_cast<uint2 *>(sK + j * RP + d4 * 4) = pk;
-            pk.x = pack_h2(vv.x, vv.y); pk.y = pack_h2(vv.z, vv.w);
-            *reinterpret_cast<uint2 *>(sV + j * RP + d4 * 4) = pk;
+    for (int it = 0; it < ntiles; it++) {
+        const int k0 = it * PM_KT;
+        if (it + 1 < ntiles) {
+            load_tile(it + 1); // the buffer it overwrites was released by the barrier that ended iteration it-1
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
+        const __half *sK = sKV + (it & 1) * 2 * PM_KT * RP;
+        const uint32_t sV_addr = sKV_addr + (uint32_t)(((it & 1) * 2 + 1) * PM_KT * RP * 2);
         float s[8][4];
 #pragma unroll
         for (int nb = 0; nb < 8; nb++) s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.0f;
@@ -388,6 +431,7 @@ __global__ void __launch_bounds__(PM_THREADS) k_pf_attention_mma(const float *__
                 mma_f16_16816(o[nb + 1], pa, b2, b3);
             }
         }
+        __syncthreads(); // every warp is done with this stage before the next iteration's prefetch overwrites it
     }
     const float inv0 = l0 > 0.0f ? 1.0f / l0 : 0.0f, inv1 = l1 > 0.0f ? 1.0f / l1 : 0.0f;
     if (tb0 < n) {

@@ -271,7 +271,7 @@ inline int gemm_launch(const CUtensorMap &a, const CUtensorMap &b, const CUtenso
 
 // 3 stages of 32 KB: two CTAs fit one SM (2 x 99 KB shared memory, 2 x 128 TMEM columns), so one CTA's
 // epilogue overlaps the other's main loop.
-constexpr int GEMM_STAGES = 3;
+constexpr int GEMM_STAGES = 3, GEMM_STAGES_DEEP = 6;
 
 // Test/measurement entry: C[M,N] (+)= A[M,K] * B[N,K]^T ; M, N multiples of 128, K multiple of 64.  Device pointers.
 inline int gemm_f16(const __half *A, const __half *B, float *C, int M, int N, int K, int stages, int resid, cudaStream_t stream) {
@@ -281,6 +281,7 @@ inline int gemm_f16(const __half *A, const __half *B, float *C, int M, int N, in
     if ((rc = make_map(&ma, A, (uint64_t)M, (uint64_t)K, BM))) return rc;
     if ((rc = make_map(&mb, B, (uint64_t)N, (uint64_t)K, BN))) return rc;
     if ((rc = make_map_c(&mc, C, (uint64_t)M, (uint64_t)N))) return rc;
+    if (resid && stages == 6) return gemm_launch<GEMM_RESID, 6>(ma, mb, mb, mc, C, N, M, M / BM, N / BN, K, stream);
     if (resid) return gemm_launch<GEMM_RESID, GEMM_STAGES>(ma, mb, mb, mc, C, N, M, M / BM, N / BN, K, stream);
     if (stages == 4) return gemm_launch<GEMM_F32, 4>(ma, mb, mb, mc, C, N, M, M / BM, N / BN, K, stream);
     if (stages == 6) return gemm_launch<GEMM_F32, 6>(ma, mb, mb, mc, C, N, M, M / BM, N / BN, K, stream);
