@@ -44,6 +44,51 @@ def peaks():
     return FALLBACK_HBM_GBS, "fallback"
 
 
+FALLBACK_TENSOR_TFLOPS = 2250.0  # nominal dense bf16/fp16
+
+
+def tensor_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            j = json.load(f)
+        return float(j["bf16_tflops"]), float(j.get("bf16_tflops_sustained", j["bf16_tflops"])), "measured (cuBLAS bf16 8192^3; fp16 shares the rate)"
+    return FALLBACK_TENSOR_TFLOPS, FALLBACK_TENSOR_TFLOPS, "fallback (nominal)"
+
+
+def prefill_leg(pkg, lb, local: int, n: int, reps: int):
+    """BASELINE config 3: Llama-3-8B FP16, --batch-prefill-size 512, pp512 from depth 0 (LlamaBench `pp`
+    semantics: forward only, no logits).  Tensor-core path: TMA + tcgen05 GEMMs, csrc/prefill*.cuh."""
+    shape = pkg.synth.SHAPES[WORKLOAD]
+    F16 = pkg.gguf.GGMLType.F16
+    model = pkg.loader.model_from_tensors(shape, F16, pkg.synth.build_tensors_fast(shape, F16, seed=1234, device=f"cuda:{local}"), n + 8)
+    plan = pkg.B200MasterPlan.initialize_plan(model, prefill_batch_size=n, device=local)
+    toks = np.asarray(lb.synthetic_tokens(shape.vocab, n), dtype=np.int32)
+    mode = plan.prefill_info()[0]
+    dev, wall = [], []
+    for r in range(3 + reps):  # 3 untimed warm-up chunks
+        t0 = time.perf_counter()
+        plan.forward_batch_prefill(toks, 0)  # host tokens in, synchronous: the e2e call
+        t1 = time.perf_counter()
+        if r >= 3:
+            dev.append(plan.prefill_info()[2])
+            wall.append((t1 - t0) * 1e3)
+    launches = plan.prefill_info()[1]
+    plan.free()
+    d, w = float(np.mean(dev)), float(np.mean(wall))
+    gemm = 2.0 * shape.matmul_elements_no_head() * n
+    att = 4.0 * shape.q_dim * shape.n_layers * (n * (n + 1) / 2.0)
+    burst, sustained, src = tensor_peak()
+    tf = (gemm + att) / (d * 1e-3) / 1e12
+    return {"metric": "prefill_tokens_per_s", "value": n / d * 1e3, "unit": "tok/s", "ms_per_chunk": d, "reps": reps, "dtype": "f16 operands, f32 accumulate (TMEM)",
+            "e2e": {"value": n / w * 1e3, "unit": "tok/s", "h2d_bytes_per_step": 4 * n, "d2h_bytes_per_step": 0},
+            "gpu_launches": launches, "mode": "tensor_core" if mode == 1 else "exact",
+            "config": {"workload": f"Llama-3-8B-shaped synthetic GGUF, FP16, pp{n} in one chunk (--batch-prefill-size {n}) from depth 0, KV cache only (no logits)",
+                       "l2": "inputs larger than L2 (15.0 GB of FP16 weights per chunk)"},
+            "roofline": {"kernel": "whole prefill chunk (k_gemm_f16_tcgen05 = 85 % of it, profiles/)", "bound": "tensor", "achieved": tf, "peak": burst, "peak_sustained": sustained,
+                         "peak_source": src, "unit": "TFLOP/s", "frac": tf / burst, "flop_per_chunk": {"gemm": gemm, "attention": att}, "traffic": None}}
+
+
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
@@ -129,6 +174,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU-baseline work")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-pp", action="store_true", help="skip the pp512 tensor-core prefill leg")
     args = ap.parse_args()
     K, W = args.steps, max(args.warmup, 3)
 
@@ -252,6 +298,9 @@ def main():
         line["cpu_baseline"] = {"value": tps, "unit": "tok/s", "cores": cores, "kind": "port",
                                 "sample": f"{n} decode steps of the same workload in {dt:.1f} s (C restatement of InferenceCore.forwardJava, -O2, OpenMP rows)"}
     plan.free()
+    if not args.no_pp and world == 1:
+        del model, plan
+        line["pp512"] = prefill_leg(pkg, lb, local, 512, 5)
     print(json.dumps(line))
     if world > 1:
         dist.barrier()

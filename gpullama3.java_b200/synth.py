@@ -41,6 +41,10 @@ class Shape:
         per_layer = 2 * self.q_dim * self.dim + 2 * self.kv_dim * self.dim + 3 * self.hidden * self.dim
         return self.n_layers * per_layer + self.vocab * self.dim
 
+    def matmul_elements_no_head(self) -> int:
+        """Weight elements a prefill token multiplies (no lm_head: prefill skips logits)."""
+        return self.matmul_elements() - self.vocab * self.dim
+
 
 SHAPES = {
     # tiny parity shapes (oracle finishes in milliseconds)
