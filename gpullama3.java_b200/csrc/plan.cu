@@ -683,7 +683,7 @@ int prefill_init(b200_plan *p) {
     if (kv_mul > 64 || (kv_mul & (kv_mul - 1))) { c.why = "tensor-core prefill needs a power-of-two GQA ratio <= 64"; return B200_OK; }
     if (g.dim % 128 || p->qd % 128 || nqkv % 128 || g.hidden_dim % 64) { c.why = "tensor-core prefill needs dim, q width and q+k+v width multiples of 128, hidden a multiple of 64"; return B200_OK; }
     if (!pg::encode_fn()) { c.why = "cuTensorMapEncodeTiled not available from the driver"; return B200_OK; }
-    c.bpad = (c.batch + pg::BM - 1) / pg::BM * pg::BM;
+    c.bpad = (c.batch + 255) / 256 * 256; // whole CTA-pair tiles
     int rc;
     if ((rc = dalloc(p, &c.X, (size_t)c.bpad * g.dim * 4))) return rc;
     if ((rc = dalloc(p, &c.QKV, (size_t)c.bpad * nqkv * 4))) return rc;
@@ -708,7 +708,12 @@ int prefill_init(b200_plan *p) {
         PrefillLayerMaps &m = c.maps[l];
         ok = pg::make_map(&m.qkv, L.qkv.qs, nqkv, g.dim, pg::BN) == 0 && pg::make_map(&m.wo, L.wo.qs, g.dim, p->qd, pg::BN) == 0 &&
              pg::make_map(&m.w1, L.w1.qs, g.hidden_dim, g.dim, pg::BN / 2) == 0 && pg::make_map(&m.w3, L.w3.qs, g.hidden_dim, g.dim, pg::BN / 2) == 0 &&
-             pg::make_map(&m.w2, L.w2.qs, g.dim, g.hidden_dim, pg::BN) == 0;
+             pg::make_map(&m.w2, L.w2.qs, g.dim, g.hidden_dim, pg::BN) == 0 && pg::make_map(&m.w1p, L.w1.qs, g.hidden_dim, g.dim, 128) == 0 &&
+             pg::make_map(&m.w3p, L.w3.qs, g.hidden_dim, g.dim, 128) == 0;
+    }
+    {
+        const char *e = getenv("B200_GEMM_2CTA");
+        c.pair = !(e && e[0] == '0') && nqkv % 256 == 0 && g.dim % 256 == 0 && g.hidden_dim % 128 == 0;
     }
     if (!ok) { c.why = "cuTensorMapEncodeTiled rejected a tensor map"; return B200_OK; }
     if (g.head_size == 128) {
@@ -740,12 +745,25 @@ int prefill_forward(b200_plan *p, int n, int start_pos, int *launches) {
     constexpr int ST = pg::GEMM_STAGES, DEEP = pg::GEMM_STAGES_DEEP;
     // a GEMM that fits one wave has one CTA per SM anyway: give it the deep ring; otherwise two CTAs share an SM
     auto one_wave = [&](int n_tiles) { return mt * n_tiles <= p->n_sms; };
+    // CTA-pair path: M in 256-row pair tiles; the x += A W^T GEMMs (N = dim only) split K so that the grid fills the SMs --
+    // every split reduce-adds its partial product through TMA
+    const int mt2 = (n + 255) / 256 * 2;
+    auto pair_splits = [&](int n_tiles, int K) {
+        const int ctas = mt2 * n_tiles, nk = K / pg::BK;
+        int sp = p->n_sms / ctas;
+        if (sp > 4) sp = 4;
+        while (sp > 1 && nk / sp < 8) sp--;
+        return sp < 1 ? 1 : sp;
+    };
     k_pf_embed<<<n, 256, 0, s>>>(c.tok, p->emb, c.X, g.dim); nl++;
     for (int l = 0; l < g.n_layers; l++) {
         const LayerW &L = p->layers[l];
         const PrefillLayerMaps &m = c.maps[l];
         float *kc = p->key_cache + (size_t)l * ctx_kv, *vc = p->value_cache + (size_t)l * ctx_kv;
         k_pf_rmsnorm_f16<<<n, 256, 0, s>>>(c.X, L.attn_norm, g.rms_norm_eps, g.dim, c.A16); nl++;
+        if (c.pair) {
+            if (pg::gemm2_launch<pg::GEMM_F32, 256, pg::GEMM2_STAGES_256>(c.mA, m.qkv, m.qkv, c.mQKV, c.QKV, nqkv, n, mt2, nqkv / 256, g.dim, s)) return fail(p, B200_ERR_CUDA, "QKV GEMM launch failed");
+        } else
         if (one_wave(nqkv / pg::BN) ? pg::gemm_launch<pg::GEMM_F32, DEEP>(c.mA, m.qkv, m.qkv, c.mQKV, c.QKV, nqkv, n, mt, nqkv / pg::BN, g.dim, s)
                                     : pg::gemm_launch<pg::GEMM_F32, ST>(c.mA, m.qkv, m.qkv, c.mQKV, c.QKV, nqkv, n, mt, nqkv / pg::BN, g.dim, s))
             return fail(p, B200_ERR_CUDA, "QKV GEMM launch failed");
@@ -767,15 +785,24 @@ int prefill_forward(b200_plan *p, int n, int start_pos, int *launches) {
             else k_pf_attention_mma<64><<<ag, PM_THREADS, pm_smem_bytes<64>(), s>>>(c.QKV, nqkv, c.KH, c.VH, p->kvd, kv_mul, n, start_pos, inv_sqrt_hs, c.ATT16, p->qd);
         }
         nl += 2;
+        if (c.pair) {
+            if (pg::gemm2_launch<pg::GEMM_RESID, 256, pg::GEMM2_STAGES_256>(c.mATT, m.wo, m.wo, c.mX, c.X, g.dim, n, mt2, g.dim / 256, p->qd, s, pair_splits(g.dim / 256, p->qd))) return fail(p, B200_ERR_CUDA, "Wo GEMM launch failed");
+        } else
         if (one_wave(g.dim / pg::BN) ? pg::gemm_launch<pg::GEMM_RESID, DEEP>(c.mATT, m.wo, m.wo, c.mX, c.X, g.dim, n, mt, g.dim / pg::BN, p->qd, s)
                                      : pg::gemm_launch<pg::GEMM_RESID, ST>(c.mATT, m.wo, m.wo, c.mX, c.X, g.dim, n, mt, g.dim / pg::BN, p->qd, s))
             return fail(p, B200_ERR_CUDA, "Wo GEMM launch failed");
         nl++;
         k_pf_rmsnorm_f16<<<n, 256, 0, s>>>(c.X, L.ffn_norm, g.rms_norm_eps, g.dim, c.A16); nl++;
+        if (c.pair) {
+            if (pg::gemm2_launch<pg::GEMM_GATEUP, 256, pg::GEMM2_STAGES_256>(c.mA, m.w1p, m.w3p, c.mX, c.H16, g.hidden_dim, n, mt2, g.hidden_dim / 128, g.dim, s)) return fail(p, B200_ERR_CUDA, "gate/up GEMM launch failed");
+        } else
         if (one_wave(g.hidden_dim / (pg::BN / 2)) ? pg::gemm_launch<pg::GEMM_GATEUP, DEEP>(c.mA, m.w1, m.w3, c.mX, c.H16, g.hidden_dim, n, mt, g.hidden_dim / (pg::BN / 2), g.dim, s)
                                                   : pg::gemm_launch<pg::GEMM_GATEUP, ST>(c.mA, m.w1, m.w3, c.mX, c.H16, g.hidden_dim, n, mt, g.hidden_dim / (pg::BN / 2), g.dim, s))
             return fail(p, B200_ERR_CUDA, "gate/up GEMM launch failed");
         nl++;
+        if (c.pair) {
+            if (pg::gemm2_launch<pg::GEMM_RESID, 256, pg::GEMM2_STAGES_256>(c.mH, m.w2, m.w2, c.mX, c.X, g.dim, n, mt2, g.dim / 256, g.hidden_dim, s, pair_splits(g.dim / 256, g.hidden_dim))) return fail(p, B200_ERR_CUDA, "W2 GEMM launch failed");
+        } else
         if (one_wave(g.dim / pg::BN) ? pg::gemm_launch<pg::GEMM_RESID, DEEP>(c.mH, m.w2, m.w2, c.mX, c.X, g.dim, n, mt, g.dim / pg::BN, g.hidden_dim, s)
                                      : pg::gemm_launch<pg::GEMM_RESID, ST>(c.mH, m.w2, m.w2, c.mX, c.X, g.dim, n, mt, g.dim / pg::BN, g.hidden_dim, s))
             return fail(p, B200_ERR_CUDA, "W2 GEMM launch failed");
@@ -1144,6 +1171,7 @@ int b200_test_seqsum(const float *terms, int32_t n, float *out, int32_t *info) {
 
 int b200_gemm_f16(const uint16_t *a, const uint16_t *b, float *c, int32_t m, int32_t n, int32_t k, int32_t iters, float *ms) {
     const int stages = getenv("B200_GEMM_STAGES") ? atoi(getenv("B200_GEMM_STAGES")) : 0;
+    const int two_cta = getenv("B200_GEMM_2CTA") ? atoi(getenv("B200_GEMM_2CTA")) : 0; // 0, 128 or 256
     const int resid = getenv("B200_GEMM_RESID") ? atoi(getenv("B200_GEMM_RESID")) : 0; // C starts at 0 and accumulates over the timed launches
     if (!a || !b || !c || m <= 0 || n <= 0 || k <= 0 || m % 128 || n % 128 || k % 64) return B200_ERR_BAD_ARG;
     __half *da = nullptr, *db = nullptr;
@@ -1156,13 +1184,13 @@ int b200_gemm_f16(const uint16_t *a, const uint16_t *b, float *c, int32_t m, int
     cudaMemcpy(da, a, (size_t)m * k * 2, cudaMemcpyHostToDevice);
     cudaMemcpy(db, b, (size_t)n * k * 2, cudaMemcpyHostToDevice);
     cudaMemset(dc, resid ? 0 : 0xFF, (size_t)m * n * 4);
-    int rc = pg::gemm_f16(da, db, dc, m, n, k, stages, resid, 0);
+    int rc = pg::gemm_f16(da, db, dc, m, n, k, stages, resid, two_cta, 0);
     cudaError_t e = cudaDeviceSynchronize();
     if (rc == 0 && e == cudaSuccess && iters > 0 && ms) {
         cudaEvent_t e0, e1;
         cudaEventCreate(&e0); cudaEventCreate(&e1);
         cudaEventRecord(e0, 0);
-        for (int i = 0; i < iters; i++) pg::gemm_f16(da, db, dc, m, n, k, stages, resid, 0);
+        for (int i = 0; i < iters; i++) pg::gemm_f16(da, db, dc, m, n, k, stages, resid, two_cta, 0);
         cudaEventRecord(e1, 0);
         e = cudaEventSynchronize(e1);
         float t = 0.f;
@@ -1171,7 +1199,7 @@ int b200_gemm_f16(const uint16_t *a, const uint16_t *b, float *c, int32_t m, int
         cudaEventDestroy(e0); cudaEventDestroy(e1);
         if (resid) { // C accumulated 1 + iters products: return exactly one
             cudaMemset(dc, 0, (size_t)m * n * 4);
-            pg::gemm_f16(da, db, dc, m, n, k, stages, resid, 0);
+            pg::gemm_f16(da, db, dc, m, n, k, stages, resid, two_cta, 0);
             e = cudaDeviceSynchronize();
         }
     }

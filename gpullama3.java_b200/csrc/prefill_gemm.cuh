@@ -216,6 +216,182 @@ __global__ void __launch_bounds__(256) k_gemm_f16_tcgen05(const __grid_constant_
     if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
 }
 
+// =====================================================================================================
+// CTA-pair version: two CTAs of a cluster (the two SMs of a TPC) compute one 256 x BN tile with
+// tcgen05.mma.cta_group::2.  Each CTA loads ITS 128 rows of A and ITS half of the B tile (BN/2 weight rows),
+// so an SM ingests 16 KB + BN/2 * 128 B per 128 x BN x 64 MACs -- twice the arithmetic intensity of the
+// single-CTA kernel at BN = 256 (the 128 x 128 tile is bound by the ~64 B/clk an SM can pull from L2).
+// Protocol (CUTLASS PipelineTmaUmmaAsync, cutlass/pipeline/sm100_pipeline.hpp): both producers issue
+// cta_group::2 TMA loads whose complete_tx lands on the LEADER's full barrier (peer bit cleared); only the
+// leader arms it (expect_tx for both CTAs' bytes), waits on it and issues the MMAs; tcgen05.commit with a
+// multicast mask frees the stage in both CTAs and finally publishes the accumulator (rows 0-127 in the
+// leader's TMEM, 128-255 in the peer's) to both epilogues, which are identical to the single-CTA ones.
+// GEMM_GATEUP: the leader's half of B is BN/2 rows of W1, the peer's half BN/2 rows of W3.
+// =====================================================================================================
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() { // every thread of both CTAs
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst), "l"(map),
+                 "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_f16_2cta(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    const uint32_t z = 0u;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n"
+        "}\n" ::"r"(tmem_c),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(z)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_2cta(uint32_t bar) { // arrives on the barrier at this offset in BOTH CTAs
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
+
+template <int BN, int STAGES> constexpr size_t smem_bytes_2cta() { return (size_t)STAGES * (BM * BK * 2 + (BN / 2) * BK * 2) + (2 * STAGES + 1) * 8 + 16 + 1024; }
+
+template <int MODE, int BN, int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+    k_gemm_f16_2cta(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_b2,
+                    const __grid_constant__ CUtensorMap tma_c, void *__restrict__ Cv, int ldc, int m_valid, int K, int kb_per_split) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    constexpr int A_BYTES = BM * BK * 2, B_BYTES = (BN / 2) * BK * 2; // per CTA and stage
+    static_assert(STAGES * (A_BYTES + B_BYTES) >= BM * BN * 4, "the C tile is staged in the operand ring");
+    uint8_t *sA = smem, *sB = smem + STAGES * A_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + STAGES * B_BYTES);
+    const uint32_t full0 = s32(bars), empty0 = s32(bars + STAGES), tmem_full = s32(bars + 2 * STAGES);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) { // the same warp of both CTAs allocates the pair's accumulator columns
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)), "r"((uint32_t)BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all(); // barriers of both CTAs initialised before any remote complete_tx / commit can land
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    // split-K (GEMM_RESID only: every split reduce-adds its partial product into x): blockIdx.z owns k-blocks [kb0, kb0 + nk)
+    const int nk_all = (K + BK - 1) / BK, kb0 = blockIdx.z * kb_per_split;
+    const int nk = nk_all - kb0 < kb_per_split ? nk_all - kb0 : kb_per_split;
+    const int m0 = blockIdx.x * BM;
+    const int n0 = blockIdx.y * (MODE == GEMM_GATEUP ? BN / 2 : BN);
+
+    if (warp == 0 && lane == 0) {
+        // ===== TMA producer (both CTAs): own A rows, own half of the B tile =====
+        const CUtensorMap *bmap = (MODE == GEMM_GATEUP && rank == 1) ? &tma_b2 : &tma_b;
+        const int brow = MODE == GEMM_GATEUP ? n0 : n0 + (int)rank * (BN / 2);
+        for (int kb = 0; kb < nk; kb++) {
+            const int st = kb % STAGES;
+            mbar_wait(empty0 + 8 * st, ((kb / STAGES) & 1) ^ 1);
+            if (rank == 0) mbar_expect_tx(full0 + 8 * st, 2 * (A_BYTES + B_BYTES));
+            tma_load_2d_2sm(s32(sA + st * A_BYTES), &tma_a, (kb0 + kb) * BK, m0, full0 + 8 * st);
+            tma_load_2d_2sm(s32(sB + st * B_BYTES), bmap, (kb0 + kb) * BK, brow, full0 + 8 * st);
+        }
+    } else if (warp == 1 && lane == 0 && rank == 0) {
+        // ===== MMA issuer: one thread of the leader CTA drives both SMs' tensor cores =====
+        constexpr uint32_t idesc = umma_idesc_f16(2 * BM, BN);
+        for (int kb = 0; kb < nk; kb++) {
+            const int st = kb % STAGES;
+            mbar_wait(full0 + 8 * st, (kb / STAGES) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint64_t da = umma_desc_sw128(s32(sA + st * A_BYTES)), db = umma_desc_sw128(s32(sB + st * B_BYTES));
+#pragma unroll
+            for (int k = 0; k < BK / 16; k++) umma_f16_2cta(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit_2cta(empty0 + 8 * st);
+        }
+        umma_commit_2cta(tmem_full);
+    }
+    __syncwarp(); // the elected producer / MMA lanes rejoin their warps
+    {
+        // ===== epilogue (both CTAs, own 128 rows): all 8 warps -- warp w reads TMEM lanes 32*(w%4).., warps 0-3 take the
+        // first half of the columns and warps 4-7 the second =====
+        mbar_wait(tmem_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int q = warp & 3, half = warp >> 2;
+        const int row = m0 + q * 32 + lane;
+        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+        if (MODE == GEMM_GATEUP) {
+            __half *C = reinterpret_cast<__half *>(Cv);
+#pragma unroll 1
+            for (int c0 = half * (BN / 4); c0 < (half + 1) * (BN / 4); c0 += 32) {
+                uint32_t g[32], u[32];
+                tmem_ld32(tlane + (uint32_t)c0, g);
+                tmem_ld32(tlane + (uint32_t)(BN / 2 + c0), u);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (row < m_valid) {
+                    uint4 *dst = reinterpret_cast<uint4 *>(C + (size_t)row * ldc + n0 + c0);
+#pragma unroll
+                    for (int v = 0; v < 4; v++) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            const float g0 = __uint_as_float(g[8 * v + 2 * e]), g1 = __uint_as_float(g[8 * v + 2 * e + 1]);
+                            const float h0 = (g0 / (1.0f + expf(-g0))) * __uint_as_float(u[8 * v + 2 * e]);
+                            const float h1 = (g1 / (1.0f + expf(-g1))) * __uint_as_float(u[8 * v + 2 * e + 1]);
+                            const __half2 hh = __floats2half2_rn(h0, h1);
+                            w[e] = *reinterpret_cast<const uint32_t *>(&hh);
+                        }
+                        dst[v] = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                }
+            }
+        } else {
+            const int rloc = q * 32 + lane;
+#pragma unroll 1
+            for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); c++) {
+                uint32_t r[32];
+                tmem_ld32(tlane + (uint32_t)(c * 32), r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                uint8_t *buf = smem + c * (BM * 32 * 4) + rloc * 128;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    uint4 o = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                    if (row >= m_valid) o = make_uint4(0u, 0u, 0u, 0u);
+                    *reinterpret_cast<uint4 *>(buf + ((j ^ (rloc & 7)) << 4)) = o;
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            if (threadIdx.x == 0) {
+#pragma unroll
+                for (int c = 0; c < BN / 32; c++) {
+                    const uint32_t src = s32(smem + c * (BM * 32 * 4));
+                    if (MODE == GEMM_RESID)
+                        asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tma_c), "r"(src),
+                                     "r"(n0 + c * 32), "r"(m0)
+                                     : "memory");
+                    else
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tma_c), "r"(src), "r"(n0 + c * 32),
+                                     "r"(m0)
+                                     : "memory");
+                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all(); // neither CTA may exit (or free TMEM) while the pair can still touch its shared memory / TMEM
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+}
+
 // ---- host side ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
                                   const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -269,15 +445,43 @@ inline int gemm_launch(const CUtensorMap &a, const CUtensorMap &b, const CUtenso
     return cudaGetLastError() == cudaSuccess ? 0 : -5;
 }
 
+// m_tiles must be even (M padded to 256).  B maps must have box rows = BN / 2.
+template <int MODE, int BN, int STAGES>
+inline int gemm2_launch(const CUtensorMap &a, const CUtensorMap &b, const CUtensorMap &b2, const CUtensorMap &c, void *C, int ldc, int m_valid, int m_tiles,
+                        int n_tiles, int K, cudaStream_t stream, int splits = 1) {
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(k_gemm_f16_2cta<MODE, BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_2cta<BN, STAGES>()) != cudaSuccess) return -4;
+        attr = true;
+    }
+    if ((m_tiles & 1) || splits < 1 || (splits > 1 && MODE != GEMM_RESID)) return -6;
+    const int nk = (K + BK - 1) / BK, per = (nk + splits - 1) / splits;
+    if ((splits - 1) * per >= nk) return -6; // an empty split would publish an unwritten accumulator
+    k_gemm_f16_2cta<MODE, BN, STAGES><<<dim3(m_tiles, n_tiles, splits), 256, smem_bytes_2cta<BN, STAGES>(), stream>>>(a, b, b2, c, C, ldc, m_valid, K, per);
+    return cudaGetLastError() == cudaSuccess ? 0 : -5;
+}
+constexpr int GEMM2_STAGES_256 = 6, GEMM2_STAGES_128 = 8; // 192 KB of operand ring per CTA either way
+
 // 3 stages of 32 KB: two CTAs fit one SM (2 x 99 KB shared memory, 2 x 128 TMEM columns), so one CTA's
 // epilogue overlaps the other's main loop.
 constexpr int GEMM_STAGES = 3, GEMM_STAGES_DEEP = 6;
 
 // Test/measurement entry: C[M,N] (+)= A[M,K] * B[N,K]^T ; M, N multiples of 128, K multiple of 64.  Device pointers.
-inline int gemm_f16(const __half *A, const __half *B, float *C, int M, int N, int K, int stages, int resid, cudaStream_t stream) {
+inline int gemm_f16(const __half *A, const __half *B, float *C, int M, int N, int K, int stages, int resid, int two_cta, cudaStream_t stream) {
     if (M % BM || N % BN || K % BK) return -3;
     CUtensorMap ma, mb, mc;
     int rc;
+    if (two_cta) { // two_cta = pair-tile width (256 or 128)
+        if (M % 256 || N % two_cta) return -3;
+        if ((rc = make_map(&ma, A, (uint64_t)M, (uint64_t)K, BM))) return rc;
+        if ((rc = make_map(&mb, B, (uint64_t)N, (uint64_t)K, two_cta / 2))) return rc;
+        if ((rc = make_map_c(&mc, C, (uint64_t)M, (uint64_t)N))) return rc;
+        if (two_cta == 256)
+            return resid ? gemm2_launch<GEMM_RESID, 256, GEMM2_STAGES_256>(ma, mb, mb, mc, C, N, M, M / BM, N / 256, K, stream, resid)
+                         : gemm2_launch<GEMM_F32, 256, GEMM2_STAGES_256>(ma, mb, mb, mc, C, N, M, M / BM, N / 256, K, stream);
+        return resid ? gemm2_launch<GEMM_RESID, 128, GEMM2_STAGES_128>(ma, mb, mb, mc, C, N, M, M / BM, N / 128, K, stream)
+                     : gemm2_launch<GEMM_F32, 128, GEMM2_STAGES_128>(ma, mb, mb, mc, C, N, M, M / BM, N / 128, K, stream);
+    }
     if ((rc = make_map(&ma, A, (uint64_t)M, (uint64_t)K, BM))) return rc;
     if ((rc = make_map(&mb, B, (uint64_t)N, (uint64_t)K, BN))) return rc;
     if ((rc = make_map_c(&mc, C, (uint64_t)M, (uint64_t)N))) return rc;
