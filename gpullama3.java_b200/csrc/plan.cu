@@ -41,6 +41,7 @@ struct b200_plan {
     DevMat emb{}, out{};
     TileMat tout{};
     bool use_stream = false, use_pdl = false;
+    bool f16_copies = false; // Q8_0 plan that also holds f16 weight matrices for the tensor-core prefill
     int n_sms = 148;
     unsigned *blk_cnt = nullptr;
     float *part_val = nullptr;
@@ -677,7 +678,11 @@ int prefill_init(b200_plan *p) {
     c.ready = false;
     c.mode = 0;
     const int kv_mul = g.n_heads / g.n_kv_heads, nqkv = p->qd + 2 * p->kvd;
-    if (p->wtype != B200_GGML_F16) { c.why = "tensor-core prefill needs FP16 weight matrices (Q8_0 plans use the exact token-by-token path)"; return B200_OK; }
+    if (p->wtype != B200_GGML_F16 && !p->f16_copies) {
+        c.why = p->use_stream ? "Q8_0 plan: the tensor-core prefill is opt-in (b200_set_prefill_mode builds f16 twins of the weight matrices, +2 bytes per weight)"
+                              : "tensor-core prefill needs FP16 weight matrices or a Q8_0 plan on the streaming path";
+        return B200_OK;
+    }
     if (g.tp_size > 1) { c.why = "tensor-core prefill is single-GPU"; return B200_OK; }
     if (g.head_size != 64 && g.head_size != 128) { c.why = "tensor-core prefill supports head sizes 64 and 128"; return B200_OK; }
     if (kv_mul > 64 || (kv_mul & (kv_mul - 1))) { c.why = "tensor-core prefill needs a power-of-two GQA ratio <= 64"; return B200_OK; }
@@ -730,6 +735,35 @@ int prefill_init(b200_plan *p) {
     c.ready = true;
     c.mode = 1;
     c.why = "";
+    return B200_OK;
+}
+
+// Q8_0 plan: f16 twins of the weight matrices, dequantised on the device from the tile-major stream (value = f16(q * scale),
+// Q8_0FloatTensor.getFloat rounded once) -- the B operands of the tensor-core GEMMs; the reference's Q8_0 MMA prefill also
+// feeds FP16 tiles (LlamaQ8_0LayersBatchPrefillMMA.java).  Built on the first b200_set_prefill_mode(TENSOR_CORE).
+int build_f16_twins(b200_plan *p) {
+    const b200_config &c = p->cfg;
+    if (p->f16_copies) return B200_OK;
+    if (p->wtype != B200_GGML_Q8_0 || !p->use_stream || c.tp_size > 1) return fail(p, B200_ERR_UNSUPPORTED, "f16 twins need a single-GPU Q8_0 plan on the streaming path");
+    for (int l = 0; l < c.n_layers; l++) {
+        LayerW &L = p->layers[l];
+        int rc;
+        if ((rc = alloc_matrix(p, L.qkv, p->qd + 2 * p->kvd, c.dim, B200_GGML_F16))) return rc;
+        if ((rc = alloc_matrix(p, L.wo, c.dim, p->qd, B200_GGML_F16))) return rc;
+        if ((rc = alloc_matrix(p, L.w1, c.hidden_dim, c.dim, B200_GGML_F16))) return rc;
+        if ((rc = alloc_matrix(p, L.w3, c.hidden_dim, c.dim, B200_GGML_F16))) return rc;
+        if ((rc = alloc_matrix(p, L.w2, c.dim, c.hidden_dim, B200_GGML_F16))) return rc;
+        auto run = [&](const TileMat &t, int gateup, const DevMat &o0, const DevMat &o1) {
+            k_tiles_to_f16<<<(unsigned)((size_t)t.rows * t.nseg), 128, 0, p->stream>>>(t, gateup, (__half *)o0.qs, (__half *)o1.qs);
+        };
+        run(L.tqkv, 0, L.qkv, L.qkv);
+        run(L.two, 0, L.wo, L.wo);
+        run(L.tgu, 1, L.w1, L.w3);
+        run(L.tw2, 0, L.w2, L.w2);
+        CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(p->stream));
+    p->f16_copies = true;
     return B200_OK;
 }
 
@@ -939,6 +973,12 @@ int b200_decode_sequence(b200_plan *p, const int32_t *tokens, int32_t n, int32_t
 
 int b200_set_prefill_mode(b200_plan *p, int32_t mode) {
     if (!p || (mode != B200_PREFILL_EXACT && mode != B200_PREFILL_TENSOR_CORE)) return B200_ERR_BAD_ARG;
+    if (mode == B200_PREFILL_TENSOR_CORE && !p->prefill.ready && p->prefill_batch > 1 && p->wtype == B200_GGML_Q8_0 && p->use_stream && p->cfg.tp_size == 1) {
+        CK(cudaSetDevice(p->device)); // opt-in on a Q8_0 plan: build the f16 twins, then the GEMM context
+        int rc = build_f16_twins(p);
+        if (rc) return rc;
+        if ((rc = prefill_init(p))) return rc;
+    }
     if (mode == B200_PREFILL_TENSOR_CORE && !p->prefill.ready) return fail(p, B200_ERR_UNSUPPORTED, "%s", p->prefill.why);
     p->prefill.mode = mode;
     return B200_OK;

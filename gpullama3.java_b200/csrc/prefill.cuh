@@ -42,7 +42,7 @@ struct PrefillCtx {
     CUtensorMap mA, mATT, mH; // GEMM A operands (f16 activations)
     CUtensorMap mX, mQKV;     // GEMM outputs written by TMA (f32)
     std::vector<PrefillLayerMaps> maps;
-    const char *why = "batched prefill not initialised";
+    const char *why = "the plan was created without a prefill batch size (prefill_batch_size <= 1)";
 };
 
 // ---- elementwise kernels ------------------------------------------------------------------------
@@ -302,6 +302,11 @@ __device__ __forceinline__ void mma_f16_16816(float (&d)[4], const uint32_t (&a)
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ float ex2_approx(float x) { // 2^x on the SFU (ex2(-inf) = 0)
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
     const __half2 h = __floats2half2_rn(lo, hi);
     return *reinterpret_cast<const uint32_t *>(&h);
@@ -318,14 +323,17 @@ __global__ void __launch_bounds__(PM_THREADS) k_pf_attention_mma(const float *__
     const int q_end = (q0 + QT < n ? q0 + QT : n), nkeys = start_pos + q_end, ntiles = (nkeys + PM_KT - 1) / PM_KT;
     const uint32_t sKV_addr = (uint32_t)__cvta_generic_to_shared(sKV);
     // K/V tile -> shared memory with cp.async (16 bytes per request, rows past nkeys zero-filled), double buffered
+    constexpr int C8 = HS / 8, JSTEP = PM_THREADS / C8; // 16-byte chunks per row; rows covered by one pass of the CTA
+    const int lc8 = tid % C8, lj0 = tid / C8;
+    const size_t gcol = (size_t)grp * HS + lc8 * 8;
+    const uint32_t ldst0 = sKV_addr + (uint32_t)((lj0 * RP + lc8 * 8) * 2);
     auto load_tile = [&](int it) {
-        const uint32_t base = sKV_addr + (uint32_t)((it & 1) * 2 * PM_KT * RP * 2);
-        constexpr int C8 = HS / 8; // 16-byte chunks per row
-        for (int idx = tid; idx < PM_KT * C8; idx += PM_THREADS) {
-            const int j = idx / C8, c8 = idx % C8, tk = it * PM_KT + j;
+        uint32_t d = ldst0 + (uint32_t)((it & 1) * 2 * PM_KT * RP * 2);
+        int tk = it * PM_KT + lj0;
+#pragma unroll
+        for (int i = 0; i < PM_KT / JSTEP; i++, tk += JSTEP, d += (uint32_t)(JSTEP * RP * 2)) {
             const int ok = tk < nkeys ? 16 : 0;
-            const size_t goff = (size_t)(ok ? tk : 0) * kvd + grp * HS + c8 * 8;
-            const uint32_t d = base + (uint32_t)((j * RP + c8 * 8) * 2);
+            const size_t goff = (size_t)(ok ? tk : 0) * kvd + gcol;
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(kh + goff), "r"(ok) : "memory");
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d + (uint32_t)(PM_KT * RP * 2)), "l"(vh + goff), "r"(ok) : "memory");
         }
@@ -333,13 +341,14 @@ __global__ void __launch_bounds__(PM_THREADS) k_pf_attention_mma(const float *__
     };
     if (ntiles > 0) load_tile(0);
 
+    const float qscale = inv_sqrt_hs * 1.4426950408889634f;
     for (int idx = tid; idx < PM_ROWS * H4; idx += PM_THREADS) {
         const int r = idx / H4, d4 = idx % H4, b = q0 + r / kv_mul, h = grp * kv_mul + r % kv_mul;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (b < n) v = *reinterpret_cast<const float4 *>(qkv + (size_t)b * ldq + h * HS + d4 * 4);
         uint2 pk;
-        pk.x = pack_h2(v.x * inv_sqrt_hs, v.y * inv_sqrt_hs);
-        pk.y = pack_h2(v.z * inv_sqrt_hs, v.w * inv_sqrt_hs);
+        pk.x = pack_h2(v.x * qscale, v.y * qscale); // scores come out in units of log2: softmax below uses ex2
+        pk.y = pack_h2(v.z * qscale, v.w * qscale);
         *reinterpret_cast<uint2 *>(sQ + r * RP + d4 * 4) = pk;
     }
     __syncthreads();
@@ -361,6 +370,9 @@ __global__ void __launch_bounds__(PM_THREADS) k_pf_attention_mma(const float *__
     const int row0 = warp * 16 + g, row1 = row0 + 8;
     const int tb0 = q0 + row0 / kv_mul, tb1 = q0 + row1 / kv_mul;
     const int qpos0 = tb0 < n ? start_pos + tb0 : -1, qpos1 = tb1 < n ? start_pos + tb1 : -1; // -1: every key masked
+    // smallest position among this warp's 16 rows (-1 when the warp holds padding rows): tiles entirely at or before it need no mask
+    const int wlast_tok = q0 + (warp * 16 + 15) / kv_mul;
+    const int wmin_pos = wlast_tok < n ? start_pos + q0 + (warp * 16) / kv_mul : -1;
 
 #pragma unroll 1
     for (int it = 0; it < ntiles; it++) {
@@ -372,41 +384,55 @@ __global__ void __launch_bounds__(PM_THREADS) k_pf_attention_mma(const float *__
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
-        const __half *sK = sKV + (it & 1) * 2 * PM_KT * RP;
+        const uint32_t sK_addr = sKV_addr + (uint32_t)((it & 1) * 2 * PM_KT * RP * 2);
         const uint32_t sV_addr = sKV_addr + (uint32_t)(((it & 1) * 2 + 1) * PM_KT * RP * 2);
         float s[8][4];
 #pragma unroll
         for (int nb = 0; nb < 8; nb++) s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.0f;
+        {
+            // four 8x8 blocks of K per ldmatrix: (keys nb*8.., d kk*16..), (same keys, d+8), (keys (nb+1)*8.., d), (.., d+8)
+            const uint32_t kaddr0 = sK_addr + (uint32_t)((((lane & 7) + ((lane >> 4) << 3)) * RP + (((lane >> 3) & 1) << 3)) * 2);
 #pragma unroll
-        for (int kk = 0; kk < KS; kk++)
+            for (int kk = 0; kk < KS; kk++)
+#pragma unroll
+                for (int nb = 0; nb < 8; nb += 2) {
+                    uint32_t b0, b1, b2, b3;
+                    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                                 : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3)
+                                 : "r"(kaddr0 + (uint32_t)((nb * 8 * RP + kk * 16) * 2)));
+                    mma_f16_16816(s[nb], qf[kk], b0, b1);
+                    mma_f16_16816(s[nb + 1], qf[kk], b2, b3);
+                }
+        }
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+        if (k0 + PM_KT - 1 > wmin_pos) { // warp-uniform: some key of this tile is ahead of some row of this warp (or a row is padding)
 #pragma unroll
             for (int nb = 0; nb < 8; nb++) {
-                const __half *kp = sK + (nb * 8 + g) * RP + kk * 16 + 2 * t;
-                mma_f16_16816(s[nb], qf[kk], *reinterpret_cast<const uint32_t *>(kp), *reinterpret_cast<const uint32_t *>(kp + 8));
+                const int key = k0 + nb * 8 + 2 * t;
+                if (key > qpos0) s[nb][0] = -INFINITY;
+                if (key + 1 > qpos0) s[nb][1] = -INFINITY;
+                if (key > qpos1) s[nb][2] = -INFINITY;
+                if (key + 1 > qpos1) s[nb][3] = -INFINITY;
             }
-        float mx0 = -INFINITY, mx1 = -INFINITY;
+        }
 #pragma unroll
         for (int nb = 0; nb < 8; nb++) {
-            const int key = k0 + nb * 8 + 2 * t;
-            if (key > qpos0) s[nb][0] = -INFINITY;
-            if (key + 1 > qpos0) s[nb][1] = -INFINITY;
-            if (key > qpos1) s[nb][2] = -INFINITY;
-            if (key + 1 > qpos1) s[nb][3] = -INFINITY;
             mx0 = fmaxf(mx0, fmaxf(s[nb][0], s[nb][1]));
             mx1 = fmaxf(mx1, fmaxf(s[nb][2], s[nb][3]));
         }
         mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
         mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
         const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
-        const bool dead0 = mn0 == -INFINITY, dead1 = mn1 == -INFINITY;
-        const float al0 = dead0 ? 1.0f : expf(m0 - mn0), al1 = dead1 ? 1.0f : expf(m1 - mn1);
+        // a row with nothing visible yet keeps m = -inf: use 0 as the reference so that ex2(-inf - 0) = 0 and alpha = ex2(-inf) = 0 on l = 0
+        const float r0 = mn0 == -INFINITY ? 0.0f : mn0, r1 = mn1 == -INFINITY ? 0.0f : mn1;
+        const float al0 = ex2_approx(m0 - r0), al1 = ex2_approx(m1 - r1);
         float sum0 = 0.0f, sum1 = 0.0f;
 #pragma unroll
         for (int nb = 0; nb < 8; nb++) {
-            s[nb][0] = dead0 ? 0.0f : expf(s[nb][0] - mn0);
-            s[nb][1] = dead0 ? 0.0f : expf(s[nb][1] - mn0);
-            s[nb][2] = dead1 ? 0.0f : expf(s[nb][2] - mn1);
-            s[nb][3] = dead1 ? 0.0f : expf(s[nb][3] - mn1);
+            s[nb][0] = ex2_approx(s[nb][0] - r0);
+            s[nb][1] = ex2_approx(s[nb][1] - r0);
+            s[nb][2] = ex2_approx(s[nb][2] - r1);
+            s[nb][3] = ex2_approx(s[nb][3] - r1);
             sum0 += s[nb][0] + s[nb][1];
             sum1 += s[nb][2] + s[nb][3];
         }

@@ -411,3 +411,23 @@ __global__ void k_repack_tiles(RepackSrc src, unsigned char *dst, int rows, int 
         reinterpret_cast<unsigned short *>(u)[w] = v;
     }
 }
+
+// ---- inverse of the repack: tile-major Q8_0 stream -> row-major f16 matrix (value = f16(q * scale)) ----------------
+// One CTA per unit (group G, segment s, slot r).  Plain matrices: row 4G + r of out0.  Gate/up stream: slots 0,1 are
+// gate rows 2G, 2G+1 (out0), slots 2,3 the up rows (out1).
+__global__ void k_tiles_to_f16(TileMat W, int gateup, __half *__restrict__ out0, __half *__restrict__ out1) {
+    const long long unit_id = blockIdx.x;
+    const int r = (int)(unit_id % 4);
+    const int s = (int)((unit_id / 4) % W.nseg);
+    const long long G = unit_id / (4LL * W.nseg);
+    __half *out = gateup && (r >> 1) ? out1 : out0;
+    const long long row = gateup ? 2 * G + (r & 1) : 4 * G + r;
+    const unsigned char *u = W.base + (size_t)unit_id * W.unit_bytes;
+    const __half *sc = reinterpret_cast<const __half *>(u + W.seg);
+    __half2 *dst = reinterpret_cast<__half2 *>(out + (size_t)row * W.cols + (size_t)s * W.seg);
+    for (int i = threadIdx.x; i < W.seg / 2; i += blockDim.x) {
+        const unsigned short w = reinterpret_cast<const unsigned short *>(u)[i];
+        const float f = __half2float(sc[i >> 4]);
+        dst[i] = __floats2half2_rn((float)(signed char)(w & 0xFF) * f, (float)(signed char)(w >> 8) * f);
+    }
+}

@@ -83,6 +83,7 @@ def test_batch_prefill_matches_oracle(pkg, orc, make_model):
     m = make_model("tiny-llama", pkg.gguf.GGMLType.Q8_0, 32)
     c = m.configuration
     plan = pkg.B200MasterPlan.initialize_plan(m, prefill_batch_size=8)
+    plan.set_prefill_mode("exact")  # the token-by-token graph; the tensor-core mode is covered by test_gpu_prefill.py
     om = orc.OracleModel(m)
     stream = orc.bench_tokens(c.vocab_size, 20)
     for off in range(0, 16, 8):
@@ -138,6 +139,7 @@ def test_generation_loops_match_oracle(pkg, orc, make_model):
 def test_batch_prefill_generation_loop(pkg, orc, make_model):
     m = make_model("tiny-llama", pkg.gguf.GGMLType.Q8_0, 32)
     plan = pkg.B200MasterPlan.initialize_plan(m, prefill_batch_size=4)
+    plan.set_prefill_mode("exact")
     om = orc.OracleModel(m)
     prompt = [int(t) for t in orc.bench_tokens(m.configuration.vocab_size, 7)]
     got = pkg.engine.generate_tokens_llama_batch_prefill(plan, prompt[0], prompt, [], 20, 32, 4)

@@ -19,10 +19,12 @@ for shape in shapes:
     n_tok, batch = (160, 128) if shape.startswith("mid") else (50, 32)
     ctx = n_tok + 8
     sh = pkg.synth.SHAPES[shape]
-    F16 = pkg.gguf.GGMLType.F16
+    F16 = pkg.gguf.GGMLType.Q8_0 if os.environ.get("PREFILL_QUANT") == "q8" else pkg.gguf.GGMLType.F16
     m = pkg.loader.model_from_tensors(sh, F16, pkg.synth.build_tensors_fast(sh, F16, seed=1234), ctx)
     c = m.configuration
     plan = pkg.B200MasterPlan.initialize_plan(m, prefill_batch_size=batch)
+    if os.environ.get("PREFILL_QUANT") == "q8":
+        plan.set_prefill_mode("tensor_core")
     mode = plan.prefill_info()[0]
     toks = orc.bench_tokens(c.vocab_size, n_tok + 1)
     t0 = time.time()
@@ -55,4 +57,4 @@ for shape in shapes:
     out.append(rec)
     plan.free()
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump(out, open("gpurun_out/prefill_check.json", "w"), indent=1)
+json.dump(out, open("gpurun_out/prefill_check%s.json" % ("_q8" if os.environ.get("PREFILL_QUANT") == "q8" else ""), "w"), indent=1)
