@@ -688,7 +688,7 @@ int prefill_init(b200_plan *p) {
     if (kv_mul > 64 || (kv_mul & (kv_mul - 1))) { c.why = "tensor-core prefill needs a power-of-two GQA ratio <= 64"; return B200_OK; }
     if (g.dim % 128 || p->qd % 128 || nqkv % 128 || g.hidden_dim % 64) { c.why = "tensor-core prefill needs dim, q width and q+k+v width multiples of 128, hidden a multiple of 64"; return B200_OK; }
     if (!pg::encode_fn()) { c.why = "cuTensorMapEncodeTiled not available from the driver"; return B200_OK; }
-    c.bpad = (c.batch + 255) / 256 * 256; // whole CTA-pair tiles
+    c.bpad = (c.batch + 511) / 512 * 512; // whole units of the widest GEMM tiling (two 256-row CTA-pair tiles)
     int rc;
     if ((rc = dalloc(p, &c.X, (size_t)c.bpad * g.dim * 4))) return rc;
     if ((rc = dalloc(p, &c.QKV, (size_t)c.bpad * nqkv * 4))) return rc;
@@ -781,7 +781,11 @@ int prefill_forward(b200_plan *p, int n, int start_pos, int *launches) {
     auto one_wave = [&](int n_tiles) { return mt * n_tiles <= p->n_sms; };
     // CTA-pair path: M in 256-row pair tiles; the x += A W^T GEMMs (N = dim only) split K so that the grid fills the SMs --
     // every split reduce-adds its partial product through TMA
-    const int mt2 = (n + 255) / 256 * 2;
+    const int mt2 = (n + 255) / 256 * 2, mt4 = (n + 511) / 512 * 4;
+    // gate/up (the one multi-wave GEMM): two pair tiles of M per CTA pair, so every weight tile is fetched once per 512 rows and
+    // the per-CTA prologue/epilogue is paid half as often (measured 108 vs 114 us at B = 512; for the one-wave split-K GEMMs the
+    // wider tile only lowers the CTA count -- measured slower -- so they keep one pair tile per pair)
+    const bool wide = n > 256;
     auto pair_splits = [&](int n_tiles, int K) {
         const int ctas = mt2 * n_tiles, nk = K / pg::BK;
         int sp = p->n_sms / ctas;
@@ -820,7 +824,8 @@ int prefill_forward(b200_plan *p, int n, int start_pos, int *launches) {
         }
         nl += 2;
         if (c.pair) {
-            if (pg::gemm2_launch<pg::GEMM_RESID, 256, pg::GEMM2_STAGES_256>(c.mATT, m.wo, m.wo, c.mX, c.X, g.dim, n, mt2, g.dim / 256, p->qd, s, pair_splits(g.dim / 256, p->qd))) return fail(p, B200_ERR_CUDA, "Wo GEMM launch failed");
+            if (pg::gemm2_launch<pg::GEMM_RESID, 256, pg::GEMM2_STAGES_256>(c.mATT, m.wo, m.wo, c.mX, c.X, g.dim, n, mt2, g.dim / 256, p->qd, s, pair_splits(g.dim / 256, p->qd)))
+                return fail(p, B200_ERR_CUDA, "Wo GEMM launch failed");
         } else
         if (one_wave(g.dim / pg::BN) ? pg::gemm_launch<pg::GEMM_RESID, DEEP>(c.mATT, m.wo, m.wo, c.mX, c.X, g.dim, n, mt, g.dim / pg::BN, p->qd, s)
                                      : pg::gemm_launch<pg::GEMM_RESID, ST>(c.mATT, m.wo, m.wo, c.mX, c.X, g.dim, n, mt, g.dim / pg::BN, p->qd, s))
@@ -828,14 +833,17 @@ int prefill_forward(b200_plan *p, int n, int start_pos, int *launches) {
         nl++;
         k_pf_rmsnorm_f16<<<n, 256, 0, s>>>(c.X, L.ffn_norm, g.rms_norm_eps, g.dim, c.A16); nl++;
         if (c.pair) {
-            if (pg::gemm2_launch<pg::GEMM_GATEUP, 256, pg::GEMM2_STAGES_256>(c.mA, m.w1p, m.w3p, c.mX, c.H16, g.hidden_dim, n, mt2, g.hidden_dim / 128, g.dim, s)) return fail(p, B200_ERR_CUDA, "gate/up GEMM launch failed");
+            if (wide ? pg::gemm2_launch<pg::GEMM_GATEUP, 256, pg::GEMM2_STAGES_256_M2, 2>(c.mA, m.w1p, m.w3p, c.mX, c.H16, g.hidden_dim, n, mt4, g.hidden_dim / 128, g.dim, s)
+                     : pg::gemm2_launch<pg::GEMM_GATEUP, 256, pg::GEMM2_STAGES_256>(c.mA, m.w1p, m.w3p, c.mX, c.H16, g.hidden_dim, n, mt2, g.hidden_dim / 128, g.dim, s))
+                return fail(p, B200_ERR_CUDA, "gate/up GEMM launch failed");
         } else
         if (one_wave(g.hidden_dim / (pg::BN / 2)) ? pg::gemm_launch<pg::GEMM_GATEUP, DEEP>(c.mA, m.w1, m.w3, c.mX, c.H16, g.hidden_dim, n, mt, g.hidden_dim / (pg::BN / 2), g.dim, s)
                                                   : pg::gemm_launch<pg::GEMM_GATEUP, ST>(c.mA, m.w1, m.w3, c.mX, c.H16, g.hidden_dim, n, mt, g.hidden_dim / (pg::BN / 2), g.dim, s))
             return fail(p, B200_ERR_CUDA, "gate/up GEMM launch failed");
         nl++;
         if (c.pair) {
-            if (pg::gemm2_launch<pg::GEMM_RESID, 256, pg::GEMM2_STAGES_256>(c.mH, m.w2, m.w2, c.mX, c.X, g.dim, n, mt2, g.dim / 256, g.hidden_dim, s, pair_splits(g.dim / 256, g.hidden_dim))) return fail(p, B200_ERR_CUDA, "W2 GEMM launch failed");
+            if (pg::gemm2_launch<pg::GEMM_RESID, 256, pg::GEMM2_STAGES_256>(c.mH, m.w2, m.w2, c.mX, c.X, g.dim, n, mt2, g.dim / 256, g.hidden_dim, s, pair_splits(g.dim / 256, g.hidden_dim)))
+                return fail(p, B200_ERR_CUDA, "W2 GEMM launch failed");
         } else
         if (one_wave(g.dim / pg::BN) ? pg::gemm_launch<pg::GEMM_RESID, DEEP>(c.mH, m.w2, m.w2, c.mX, c.X, g.dim, n, mt, g.dim / pg::BN, g.hidden_dim, s)
                                      : pg::gemm_launch<pg::GEMM_RESID, ST>(c.mH, m.w2, m.w2, c.mX, c.X, g.dim, n, mt, g.dim / pg::BN, g.hidden_dim, s))

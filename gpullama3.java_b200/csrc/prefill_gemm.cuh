@@ -257,15 +257,22 @@ __device__ __forceinline__ void umma_commit_2cta(uint32_t bar) { // arrives on t
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
 }
 
-template <int BN, int STAGES> constexpr size_t smem_bytes_2cta() { return (size_t)STAGES * (BM * BK * 2 + (BN / 2) * BK * 2) + (2 * STAGES + 1) * 8 + 16 + 1024; }
+// MT = 256-row pair tiles of M that one CTA pair computes against the SAME B tile (MT x BN TMEM columns): with MT = 2 a
+// 512-token chunk re-uses every weight tile for all its rows, so an SM ingests 32 + BN/4 KB per 2 x 128 x BN x 64 MACs
+// (170 FLOP/B at BN = 256 -- tensor-pipe bound instead of L2-ingest bound) and the fixed prologue/epilogue is paid once.
+template <int BN, int STAGES, int MT> constexpr size_t smem_bytes_2cta() {
+    return (size_t)STAGES * (MT * BM * BK * 2 + (BN / 2) * BK * 2) + (2 * STAGES + 1) * 8 + 16 + 1024;
+}
 
-template <int MODE, int BN, int STAGES>
+template <int MODE, int BN, int STAGES, int MT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
     k_gemm_f16_2cta(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_b2,
                     const __grid_constant__ CUtensorMap tma_c, void *__restrict__ Cv, int ldc, int m_valid, int K, int kb_per_split) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    constexpr int A_BYTES = BM * BK * 2, B_BYTES = (BN / 2) * BK * 2; // per CTA and stage
+    constexpr int A1_BYTES = BM * BK * 2, A_BYTES = MT * A1_BYTES, B_BYTES = (BN / 2) * BK * 2; // per CTA and stage
+    constexpr int TCOLS = MT * BN;
+    static_assert(TCOLS == 128 || TCOLS == 256 || TCOLS == 512, "TMEM allocations are powers of two");
     static_assert(STAGES * (A_BYTES + B_BYTES) >= BM * BN * 4, "the C tile is staged in the operand ring");
     uint8_t *sA = smem, *sB = smem + STAGES * A_BYTES;
     uint64_t *bars = reinterpret_cast<uint64_t *>(sB + STAGES * B_BYTES);
@@ -280,7 +287,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) { // the same warp of both CTAs allocates the pair's accumulator columns
-        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)), "r"((uint32_t)BN) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)), "r"((uint32_t)TCOLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -290,18 +297,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
     // split-K (GEMM_RESID only: every split reduce-adds its partial product into x): blockIdx.z owns k-blocks [kb0, kb0 + nk)
     const int nk_all = (K + BK - 1) / BK, kb0 = blockIdx.z * kb_per_split;
     const int nk = nk_all - kb0 < kb_per_split ? nk_all - kb0 : kb_per_split;
-    const int m0 = blockIdx.x * BM;
+    // rows of this CTA in pair tile mt: m_base + mt * 256 + rank * 128 .. + 127
+    const int m_base = (int)(blockIdx.x >> 1) * (MT * 2 * BM) + (int)rank * BM;
     const int n0 = blockIdx.y * (MODE == GEMM_GATEUP ? BN / 2 : BN);
 
     if (warp == 0 && lane == 0) {
-        // ===== TMA producer (both CTAs): own A rows, own half of the B tile =====
+        // ===== TMA producer (both CTAs): own A rows of every pair tile, own half of the B tile =====
         const CUtensorMap *bmap = (MODE == GEMM_GATEUP && rank == 1) ? &tma_b2 : &tma_b;
         const int brow = MODE == GEMM_GATEUP ? n0 : n0 + (int)rank * (BN / 2);
         for (int kb = 0; kb < nk; kb++) {
             const int st = kb % STAGES;
             mbar_wait(empty0 + 8 * st, ((kb / STAGES) & 1) ^ 1);
             if (rank == 0) mbar_expect_tx(full0 + 8 * st, 2 * (A_BYTES + B_BYTES));
-            tma_load_2d_2sm(s32(sA + st * A_BYTES), &tma_a, (kb0 + kb) * BK, m0, full0 + 8 * st);
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++)
+                tma_load_2d_2sm(s32(sA + st * A_BYTES + mt * A1_BYTES), &tma_a, (kb0 + kb) * BK, m_base + mt * 2 * BM, full0 + 8 * st);
             tma_load_2d_2sm(s32(sB + st * B_BYTES), bmap, (kb0 + kb) * BK, brow, full0 + 8 * st);
         }
     } else if (warp == 1 && lane == 0 && rank == 0) {
@@ -311,85 +321,95 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
             const int st = kb % STAGES;
             mbar_wait(full0 + 8 * st, (kb / STAGES) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint64_t da = umma_desc_sw128(s32(sA + st * A_BYTES)), db = umma_desc_sw128(s32(sB + st * B_BYTES));
+            const uint64_t db = umma_desc_sw128(s32(sB + st * B_BYTES));
 #pragma unroll
-            for (int k = 0; k < BK / 16; k++) umma_f16_2cta(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int mt = 0; mt < MT; mt++) {
+                const uint64_t da = umma_desc_sw128(s32(sA + st * A_BYTES + mt * A1_BYTES));
+#pragma unroll
+                for (int k = 0; k < BK / 16; k++) umma_f16_2cta(tmem_base + (uint32_t)(mt * BN), da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
             umma_commit_2cta(empty0 + 8 * st);
         }
         umma_commit_2cta(tmem_full);
     }
     __syncwarp(); // the elected producer / MMA lanes rejoin their warps
     {
-        // ===== epilogue (both CTAs, own 128 rows): all 8 warps -- warp w reads TMEM lanes 32*(w%4).., warps 0-3 take the
-        // first half of the columns and warps 4-7 the second =====
+        // ===== epilogue (both CTAs, own 128 rows of each pair tile): all 8 warps -- warp w reads TMEM lanes 32*(w%4).., warps 0-3
+        // take the first half of the columns and warps 4-7 the second =====
         mbar_wait(tmem_full, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int q = warp & 3, half = warp >> 2;
-        const int row = m0 + q * 32 + lane;
-        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
-        if (MODE == GEMM_GATEUP) {
-            __half *C = reinterpret_cast<__half *>(Cv);
 #pragma unroll 1
-            for (int c0 = half * (BN / 4); c0 < (half + 1) * (BN / 4); c0 += 32) {
-                uint32_t g[32], u[32];
-                tmem_ld32(tlane + (uint32_t)c0, g);
-                tmem_ld32(tlane + (uint32_t)(BN / 2 + c0), u);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (row < m_valid) {
-                    uint4 *dst = reinterpret_cast<uint4 *>(C + (size_t)row * ldc + n0 + c0);
+        for (int mt = 0; mt < MT; mt++) {
+            const int m0 = m_base + mt * 2 * BM;
+            const int row = m0 + q * 32 + lane;
+            const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * BN);
+            if (MODE == GEMM_GATEUP) {
+                __half *C = reinterpret_cast<__half *>(Cv);
+#pragma unroll 1
+                for (int c0 = half * (BN / 4); c0 < (half + 1) * (BN / 4); c0 += 32) {
+                    uint32_t g[32], u[32];
+                    tmem_ld32(tlane + (uint32_t)c0, g);
+                    tmem_ld32(tlane + (uint32_t)(BN / 2 + c0), u);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (row < m_valid) {
+                        uint4 *dst = reinterpret_cast<uint4 *>(C + (size_t)row * ldc + n0 + c0);
 #pragma unroll
-                    for (int v = 0; v < 4; v++) {
-                        uint32_t w[4];
+                        for (int v = 0; v < 4; v++) {
+                            uint32_t w[4];
 #pragma unroll
-                        for (int e = 0; e < 4; e++) {
-                            const float g0 = __uint_as_float(g[8 * v + 2 * e]), g1 = __uint_as_float(g[8 * v + 2 * e + 1]);
-                            const float h0 = (g0 / (1.0f + expf(-g0))) * __uint_as_float(u[8 * v + 2 * e]);
-                            const float h1 = (g1 / (1.0f + expf(-g1))) * __uint_as_float(u[8 * v + 2 * e + 1]);
-                            const __half2 hh = __floats2half2_rn(h0, h1);
-                            w[e] = *reinterpret_cast<const uint32_t *>(&hh);
+                            for (int e = 0; e < 4; e++) {
+                                const float g0 = __uint_as_float(g[8 * v + 2 * e]), g1 = __uint_as_float(g[8 * v + 2 * e + 1]);
+                                const float h0 = (g0 / (1.0f + expf(-g0))) * __uint_as_float(u[8 * v + 2 * e]);
+                                const float h1 = (g1 / (1.0f + expf(-g1))) * __uint_as_float(u[8 * v + 2 * e + 1]);
+                                const __half2 hh = __floats2half2_rn(h0, h1);
+                                w[e] = *reinterpret_cast<const uint32_t *>(&hh);
+                            }
+                            dst[v] = make_uint4(w[0], w[1], w[2], w[3]);
                         }
-                        dst[v] = make_uint4(w[0], w[1], w[2], w[3]);
                     }
                 }
-            }
-        } else {
-            const int rloc = q * 32 + lane;
+            } else {
+                if (m0 >= m_valid) break; // CTA-uniform: nothing of this (and any later) pair tile is stored
+                const int rloc = q * 32 + lane;
 #pragma unroll 1
-            for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); c++) {
-                uint32_t r[32];
-                tmem_ld32(tlane + (uint32_t)(c * 32), r);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                uint8_t *buf = smem + c * (BM * 32 * 4) + rloc * 128;
+                for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); c++) {
+                    uint32_t r[32];
+                    tmem_ld32(tlane + (uint32_t)(c * 32), r);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    uint8_t *buf = smem + c * (BM * 32 * 4) + rloc * 128;
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    uint4 o = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-                    if (row >= m_valid) o = make_uint4(0u, 0u, 0u, 0u);
-                    *reinterpret_cast<uint4 *>(buf + ((j ^ (rloc & 7)) << 4)) = o;
+                    for (int j = 0; j < 8; j++) {
+                        uint4 o = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                        if (row >= m_valid) o = make_uint4(0u, 0u, 0u, 0u);
+                        *reinterpret_cast<uint4 *>(buf + ((j ^ (rloc & 7)) << 4)) = o;
+                    }
                 }
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncthreads();
-            if (threadIdx.x == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncthreads();
+                if (threadIdx.x == 0) {
 #pragma unroll
-                for (int c = 0; c < BN / 32; c++) {
-                    const uint32_t src = s32(smem + c * (BM * 32 * 4));
-                    if (MODE == GEMM_RESID)
-                        asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tma_c), "r"(src),
-                                     "r"(n0 + c * 32), "r"(m0)
-                                     : "memory");
-                    else
-                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tma_c), "r"(src), "r"(n0 + c * 32),
-                                     "r"(m0)
-                                     : "memory");
+                    for (int c = 0; c < BN / 32; c++) {
+                        const uint32_t src = s32(smem + c * (BM * 32 * 4));
+                        if (MODE == GEMM_RESID)
+                            asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tma_c), "r"(src),
+                                         "r"(n0 + c * 32), "r"(m0)
+                                         : "memory");
+                        else
+                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tma_c), "r"(src),
+                                         "r"(n0 + c * 32), "r"(m0)
+                                         : "memory");
+                    }
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); // also frees the staging buffer for the next pair tile
                 }
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                if (MT > 1) __syncthreads();
             }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     cluster_sync_all(); // neither CTA may exit (or free TMEM) while the pair can still touch its shared memory / TMEM
-    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TCOLS) : "memory");
 }
 
 // ---- host side ----
@@ -445,22 +465,24 @@ inline int gemm_launch(const CUtensorMap &a, const CUtensorMap &b, const CUtenso
     return cudaGetLastError() == cudaSuccess ? 0 : -5;
 }
 
-// m_tiles must be even (M padded to 256).  B maps must have box rows = BN / 2.
-template <int MODE, int BN, int STAGES>
+// m_tiles = 128-row tiles of M, a multiple of 2 * MT (M padded to MT * 256).  B maps must have box rows = BN / 2.
+template <int MODE, int BN, int STAGES, int MT = 1>
 inline int gemm2_launch(const CUtensorMap &a, const CUtensorMap &b, const CUtensorMap &b2, const CUtensorMap &c, void *C, int ldc, int m_valid, int m_tiles,
                         int n_tiles, int K, cudaStream_t stream, int splits = 1) {
     static bool attr = false;
     if (!attr) {
-        if (cudaFuncSetAttribute(k_gemm_f16_2cta<MODE, BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_2cta<BN, STAGES>()) != cudaSuccess) return -4;
+        if (cudaFuncSetAttribute(k_gemm_f16_2cta<MODE, BN, STAGES, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_2cta<BN, STAGES, MT>()) != cudaSuccess)
+            return -4;
         attr = true;
     }
-    if ((m_tiles & 1) || splits < 1 || (splits > 1 && MODE != GEMM_RESID)) return -6;
+    if (m_tiles % (2 * MT) || splits < 1 || (splits > 1 && MODE != GEMM_RESID)) return -6;
     const int nk = (K + BK - 1) / BK, per = (nk + splits - 1) / splits;
     if ((splits - 1) * per >= nk) return -6; // an empty split would publish an unwritten accumulator
-    k_gemm_f16_2cta<MODE, BN, STAGES><<<dim3(m_tiles, n_tiles, splits), 256, smem_bytes_2cta<BN, STAGES>(), stream>>>(a, b, b2, c, C, ldc, m_valid, K, per);
+    k_gemm_f16_2cta<MODE, BN, STAGES, MT><<<dim3(m_tiles / MT, n_tiles, splits), 256, smem_bytes_2cta<BN, STAGES, MT>(), stream>>>(a, b, b2, c, C, ldc, m_valid, K, per);
     return cudaGetLastError() == cudaSuccess ? 0 : -5;
 }
 constexpr int GEMM2_STAGES_256 = 6, GEMM2_STAGES_128 = 8; // 192 KB of operand ring per CTA either way
+constexpr int GEMM2_STAGES_256_M2 = 4;                    // 4 x (32 KB of A + 16 KB of B)
 
 // 3 stages of 32 KB: two CTAs fit one SM (2 x 99 KB shared memory, 2 x 128 TMEM columns), so one CTA's
 // epilogue overlaps the other's main loop.
@@ -472,10 +494,16 @@ inline int gemm_f16(const __half *A, const __half *B, float *C, int M, int N, in
     CUtensorMap ma, mb, mc;
     int rc;
     if (two_cta) { // two_cta = pair-tile width (256 or 128)
-        if (M % 256 || N % two_cta) return -3;
+        const int bn = two_cta == 512 ? 256 : two_cta;
+        if (M % 256 || N % bn) return -3;
         if ((rc = make_map(&ma, A, (uint64_t)M, (uint64_t)K, BM))) return rc;
-        if ((rc = make_map(&mb, B, (uint64_t)N, (uint64_t)K, two_cta / 2))) return rc;
+        if ((rc = make_map(&mb, B, (uint64_t)N, (uint64_t)K, bn / 2))) return rc;
         if ((rc = make_map_c(&mc, C, (uint64_t)M, (uint64_t)N))) return rc;
+        if (two_cta == 512) { // 256-wide pair tiles, two of them (512 rows) per CTA pair
+            if (M % 512) return -3;
+            return resid ? gemm2_launch<GEMM_RESID, 256, GEMM2_STAGES_256_M2, 2>(ma, mb, mb, mc, C, N, M, M / BM, N / 256, K, stream, resid)
+                         : gemm2_launch<GEMM_F32, 256, GEMM2_STAGES_256_M2, 2>(ma, mb, mb, mc, C, N, M, M / BM, N / 256, K, stream);
+        }
         if (two_cta == 256)
             return resid ? gemm2_launch<GEMM_RESID, 256, GEMM2_STAGES_256>(ma, mb, mb, mc, C, N, M, M / BM, N / 256, K, stream, resid)
                          : gemm2_launch<GEMM_F32, 256, GEMM2_STAGES_256>(ma, mb, mb, mc, C, N, M, M / BM, N / 256, K, stream);
