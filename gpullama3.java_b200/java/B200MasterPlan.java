@@ -52,6 +52,11 @@ public final class B200MasterPlan implements AutoCloseable {
     private static final MethodHandle DECODE = fn("b200_forward_decode", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS, ADDRESS));
     private static final MethodHandle PREFILL = fn("b200_forward_prefill", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT));
     private static final MethodHandle BATCH_PREFILL = fn("b200_forward_batch_prefill", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT));
+    private static final MethodHandle SET_PREFILL_MODE = fn("b200_set_prefill_mode", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT));
+    private static final MethodHandle DECODE_SEQUENCE = fn("b200_decode_sequence",
+            FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT, JAVA_INT, ADDRESS, ADDRESS));
+    private static final MethodHandle TP_HANDLE = fn("b200_tp_handle", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
+    private static final MethodHandle TP_ATTACH = fn("b200_tp_attach", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT));
     private static final MethodHandle KV_RESET = fn("b200_kv_reset", FunctionDescriptor.of(JAVA_INT, ADDRESS));
     private static final MethodHandle FREE = fn("b200_plan_free", FunctionDescriptor.ofVoid(ADDRESS));
     private static final MethodHandle LAST_ERROR = fn("b200_last_error", FunctionDescriptor.of(ADDRESS, ADDRESS));
@@ -63,6 +68,11 @@ public final class B200MasterPlan implements AutoCloseable {
 
     /** TornadoVMMasterPlan.initializeTornadoVMPlan(state, model): tensors are the plain mmap slices of GGUF.loadTensorsStandard. */
     public B200MasterPlan(State state, Model model, Map<String, GGMLTensorEntry> tensors, int archId, int headSize) throws Throwable {
+        this(state, model, tensors, archId, headSize, 0, 1);
+    }
+
+    /** One plan per GPU for tensor-parallel decode: every rank passes the same tensors, the library uploads its row slices. */
+    public B200MasterPlan(State state, Model model, Map<String, GGMLTensorEntry> tensors, int archId, int headSize, int tpRank, int tpSize) throws Throwable {
         Configuration c = model.configuration();
         MemorySegment cfg = arena.allocate(CONFIG);
         int[] ints = {archId, c.dim(), c.hiddenDim(), c.numberOfLayers(), c.numberOfHeads(), c.numberOfKeyValueHeads(), headSize,
@@ -71,8 +81,8 @@ public final class B200MasterPlan implements AutoCloseable {
         cfg.set(JAVA_FLOAT, 36, c.rmsNormEps());
         cfg.set(JAVA_FLOAT, 40, c.ropeTheta());
         cfg.set(JAVA_INT, 44, Integer.getInteger("llama.VectorBitSize", 512) / 32); // FloatTensor.java:21
-        cfg.set(JAVA_INT, 48, 0);
-        cfg.set(JAVA_INT, 52, 1);
+        cfg.set(JAVA_INT, 48, tpRank);
+        cfg.set(JAVA_INT, 52, tpSize);
 
         MemorySegment arr = arena.allocate(TENSOR, tensors.size());
         int i = 0;
@@ -89,7 +99,7 @@ public final class B200MasterPlan implements AutoCloseable {
         MemorySegment out = arena.allocate(ADDRESS);
         MemorySegment err = arena.allocate(512);
         int batch = TornadoVMMasterPlan.WITH_PREFILL_DECODE ? TornadoVMMasterPlan.PREFILL_BATCH_SIZE : 0;
-        int rc = (int) CREATE.invokeExact(cfg, arr, tensors.size(), batch, Integer.getInteger("b200.device", 0), out, err, 512L);
+        int rc = (int) CREATE.invokeExact(cfg, arr, tensors.size(), batch, Integer.getInteger("b200.device", tpRank), out, err, 512L);
         check(rc, err.getString(0));
         plan = out.get(ADDRESS, 0);
         logits = arena.allocate(JAVA_FLOAT, c.vocabularySize());
@@ -131,6 +141,42 @@ public final class B200MasterPlan implements AutoCloseable {
     public void forwardBatchPrefill(int[] tokens, int startPos) throws Throwable {
         try (Arena a = Arena.ofConfined()) {
             int rc = (int) BATCH_PREFILL.invokeExact(plan, a.allocateFrom(JAVA_INT, tokens), tokens.length, startPos);
+            if (rc != 0) check(rc, lastError());
+        }
+    }
+
+    /** TensorCoreSupport.java's switch: 0 = exact token-by-token prefill (bit-identical KV cache), 1 = TMA + tcgen05 GEMMs. */
+    public void setPrefillMode(int mode) throws Throwable {
+        int rc = (int) SET_PREFILL_MODE.invokeExact(plan, mode);
+        if (rc != 0) check(rc, lastError());
+    }
+
+    /** The greedy loop of InferenceEngine.generateTokensGPULlama with sampler and token feedback on the device (feedback = true),
+     *  or LlamaBench's teacher-forced loop (feedback = false): n steps from startPos, returns the argmax of every step. */
+    public int[] decodeSequence(int[] tokens, int n, int startPos, boolean feedback) throws Throwable {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment ids = a.allocate(JAVA_INT, n);
+            int rc = (int) DECODE_SEQUENCE.invokeExact(plan, a.allocateFrom(JAVA_INT, tokens), n, startPos, feedback ? 1 : 0, ids, MemorySegment.NULL);
+            if (rc != 0) check(rc, lastError());
+            return ids.toArray(JAVA_INT);
+        }
+    }
+
+    /** 64-byte CUDA-IPC handle of this rank's communication buffer; exchange with the other ranks, then attach(all handles in rank order). */
+    public byte[] tpHandle() throws Throwable {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment h = a.allocate(64);
+            int rc = (int) TP_HANDLE.invokeExact(plan, h);
+            if (rc != 0) check(rc, lastError());
+            return h.toArray(java.lang.foreign.ValueLayout.JAVA_BYTE);
+        }
+    }
+
+    public void tpAttach(byte[][] handles) throws Throwable {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment all = a.allocate(64L * handles.length);
+            for (int r = 0; r < handles.length; r++) MemorySegment.copy(handles[r], 0, all, java.lang.foreign.ValueLayout.JAVA_BYTE, 64L * r, 64);
+            int rc = (int) TP_ATTACH.invokeExact(plan, all, handles.length);
             if (rc != 0) check(rc, lastError());
         }
     }
