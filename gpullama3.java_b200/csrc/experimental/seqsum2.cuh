@@ -1,0 +1,206 @@
+// seqsum2.cuh -- ROUND-2 CANDIDATE, not compiled into libb200llama.so yet (GPU budget of round 1 was spent; the algorithm is
+// validated on the CPU by tools/seqsum2/proto.c, this CUDA version is compile-checked only: tools/seqsum2/harness.cu runs it
+// against the literal loop on a GPU).
+//
+// Same contract as block_seqsum_exact (seqsum.cuh): the bit-exact value of  s = 0; for (i) s = s + t[i]  for non-negative
+// float terms (InferenceCore.rmsnorm's accumulator, InferenceCore.java:39-48), evaluated by one CTA.  Where the round-1
+// kernel works in 32-term groups with per-warp ordered composition, entry lists and a literal first quarter (~16 us at
+// n = 4096, a third of the decode step), this version is three block-wide scans and a ~25-item serial walk:
+//   1. float prefix P over per-thread sums (E consecutive terms per thread)            -> predicted binade per thread
+//   2. a thread whose P range lies well inside one binade composes its E steps  M -> M + a[M & 1]  (seqsum.cuh: SeqPair)
+//      into one pair ("clean"); any other thread is "literal"
+//   3. segmented scan of the pairs over runs of clean threads with equal binade          (pairs compose associatively)
+//   4. item list (ballot/popc compaction): one item per literal thread and one per run
+//   5. one thread walks the items: literal = E real float adds; run = verify (exponent on entry, mantissa < 2^24 on
+//      exit) and add the integer; a failed check replays the run literally.  Predictions decide speed, never the result.
+// CPU model (20000 adversarial cases, n = 2048/4096/8192): 0 mismatches, ~3 head threads + ~24 items per sum.
+#pragma once
+#include "../seqsum.cuh"
+
+#define SEQSUM2_THREADS 1024
+#define SEQSUM2_MAXE 8           // terms per thread: n <= 8192
+#define SEQSUM2_LITERAL INT_MIN
+
+struct SeqItem {
+    int cls;          // SEQSUM2_LITERAL or the binade of a run
+    unsigned a0, a1;  // the run's composed pair
+    int last;         // thread that closes the item (its own id for a literal thread)
+};
+
+struct SeqSum2Scratch {
+    float *wsum;      // [32] warp totals -> exclusive warp prefixes
+    SeqPair *wtail;   // [32] pair of the run that is open at the end of each warp
+    int *wtail_f;     // [32] 1: that run started inside the warp
+    int *wcls_last;   // [32] class of the warp's last thread
+    int *wcls_first;  // [32] class of the warp's first thread
+    int *wcnt;        // [32] items per warp -> exclusive offsets
+    int *cls;         // [T]  class per thread (fallback walks back over it)
+    SeqItem *items;   // [T]
+    float *result;    // [1]
+    int *info;        // [2] {items, fallbacks}
+};
+__host__ __device__ inline size_t seqsum2_scratch_bytes() {
+    return 32 * 4 + 32 * sizeof(SeqPair) + 4 * 32 * 4 + SEQSUM2_THREADS * 4 + SEQSUM2_THREADS * sizeof(SeqItem) + 16 + 16;
+}
+__device__ __forceinline__ SeqSum2Scratch seqsum2_carve(unsigned char *p) { // p 16-byte aligned
+    SeqSum2Scratch s;
+    s.items = reinterpret_cast<SeqItem *>(p); p += SEQSUM2_THREADS * sizeof(SeqItem);
+    s.wtail = reinterpret_cast<SeqPair *>(p); p += 32 * sizeof(SeqPair);
+    s.cls = reinterpret_cast<int *>(p); p += SEQSUM2_THREADS * 4;
+    s.wsum = reinterpret_cast<float *>(p); p += 32 * 4;
+    s.wtail_f = reinterpret_cast<int *>(p); p += 32 * 4;
+    s.wcls_last = reinterpret_cast<int *>(p); p += 32 * 4;
+    s.wcls_first = reinterpret_cast<int *>(p); p += 32 * 4;
+    s.wcnt = reinterpret_cast<int *>(p); p += 32 * 4;
+    s.result = reinterpret_cast<float *>(p); p += 16;
+    s.info = reinterpret_cast<int *>(p);
+    return s;
+}
+
+// Segmented inclusive scan step set over one warp: f = 1 when the run containing this lane starts inside the covered range.
+__device__ __forceinline__ void seq2_warp_segscan(SeqPair &p, int &f, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned u0 = __shfl_up_sync(0xffffffffu, p.a0, d), u1 = __shfl_up_sync(0xffffffffu, p.a1, d);
+        const int fu = __shfl_up_sync(0xffffffffu, f, d);
+        if (lane >= d && !f) {
+            SeqPair L;
+            L.a0 = u0; L.a1 = u1;
+            p = seq_compose(L, p);
+            f = fu;
+        }
+    }
+}
+
+// sq: n terms in shared memory, padded with zeros up to SEQSUM2_THREADS * E.  All SEQSUM2_THREADS threads call this.
+__device__ float block_seqsum_exact_v2(const float *sq, int n, SeqSum2Scratch sc) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int E = (n + SEQSUM2_THREADS - 1) / SEQSUM2_THREADS;
+    const float *mine = sq + tid * E;
+
+    // ---- 1. float prefix over per-thread sums
+    float loc = 0.0f;
+    for (int k = 0; k < E; k++) loc += mine[k];
+    float inc = loc;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const float u = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += u;
+    }
+    if (lane == 31) sc.wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const float w = sc.wsum[lane];
+        float v = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const float u = __shfl_up_sync(0xffffffffu, v, d);
+            if (lane >= d) v += u;
+        }
+        sc.wsum[lane] = v - w; // exclusive
+    }
+    __syncthreads();
+    const float wex = sc.wsum[warp];
+    const float p_end = wex + inc, p_start = wex + (inc - loc);
+
+    // ---- 2. classify, compose the thread's own steps
+    int cls = SEQSUM2_LITERAL;
+    SeqPair pr;
+    pr.a0 = pr.a1 = 0u;
+    {
+        const int e = f32_exponent(p_start);
+        if (p_start > 0.0f && e > -100 && f32_exponent(p_end) == e) {
+            const float b = __uint_as_float((unsigned)(e + 127) << 23);
+            // margin 2^-9: the sequential sum deviates from any exact prefix by < n * 2^-24 relative (n <= 8192 -> 2^-11)
+            if (p_start >= b * (1.0f + 0x1p-9f) && p_end <= 2.0f * b * (1.0f - 0x1p-9f)) {
+                bool ok = true;
+                for (int k = 0; k < E; k++) {
+                    SeqPair q;
+                    if (!seq_pair(mine[k], e, q)) { ok = false; break; }
+                    pr = seq_compose(pr, q);
+                }
+                if (ok) cls = e;
+            }
+        }
+    }
+    sc.cls[tid] = cls;
+    if (lane == 31) sc.wcls_last[warp] = cls;
+    if (lane == 0) sc.wcls_first[warp] = cls;
+    __syncthreads();
+
+    // ---- 3. segmented scan over runs of clean threads with equal binade
+    int prev_cls = __shfl_up_sync(0xffffffffu, cls, 1);
+    if (lane == 0) prev_cls = warp ? sc.wcls_last[warp - 1] : SEQSUM2_LITERAL;
+    int next_cls = __shfl_down_sync(0xffffffffu, cls, 1);
+    if (lane == 31) next_cls = warp < 31 ? sc.wcls_first[warp + 1] : SEQSUM2_LITERAL;
+    const bool clean = cls != SEQSUM2_LITERAL;
+    int f = (clean && prev_cls == cls) ? 0 : 1; // 1 = a run (or a literal thread) starts here
+    seq2_warp_segscan(pr, f, lane);
+    if (lane == 31) { sc.wtail[warp] = pr; sc.wtail_f[warp] = f; }
+    __syncthreads();
+    if (warp == 0) { // carry[w] = pair of the run that is still open when warp w begins (scan over the warp tails)
+        SeqPair t = sc.wtail[lane];
+        int tf = sc.wtail_f[lane];
+        seq2_warp_segscan(t, tf, lane);
+        sc.wtail[lane] = t; // inclusive: run open at the END of warp `lane`, composed from its true start
+    }
+    __syncthreads();
+    if (!f && warp > 0) pr = seq_compose(sc.wtail[warp - 1], pr); // f == 0 in warp 0 cannot happen (thread 0 always starts a run)
+
+    // ---- 4. item list
+    const bool is_item = !clean || next_cls != cls;
+    const unsigned bal = __ballot_sync(0xffffffffu, is_item);
+    if (lane == 0) sc.wcnt[warp] = __popc(bal);
+    __syncthreads();
+    if (warp == 0) {
+        const int c = sc.wcnt[lane];
+        int v = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, v, d);
+            if (lane >= d) v += u;
+        }
+        sc.wcnt[lane] = v - c;
+        if (lane == 31) sc.info[0] = v;
+    }
+    __syncthreads();
+    if (is_item) {
+        SeqItem it;
+        it.cls = cls; it.a0 = pr.a0; it.a1 = pr.a1; it.last = tid;
+        sc.items[sc.wcnt[warp] + __popc(bal & ((1u << lane) - 1u))] = it;
+    }
+    __syncthreads();
+
+    // ---- 5. resolver
+    if (tid == 0) {
+        const int n_items = sc.info[0];
+        float s = 0.0f;
+        int fallbacks = 0;
+        for (int i = 0; i < n_items; i++) {
+            const SeqItem it = sc.items[i];
+            if (it.cls == SEQSUM2_LITERAL) {
+                const float *q = sq + it.last * E;
+                for (int k = 0; k < E; k++) s = __fadd_rn(s, q[k]);
+                continue;
+            }
+            const unsigned sb = __float_as_uint(s);
+            bool ok = f32_exponent(s) == it.cls && (sb >> 23) != 0u;
+            if (ok) {
+                const unsigned M = (sb & 0x7fffffu) | 0x800000u;
+                const unsigned M2 = M + ((M & 1u) ? it.a1 : it.a0);
+                if (M2 < (1u << 24)) s = __uint_as_float(((unsigned)(it.cls + 127) << 23) | (M2 & 0x7fffffu));
+                else ok = false;
+            }
+            if (!ok) { // misprediction: replay the run literally (its first thread: walk back over equal classes)
+                int first = it.last;
+                while (first > 0 && sc.cls[first - 1] == it.cls) first--;
+                for (int k = first * E; k < (it.last + 1) * E; k++) s = __fadd_rn(s, sq[k]);
+                fallbacks++;
+            }
+        }
+        sc.result[0] = s;
+        sc.info[1] = fallbacks;
+    }
+    __syncthreads();
+    return sc.result[0];
+}
