@@ -14,6 +14,9 @@
 #pragma once
 #include "common.cuh"
 #include "seqsum.cuh"
+#ifdef B200_SEQSUM_V2 // opt-in build (B200_NVCC_DEFINES=B200_SEQSUM_V2): the round-2 accumulator, see tools/seqsum2/README.md
+#include "experimental/seqsum2.cuh"
+#endif
 
 enum { MODE_STORE = 0, MODE_RESID = 1 };
 
@@ -39,7 +42,12 @@ __device__ __forceinline__ float emb_get(const DevMat &e, int token, int i) {
 // One CTA.  Outputs: xq/xs (Q8_0 activation for the following matvec) and/or xb (float).
 // ------------------------------------------------------------------------------------------
 #define NORM_THREADS SEQSUM_THREADS
+#ifdef B200_SEQSUM_V2
+__host__ __device__ inline int norm_padded(int dim) { return (dim + SEQSUM2_THREADS - 1) / SEQSUM2_THREADS * SEQSUM2_THREADS; }
+__host__ __device__ inline size_t norm_smem_bytes(int dim) { return (size_t)norm_padded(dim) * 4 + 16 + seqsum2_scratch_bytes(); }
+#else
 __host__ __device__ inline size_t norm_smem_bytes(int dim) { return (size_t)dim * 4 + 16 + seqsum_scratch_bytes(dim); }
+#endif
 
 template <bool EMBED>
 __global__ void __launch_bounds__(NORM_THREADS, 1) k_rmsnorm_quant(float *__restrict__ x, const StepState *__restrict__ st,
@@ -51,7 +59,12 @@ __global__ void __launch_bounds__(NORM_THREADS, 1) k_rmsnorm_quant(float *__rest
     // (the following matvec's CTA for this SM simply starts a little later).
     extern __shared__ __align__(16) float sm[];
     float *sq = sm;
+#ifdef B200_SEQSUM_V2
+    SeqSum2Scratch scratch = seqsum2_carve(reinterpret_cast<unsigned char *>(sm + norm_padded(dim)));
+    for (int i = dim + threadIdx.x; i < norm_padded(dim); i += NORM_THREADS) sq[i] = 0.0f;
+#else
     SeqSumScratch scratch = seqsum_carve(reinterpret_cast<unsigned char *>(sm + dim), dim);
+#endif
     __shared__ float s_ss;
     const int tid = threadIdx.x;
     long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
@@ -76,7 +89,11 @@ __global__ void __launch_bounds__(NORM_THREADS, 1) k_rmsnorm_quant(float *__rest
     __syncthreads();
     if (prof) t2 = clock64();
     // ss = sequential float sum of the squares (exact, parallel: seqsum.cuh)
+#ifdef B200_SEQSUM_V2
+    float ss = block_seqsum_exact_v2(sq, dim, scratch);
+#else
     float ss = block_seqsum_exact(sq, dim, scratch, prof ? prof + 8 : nullptr);
+#endif
     if (prof) t3 = clock64();
     if (EMBED) __threadfence_block(); // x[] written above by other threads of this block
     if (tid == 0) {
@@ -118,7 +135,11 @@ __global__ void __launch_bounds__(NORM_THREADS, 1) k_rmsnorm_quant(float *__rest
     if (prof) {
         __syncthreads();
         if (tid == 0) { long long t4 = clock64(); prof[0] = t1 - t0; prof[1] = t2 - t1; prof[2] = t3 - t2; prof[3] = t4 - t3;
-                        prof[4] = scratch.info[0]; prof[5] = scratch.info[1]; prof[6] = scratch.info[2]; }
+                        prof[4] = scratch.info[0]; prof[5] = scratch.info[1];
+#ifndef B200_SEQSUM_V2
+                        prof[6] = scratch.info[2];
+#endif
+        }
     }
 }
 
@@ -127,12 +148,21 @@ __global__ void __launch_bounds__(NORM_THREADS, 1) k_rmsnorm_quant(float *__rest
 __global__ void __launch_bounds__(NORM_THREADS, 1) k_test_seqsum(const float *__restrict__ terms, int n, float *__restrict__ out, int *__restrict__ info) {
     extern __shared__ __align__(16) float sm[];
     float *sq = sm;
+#ifdef B200_SEQSUM_V2
+    const int np = norm_padded(n);
+    SeqSum2Scratch scratch = seqsum2_carve(reinterpret_cast<unsigned char *>(sm + np));
+#else
     const int np = (n + 31) & ~31;
     SeqSumScratch scratch = seqsum_carve(reinterpret_cast<unsigned char *>(sm + np), np);
+#endif
     for (int i = threadIdx.x; i < np; i += blockDim.x) sq[i] = i < n ? terms[i] : 0.0f;
     if (threadIdx.x == 0) { scratch.info[0] = -1; scratch.info[1] = -2; }
     __syncthreads();
+#ifdef B200_SEQSUM_V2
+    float s = block_seqsum_exact_v2(sq, n, scratch);
+#else
     float s = block_seqsum_exact(sq, np, scratch);
+#endif
     if (threadIdx.x == 0) { out[0] = s; info[0] = scratch.info[0]; info[1] = scratch.info[1]; }
 }
 

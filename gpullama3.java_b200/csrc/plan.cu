@@ -1203,7 +1203,11 @@ int b200_test_seqsum(const float *terms, int32_t n, float *out, int32_t *info) {
     if (!terms || !out || n <= 0 || n > 8192) return B200_ERR_BAD_ARG;
     float *d = nullptr, *o = nullptr;
     if (cudaMalloc(&d, (size_t)n * 4) != cudaSuccess || cudaMalloc(&o, 16) != cudaSuccess) return B200_ERR_OOM;
+#ifdef B200_SEQSUM_V2
+    size_t smem = norm_smem_bytes(n);
+#else
     size_t smem = (size_t)((n + 31) & ~31) * 4 + seqsum_scratch_bytes((n + 31) & ~31);
+#endif
     cudaFuncSetAttribute(k_test_seqsum, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaMemcpy(d, terms, (size_t)n * 4, cudaMemcpyHostToDevice);
     k_test_seqsum<<<1, NORM_THREADS, smem>>>(d, n, o, reinterpret_cast<int *>(o) + 1);
