@@ -64,5 +64,23 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+TOK_LIB = os.path.join(CSRC, "libb200tok.so")
+TOK_SRC = os.path.join(CSRC, "tokenizer.cpp")
+
+
+def build_tokenizer(force: bool = False) -> str:
+    """libb200tok.so: the native BPE tokenizer (CPU only, plain g++)."""
+    hdr = os.path.join(HERE, "..", "include", "b200tok.h")
+    if not force and os.path.exists(TOK_LIB) and os.path.getmtime(TOK_LIB) >= max(os.path.getmtime(TOK_SRC), os.path.getmtime(hdr)):
+        return TOK_LIB
+    cxx = os.environ.get("CXX", "g++")
+    r = subprocess.run([cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", TOK_LIB, TOK_SRC], capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("g++ failed building libb200tok.so")
+    return TOK_LIB
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
+    print(build_tokenizer(force="--force" in sys.argv))

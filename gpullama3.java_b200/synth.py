@@ -89,6 +89,86 @@ def encode(x: np.ndarray, ggml_type: int) -> np.ndarray:
     raise ValueError(ggml_type)
 
 
+# ---- synthetic byte-level BPE vocabulary (no real tokenizer files offline) --------------------------------------
+_CORPUS = ("the quick brown fox jumps over the lazy dog. she sells sea shells by the sea shore; it's what they've done, "
+           "isn't it? numbers 12345 and 2024-09-24, prices $3.50 or 100%. GPU kernels stream weights: decode, prefill, "
+           "attention! Grüße aus München, naïve café, 東京 こんにちは, emoji 🙂🚀. user system assistant\n\ttabs and  double  spaces ")
+
+LLAMA_SPECIALS = ["<|begin_of_text|>", "<|end_of_text|>", "<|reserved_special_token_0|>", "<|reserved_special_token_1|>", "<|finetune_right_pad_id|>",
+                  "<|reserved_special_token_2|>", "<|start_header_id|>", "<|end_header_id|>", "<|eom_id|>", "<|eot_id|>", "<|python_tag|>"]
+QWEN3_SPECIALS = ["<|endoftext|>", "<|im_start|>", "<|im_end|>", "<|object_ref_start|>", "<|object_ref_end|>", "<|box_start|>", "<|box_end|>",
+                  "<tool_call>", "</tool_call>", "<think>", "</think>"]
+
+
+def gpt2_byte_symbols() -> list[str]:
+    """The 256 single-symbol tokens, indexed by byte value (the GPT-2 bytes_to_unicode table, LlamaTokenizer.java:98-116)."""
+    keep = set(range(ord("!"), ord("~") + 1)) | set(range(0xA1, 0xAD)) | set(range(0xAE, 0x100))
+    out, n = [], 0
+    for b in range(256):
+        if b in keep:
+            out.append(chr(b))
+        else:
+            out.append(chr(256 + n))
+            n += 1
+    return out
+
+
+def build_vocab(vocab_size: int, arch: str = "llama", seed: int = 1234):
+    """(tokens, merge_lines, token_types, base_tokens): 256 byte symbols, BPE merges trained on a small fixed corpus
+    (ids in merge order, so the vocabulary is a consistent BPE vocabulary), padding tokens, then the special tokens."""
+    specials = QWEN3_SPECIALS if arch == "qwen3" else LLAMA_SPECIALS
+    n_merges = vocab_size - 256 - len(specials)
+    if n_merges < 0:
+        raise ValueError("vocabulary too small for the byte symbols and the special tokens")
+    sym = gpt2_byte_symbols()
+    rng = np.random.default_rng(seed)
+    words_src = _CORPUS.split(" ")
+    text = " ".join(words_src[i] for i in rng.integers(0, len(words_src), 4000))
+    words: dict[tuple, int] = {}
+    for w in text.split(" "):
+        key = tuple(sym[b] for b in (" " + w).encode("utf-8"))
+        words[key] = words.get(key, 0) + 1
+    tokens, merges = list(sym), []
+    have = set(tokens)
+    while len(merges) < n_merges:
+        counts: dict[tuple, int] = {}
+        for w, c in words.items():
+            for a, b in zip(w, w[1:]):
+                counts[(a, b)] = counts.get((a, b), 0) + c
+        cand = [(c, p) for p, c in counts.items() if p[0] + p[1] not in have]
+        if not cand:
+            break
+        _, (a, b) = max(cand, key=lambda t: (t[0], t[1]))
+        merges.append(f"{a} {b}")
+        tokens.append(a + b)
+        have.add(a + b)
+        new_words = {}
+        for w, c in words.items():
+            out, i = [], 0
+            while i < len(w):
+                if i + 1 < len(w) and w[i] == a and w[i + 1] == b:
+                    out.append(a + b)
+                    i += 2
+                else:
+                    out.append(w[i])
+                    i += 1
+            new_words[tuple(out)] = new_words.get(tuple(out), 0) + c
+        words = new_words
+    pad = 0
+    while len(tokens) < vocab_size - len(specials):  # corpus exhausted: unused filler tokens (type 5 = unused)
+        tokens.append(f"[PAD{pad}]")
+        pad += 1
+    base = len(tokens)
+    tokens += specials
+    types = [1] * base + [3] * len(specials)  # 1 normal, 3 control
+    for i in range(base - pad, base):
+        types[i] = 5
+    if arch == "qwen3":
+        for t in ("<think>", "</think>", "<tool_call>", "</tool_call>"):
+            types[tokens.index(t)] = 4  # user defined: displayed (Qwen3Tokenizer.shouldDisplayToken)
+    return tokens, merges, types, base
+
+
 def metadata_for(shape: Shape, quant: int, name: str) -> dict:
     a = shape.arch
     md = {
@@ -108,6 +188,13 @@ def metadata_for(shape: Shape, quant: int, name: str) -> dict:
     if a == "qwen3":
         md["qwen3.attention.key_length"] = shape.head_size
         md["qwen3.attention.value_length"] = shape.head_size
+    if shape.vocab <= 4096:  # tokenizer section (GGUF keys the loaders read: tokenizer.ggml.tokens / merges / token_type)
+        tokens, merges, types, base = build_vocab(shape.vocab, a)
+        md["tokenizer.ggml.model"] = "gpt2"
+        md["tokenizer.ggml.tokens"] = tokens
+        md["tokenizer.ggml.merges"] = merges
+        md["tokenizer.ggml.token_type"] = types
+        md["b200.synthetic.base_tokens"] = base  # the reference hard-codes 128000 for Llama-3 (LlamaTokenizer.java:45)
     return md
 
 
