@@ -1,0 +1,18 @@
+#!/bin/bash
+# First GPU call of round 2 (one `gpurun --timeout 900 -- 'bash tools/r2_first_run.sh'`): validates and times the
+# round-2 RMSNorm accumulator (tools/seqsum2/README.md) and records the new decode timeline.  Writes to gpurun_out/.
+set -u
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+{
+  echo "== 1. stand-alone harness: v2 vs the literal loop, v1 vs v2 timing"
+  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -fmad=false -I gpullama3.java_b200/csrc -o /tmp/seqsum2_harness tools/seqsum2/harness.cu \
+    && for n in 4096 2048 8192 2560; do timeout 120 /tmp/seqsum2_harness $n 1500; done
+  echo "== 2. library built with the v2 accumulator: bit-exact decode tests + adversarial sums"
+  B200_NVCC_DEFINES=B200_SEQSUM_V2 python -c "import __graft_entry__ as g; g.build()" \
+    && B200_NVCC_DEFINES=B200_SEQSUM_V2 timeout 400 python -m pytest tests/test_gpu_parity.py -x -q 2>&1 | tail -5
+  echo "== 3. decode timeline with v2 (compare with profiles/decode_timeline_r1.txt: rmsnorm 17.6 us x 65)"
+  B200_NVCC_DEFINES=B200_SEQSUM_V2 timeout 200 python tools/trace.py llama-3-8b 64 2>&1 | tail -12
+  echo "== 4. back to the default build"
+  python -c "import __graft_entry__ as g; g.build()"
+} 2>&1 | tee gpurun_out/r2_first_run.log
