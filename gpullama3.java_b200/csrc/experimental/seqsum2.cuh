@@ -72,10 +72,19 @@ __device__ __forceinline__ void seq2_warp_segscan(SeqPair &p, int &f, int lane) 
     }
 }
 
-// sq: n terms in shared memory, padded with zeros up to SEQSUM2_THREADS * E.  All SEQSUM2_THREADS threads call this.
-__device__ float block_seqsum_exact_v2(const float *sq, int n, SeqSum2Scratch sc) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int E = (n + SEQSUM2_THREADS - 1) / SEQSUM2_THREADS;
+struct SeqSum2BlockSync {
+    __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+
+// sq: n terms in shared memory, padded with zeros up to T * E (E = ceil(n / T)).  Exactly T threads (a multiple of 32, at most
+// SEQSUM2_THREADS) call this with tid in [0, T); `sync` is a barrier over those T threads (the whole CTA, or a named barrier
+// over a subset of its warps as in the persistent decode kernel).
+template <int T, class Sync>
+__device__ float block_seqsum_exact_v2_t(const float *sq, int n, SeqSum2Scratch sc, int tid, Sync sync) {
+    static_assert(T % 32 == 0 && T <= SEQSUM2_THREADS, "T threads = T/32 whole warps");
+    constexpr int NW = T / 32;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int E = (n + T - 1) / T;
     const float *mine = sq + tid * E;
 
     // ---- 1. float prefix over per-thread sums
@@ -88,18 +97,18 @@ __device__ float block_seqsum_exact_v2(const float *sq, int n, SeqSum2Scratch sc
         if (lane >= d) inc += u;
     }
     if (lane == 31) sc.wsum[warp] = inc;
-    __syncthreads();
+    sync();
     if (warp == 0) {
-        const float w = sc.wsum[lane];
+        const float w = lane < NW ? sc.wsum[lane] : 0.0f;
         float v = w;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const float u = __shfl_up_sync(0xffffffffu, v, d);
             if (lane >= d) v += u;
         }
-        sc.wsum[lane] = v - w; // exclusive
+        if (lane < NW) sc.wsum[lane] = v - w; // exclusive
     }
-    __syncthreads();
+    sync();
     const float wex = sc.wsum[warp];
     const float p_end = wex + inc, p_start = wex + (inc - loc);
 
@@ -126,50 +135,52 @@ __device__ float block_seqsum_exact_v2(const float *sq, int n, SeqSum2Scratch sc
     sc.cls[tid] = cls;
     if (lane == 31) sc.wcls_last[warp] = cls;
     if (lane == 0) sc.wcls_first[warp] = cls;
-    __syncthreads();
+    sync();
 
     // ---- 3. segmented scan over runs of clean threads with equal binade
     int prev_cls = __shfl_up_sync(0xffffffffu, cls, 1);
     if (lane == 0) prev_cls = warp ? sc.wcls_last[warp - 1] : SEQSUM2_LITERAL;
     int next_cls = __shfl_down_sync(0xffffffffu, cls, 1);
-    if (lane == 31) next_cls = warp < 31 ? sc.wcls_first[warp + 1] : SEQSUM2_LITERAL;
+    if (lane == 31) next_cls = warp < NW - 1 ? sc.wcls_first[warp + 1] : SEQSUM2_LITERAL;
     const bool clean = cls != SEQSUM2_LITERAL;
     int f = (clean && prev_cls == cls) ? 0 : 1; // 1 = a run (or a literal thread) starts here
     seq2_warp_segscan(pr, f, lane);
     if (lane == 31) { sc.wtail[warp] = pr; sc.wtail_f[warp] = f; }
-    __syncthreads();
+    sync();
     if (warp == 0) { // carry[w] = pair of the run that is still open when warp w begins (scan over the warp tails)
-        SeqPair t = sc.wtail[lane];
-        int tf = sc.wtail_f[lane];
+        SeqPair t;
+        t.a0 = t.a1 = 0u;
+        int tf = 1;
+        if (lane < NW) { t = sc.wtail[lane]; tf = sc.wtail_f[lane]; }
         seq2_warp_segscan(t, tf, lane);
-        sc.wtail[lane] = t; // inclusive: run open at the END of warp `lane`, composed from its true start
+        if (lane < NW) sc.wtail[lane] = t; // inclusive: run open at the END of warp `lane`, composed from its true start
     }
-    __syncthreads();
+    sync();
     if (!f && warp > 0) pr = seq_compose(sc.wtail[warp - 1], pr); // f == 0 in warp 0 cannot happen (thread 0 always starts a run)
 
     // ---- 4. item list
     const bool is_item = !clean || next_cls != cls;
     const unsigned bal = __ballot_sync(0xffffffffu, is_item);
     if (lane == 0) sc.wcnt[warp] = __popc(bal);
-    __syncthreads();
+    sync();
     if (warp == 0) {
-        const int c = sc.wcnt[lane];
+        const int c = lane < NW ? sc.wcnt[lane] : 0;
         int v = c;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const int u = __shfl_up_sync(0xffffffffu, v, d);
             if (lane >= d) v += u;
         }
-        sc.wcnt[lane] = v - c;
+        if (lane < NW) sc.wcnt[lane] = v - c;
         if (lane == 31) sc.info[0] = v;
     }
-    __syncthreads();
+    sync();
     if (is_item) {
         SeqItem it;
         it.cls = cls; it.a0 = pr.a0; it.a1 = pr.a1; it.last = tid;
         sc.items[sc.wcnt[warp] + __popc(bal & ((1u << lane) - 1u))] = it;
     }
-    __syncthreads();
+    sync();
 
     // ---- 5. resolver
     if (tid == 0) {
@@ -201,6 +212,11 @@ __device__ float block_seqsum_exact_v2(const float *sq, int n, SeqSum2Scratch sc
         sc.result[0] = s;
         sc.info[1] = fallbacks;
     }
-    __syncthreads();
+    sync();
     return sc.result[0];
+}
+
+// The whole-CTA form used by k_rmsnorm_quant (B200_SEQSUM_V2): SEQSUM2_THREADS threads, __syncthreads.
+__device__ __forceinline__ float block_seqsum_exact_v2(const float *sq, int n, SeqSum2Scratch sc) {
+    return block_seqsum_exact_v2_t<SEQSUM2_THREADS>(sq, n, sc, (int)threadIdx.x, SeqSum2BlockSync());
 }

@@ -18,6 +18,17 @@ __global__ void __launch_bounds__(SEQSUM2_THREADS, 1) k_v2(const float *t, int n
     const float s = block_seqsum_exact_v2(sq, n, sc);
     if (threadIdx.x == 0) { out[0] = s; info[0] = sc.info[0]; info[1] = sc.info[1]; }
 }
+// the 256-thread form the persistent decode kernel uses (every CTA sums redundantly with its 8 consumer warps)
+__global__ void __launch_bounds__(256, 1) k_v2_256(const float *t, int n, float *out, int *info) {
+    extern __shared__ __align__(16) unsigned char sm3[];
+    const int E = (n + 255) / 256, np = 256 * E;
+    float *sq = reinterpret_cast<float *>(sm3);
+    SeqSum2Scratch sc = seqsum2_carve(sm3 + (size_t)np * 4);
+    for (int i = threadIdx.x; i < np; i += 256) sq[i] = i < n ? t[i] : 0.0f;
+    __syncthreads();
+    const float s = block_seqsum_exact_v2_t<256>(sq, n, sc, (int)threadIdx.x, SeqSum2BlockSync());
+    if (threadIdx.x == 0) { out[0] = s; info[0] = sc.info[0]; info[1] = sc.info[1]; }
+}
 __global__ void __launch_bounds__(SEQSUM_THREADS, 1) k_v1(const float *t, int n, float *out) {
     extern __shared__ __align__(16) unsigned char sm1[];
     float *sq = reinterpret_cast<float *>(sm1);
@@ -43,6 +54,8 @@ int main(int argc, char **argv) {
     const size_t smem2 = (size_t)SEQSUM2_THREADS * E * 4 + seqsum2_scratch_bytes(), smem1 = (size_t)n * 4 + seqsum_scratch_bytes(n);
     cudaFuncSetAttribute(k_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
     cudaFuncSetAttribute(k_v1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+    const size_t smem3 = (size_t)256 * ((n + 255) / 256) * 4 + seqsum2_scratch_bytes();
+    cudaFuncSetAttribute(k_v2_256, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
     long bad = 0, items = 0, fb = 0;
     for (int c = 0; c < cases; c++) {
         const int kind = c % 10;
@@ -72,22 +85,26 @@ int main(int argc, char **argv) {
         cudaMemcpy(info, dinfo, 8, cudaMemcpyDeviceToHost);
         float ref = s;
         if (memcmp(&got, &ref, 4)) { if (bad < 5) printf("MISMATCH case %d kind %d: gpu %.9g literal %.9g\n", c, kind, got, ref); bad++; }
+        k_v2_256<<<1, 256, smem3>>>(dt, n, dout, dinfo);
+        cudaMemcpy(&got, dout, 4, cudaMemcpyDeviceToHost);
+        if (memcmp(&got, &ref, 4)) { if (bad < 5) printf("MISMATCH (256 threads) case %d kind %d: gpu %.9g literal %.9g\n", c, kind, got, ref); bad++; }
         items += info[0]; fb += info[1];
     }
     printf("n=%d cases=%d mismatches=%ld items/case=%.1f fallbacks/case=%.3f (%s)\n", n, cases, bad, (double)items / cases, (double)fb / cases, cudaGetErrorString(cudaGetLastError()));
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     float ms;
-    for (int which = 0; which < 2; which++) {
+    for (int which = 0; which < 3; which++) {
         cudaEventRecord(e0);
         for (int r = 0; r < 200; r++) {
-            if (which) k_v2<<<1, SEQSUM2_THREADS, smem2>>>(dt, n, dout, dinfo);
+            if (which == 2) k_v2_256<<<1, 256, smem3>>>(dt, n, dout, dinfo);
+            else if (which) k_v2<<<1, SEQSUM2_THREADS, smem2>>>(dt, n, dout, dinfo);
             else k_v1<<<1, SEQSUM_THREADS, smem1>>>(dt, n, dout);
         }
         cudaEventRecord(e1);
         cudaEventSynchronize(e1);
         cudaEventElapsedTime(&ms, e0, e1);
-        printf("%s: %.2f us per launch (back-to-back launches, includes ~2 us launch overhead)\n", which ? "v2" : "v1", ms * 1000.f / 200);
+        printf("%s: %.2f us per launch (back-to-back launches, includes ~2 us launch overhead)\n", which == 2 ? "v2 (256 threads)" : which ? "v2" : "v1", ms * 1000.f / 200);
     }
     return bad != 0;
 }
