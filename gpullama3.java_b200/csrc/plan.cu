@@ -6,6 +6,12 @@
 #include "decode_kernels.cuh"
 #include "prefill.cuh"
 #include "stream_matvec.cuh"
+#ifdef B200_PERSISTENT_DECODE // opt-in build: one persistent kernel per token (experimental/decode_persistent.cuh; needs B200_SEQSUM_V2)
+#ifndef B200_SEQSUM_V2
+#error "B200_PERSISTENT_DECODE needs B200_SEQSUM_V2 (the 256-thread exact accumulator)"
+#endif
+#include "experimental/decode_persistent.cuh"
+#endif
 
 #include <math.h>
 #include <stdarg.h>
@@ -78,6 +84,10 @@ struct b200_plan {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
     PrefillCtx prefill;
+#ifdef B200_PERSISTENT_DECODE
+    PdLayer *pd_layers = nullptr; // device copies of the per-layer descriptors of the persistent decode kernel
+    unsigned *pd_sync = nullptr;  // its epoch counters
+#endif
 };
 
 namespace {
@@ -412,10 +422,81 @@ int enqueue_forward(b200_plan *p, bool with_logits, int *launches, bool trace = 
     return B200_OK;
 }
 
+#ifdef B200_PERSISTENT_DECODE
+// One launch per token (experimental/decode_persistent.cuh).  Returns B200_ERR_UNSUPPORTED when the plan does not fit the
+// draft's restrictions, in which case the caller falls back to the multi-kernel graph.
+int pd_prepare(b200_plan *p, PdSmem *layout) { // checks + allocations only (never launches: the KV cache must stay zero-initialised)
+    const b200_config &c = p->cfg;
+    if (!p->use_stream || p->tp.n > 1 || c.tp_size > 1) return B200_ERR_UNSUPPORTED;
+    const int seg = p->layers[0].tqkv.seg;
+    for (const LayerW &L : p->layers)
+        if (L.tqkv.seg != seg || L.two.seg != seg || L.tgu.seg != seg || L.tw2.seg != seg) return B200_ERR_UNSUPPORTED;
+    if (p->tout.seg != seg) return B200_ERR_UNSUPPORTED;
+    if (c.head_size != 64 && c.head_size != 128) return B200_ERR_UNSUPPORTED;
+    if (c.n_heads > p->n_sms) return B200_ERR_UNSUPPORTED;
+    int maxdyn = 0;
+    CK(cudaDeviceGetAttribute(&maxdyn, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device));
+    const PdSmem L = pd_layout(c.dim, p->qd, c.hidden_dim, c.head_size, c.context_length, seg, (size_t)maxdyn);
+    if (L.stages < 4) return B200_ERR_UNSUPPORTED;
+    if (!p->pd_layers) {
+        std::vector<PdLayer> h(c.n_layers);
+        const size_t ctx_kv = (size_t)c.context_length * p->kvd;
+        for (int l = 0; l < c.n_layers; l++) {
+            const LayerW &W = p->layers[l];
+            h[l].qkv = W.tqkv; h[l].wo = W.two; h[l].gu = W.tgu; h[l].w2 = W.tw2;
+            h[l].attn_norm = W.attn_norm; h[l].ffn_norm = W.ffn_norm; h[l].q_norm = W.q_norm; h[l].k_norm = W.k_norm;
+            h[l].kc = p->key_cache + (size_t)l * ctx_kv;
+            h[l].vc = p->value_cache + (size_t)l * ctx_kv;
+        }
+        int rc;
+        if ((rc = dalloc(p, &p->pd_layers, h.size() * sizeof(PdLayer)))) return rc;
+        CK(cudaMemcpy(p->pd_layers, h.data(), h.size() * sizeof(PdLayer), cudaMemcpyHostToDevice));
+        if ((rc = dalloc(p, &p->pd_sync, PD_S_WORDS * 4))) return rc;
+        CK(cudaMemset(p->pd_sync, 0, PD_S_WORDS * 4));
+    }
+    if (c.head_size == 128) CK(cudaFuncSetAttribute(k_decode_persistent<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    else CK(cudaFuncSetAttribute(k_decode_persistent<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    *layout = L;
+    return B200_OK;
+}
+
+int enqueue_persistent(b200_plan *p, bool with_logits, int *launches, const PdSmem &L) {
+    const b200_config &c = p->cfg;
+    PdArgs a;
+    a.layers = p->pd_layers; a.n_layers = c.n_layers; a.lm_head = p->tout; a.out_norm = p->out_norm; a.emb = p->emb;
+    a.dim = c.dim; a.hidden = c.hidden_dim; a.qd = p->qd; a.kvd = p->kvd; a.n_heads = c.n_heads; a.n_kv_heads = c.n_kv_heads;
+    a.head_size = c.head_size; a.arch = c.arch; a.vocab = c.vocab_size; a.ctx = c.context_length;
+    a.eps = c.rms_norm_eps; a.sqrt_hs = (float)sqrt((double)c.head_size);
+    a.rope_cr = p->rope_cr; a.rope_ci = p->rope_ci;
+    a.st = p->st; a.seq_tokens = p->seq_tokens; a.out_ids = p->out_ids;
+    a.x = p->x; a.qkv = p->qkv; a.hb = p->hb; a.logits = p->logits;
+    a.attq = p->attq; a.atts = p->atts; a.hq = p->hq; a.hs = p->hs; a.blk_cnt = p->blk_cnt;
+    a.part_val = p->part_val; a.part_idx = p->part_idx; a.sync = p->pd_sync; a.with_logits = with_logits ? 1 : 0;
+    if (c.head_size == 128) k_decode_persistent<128><<<p->n_sms, SMV_THREADS, L.total, p->stream>>>(a, L);
+    else k_decode_persistent<64><<<p->n_sms, SMV_THREADS, L.total, p->stream>>>(a, L);
+    CK(cudaGetLastError());
+    if (launches) *launches = 1;
+    return B200_OK;
+}
+#endif
+
 int capture(b200_plan *p, bool with_logits, cudaGraphExec_t *exec, int *launches, bool trace = false) {
     cudaGraph_t g = nullptr;
+#ifdef B200_PERSISTENT_DECODE
+    bool persistent = !trace && !getenv("B200_NO_PERSISTENT") && p->use_stream && p->tp.n == 1 && p->cfg.tp_size == 1;
+    PdSmem pd_L{};
+    if (persistent) { // allocations cannot happen inside a capture
+        const int rc0 = pd_prepare(p, &pd_L);
+        if (rc0 == B200_ERR_UNSUPPORTED) persistent = false;
+        else if (rc0) return rc0;
+    }
+#endif
     CK(cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal));
+#ifdef B200_PERSISTENT_DECODE
+    int rc = persistent ? enqueue_persistent(p, with_logits, launches, pd_L) : enqueue_forward(p, with_logits, launches, trace);
+#else
     int rc = enqueue_forward(p, with_logits, launches, trace);
+#endif
     cudaError_t e = cudaStreamEndCapture(p->stream, &g);
     if (rc) { if (g) cudaGraphDestroy(g); return rc; }
     if (e != cudaSuccess) return fail(p, B200_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));

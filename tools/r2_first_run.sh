@@ -13,6 +13,13 @@ mkdir -p gpurun_out
     && B200_NVCC_DEFINES=B200_SEQSUM_V2 timeout 400 python -m pytest tests/test_gpu_parity.py -x -q 2>&1 | tail -5
   echo "== 3. decode timeline with v2 (compare with profiles/decode_timeline_r1.txt: rmsnorm 17.6 us x 65)"
   B200_NVCC_DEFINES=B200_SEQSUM_V2 timeout 200 python tools/trace.py llama-3-8b 64 2>&1 | tail -12
-  echo "== 4. back to the default build"
+  echo "== 4. persistent decode kernel (experimental/decode_persistent.cuh): smallest bit-exact test first, under a short timeout"
+  export B200_NVCC_DEFINES="B200_SEQSUM_V2 B200_PERSISTENT_DECODE"
+  python -c "import __graft_entry__ as g; g.build()" \
+    && timeout 150 python -m pytest tests/test_gpu_parity.py -x -q -k "decode_q8_bit_exact" 2>&1 | tail -5 \
+    && timeout 300 python -m pytest tests/test_gpu_parity.py -x -q 2>&1 | tail -5 \
+    && timeout 200 python bench.py --no-cpu --no-pp --steps 64 2>&1 | tail -1 | cut -c1-400
+  unset B200_NVCC_DEFINES
+  echo "== 5. back to the default build"
   python -c "import __graft_entry__ as g; g.build()"
 } 2>&1 | tee gpurun_out/r2_first_run.log
