@@ -27,7 +27,9 @@
 #define PD_CT (SMV_CONSUMER_WARPS * 32) // consumer threads
 #define PD_MAX_STAGES 24
 
-enum { PD_S_QKV = 0, PD_S_ATT = 1, PD_S_WO = 2, PD_S_GU = 3, PD_S_W2 = 4, PD_S_LM = 5, PD_S_TICK = 8, PD_S_WORDS = 16 };
+enum { PD_S_QKV = 0, PD_S_ATT = 1, PD_S_WO = 2, PD_S_GU = 3, PD_S_W2 = 4, PD_S_LM = 5, PD_S_TICK = 8, PD_S_LMTICK = 9, PD_S_WORDS = 16 };
+// PD_S_TICK counts launches (epoch of the per-layer counters); PD_S_LMTICK counts launches that ran the lm_head (the prefill
+// graph does not), which is the epoch of PD_S_LM.
 
 struct PdLayer {
     TileMat qkv, wo, gu, w2;
@@ -489,6 +491,7 @@ __global__ void __launch_bounds__(SMV_THREADS, 1) k_decode_persistent(PdArgs a, 
     // ===== consumers =====
     const int token = a.st->token, pos = a.st->pos;
     const unsigned tick = *reinterpret_cast<volatile unsigned *>(a.sync + PD_S_TICK);
+    const unsigned lmtick = *reinterpret_cast<volatile unsigned *>(a.sync + PD_S_LMTICK);
     const unsigned nC = gridDim.x, nL = (unsigned)a.n_layers;
     unsigned seq_base = 0;
     for (int l = 0; l < a.n_layers; l++) {
@@ -522,7 +525,7 @@ __global__ void __launch_bounds__(SMV_THREADS, 1) k_decode_persistent(PdArgs a, 
         pd_consume_matrix<SMV_STORE>(a.lm_head, a, smem, L, bar0, rel, seq_base, a.logits, true, false, token, tid);
         pd_arrive(a.sync + PD_S_LM, tid);
         if (blockIdx.x != 0) return;
-        pd_wait(a.sync + PD_S_LM, (tick + 1u) * nC, tid);
+        pd_wait(a.sync + PD_S_LM, (lmtick + 1u) * nC, tid);
         // FloatTensor.argmax over the per-CTA (max, first index) pairs: copy of k_argmax_advance
         float best = -INFINITY;
         best_i = 0x7fffffff;
@@ -555,5 +558,6 @@ __global__ void __launch_bounds__(SMV_THREADS, 1) k_decode_persistent(PdArgs a, 
         st->step = next;
         st->pos = st->pos + 1;
         *reinterpret_cast<volatile unsigned *>(a.sync + PD_S_TICK) = tick + 1u;
+        if (a.with_logits) *reinterpret_cast<volatile unsigned *>(a.sync + PD_S_LMTICK) = lmtick + 1u;
     }
 }
