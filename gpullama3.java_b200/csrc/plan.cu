@@ -800,6 +800,8 @@ int prefill_init(b200_plan *p) {
     {
         const char *e = getenv("B200_GEMM_2CTA");
         c.pair = !(e && e[0] == '0') && nqkv % 256 == 0 && g.dim % 256 == 0 && g.hidden_dim % 128 == 0;
+        const char *e2 = getenv("B200_GEMM_PERSIST"); // round-2 candidate: persistent CTA-pair kernel for QKV and gate/up (compile-checked only)
+        c.persist = e2 && e2[0] == '1';
     }
     if (!ok) { c.why = "cuTensorMapEncodeTiled rejected a tensor map"; return B200_OK; }
     if (g.head_size == 128) {
@@ -880,7 +882,9 @@ int prefill_forward(b200_plan *p, int n, int start_pos, int *launches) {
         const PrefillLayerMaps &m = c.maps[l];
         float *kc = p->key_cache + (size_t)l * ctx_kv, *vc = p->value_cache + (size_t)l * ctx_kv;
         k_pf_rmsnorm_f16<<<n, 256, 0, s>>>(c.X, L.attn_norm, g.rms_norm_eps, g.dim, c.A16); nl++;
-        if (c.pair) {
+        if (c.pair && c.persist) { // round-2 candidate, B200_GEMM_PERSIST=1
+            if (pg::gemm2_persist_launch<pg::GEMM_F32, 256, pg::GEMM2_PERSIST_STAGES_256>(c.mA, m.qkv, m.qkv, c.mQKV, c.QKV, nqkv, n, mt2, nqkv / 256, g.dim, p->n_sms, s)) return fail(p, B200_ERR_CUDA, "QKV GEMM launch failed");
+        } else if (c.pair) {
             if (pg::gemm2_launch<pg::GEMM_F32, 256, pg::GEMM2_STAGES_256>(c.mA, m.qkv, m.qkv, c.mQKV, c.QKV, nqkv, n, mt2, nqkv / 256, g.dim, s)) return fail(p, B200_ERR_CUDA, "QKV GEMM launch failed");
         } else
         if (one_wave(nqkv / pg::BN) ? pg::gemm_launch<pg::GEMM_F32, DEEP>(c.mA, m.qkv, m.qkv, c.mQKV, c.QKV, nqkv, n, mt, nqkv / pg::BN, g.dim, s)
@@ -913,7 +917,9 @@ int prefill_forward(b200_plan *p, int n, int start_pos, int *launches) {
             return fail(p, B200_ERR_CUDA, "Wo GEMM launch failed");
         nl++;
         k_pf_rmsnorm_f16<<<n, 256, 0, s>>>(c.X, L.ffn_norm, g.rms_norm_eps, g.dim, c.A16); nl++;
-        if (c.pair) {
+        if (c.pair && c.persist) { // round-2 candidate, B200_GEMM_PERSIST=1
+            if (pg::gemm2_persist_launch<pg::GEMM_GATEUP, 256, pg::GEMM2_PERSIST_STAGES_256>(c.mA, m.w1p, m.w3p, c.mX, c.H16, g.hidden_dim, n, mt2, g.hidden_dim / 128, g.dim, p->n_sms, s)) return fail(p, B200_ERR_CUDA, "gate/up GEMM launch failed");
+        } else if (c.pair) {
             if (wide ? pg::gemm2_launch<pg::GEMM_GATEUP, 256, pg::GEMM2_STAGES_256_M2, 2>(c.mA, m.w1p, m.w3p, c.mX, c.H16, g.hidden_dim, n, mt4, g.hidden_dim / 128, g.dim, s)
                      : pg::gemm2_launch<pg::GEMM_GATEUP, 256, pg::GEMM2_STAGES_256>(c.mA, m.w1p, m.w3p, c.mX, c.H16, g.hidden_dim, n, mt2, g.hidden_dim / 128, g.dim, s))
                 return fail(p, B200_ERR_CUDA, "gate/up GEMM launch failed");

@@ -412,6 +412,180 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
     if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TCOLS) : "memory");
 }
 
+// =====================================================================================================
+// ROUND-2 CANDIDATE (compile-checked only; selected by B200_GEMM_PERSIST=1, never by default): the CTA-pair GEMM as a
+// PERSISTENT kernel.  One cluster per TPC walks tiles t = cluster + i * clusters (M pair tiles fastest, so neighbouring
+// clusters share a weight tile in L2); the accumulator is double buffered in TMEM (2 x BN columns), so while the four
+// epilogue warps drain tile i the MMA thread already accumulates tile i+1 and the producers are loading tile i+2 --
+// prologue, pipeline fill and epilogue no longer sit on the critical path of every tile (they are ~25 % of a K = 4096 tile
+// in k_gemm_f16_2cta).  New synchronisation relative to the non-persistent kernel: tmem_full[2] (leader MMA -> both
+// epilogues, multicast commit) and tmem_empty[2] on the LEADER (count 8 = 4 epilogue warps x 2 CTAs, remote
+// mbarrier.arrive through the cluster window), plus two 16 KB C staging buffers of their own (the operand ring is busy).
+// =====================================================================================================
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) { // arrive on the barrier at this offset in the pair's even CTA
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & 0xFEFFFFFFu) : "memory");
+}
+
+template <int BN, int STAGES> constexpr size_t smem_bytes_2cta_persist() {
+    return (size_t)STAGES * (BM * BK * 2 + (BN / 2) * BK * 2) + 2 * (BM * 32 * 4) + (2 * STAGES + 4) * 8 + 16 + 1024;
+}
+
+template <int MODE, int BN, int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+    k_gemm_f16_2cta_persist(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_b2,
+                            const __grid_constant__ CUtensorMap tma_c, void *__restrict__ Cv, int ldc, int m_valid, int K, int m_pairs, int n_tiles) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    constexpr int A_BYTES = BM * BK * 2, B_BYTES = (BN / 2) * BK * 2, CST_BYTES = BM * 32 * 4;
+    static_assert(2 * BN <= 512, "two accumulators must fit the 512 TMEM columns");
+    uint8_t *sA = smem, *sB = smem + STAGES * A_BYTES, *sC = sB + STAGES * B_BYTES; // sC: two staging buffers, 1024-byte aligned
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sC + 2 * CST_BYTES);
+    const uint32_t full0 = s32(bars), empty0 = s32(bars + STAGES), tfull0 = s32(bars + 2 * STAGES), tempty0 = s32(bars + 2 * STAGES + 2);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 4);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        for (int b = 0; b < 2; b++) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)), "r"((uint32_t)(2 * BN)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    const int nk = (K + BK - 1) / BK;
+    const int n_clusters = (int)(gridDim.x >> 1), cid = (int)(blockIdx.x >> 1), total = m_pairs * n_tiles;
+
+    if (warp == 0 && lane == 0) {
+        // ===== TMA producer (both CTAs) =====
+        const CUtensorMap *bmap = (MODE == GEMM_GATEUP && rank == 1) ? &tma_b2 : &tma_b;
+        int it = 0; // running k-block counter across tiles: the ring never drains between tiles
+        for (int t = cid; t < total; t += n_clusters) {
+            const int mp = t % m_pairs, nt = t / m_pairs;
+            const int m0 = mp * 2 * BM + (int)rank * BM;
+            const int n0 = nt * (MODE == GEMM_GATEUP ? BN / 2 : BN);
+            const int brow = MODE == GEMM_GATEUP ? n0 : n0 + (int)rank * (BN / 2);
+            for (int kb = 0; kb < nk; kb++, it++) {
+                const int st = it % STAGES;
+                mbar_wait(empty0 + 8 * st, ((it / STAGES) & 1) ^ 1);
+                if (rank == 0) mbar_expect_tx(full0 + 8 * st, 2 * (A_BYTES + B_BYTES));
+                tma_load_2d_2sm(s32(sA + st * A_BYTES), &tma_a, kb * BK, m0, full0 + 8 * st);
+                tma_load_2d_2sm(s32(sB + st * B_BYTES), bmap, kb * BK, brow, full0 + 8 * st);
+            }
+        }
+    } else if (warp == 1 && lane == 0 && rank == 0) {
+        // ===== MMA issuer (leader): accumulator buffer i & 1 =====
+        constexpr uint32_t idesc = umma_idesc_f16(2 * BM, BN);
+        int it = 0, i = 0;
+        for (int t = cid; t < total; t += n_clusters, i++) {
+            const int buf = i & 1;
+            mbar_wait(tempty0 + 8 * buf, ((i >> 1) & 1) ^ 1); // both CTAs' epilogues have drained this buffer (first two uses pass at once)
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int kb = 0; kb < nk; kb++, it++) {
+                const int st = it % STAGES;
+                mbar_wait(full0 + 8 * st, (it / STAGES) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint64_t da = umma_desc_sw128(s32(sA + st * A_BYTES)), db = umma_desc_sw128(s32(sB + st * B_BYTES));
+#pragma unroll
+                for (int k = 0; k < BK / 16; k++) umma_f16_2cta(tmem_base + (uint32_t)(buf * BN), da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                umma_commit_2cta(empty0 + 8 * st);
+            }
+            umma_commit_2cta(tfull0 + 8 * buf);
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue (both CTAs): four warps, warp w owns TMEM lanes 32 * (w - 4) =====
+        const int q = warp & 3, et = threadIdx.x - 128; // et: 0..127 within the epilogue group
+        int i = 0, chunk = 0;                         // chunk: running count of staged 32-column chunks (staging buffer = chunk & 1)
+        for (int t = cid; t < total; t += n_clusters, i++) {
+            const int buf = i & 1;
+            const int mp = t % m_pairs, nt = t / m_pairs;
+            const int m0 = mp * 2 * BM + (int)rank * BM;
+            const int n0 = nt * (MODE == GEMM_GATEUP ? BN / 2 : BN);
+            const int row = m0 + q * 32 + lane;
+            mbar_wait(tfull0 + 8 * buf, (i >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
+            if (MODE == GEMM_GATEUP) {
+                __half *C = reinterpret_cast<__half *>(Cv);
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN / 2; c0 += 32) {
+                    uint32_t g[32], u[32];
+                    tmem_ld32(tlane + (uint32_t)c0, g);
+                    tmem_ld32(tlane + (uint32_t)(BN / 2 + c0), u);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (c0 + 32 >= BN / 2) { // last TMEM read of this tile: hand the accumulator back before the (slow) stores
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_leader(tempty0 + 8 * buf);
+                    }
+                    if (row < m_valid) {
+                        uint4 *dst = reinterpret_cast<uint4 *>(C + (size_t)row * ldc + n0 + c0);
+#pragma unroll
+                        for (int v = 0; v < 4; v++) {
+                            uint32_t w[4];
+#pragma unroll
+                            for (int e = 0; e < 4; e++) {
+                                const float g0 = __uint_as_float(g[8 * v + 2 * e]), g1 = __uint_as_float(g[8 * v + 2 * e + 1]);
+                                const float h0 = (g0 / (1.0f + expf(-g0))) * __uint_as_float(u[8 * v + 2 * e]);
+                                const float h1 = (g1 / (1.0f + expf(-g1))) * __uint_as_float(u[8 * v + 2 * e + 1]);
+                                const __half2 hh = __floats2half2_rn(h0, h1);
+                                w[e] = *reinterpret_cast<const uint32_t *>(&hh);
+                            }
+                            dst[v] = make_uint4(w[0], w[1], w[2], w[3]);
+                        }
+                    }
+                }
+            } else {
+                const int rloc = q * 32 + lane;
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; c++, chunk++) {
+                    uint32_t r[32];
+                    tmem_ld32(tlane + (uint32_t)(c * 32), r);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (c == BN / 32 - 1) {
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_leader(tempty0 + 8 * buf);
+                    }
+                    uint8_t *cst = sC + (chunk & 1) * CST_BYTES;
+                    if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); // the store that used this buffer two chunks ago has read it
+                    asm volatile("bar.sync 2, 128;" ::: "memory");
+                    uint8_t *dstp = cst + rloc * 128;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        uint4 o = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                        if (row >= m_valid) o = make_uint4(0u, 0u, 0u, 0u);
+                        *reinterpret_cast<uint4 *>(dstp + ((j ^ (rloc & 7)) << 4)) = o;
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    asm volatile("bar.sync 2, 128;" ::: "memory");
+                    if (et == 0) {
+                        if (MODE == GEMM_RESID)
+                            asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tma_c), "r"(s32(cst)),
+                                         "r"(n0 + c * 32), "r"(m0)
+                                         : "memory");
+                        else
+                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tma_c), "r"(s32(cst)),
+                                         "r"(n0 + c * 32), "r"(m0)
+                                         : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                }
+            }
+        }
+        if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    __syncwarp(); // the elected producer / MMA / store lanes rejoin their warps before the aligned cluster barrier
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN)) : "memory");
+}
+
 // ---- host side ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
                                   const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -484,6 +658,27 @@ inline int gemm2_launch(const CUtensorMap &a, const CUtensorMap &b, const CUtens
 constexpr int GEMM2_STAGES_256 = 6, GEMM2_STAGES_128 = 8; // 192 KB of operand ring per CTA either way
 constexpr int GEMM2_STAGES_256_M2 = 4;                    // 4 x (32 KB of A + 16 KB of B)
 
+// Persistent variant (round-2 candidate).  n_sms: SMs of the device; the grid is the largest even number of CTAs <= n_sms.
+template <int MODE, int BN, int STAGES>
+inline int gemm2_persist_launch(const CUtensorMap &a, const CUtensorMap &b, const CUtensorMap &b2, const CUtensorMap &c, void *C, int ldc, int m_valid, int m_tiles,
+                                int n_tiles, int K, int n_sms, cudaStream_t stream) {
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(k_gemm_f16_2cta_persist<MODE, BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_2cta_persist<BN, STAGES>()) !=
+            cudaSuccess)
+            return -4;
+        attr = true;
+    }
+    if (m_tiles & 1) return -6;
+    const int m_pairs = m_tiles / 2, total = m_pairs * n_tiles;
+    int clusters = n_sms / 2;
+    if (clusters > total) clusters = total;
+    if (clusters < 1) return -6;
+    k_gemm_f16_2cta_persist<MODE, BN, STAGES><<<dim3(2 * clusters), 256, smem_bytes_2cta_persist<BN, STAGES>(), stream>>>(a, b, b2, c, C, ldc, m_valid, K, m_pairs, n_tiles);
+    return cudaGetLastError() == cudaSuccess ? 0 : -5;
+}
+constexpr int GEMM2_PERSIST_STAGES_256 = 5; // 5 x 32 KB of operands + 2 x 16 KB of C staging
+
 // 3 stages of 32 KB: two CTAs fit one SM (2 x 99 KB shared memory, 2 x 128 TMEM columns), so one CTA's
 // epilogue overlaps the other's main loop.
 constexpr int GEMM_STAGES = 3, GEMM_STAGES_DEEP = 6;
@@ -494,11 +689,18 @@ inline int gemm_f16(const __half *A, const __half *B, float *C, int M, int N, in
     CUtensorMap ma, mb, mc;
     int rc;
     if (two_cta) { // two_cta = pair-tile width (256 or 128)
-        const int bn = two_cta == 512 ? 256 : two_cta;
+        const int bn = (two_cta == 512 || two_cta == 1256) ? 256 : two_cta;
         if (M % 256 || N % bn) return -3;
         if ((rc = make_map(&ma, A, (uint64_t)M, (uint64_t)K, BM))) return rc;
         if ((rc = make_map(&mb, B, (uint64_t)N, (uint64_t)K, bn / 2))) return rc;
         if ((rc = make_map_c(&mc, C, (uint64_t)M, (uint64_t)N))) return rc;
+        if (two_cta == 1256) { // persistent CTA-pair kernel, 256-wide pair tiles (round-2 candidate)
+            int dev = 0, sms = 148;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            return resid ? gemm2_persist_launch<GEMM_RESID, 256, GEMM2_PERSIST_STAGES_256>(ma, mb, mb, mc, C, N, M, M / BM, N / 256, K, sms, stream)
+                         : gemm2_persist_launch<GEMM_F32, 256, GEMM2_PERSIST_STAGES_256>(ma, mb, mb, mc, C, N, M, M / BM, N / 256, K, sms, stream);
+        }
         if (two_cta == 512) { // 256-wide pair tiles, two of them (512 rows) per CTA pair
             if (M % 512) return -3;
             return resid ? gemm2_launch<GEMM_RESID, 256, GEMM2_STAGES_256_M2, 2>(ma, mb, mb, mc, C, N, M, M / BM, N / 256, K, stream, resid)

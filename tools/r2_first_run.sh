@@ -20,6 +20,12 @@ mkdir -p gpurun_out
     && timeout 300 python -m pytest tests/test_gpu_parity.py -x -q 2>&1 | tail -5 \
     && timeout 200 python bench.py --no-cpu --no-pp --steps 64 2>&1 | tail -1 | cut -c1-400
   unset B200_NVCC_DEFINES
-  echo "== 5. back to the default build"
+  echo "== 5. persistent CTA-pair GEMM (prefill_gemm.cuh, k_gemm_f16_2cta_persist): stand-alone check, then the prefill tests and pp512 with it"
+  python -c "import __graft_entry__ as g; g.build()"
+  B200_GEMM_2CTA=1256 timeout 90 python tools/gemm_check.py --big 2>&1 | tail -7
+  B200_GEMM_2CTA=1256 B200_GEMM_RESID=1 timeout 60 python tools/gemm_check.py 2>&1 | tail -2
+  B200_GEMM_PERSIST=1 timeout 300 python -m pytest tests/test_gpu_prefill.py -x -q 2>&1 | tail -3
+  B200_GEMM_PERSIST=1 timeout 200 python tools/pp_bench.py llama-3-8b 512 5 2>&1 | tail -1
+  echo "== 6. back to the default build"
   python -c "import __graft_entry__ as g; g.build()"
 } 2>&1 | tee gpurun_out/r2_first_run.log
