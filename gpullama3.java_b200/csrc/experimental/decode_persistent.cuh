@@ -62,7 +62,7 @@ struct PdArgs {
 };
 
 struct PdSmem {
-    size_t off_bar, off_xq, off_xs, off_nbuf, off_seq, off_terms, off_hvals, off_misc, off_ring, total;
+    size_t off_bar, off_xq, off_xs, off_nbuf, off_xbuf, off_seq, off_terms, off_hvals, off_misc, off_ring, total;
     int stages, stage_bytes, nbs_pad, nbuf_floats;
 };
 
@@ -83,6 +83,8 @@ __host__ __device__ inline PdSmem pd_layout(int dim, int qd, int hidden, int hea
     L.off_xs = o; o += (size_t)(maxc / 32) * 4;
     o = (o + 15) & ~(size_t)15;
     L.off_nbuf = o; o += (size_t)L.nbuf_floats * 4; // squares of the norm | q,k,out,att of the attention (time-disjoint)
+    o = (o + 15) & ~(size_t)15;
+    L.off_xbuf = o; o += (size_t)dim * 4; // the residual stream, kept between the two passes of the norm
     o = (o + 15) & ~(size_t)15;
     L.off_seq = o; o += seqsum2_scratch_bytes();
     o = (o + 15) & ~(size_t)15;
@@ -272,17 +274,45 @@ __device__ __forceinline__ void pd_consume_matrix(const TileMat &W, const PdArgs
 }
 
 // ---- RMSNorm of the residual stream into THIS CTA's activation buffer (arithmetic of k_rmsnorm_quant) ----------------------
+__device__ __forceinline__ float4 pd_ldcg128(const float *p) {
+    float4 v;
+    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
 __device__ __forceinline__ void pd_norm_to_smem(const PdArgs &a, const float *w, bool from_emb, int token, unsigned char *smem, const PdSmem &L, int tid) {
     const int lane = tid & 31, warp = tid >> 5, dim = a.dim;
     float *sq = reinterpret_cast<float *>(smem + L.off_nbuf);
+    float *xb = reinterpret_cast<float *>(smem + L.off_xbuf);
     float *misc = reinterpret_cast<float *>(smem + L.off_misc);
     SeqSum2Scratch scratch = seqsum2_carve(smem + L.off_seq);
     const int dim_pad = (dim + PD_CT - 1) / PD_CT * PD_CT;
-    for (int i = tid; i < dim_pad; i += PD_CT) {
-        float v = 0.0f;
-        if (i < dim) v = from_emb ? emb_get(a.emb, token, i) : ldcg_f32c(a.x + i);
-        sq[i] = __fmul_rn(v, v);
+    if (from_emb) { // first layer: the embedding row (quantised table: element-wise)
+        for (int i = tid; i < dim; i += PD_CT) {
+            const float v = emb_get(a.emb, token, i);
+            xb[i] = v;
+            sq[i] = __fmul_rn(v, v);
+        }
+    } else { // x from L2: four independent 16-byte loads in flight per thread, one round trip for dim <= 4096
+        const int n4 = dim >> 2;
+        for (int base = 0; base < n4; base += 4 * PD_CT) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i4 = base + u * PD_CT + tid;
+                v[u] = i4 < n4 ? pd_ldcg128(a.x + 4 * i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i4 = base + u * PD_CT + tid;
+                if (i4 < n4) {
+                    reinterpret_cast<float4 *>(xb)[i4] = v[u];
+                    reinterpret_cast<float4 *>(sq)[i4] = make_float4(__fmul_rn(v[u].x, v[u].x), __fmul_rn(v[u].y, v[u].y), __fmul_rn(v[u].z, v[u].z), __fmul_rn(v[u].w, v[u].w));
+                }
+            }
+        }
     }
+    for (int i = dim + tid; i < dim_pad; i += PD_CT) sq[i] = 0.0f;
     consumer_bar_sync();
     float ss = block_seqsum_exact_v2_t<PD_CT>(sq, dim, scratch, tid, PdConsumerSync());
     if (tid == 0) {
@@ -296,22 +326,18 @@ __device__ __forceinline__ void pd_norm_to_smem(const PdArgs &a, const float *w,
     float *sxs = reinterpret_cast<float *>(smem + L.off_xs);
     const int nb = dim / 32;
 #pragma unroll 1
-    for (int b0 = warp; b0 < nb; b0 += 4 * SMV_CONSUMER_WARPS) {
-        float xv[4], wv[4];
+    for (int b0 = warp; b0 < nb; b0 += 8 * SMV_CONSUMER_WARPS) { // 8 norm-weight loads in flight per lane; x comes from shared memory
+        float wv[8];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int u = 0; u < 8; u++) {
             const int b = b0 + u * SMV_CONSUMER_WARPS;
-            xv[u] = 0.0f; wv[u] = 0.0f;
-            if (b < nb) {
-                xv[u] = from_emb ? emb_get(a.emb, token, b * 32 + lane) : ldcg_f32c(a.x + b * 32 + lane);
-                wv[u] = w[b * 32 + lane];
-            }
+            wv[u] = b < nb ? __ldg(w + b * 32 + lane) : 0.0f;
         }
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int u = 0; u < 8; u++) {
             const int b = b0 + u * SMV_CONSUMER_WARPS;
             if (b < nb) {
-                const float v = __fmul_rn(wv[u], __fmul_rn(ss, xv[u]));
+                const float v = __fmul_rn(wv[u], __fmul_rn(ss, xb[b * 32 + lane]));
                 float as;
                 const int q = quant_block_lane(v, as);
                 sxq[b * 32 + lane] = (int8_t)q;
