@@ -19,7 +19,8 @@ if "--big" in sys.argv:
     shapes += [(512, 6144, 4096), (512, 28672, 4096), (512, 4096, 14336), (4096, 4096, 4096), (8192, 8192, 8192)]
 two = int(os.environ.get("B200_GEMM_2CTA", "0"))
 for (m, n, k) in shapes:
-    if two and (m % 256 or n % two):
+    bn = 256 if two in (512, 1256) else two  # 512: two pair tiles per CTA pair; 1256: persistent pair kernel
+    if two and (m % (512 if two == 512 else 256) or n % bn):
         continue
     a = (rng.standard_normal((m, k)) * 0.5).astype(np.float16)
     b = (rng.standard_normal((n, k)) * 0.5).astype(np.float16)
