@@ -162,3 +162,30 @@ class OracleLlamaChatFormat:
         if append_assistant_turn:
             out += self.encode_header("assistant")  # ChatFormat.Role.ASSISTANT = new Role("assistant") (ChatFormat.java:246)
         return out
+
+
+class OracleQwen3ChatFormat:
+    """Qwen3ChatFormat.java:26-183, ChatML branch (chat tokens of Qwen3ModelLoader.java:89)."""
+
+    def __init__(self, tok: OracleTokenizer, think_start: int, think_end: int):
+        st = tok.special_tokens
+        self.tok = tok
+        self.im_start = st.get("<|im_start|>", -1)
+        self.im_end = st.get("<|im_end|>", -1)
+        self.end_of_text = st.get("<|end_of_text|>", -1)
+        self.end_of_text_fim = st.get("<|endoftext|>", -1)
+        self.think_start, self.think_end = think_start, think_end
+
+    def encode_header(self, role: str) -> list[int]:
+        return [self.im_start] + self.tok.encode(role) + self.tok.encode("\n")
+
+    def encode_message(self, role: str, content: str) -> list[int]:
+        return self.encode_header(role) + self.tok.encode(content.strip()) + [self.im_end] + self.tok.encode("\n")
+
+    def stop_tokens(self) -> set[int]:
+        return {t for t in (self.im_end, self.end_of_text, self.end_of_text_fim) if t != -1}
+
+    def thinking_control(self, enable: bool) -> list[int]:
+        if enable:
+            return []
+        return [self.think_start] + self.tok.encode("\n\n") + [self.think_end] + self.tok.encode("\n\n")

@@ -152,6 +152,20 @@ def test_special_tokens_and_chat_format(pkg, tor, vocabs):
     assert q.should_display_token(q.think_start_token) and not q.should_display_token(q.get_special_tokens()["<|im_end|>"])
 
 
+def test_qwen3_chat_format(pkg, tor, vocabs):
+    q, oq = make_pair(pkg, tor, vocabs, "qwen3")
+    fmt = pkg.chat_format.Qwen3ChatFormat(q)
+    ofmt = tor.OracleQwen3ChatFormat(oq, q.tokens.index("<think>"), q.tokens.index("</think>"))
+    M = pkg.chat_format.Message
+    for role, content in [("system", " You are helpful.\n"), ("user", "What's 7*6?"), ("assistant", "42")]:
+        assert fmt.encode_message(M(role, content)) == ofmt.encode_message(role, content)
+    assert fmt.encode_header(M("assistant", "")) == ofmt.encode_header("assistant")
+    assert fmt.get_begin_of_text() == q.get_special_tokens()["<|im_start|>"]
+    assert fmt.get_stop_tokens() == ofmt.stop_tokens() == {q.get_special_tokens()["<|im_end|>"], q.get_special_tokens()["<|endoftext|>"]}
+    assert fmt.encode_thinking_control(True) == [] and fmt.encode_thinking_control(False) == ofmt.thinking_control(False)
+    assert fmt.encode_thinking_control(False)[0] == q.think_start_token and q.decode(fmt.encode_thinking_control(False)) == "<think>\n\n</think>\n\n"
+
+
 def test_error_conventions(pkg):
     sym = pkg.synth.gpt2_byte_symbols()
     with pytest.raises(pkg.tokenizer.TokenizerError, match="missing from the vocabulary"):
