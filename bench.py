@@ -167,6 +167,7 @@ def cpu_leg(orc, model, tokens, budget_s: float, max_tokens: int):
 
 
 def main():
+    global WORKLOAD
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=128)
@@ -175,8 +176,12 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU-baseline work")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-pp", action="store_true", help="skip the pp512 tensor-core prefill leg")
+    ap.add_argument("--workload", default=WORKLOAD, choices=["llama-3-8b", "llama-3-70b", "llama-3.2-1b", "qwen3-4b"],
+                    help="shape of the synthetic model (default: the BASELINE headline, Llama-3-8B; 70B is BASELINE config 5, meant for --gpus 2/4/8)")
     args = ap.parse_args()
     K, W = args.steps, max(args.warmup, 3)
+    WORKLOAD = args.workload
+    pretty = {"llama-3-8b": "Llama-3-8B", "llama-3-70b": "Llama-3-70B", "llama-3.2-1b": "Llama-3.2-1B", "qwen3-4b": "Qwen3-4B"}[WORKLOAD]
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -186,9 +191,9 @@ def main():
     shape = pkg.synth.SHAPES[WORKLOAD]
     ctx = W + K + 8  # LlamaBench: depth + tokens + 8 (LlamaBench.java:174)
     tokens = np.asarray(lb.synthetic_tokens(shape.vocab, W + K), dtype=np.int32)
-    config = {"workload": f"Llama-3-8B-shaped synthetic GGUF, Q8_0, tg{K} single-stream decode from depth {W}",
+    config = {"workload": f"{pretty}-shaped synthetic GGUF, Q8_0, tg{K} single-stream decode from depth {W}",
               "weights": "seeded N(0,1/sqrt(fan_in)) quantised with the ggml Q8_0 rule; tokens java.util.Random(42)",
-              "context": ctx, "l2": "inputs larger than L2 (7.97 GB of weights stream per step vs 126 MB L2)"}
+              "context": ctx, "l2": f"inputs larger than L2 ({shape.matmul_elements() // 32 * 34 / 1e9:.2f} GB of weights stream per step vs 126 MB L2)"}
 
     if args.impl == "reference":
         if world > 1 and rank != 0:
@@ -287,7 +292,7 @@ def main():
                      "bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                      "bytes_per_launch": k_bytes, "ms_per_launch": k_ms,
                      # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, ncu --set full, profiles/r1_stream_matvec_full.ncu-rep
-                     "traffic": 124823296 + 3408640 if world == 1 else None,
+                     "traffic": 124823296 + 3408640 if (world == 1 and WORKLOAD == "llama-3-8b") else None,
                      "whole_step": {"algorithmic_bytes_per_token": ab, "achieved": step_gbs, "frac": step_gbs / peak},
                      "other_kernels": per_kernel},
         "load": {"synthesise_s": gen_s, "upload_repack_s": load_s, "device_bytes": plan.device_bytes},
@@ -298,7 +303,7 @@ def main():
         line["cpu_baseline"] = {"value": tps, "unit": "tok/s", "cores": cores, "kind": "port",
                                 "sample": f"{n} decode steps of the same workload in {dt:.1f} s (C restatement of InferenceCore.forwardJava, -O2, OpenMP rows)"}
     plan.free()
-    if not args.no_pp and world == 1:
+    if not args.no_pp and world == 1 and WORKLOAD == "llama-3-8b":  # BASELINE config 3 is the 8B FP16 model
         del model, plan
         line["pp512"] = prefill_leg(pkg, lb, local, 512, 5)
     print(json.dumps(line))
