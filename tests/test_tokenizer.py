@@ -113,6 +113,21 @@ def test_encode_decode_parity_with_oracle(pkg, tor, vocabs, arch):
     nat.close()
 
 
+@pytest.mark.parametrize("arch", ["llama", "qwen3"])
+def test_committed_tokenizer_fixture(pkg, tor, vocabs, arch):
+    """Regression pin (tests/golden/tokenizer_golden.json, self-generated by make_tokenizer_golden.py): the synthetic
+    vocabulary, the oracle and the native encoder all still produce the committed ids."""
+    import hashlib
+    import json
+    with open(os.path.join(ROOT, "tests", "golden", "tokenizer_golden.json")) as f:
+        gold = json.load(f)[arch]
+    tokens, merges, _, _ = vocabs[arch]
+    assert hashlib.sha256("\n".join(tokens + merges).encode()).hexdigest() == gold["vocab_sha"]
+    nat, orc = make_pair(pkg, tor, vocabs, arch)
+    for text, ids in gold["cases"]:
+        assert nat.encode_as_list(text) == ids == orc.encode(text), repr(text)
+
+
 def test_merge_priority_is_the_merged_token_id_not_the_merge_order(pkg, tor):
     """Adversarial vocabulary: the merge list says (a,b) first, but the merged token of (b,c) has the lower id, and a
     later merge consumes the product of an earlier one with a lower id -- the reference's loop semantics decide."""
