@@ -9,10 +9,13 @@ LlamaBench.java:188-193) over a seeded synthetic GGUF-layout model of the real L
                CUDA-event time on the plan's stream, max over ranks)
   e2e          tok/s through the reference-facing call b200_forward_decode with HOST buffers:
                every step copies the token/position H2D and the argmax D2H inside the timed region
-  roofline     dominant kernel (fused gate/up dequant-matvec) timed stand-alone with CUDA events;
-               achieved = algorithmic bytes / avg launch time, peak = MEASURED_PEAKS.json hbm_gbs
+  roofline     the WHOLE decode step (one persistent kernel per token: the dominant kernel IS the step):
+               achieved = algorithmic bytes per token / device time per token, peak = MEASURED_PEAKS.json
+               hbm_gbs; the stand-alone streaming matvecs are listed under roofline.other_kernels
   cpu_baseline the oracle (CPU restatement of the reference's onGPU=false path) on this box's
                host cores, bounded sample
+  parity       in the same run: greedy ids of the first steps GPU == oracle, max|dlogit| of step 0
+               (BASELINE.md section 3); a mismatch exits non-zero
 `--impl reference` times only that CPU restatement (the reference itself needs a JDK + TornadoVM,
 neither is installable here).
 """
@@ -151,19 +154,41 @@ def build_model(pkg, ctx: int, device: str | None):
 
 def cpu_leg(orc, model, tokens, budget_s: float, max_tokens: int):
     """Times the CPU restatement (per-row activation quantisation exactly as the reference does,
-    Q8_0FloatTensor.java:100-117; rows over all host cores like Parallel.parallelFor)."""
+    Q8_0FloatTensor.java:100-117; rows over all host cores like Parallel.parallelFor) on the bench's own
+    token stream from position 0, and keeps what the parity gate needs: step 0's logits, every step's argmax."""
+    cores = orc.use_all_cores()  # torchrun exports OMP_NUM_THREADS=1: set the thread count explicitly
     om = orc.OracleModel(model, per_row_quant=True)
-    cores = int(orc.lib().oracle_omp_threads())
-    om.forward(int(tokens[0]), 0)  # untimed warm-up (page-in)
+    lg0 = om.forward(int(tokens[0]), 0).copy()  # untimed warm-up (page-in); position 0 of the stream
+    ids = [orc.argmax(lg0)]
     n, t0 = 0, time.perf_counter()
     while n < max_tokens:
-        om.forward(int(tokens[1 + n]), 1 + n)
+        ids.append(orc.argmax(om.forward(int(tokens[1 + n]), 1 + n)))
         n += 1
         if time.perf_counter() - t0 > budget_s:
             break
     dt = time.perf_counter() - t0
     om.close()
-    return n / dt, n, dt, cores
+    return n / dt, n, dt, cores, {"logits0": lg0, "ids": ids}
+
+
+def parity_gate(plan, tokens, ref, want_logits: bool):
+    """the GPU path on the same tokens/positions the oracle just ran.  Teacher-forced (LlamaBench's
+    token stream), so every step is an independent check of logits -> argmax at a growing KV depth."""
+    plan.kv_reset()
+    n = len(ref["ids"])
+    got, dmax = [], None
+    for i in range(n):
+        lg, am = plan.forward_decode(int(tokens[i]), i, logits=want_logits and i == 0)
+        got.append(int(am))
+        if want_logits and i == 0:
+            dmax = float(np.abs(lg - ref["logits0"]).max())
+            bit_equal = bool(np.array_equal(lg.view(np.uint32), ref["logits0"].view(np.uint32)))
+    out = {"steps": n, "ids_equal": got == [int(v) for v in ref["ids"]], "against": "oracle (CPU restatement of InferenceCore.forwardJava), same tokens and positions"}
+    if dmax is not None:
+        out["max_abs_dlogit"] = dmax
+        out["logits_bit_equal"] = bit_equal
+        out["tolerance"] = "0 (decode reproduces the CPU path's float order; FP16-scale 2^-8*max|logit| would be the north-star bound)"
+    return out
 
 
 def main():
@@ -176,6 +201,9 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU-baseline work")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-pp", action="store_true", help="skip the pp512 tensor-core prefill leg")
+    ap.add_argument("--decode-mode", default="default", choices=["default", "persistent", "graph"],
+                    help="decode implementation: one persistent kernel per token, or the round-1 CUDA graph of ~7 kernels per layer")
+    ap.add_argument("--depth", type=int, default=-1, help="LlamaBench -d: KV positions filled before the timed steps (default: the warm-up steps)")
     ap.add_argument("--workload", default=WORKLOAD, choices=["llama-3-8b", "llama-3-70b", "llama-3.2-1b", "qwen3-4b"],
                     help="shape of the synthetic model (default: the BASELINE headline, Llama-3-8B; 70B is BASELINE config 5, meant for --gpus 2/4/8)")
     args = ap.parse_args()
@@ -189,9 +217,10 @@ def main():
     pkg = ge.import_package()
     lb = pkg.llama_bench
     shape = pkg.synth.SHAPES[WORKLOAD]
-    ctx = W + K + 8  # LlamaBench: depth + tokens + 8 (LlamaBench.java:174)
-    tokens = np.asarray(lb.synthetic_tokens(shape.vocab, W + K), dtype=np.int32)
-    config = {"workload": f"{pretty}-shaped synthetic GGUF, Q8_0, tg{K} single-stream decode from depth {W}",
+    D = max(W, args.depth)  # LlamaBench -d: positions filled before the timed steps; the fill doubles as the warm-up
+    ctx = D + K + 8  # LlamaBench: depth + tokens + 8 (LlamaBench.java:174)
+    tokens = np.asarray(lb.synthetic_tokens(shape.vocab, D + K), dtype=np.int32)
+    config = {"workload": f"{pretty}-shaped synthetic GGUF, Q8_0, tg{K} single-stream decode from depth {D}",
               "weights": "seeded N(0,1/sqrt(fan_in)) quantised with the ggml Q8_0 rule; tokens java.util.Random(42)",
               "context": ctx, "l2": f"inputs larger than L2 ({shape.matmul_elements() // 32 * 34 / 1e9:.2f} GB of weights stream per step vs 126 MB L2)"}
 
@@ -201,7 +230,7 @@ def main():
         orc = ge.import_oracle()
         _, model, _ = build_model(pkg, ctx, None)
         budget = max(10.0, min(120.0, 8.0 * (K + W)))  # bounded sample: the whole run ends within minutes
-        tps, n, dt, cores = cpu_leg(orc, model, tokens, budget, max(1, min(K, W + K - 1)))
+        tps, n, dt, cores, _ = cpu_leg(orc, model, tokens, budget, max(1, min(K, D + K - 1)))
         line = {"metric": "decode_tokens_per_s", "value": tps, "unit": "tok/s", "n_gpus": args.gpus, "steps": K, "warmup": W,
                 "ms_per_step": 1e3 / tps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "q8_0xq8_0->int32, f32 accumulate",
                 "data": "synthetic", "impl": "reference", "config": config,
@@ -228,29 +257,37 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    if args.decode_mode != "default":
+        plan.set_decode_mode(args.decode_mode)
+    dmode, launches_per_step, ring_stages, pd_smem = plan.decode_info()
     sampler = ClockSampler(local)
-    # ---- value: device loop, tokens resident in HBM ------------------------------------------
-    plan.decode_sequence(tokens[:W], W, 0)  # W untimed warm-up steps (positions 0..W-1)
-    barrier()
     if rank == 0:
-        sampler.start()
-    ids, ms = plan.decode_sequence(tokens[W:W + K], K, W)
+        sampler.start()  # nvidia-smi forks BEFORE the barrier: no rank waits on it inside the timed region
+    # ---- value: device loop, tokens resident in HBM ------------------------------------------
+    plan.decode_sequence(tokens[:D], D, 0)  # D >= W untimed warm-up steps (positions 0..D-1)
     barrier()
+    ids, ms = plan.decode_sequence(tokens[D:D + K], K, D)
+    barrier()
+    ms_rank = [ms]
     if world > 1:
         t = torch.tensor([ms], device=f"cuda:{local}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        ms_rank = [float(v.item()) for v in allt]
+        ms = max(ms_rank)
     value = K / (ms / 1e3)  # one stream; under --gpus N the model is tensor-parallel over N ranks (strong scaling)
 
     # ---- e2e: reference-facing call, host token in / host argmax out every step ----------------
     plan.kv_reset()
-    for i in range(W):
+    if D > W:
+        plan.decode_sequence(tokens[:D - W], D - W, 0)
+    for i in range(D - W, D):  # W untimed warm-up calls through the same entry point
         plan.forward_decode(int(tokens[i]), i, logits=False)
     barrier()
     t0 = time.perf_counter()
     e2e_ids = []
     for i in range(K):
-        _, am = plan.forward_decode(int(tokens[W + i]), W + i, logits=False)
+        _, am = plan.forward_decode(int(tokens[D + i]), D + i, logits=False)
         e2e_ids.append(am)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
@@ -262,46 +299,63 @@ def main():
     assert list(ids) == e2e_ids, "device loop and per-step API disagree"
 
     if rank != 0:
+        if not args.no_cpu:  # tensor-parallel parity gate: rank 0 runs the oracle, every rank issues the same forwards
+            box = [None]
+            dist.broadcast_object_list(box, src=0)
+            n_par = int(box[0])
+            plan.kv_reset()
+            for i in range(n_par):
+                plan.forward_decode(int(tokens[i]), i, logits=False)
         plan.free()
         dist.barrier()
         dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the dominant kernel ----------------------------------------------------------
+    # ---- roofline: the whole decode step (in persistent mode it is ONE kernel launch) ------------------
     peak, peak_src = peaks()
-    ab = algorithmic_bytes_per_token(shape, True, W + (K - 1) / 2.0)
-    step_gbs = ab["total"] / world * value / 1e9  # per-GPU bytes per token x tok/s
+    ab = algorithmic_bytes_per_token(shape, True, D + (K - 1) / 2.0)
+    step_bytes = ab["total"] / world                 # algorithmic bytes one GPU must read per token
+    step_gbs = step_bytes * value / 1e9              # ... x tok/s
     per_kernel = {}
-    if world == 1:
-        k_ms, k_bytes = plan.time_kernel(0, reps=3)
-        achieved = k_bytes / (k_ms / 1e3) / 1e9
-        for which, name in ((1, "down_proj"), (2, "qkv"), (3, "attn_out"), (4, "lm_head")):
+    if world == 1:  # the stand-alone streaming matvecs of the graph path, for context (b200_time_kernel, PDL off)
+        for which, name in ((0, "gate_up"), (1, "down_proj"), (2, "qkv"), (3, "attn_out"), (4, "lm_head")):
             m, b = plan.time_kernel(which, reps=3 if which != 4 else 1)
-            per_kernel[name] = {"ms": m, "GB/s": b / (m / 1e3) / 1e9}
-    else:  # the stand-alone kernel timer is single-GPU; report the whole-step figure per GPU
-        k_ms, k_bytes, achieved = None, None, step_gbs
+            per_kernel[name] = {"ms": m, "GB/s": b / (m / 1e3) / 1e9, "bytes": b}
+    persistent = dmode == 1
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r2_decode_traffic.json")  # dram bytes per launch from the committed ncu --set full capture
+    if world == 1 and WORKLOAD == "llama-3-8b" and os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("persistent" if persistent else "graph")
     line = {
         "metric": "decode_tokens_per_s", "value": value, "unit": "tok/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak" if world == 1 else "strong", "vs_baseline": None,
         "dtype": "q8_0xq8_0->int32, f32 accumulate", "data": "synthetic", "config": config,
         "parallelism": "single GPU" if world == 1 else f"tp{world}: row-sharded weights, in-kernel all-gather over NVLink peer memory (bit-exact with tp1)",
+        "decode_mode": "persistent (1 kernel per token)" if persistent else f"graph ({launches_per_step} kernels per token)",
         "e2e": {"value": K / e2e_s, "unit": "tok/s", "h2d_bytes_per_step": 32, "d2h_bytes_per_step": 4},
-        "gpu_launches": plan.launches_per_decode * K,
+        "gpu_launches": launches_per_step * K,
         "clocks": clocks,
-        "roofline": {"kernel": "k_stream_matvec_q8<GATEUP> (TMA-ring fused gate/up dequant-matvec + SwiGLU + Q8_0 requantise), timed stand-alone without PDL prefetch" if world == 1 else "whole decode step per GPU",
-                     "bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                     "bytes_per_launch": k_bytes, "ms_per_launch": k_ms,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, ncu --set full, profiles/r1_stream_matvec_full.ncu-rep
-                     "traffic": 124823296 + 3408640 if (world == 1 and WORKLOAD == "llama-3-8b") else None,
-                     "whole_step": {"algorithmic_bytes_per_token": ab, "achieved": step_gbs, "frac": step_gbs / peak},
+        "ms_per_step_by_rank": [m / K for m in ms_rank],
+        "roofline": {"kernel": ("k_decode_persistent: the whole token (all layers + lm_head + argmax) in one launch; " if persistent else "whole decode step (CUDA graph); ")
+                               + ("per GPU" if world > 1 else "single GPU"),
+                     "bound": "hbm", "achieved": step_gbs, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": step_gbs / peak,
+                     "bytes_per_launch": step_bytes if persistent else step_bytes / launches_per_step, "ms_per_launch": ms / K if persistent else ms / K / launches_per_step,
+                     "algorithmic_bytes_per_token": ab, "traffic": traffic,
+                     "persistent_kernel": {"ring_stages": ring_stages, "smem_bytes": pd_smem} if persistent else None,
                      "other_kernels": per_kernel},
         "load": {"synthesise_s": gen_s, "upload_repack_s": load_s, "device_bytes": plan.device_bytes},
     }
-    if not args.no_cpu and world == 1:
+    if not args.no_cpu:
         orc = ge.import_oracle()
-        tps, n, dt, cores = cpu_leg(orc, model, tokens, args.cpu_budget, 16)
-        line["cpu_baseline"] = {"value": tps, "unit": "tok/s", "cores": cores, "kind": "port",
-                                "sample": f"{n} decode steps of the same workload in {dt:.1f} s (C restatement of InferenceCore.forwardJava, -O2, OpenMP rows)"}
+        # N = 1: the reported CPU baseline (bounded sample).  N > 1: a short run, only to carry driver-visible TP parity.
+        tps, n, dt, cores, ref = cpu_leg(orc, model, tokens, args.cpu_budget if world == 1 else 6.0, 16 if world == 1 else 4)
+        if world == 1:
+            line["cpu_baseline"] = {"value": tps, "unit": "tok/s", "cores": cores, "kind": "port",
+                                    "sample": f"{n} decode steps of the same workload in {dt:.1f} s (C restatement of InferenceCore.forwardJava, -O2, OpenMP rows)"}
+        if world > 1:  # the other ranks wait here, then run the same parity calls (TP: every rank issues the same forwards)
+            dist.broadcast_object_list([len(ref["ids"])], src=0)
+        line["parity"] = parity_gate(plan, tokens, ref, want_logits=world == 1)
     plan.free()
     if not args.no_pp and world == 1 and WORKLOAD == "llama-3-8b":  # BASELINE config 3 is the 8B FP16 model
         del model, plan
@@ -310,6 +364,9 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if "parity" in line and not line["parity"]["ids_equal"]:
+        sys.stderr.write("PARITY FAILURE: GPU greedy ids differ from the oracle\n")
+        return 3
     return 0
 
 

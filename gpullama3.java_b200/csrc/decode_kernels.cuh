@@ -14,9 +14,7 @@
 #pragma once
 #include "common.cuh"
 #include "seqsum.cuh"
-#ifdef B200_SEQSUM_V2 // opt-in build (B200_NVCC_DEFINES=B200_SEQSUM_V2): the round-2 accumulator, see tools/seqsum2/README.md
-#include "experimental/seqsum2.cuh"
-#endif
+#include "seqsum2.cuh"
 
 enum { MODE_STORE = 0, MODE_RESID = 1 };
 
@@ -42,29 +40,22 @@ __device__ __forceinline__ float emb_get(const DevMat &e, int token, int i) {
 // One CTA.  Outputs: xq/xs (Q8_0 activation for the following matvec) and/or xb (float).
 // ------------------------------------------------------------------------------------------
 #define NORM_THREADS SEQSUM_THREADS
-#ifdef B200_SEQSUM_V2
+static_assert(SEQSUM_THREADS == SEQSUM2_THREADS, "both accumulators run on the whole norm CTA");
 __host__ __device__ inline int norm_padded(int dim) { return (dim + SEQSUM2_THREADS - 1) / SEQSUM2_THREADS * SEQSUM2_THREADS; }
-__host__ __device__ inline size_t norm_smem_bytes(int dim) { return (size_t)norm_padded(dim) * 4 + 16 + seqsum2_scratch_bytes(); }
-#else
-__host__ __device__ inline size_t norm_smem_bytes(int dim) { return (size_t)dim * 4 + 16 + seqsum_scratch_bytes(dim); }
-#endif
+// V2 = seqsum2.cuh (three scans + a short serial walk), otherwise the round-1 accumulator seqsum.cuh
+__host__ __device__ inline size_t norm_smem_bytes(int dim, bool v2) {
+    return v2 ? (size_t)norm_padded(dim) * 4 + 16 + seqsum2_scratch_bytes() : (size_t)dim * 4 + 16 + seqsum_scratch_bytes(dim);
+}
 
-template <bool EMBED>
+template <bool EMBED, bool V2>
 __global__ void __launch_bounds__(NORM_THREADS, 1) k_rmsnorm_quant(float *__restrict__ x, const StepState *__restrict__ st,
                                                                DevMat emb, const float *__restrict__ w, float eps, int dim,
                                                                int8_t *__restrict__ xq, float *__restrict__ xs,
                                                                float *__restrict__ xb, long long *__restrict__ prof, TraceBuf tr, TpCtx tp, int tp_wait_op) {
-    // One CTA of 1024 threads: every per-group step of the exact sum is a long dependent chain, so the
-    // groups are spread over 32 warps.  Under PDL this CTA only has to fit next to ONE streaming-matvec CTA
+    // One CTA of 1024 threads.  Under PDL this CTA only has to fit next to ONE streaming-matvec CTA
     // (the following matvec's CTA for this SM simply starts a little later).
     extern __shared__ __align__(16) float sm[];
     float *sq = sm;
-#ifdef B200_SEQSUM_V2
-    SeqSum2Scratch scratch = seqsum2_carve(reinterpret_cast<unsigned char *>(sm + norm_padded(dim)));
-    for (int i = dim + threadIdx.x; i < norm_padded(dim); i += NORM_THREADS) sq[i] = 0.0f;
-#else
-    SeqSumScratch scratch = seqsum_carve(reinterpret_cast<unsigned char *>(sm + dim), dim);
-#endif
     __shared__ float s_ss;
     const int tid = threadIdx.x;
     long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
@@ -86,14 +77,22 @@ __global__ void __launch_bounds__(NORM_THREADS, 1) k_rmsnorm_quant(float *__rest
         else v = ldcg_f32c(x + i);
         sq[i] = __fmul_rn(v, v);
     }
+    if (V2)
+        for (int i = dim + tid; i < norm_padded(dim); i += NORM_THREADS) sq[i] = 0.0f;
     __syncthreads();
     if (prof) t2 = clock64();
-    // ss = sequential float sum of the squares (exact, parallel: seqsum.cuh)
-#ifdef B200_SEQSUM_V2
-    float ss = block_seqsum_exact_v2(sq, dim, scratch);
-#else
-    float ss = block_seqsum_exact(sq, dim, scratch, prof ? prof + 8 : nullptr);
-#endif
+    // ss = sequential float sum of the squares (exact, parallel)
+    float ss;
+    int info0 = 0, info1 = 0, info2 = 0;
+    if (V2) {
+        SeqSum2Scratch scratch = seqsum2_carve(reinterpret_cast<unsigned char *>(sm + norm_padded(dim)));
+        ss = block_seqsum_exact_v2(sq, dim, scratch);
+        if (prof && tid == 0) { info0 = scratch.info[0]; info1 = scratch.info[1]; }
+    } else {
+        SeqSumScratch scratch = seqsum_carve(reinterpret_cast<unsigned char *>(sm + dim), dim);
+        ss = block_seqsum_exact(sq, dim, scratch, prof ? prof + 8 : nullptr);
+        if (prof && tid == 0) { info0 = scratch.info[0]; info1 = scratch.info[1]; info2 = scratch.info[2]; }
+    }
     if (prof) t3 = clock64();
     if (EMBED) __threadfence_block(); // x[] written above by other threads of this block
     if (tid == 0) {
@@ -135,34 +134,34 @@ __global__ void __launch_bounds__(NORM_THREADS, 1) k_rmsnorm_quant(float *__rest
     if (prof) {
         __syncthreads();
         if (tid == 0) { long long t4 = clock64(); prof[0] = t1 - t0; prof[1] = t2 - t1; prof[2] = t3 - t2; prof[3] = t4 - t3;
-                        prof[4] = scratch.info[0]; prof[5] = scratch.info[1];
-#ifndef B200_SEQSUM_V2
-                        prof[6] = scratch.info[2];
-#endif
-        }
+                        prof[4] = info0; prof[5] = info1; prof[6] = info2; }
     }
 }
 
-// Test hook: the sequential-sum emulation on arbitrary non-negative terms (padded with zeros to a
-// multiple of 32: adding +0 never changes a sum of non-negative floats).
+// Test hooks: the sequential-sum emulations on arbitrary non-negative terms (padded with zeros: adding +0 never
+// changes a sum of non-negative floats).
 __global__ void __launch_bounds__(NORM_THREADS, 1) k_test_seqsum(const float *__restrict__ terms, int n, float *__restrict__ out, int *__restrict__ info) {
     extern __shared__ __align__(16) float sm[];
     float *sq = sm;
-#ifdef B200_SEQSUM_V2
-    const int np = norm_padded(n);
-    SeqSum2Scratch scratch = seqsum2_carve(reinterpret_cast<unsigned char *>(sm + np));
-#else
     const int np = (n + 31) & ~31;
     SeqSumScratch scratch = seqsum_carve(reinterpret_cast<unsigned char *>(sm + np), np);
-#endif
     for (int i = threadIdx.x; i < np; i += blockDim.x) sq[i] = i < n ? terms[i] : 0.0f;
     if (threadIdx.x == 0) { scratch.info[0] = -1; scratch.info[1] = -2; }
     __syncthreads();
-#ifdef B200_SEQSUM_V2
-    float s = block_seqsum_exact_v2(sq, n, scratch);
-#else
     float s = block_seqsum_exact(sq, np, scratch);
-#endif
+    if (threadIdx.x == 0) { out[0] = s; info[0] = scratch.info[0]; info[1] = scratch.info[1]; }
+}
+// seqsum2.cuh with T threads (1024: the norm kernel's form; 256: the persistent decode kernel's form)
+template <int T>
+__global__ void __launch_bounds__(T, 1) k_test_seqsum2(const float *__restrict__ terms, int n, float *__restrict__ out, int *__restrict__ info) {
+    extern __shared__ __align__(16) float sm[];
+    float *sq = sm;
+    const int E = (n + T - 1) / T, np = T * E;
+    SeqSum2Scratch scratch = seqsum2_carve(reinterpret_cast<unsigned char *>(sm + np), T);
+    for (int i = threadIdx.x; i < np; i += T) sq[i] = i < n ? terms[i] : 0.0f;
+    if (threadIdx.x == 0) { scratch.info[0] = -1; scratch.info[1] = -2; }
+    __syncthreads();
+    const float s = block_seqsum_exact_v2_t<T>(sq, n, scratch, (int)threadIdx.x, SeqSum2BlockSync());
     if (threadIdx.x == 0) { out[0] = s; info[0] = scratch.info[0]; info[1] = scratch.info[1]; }
 }
 
@@ -415,11 +414,12 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attention(float *__restrict__ q
                                                           const float *__restrict__ qnorm_w, const float *__restrict__ knorm_w,
                                                           float eps, float sqrt_hs, int8_t *__restrict__ xq,
                                                           float *__restrict__ xs, float *__restrict__ xb, TraceBuf tr, TpCtx tp,
-                                                          unsigned tp_out_op, int head_base) {
-    extern __shared__ __align__(16) float sm[]; // q[HS] | k[HS] | out[HS] | att[ctx]
+                                                          unsigned tp_out_op, int head_base, float *att_scratch, int ctx) {
+    extern __shared__ __align__(16) float sm[]; // q[HS] | k[HS] | out[HS] | att[ctx] (att in global scratch for long contexts)
     __shared__ float red[ATT_THREADS / 32];
     __shared__ float s_val[2];
-    float *sq = sm, *sk = sm + HS, *so = sm + 2 * HS, *att = sm + 3 * HS;
+    float *sq = sm, *sk = sm + HS, *so = sm + 2 * HS;
+    float *att = att_scratch ? att_scratch + (size_t)blockIdx.x * ctx : sm + 3 * HS;
     const int h = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int HALF = HS / 2;
     trace_entry(tr);

@@ -1,40 +1,48 @@
-// decode_persistent.cuh -- ROUND-2 CANDIDATE: ONE persistent kernel per decoded token instead of
-// 227 dependent launches.  Compile-checked only (opt-in build: B200_NVCC_DEFINES="B200_SEQSUM_V2 B200_PERSISTENT_DECODE"); the
-// arithmetic of every phase is a copy of the validated round-1 kernels (k_stream_matvec_q8, k_rmsnorm_quant, k_attention,
-// k_argmax_advance), what is NEW and untested is the orchestration:
+// decode_persistent.cuh -- ONE persistent kernel per decoded token (sm_100a), replacing the 227 dependent launches of
+// the round-1 decode graph (and, in the reference, TornadoVMMasterPlanSingleToken.tornadoVMForwardDecode's N+2 TaskGraph
+// executions, TornadoVMMasterPlanSingleToken.java:68-95).  The arithmetic of every phase is the bit-exact CPU order of
+// decode_kernels.cuh / stream_matvec.cuh (InferenceCore.java:50-172, 565-697); what this file adds is the orchestration:
 //
-//   * grid = one CTA per SM, 8 consumer warps + 1 producer warp, all resident for the whole token;
+//   * grid = one CTA per SM (cooperative launch: co-residency is checked by the driver), 8 consumer warps + 1 producer
+//     warp, resident for the whole token;
 //   * the producer thread walks the tile-major weight stream of EVERY matrix of the token in consumption order (QKV, Wo,
-//     gate/up, W2 per layer, then lm_head) through one shared-memory ring: weight addresses never depend on activations, so
-//     HBM keeps streaming across what used to be kernel boundaries (the round-1 graph drained and refilled a 96 KB ring 225
-//     times per token);
-//   * phases are separated by device-scope epoch counters (monotone, never reset: target = (tick * layers + layer + 1) *
-//     arrivers -- the scheme of the tensor-parallel flags, common.cuh) instead of kernel boundaries: 5 per layer
-//     (QKV rows complete -> attention; attention heads complete -> Wo; x complete -> norm; hidden activation complete -> W2;
-//     x complete -> next layer);
-//   * RMSNorm is computed REDUNDANTLY by every CTA straight into its own shared-memory activation buffer (exact accumulator:
-//     seqsum2.cuh with 256 threads), which removes two of the seven dependencies of a layer and the xq/xs round trip;
-//   * attention heads run on the first n_heads CTAs with the consumer warps (same code as k_attention);
-//   * the embedding row is read in place: layer 0's norm squares the embedding row and layer 0's Wo epilogue writes
-//     x = emb + Wo*att, so no "x = embedding" pass and no grid sync before the first layer.
-// Restrictions of this draft: Q8_0 streaming path, single GPU, every matrix with the same tile size (true for the Llama /
-// Qwen3 shapes: segments of 2048 columns).
+//     gate/up, W2 per layer, then lm_head) through one shared-memory ring of 1-D bulk copies: weight addresses never
+//     depend on activations, so HBM keeps streaming across what used to be kernel boundaries; when the ring is full
+//     (consumers stalled at a dependency) it keeps HBM busy by prefetching the next tiles into L2 (`l2_ahead`);
+//   * phases are separated by epoch counters instead of kernel boundaries, five per layer:
+//         QKV rows -> attention | attention heads -> Wo | x -> ffn norm | hidden activation -> W2 | x -> next layer.
+//     Counters are monotone and never reset: target = (tick * layers + layer + 1) * arrivers, where tick counts launches.
+//     Under tensor parallelism the last local arriver of an exchanging phase raises epoch flags on every rank (NVLink
+//     peer stores, system-scope fences) and waiters poll the flags of all ranks: the all-gathers of common.cuh, now
+//     inside one kernel;
+//   * RMSNorm is computed REDUNDANTLY by every CTA straight into its own shared-memory activation buffer (exact
+//     accumulator: seqsum2.cuh on the 256 consumer threads), which removes two of the seven dependencies of a layer
+//     and the xq/xs round trip;
+//   * attention heads run on the first n_heads CTAs with the consumer warps; the score row lives in shared memory, or
+//     in a global scratch row when the context is too long for it;
+//   * the embedding row is consumed in place: layer 0's norm squares the embedding row and layer 0's Wo epilogue
+//     writes x = emb + Wo*att, so there is no "x = embedding" pass and no grid sync before the first layer;
+//   * every spin has a deadline (%globaltimer): a lost peer or a desynchronised call sequence sets an error word the
+//     host checks after the launch instead of hanging the GPU.
 #pragma once
-#include "../decode_kernels.cuh"
-#include "../stream_matvec.cuh"
+#include "decode_kernels.cuh"
 #include "seqsum2.cuh"
+#include "stream_matvec.cuh"
 
 #define PD_CT (SMV_CONSUMER_WARPS * 32) // consumer threads
-#define PD_MAX_STAGES 24
+#define PD_MAX_STAGES 32
+#define PD_TIMEOUT_NS 4000000000ull    // 4 s: far beyond any legitimate wait, well under gpurun's limits
+#define PD_STAMPS 10                    // trace stamps per layer and CTA
 
-enum { PD_S_QKV = 0, PD_S_ATT = 1, PD_S_WO = 2, PD_S_GU = 3, PD_S_W2 = 4, PD_S_LM = 5, PD_S_TICK = 8, PD_S_LMTICK = 9, PD_S_WORDS = 16 };
+enum { PD_S_QKV = 0, PD_S_ATT = 1, PD_S_WO = 2, PD_S_GU = 3, PD_S_W2 = 4, PD_S_LM = 5, PD_S_ARG = 6, PD_S_SLOTS = 8,
+       PD_S_TICK = 8, PD_S_LMTICK = 9, PD_S_ERR = 10, PD_S_WORDS = 16 };
 // PD_S_TICK counts launches (epoch of the per-layer counters); PD_S_LMTICK counts launches that ran the lm_head (the prefill
-// graph does not), which is the epoch of PD_S_LM.
+// graph does not), which is the epoch of PD_S_LM / PD_S_ARG.  PD_S_ERR != 0: a wait timed out (value = 1 + slot).
 
 struct PdLayer {
     TileMat qkv, wo, gu, w2;
     const float *attn_norm, *ffn_norm, *q_norm, *k_norm;
-    float *kc, *vc; // this layer's FP32 KV cache
+    float *kc, *vc; // this layer's FP32 KV cache (this rank's KV heads)
 };
 
 struct PdArgs {
@@ -43,7 +51,9 @@ struct PdArgs {
     TileMat lm_head;
     const float *out_norm;
     DevMat emb;
-    int dim, hidden, qd, kvd, n_heads, n_kv_heads, head_size, arch, vocab, ctx;
+    int dim, hidden, qd;     // full widths (qd = columns of Wo)
+    int n_heads, n_kv_heads; // of THIS rank
+    int head_size, arch, ctx;
     float eps, sqrt_hs;
     const float *rope_cr, *rope_ci;
     StepState *st;
@@ -57,8 +67,16 @@ struct PdArgs {
     unsigned *blk_cnt;
     float *part_val;
     int *part_idx;
-    unsigned *sync; // [PD_S_WORDS] epoch counters + tick
+    unsigned *sync;            // [PD_S_WORDS] local epoch counters, ticks, error word
+    unsigned *host_err;        // mapped pinned host word: receives the error code so the host sees it without a copy
+    float *att_scratch;        // [n_heads][ctx] score rows in global memory, or NULL: rows live in shared memory
+    unsigned long long *trace; // [gridDim.x][n_layers + 1][PD_STAMPS] %globaltimer stamps, or NULL
     int with_logits;
+    unsigned l2_ahead;         // tiles the producer may prefetch into L2 beyond the ring while the ring is full
+    // tensor parallelism (tp.n == 1: everything below unused)
+    TpCtx tp;
+    unsigned pd_flags_off;     // offset of the persistent kernel's epoch flags [PD_S_SLOTS][TP_MAX] in every rank's comm buffer
+    int head_base, dim_base, hid_base, voc_base; // global index of this rank's first head / residual row / hidden unit / vocab row
 };
 
 struct PdSmem {
@@ -66,15 +84,16 @@ struct PdSmem {
     int stages, stage_bytes, nbs_pad, nbuf_floats;
 };
 
-__host__ __device__ inline PdSmem pd_layout(int dim, int qd, int hidden, int head_size, int ctx, int seg, size_t budget) {
+// max_seg = widest column segment of any matrix of the plan; att_floats = 3*head_size + ctx when the score row lives in
+// shared memory, 3*head_size otherwise.
+__host__ __device__ inline PdSmem pd_layout(int dim, int qd, int hidden, int att_floats, int max_seg, size_t budget) {
     PdSmem L;
-    const int unit = smv_unit_bytes(seg);
+    const int unit = smv_unit_bytes(max_seg);
     L.stage_bytes = (4 * unit + 127) & ~127;
-    L.nbs_pad = (seg / 32) | 1;
+    L.nbs_pad = (max_seg / 32) | 1;
     int maxc = dim > qd ? dim : qd;
     if (hidden > maxc) maxc = hidden;
     const int dim_pad = (dim + PD_CT - 1) / PD_CT * PD_CT;
-    const int att_floats = 3 * head_size + ctx;
     L.nbuf_floats = dim_pad > att_floats ? dim_pad : att_floats;
     size_t o = 0;
     L.off_bar = o; o += 2 * PD_MAX_STAGES * 8 + PD_MAX_STAGES * 4;
@@ -86,7 +105,7 @@ __host__ __device__ inline PdSmem pd_layout(int dim, int qd, int hidden, int hea
     o = (o + 15) & ~(size_t)15;
     L.off_xbuf = o; o += (size_t)dim * 4; // the residual stream, kept between the two passes of the norm
     o = (o + 15) & ~(size_t)15;
-    L.off_seq = o; o += seqsum2_scratch_bytes();
+    L.off_seq = o; o += seqsum2_scratch_bytes(PD_CT);
     o = (o + 15) & ~(size_t)15;
     L.off_terms = o; o += (size_t)SMV_CONSUMER_WARPS * 4 * L.nbs_pad * 4;
     L.off_hvals = o; o += SMV_HVALS * 4;
@@ -101,49 +120,171 @@ __host__ __device__ inline PdSmem pd_layout(int dim, int qd, int hidden, int hea
     return L;
 }
 
-__device__ __forceinline__ unsigned pd_ld_acquire(const unsigned *p) {
+// ---- bounded waits ----------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned pd_ld_acquire_gpu(const unsigned *p) {
     unsigned v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned pd_ld_acquire_sys(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// one thread: spin until *p >= target (wrap-safe); gives up after PD_TIMEOUT_NS or as soon as another waiter gave up
+template <bool SYS> __device__ __noinline__ void pd_spin(const unsigned *p, unsigned target, unsigned *err, unsigned *host_err, unsigned code) {
+    unsigned it = 0;
+    unsigned long long t0 = 0;
+    for (;;) {
+        const unsigned v = SYS ? pd_ld_acquire_sys(p) : pd_ld_acquire_gpu(p);
+        if ((int)(v - target) >= 0) return;
+        if ((++it & 255u) == 0u) {
+            if (*reinterpret_cast<volatile unsigned *>(err)) return;
+            const unsigned long long now = gtime();
+            if (!t0) t0 = now;
+            else if (now - t0 > PD_TIMEOUT_NS) {
+                atomicCAS(err, 0u, code);
+                *reinterpret_cast<volatile unsigned *>(host_err) = code;
+                return;
+            }
+        }
+    }
+}
+
 struct PdConsumerSync {
     __device__ __forceinline__ void operator()() const { consumer_bar_sync(); }
 };
-// every consumer thread calls these; the CTA's stores (made before the barrier) are published by thread 0's fence + atomic
-__device__ __forceinline__ void pd_arrive(unsigned *cnt, int tid) {
+
+// Every consumer thread calls these.  `cross`: the phase's outputs are consumed by other ranks too (tensor parallelism):
+// the CTA's peer stores (made before the barrier) are published by thread 0's system-scope fence, and the LAST local
+// arriver raises this rank's epoch flag on every rank.
+__device__ __forceinline__ void pd_arrive(const PdArgs &a, int slot, unsigned target, unsigned epoch, bool cross, int tid) {
     consumer_bar_sync();
-    if (tid == 0) { __threadfence(); atomicAdd(cnt, 1u); }
+    if (tid == 0) {
+        const bool x = cross && a.tp.n > 1;
+        if (x) __threadfence_system();
+        else __threadfence();
+        const unsigned old = atomicAdd(a.sync + slot, 1u);
+        if (x && old + 1u == target) {
+            __threadfence_system();
+            for (int k = 0; k < a.tp.n; k++) {
+                unsigned *f = reinterpret_cast<unsigned *>(a.tp.peer[k] + a.pd_flags_off) + slot * TP_MAX + a.tp.rank;
+                asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory");
+            }
+        }
+    }
 }
-__device__ __forceinline__ void pd_wait(const unsigned *cnt, unsigned target, int tid) {
-    if (tid == 0)
-        while ((int)(pd_ld_acquire(cnt) - target) < 0) {}
+__device__ __forceinline__ void pd_wait(const PdArgs &a, int slot, unsigned target, unsigned epoch, bool cross, int tid) {
+    if (tid == 0) {
+        if (cross && a.tp.n > 1) {
+            const unsigned *f = reinterpret_cast<const unsigned *>(a.tp.peer[a.tp.rank] + a.pd_flags_off) + slot * TP_MAX;
+            for (int k = 0; k < a.tp.n; k++) pd_spin<true>(f + k, epoch, a.sync + PD_S_ERR, a.host_err, 1u + (unsigned)slot);
+        } else pd_spin<false>(a.sync + slot, target, a.sync + PD_S_ERR, a.host_err, 1u + (unsigned)slot);
+    }
     consumer_bar_sync();
 }
 
+__device__ __forceinline__ void pd_stamp(const PdArgs &a, int layer, int k, int tid) {
+    if (a.trace && tid == 0) a.trace[((size_t)blockIdx.x * (a.n_layers + 1) + layer) * PD_STAMPS + k] = gtime();
+}
+
 // ---- producer: the whole token's weight stream, in consumption order ----------------------------------------------------
-__device__ __forceinline__ void pd_produce_matrix(const TileMat &W, unsigned char *smem, const PdSmem &L, unsigned bar0, unsigned &seq) {
-    const int S = L.stages, ngroups = W.rows >> 2;
-    const int g0 = (int)(((long long)blockIdx.x * ngroups) / gridDim.x), g1 = (int)(((long long)(blockIdx.x + 1) * ngroups) / gridDim.x);
-    const unsigned tile_bytes = 4u * (unsigned)W.unit_bytes;
-    for (int gb = g0; gb < g1; gb += SMV_CONSUMER_WARPS) {
-        const int nw = min(SMV_CONSUMER_WARPS, g1 - gb);
-        for (int s = 0; s < W.nseg; s++)
-            for (int w = 0; w < nw; w++, seq++) {
-                const int st = seq % S;
-                const unsigned ph = (seq / S) & 1u;
-                mbar_wait(bar0 + 8 * (PD_MAX_STAGES + st), ph ^ 1u);
-                const unsigned full = bar0 + 8 * st;
-                mbar_expect_tx(full, tile_bytes);
-                bulk_g2s(smem_u32(smem + L.off_ring + (size_t)st * L.stage_bytes), W.base + ((size_t)(gb + w) * W.nseg + s) * tile_bytes, tile_bytes, full);
+// Cursor over this CTA's tiles of matrix 0..n_mats-1 (4 per layer, then the lm_head): the same walk the consumers make.
+struct PdWalk {
+    const PdArgs *a;
+    int n_mats, mi;
+    TileMat W;
+    int g1, gb, nw, s, w;
+    unsigned tile_bytes;
+    __device__ __forceinline__ void open() { // position on the first tile of matrix mi (skipping matrices this CTA has no rows of)
+        for (; mi < n_mats; mi++) {
+            const int l = mi >> 2;
+            if (l < a->n_layers) {
+                const PdLayer &Ly = a->layers[l];
+                const int k = mi & 3;
+                W = k == 0 ? Ly.qkv : k == 1 ? Ly.wo : k == 2 ? Ly.gu : Ly.w2;
+            } else W = a->lm_head;
+            const int ngroups = W.rows >> 2;
+            gb = (int)(((long long)blockIdx.x * ngroups) / gridDim.x);
+            g1 = (int)(((long long)(blockIdx.x + 1) * ngroups) / gridDim.x);
+            if (gb < g1) {
+                nw = min(SMV_CONSUMER_WARPS, g1 - gb);
+                s = 0; w = 0;
+                tile_bytes = 4u * (unsigned)W.unit_bytes;
+                return;
             }
+        }
+    }
+    __device__ __forceinline__ void init(const PdArgs *args) {
+        a = args;
+        n_mats = 4 * a->n_layers + (a->with_logits ? 1 : 0);
+        mi = 0;
+        open();
+    }
+    __device__ __forceinline__ bool valid() const { return mi < n_mats; }
+    __device__ __forceinline__ const unsigned char *addr() const { return W.base + ((size_t)(gb + w) * W.nseg + s) * tile_bytes; }
+    __device__ __forceinline__ void next() {
+        if (++w < nw) return;
+        w = 0;
+        if (++s < W.nseg) return;
+        s = 0;
+        gb += SMV_CONSUMER_WARPS;
+        if (gb < g1) { nw = min(SMV_CONSUMER_WARPS, g1 - gb); return; }
+        mi++;
+        open();
+    }
+};
+
+__device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0u;
+}
+
+__device__ __forceinline__ void pd_produce(const PdArgs &a, unsigned char *smem, const PdSmem &L, unsigned bar0) {
+    const int S = L.stages;
+    PdWalk cur, pf;
+    cur.init(&a);
+    pf = cur;
+    unsigned seq = 0, pf_seq = 0; // tiles issued into the ring / tiles covered by the L2 prefetch cursor
+    for (; cur.valid(); cur.next(), seq++) {
+        const int st = seq % S;
+        const unsigned ph = (seq / S) & 1u;
+        const unsigned empty = bar0 + 8 * (PD_MAX_STAGES + st);
+        if (a.l2_ahead) {
+            // The slot is still occupied: the consumers are behind (stalled at a dependency).  Keep HBM busy by pulling
+            // the tiles beyond the ring into L2, at most l2_ahead tiles ahead of the ring's own requests.
+            while (!mbar_try_wait(empty, ph ^ 1u)) {
+                if (pf_seq < seq + (unsigned)S) { // the ring itself covers [seq, seq + S)
+                    while (pf_seq < seq + (unsigned)S && pf.valid()) { pf.next(); pf_seq++; }
+                }
+                if (pf.valid() && pf_seq < seq + (unsigned)S + a.l2_ahead) {
+                    bulk_prefetch_l2(pf.addr(), pf.tile_bytes);
+                    pf.next();
+                    pf_seq++;
+                }
+            }
+        } else mbar_wait(empty, ph ^ 1u);
+        const unsigned full = bar0 + 8 * st;
+        mbar_expect_tx(full, cur.tile_bytes);
+        bulk_g2s(smem_u32(smem + L.off_ring + (size_t)st * L.stage_bytes), cur.addr(), cur.tile_bytes, full);
     }
 }
 
 // ---- consumers: one matrix (the loop of k_stream_matvec_q8, activation already in shared memory) --------------------------
 // l0_emb: layer 0's Wo writes x = embedding + acc (the embedding row is never copied into x beforehand).
+// row_base: global index of this rank's first output row (RESID, STORE/argmax) or hidden unit (GATEUP).
 template <int MODE>
 __device__ __forceinline__ void pd_consume_matrix(const TileMat &W, const PdArgs &a, unsigned char *smem, const PdSmem &L, unsigned bar0, volatile unsigned *rel,
-                                                  unsigned &seq_base, float *out, bool argmax, bool l0_emb, int token, int tid) {
+                                                  unsigned &seq_base, float *out, bool argmax, bool l0_emb, int token, int row_base, int tid) {
     const int lane = tid & 31, warp = tid >> 5, S = L.stages;
     const int ngroups = W.rows >> 2;
     const int g0 = (int)(((long long)blockIdx.x * ngroups) / gridDim.x), g1 = (int)(((long long)(blockIdx.x + 1) * ngroups) / gridDim.x);
@@ -198,7 +339,7 @@ __device__ __forceinline__ void pd_consume_matrix(const TileMat &W, const PdArgs
                 }
                 if (lane < 4) {
                     const float *t = terms + lane * L.nbs_pad;
-                    for (int b = 0; b < nbs; b++) acc = __fadd_rn(acc, t[b]);
+                    for (int b = 0; b < nbs; b++) acc = __fadd_rn(acc, t[b]); // strictly in block order
                 }
                 __syncwarp();
             }
@@ -213,17 +354,22 @@ __device__ __forceinline__ void pd_consume_matrix(const TileMat &W, const PdArgs
             } else if (lane < 4) {
                 const size_t row = (size_t)4 * G + lane;
                 if (MODE == SMV_RESID) {
-                    const float base = l0_emb ? emb_get(a.emb, token, (int)row) : out[row];
-                    out[row] = __fadd_rn(base, acc);
+                    const size_t grow = (size_t)row_base + row;
+                    const float base = l0_emb ? emb_get(a.emb, token, (int)grow) : out[grow];
+                    const float v = __fadd_rn(base, acc); // x[i] = x[i] + xb2[i]
+                    if (a.tp.n > 1) { // all-gather of the residual stream: this rank's rows go to every rank
+                        for (int k = 0; k < a.tp.n; k++) tp_ptr<float>(a.tp, k, a.tp.off_x)[grow] = v;
+                    } else out[grow] = v;
                 } else {
                     out[row] = acc;
-                    if (acc > best) { best = acc; best_i = (int)row; }
+                    const int grow = row_base + (int)row;
+                    if (acc > best) { best = acc; best_i = grow; } // rows ascend per lane: first maximum kept
                 }
             }
         }
         seq_base += (unsigned)(nseg * nw);
     }
-    if (MODE == SMV_GATEUP) { // Q8_0 quantisation of the hidden activation: copy of k_stream_matvec_q8's epilogue
+    if (MODE == SMV_GATEUP) { // Q8_0 quantisation of the hidden activation: k_stream_matvec_q8's epilogue
         consumer_bar_sync();
         const int u0 = 2 * g0, u1 = 2 * g1;
         if (u1 > u0) {
@@ -235,7 +381,7 @@ __device__ __forceinline__ void pd_consume_matrix(const TileMat &W, const PdArgs
                 else {
                     unsigned old = 0;
                     if (lane == 0) {
-                        __threadfence();
+                        __threadfence(); // cumulative: publishes the hb stores of the whole CTA (ordered by the barrier above)
                         old = atomicAdd(&a.blk_cnt[blk], (unsigned)(hi - lo));
                     }
                     old = __shfl_sync(0xffffffffu, old, 0);
@@ -249,8 +395,16 @@ __device__ __forceinline__ void pd_consume_matrix(const TileMat &W, const PdArgs
                 if (mine) {
                     float as;
                     const int q = quant_block_lane(v, as);
-                    a.hq[(blk << 5) + lane] = (int8_t)q;
-                    if (lane == 0) a.hs[blk] = as;
+                    const int gblk = (row_base >> 5) + blk;
+                    if (a.tp.n > 1) {
+                        for (int k = 0; k < a.tp.n; k++) {
+                            tp_ptr<int8_t>(a.tp, k, a.tp.off_hq)[(gblk << 5) + lane] = (int8_t)q;
+                            if (lane == 0) tp_ptr<float>(a.tp, k, a.tp.off_hs)[gblk] = as;
+                        }
+                    } else {
+                        a.hq[(gblk << 5) + lane] = (int8_t)q;
+                        if (lane == 0) a.hs[gblk] = as;
+                    }
                 }
             }
         }
@@ -285,7 +439,7 @@ __device__ __forceinline__ void pd_norm_to_smem(const PdArgs &a, const float *w,
     float *sq = reinterpret_cast<float *>(smem + L.off_nbuf);
     float *xb = reinterpret_cast<float *>(smem + L.off_xbuf);
     float *misc = reinterpret_cast<float *>(smem + L.off_misc);
-    SeqSum2Scratch scratch = seqsum2_carve(smem + L.off_seq);
+    SeqSum2Scratch scratch = seqsum2_carve(smem + L.off_seq, PD_CT);
     const int dim_pad = (dim + PD_CT - 1) / PD_CT * PD_CT;
     if (from_emb) { // first layer: the embedding row (quantised table: element-wise)
         for (int i = tid; i < dim; i += PD_CT) {
@@ -348,7 +502,7 @@ __device__ __forceinline__ void pd_norm_to_smem(const PdArgs &a, const float *w,
     consumer_bar_sync();
 }
 
-// a quantised activation vector produced by other CTAs (attention output, hidden activation) -> shared memory
+// a quantised activation vector produced by other CTAs / ranks (attention output, hidden activation) -> shared memory
 __device__ __forceinline__ void pd_load_act(const int8_t *q, const float *s, int cols, unsigned char *smem, const PdSmem &L, int tid) {
     int4 *sxq = reinterpret_cast<int4 *>(smem + L.off_xq);
     float *sxs = reinterpret_cast<float *>(smem + L.off_xs);
@@ -358,13 +512,15 @@ __device__ __forceinline__ void pd_load_act(const int8_t *q, const float *s, int
     consumer_bar_sync();
 }
 
-// ---- one attention head with the consumer warps: copy of k_attention's body (single GPU, Q8_0 output) -----------------------
+// ---- one attention head with the consumer warps: k_attention's body (exact CPU order, InferenceCore.java:98-137) -------------
+// h = local head index on this rank.
 template <int HS>
 __device__ __forceinline__ void pd_attention_head(const PdArgs &a, const PdLayer &Ly, int h, int pos, unsigned char *smem, const PdSmem &L, int tid) {
     float *sm = reinterpret_cast<float *>(smem + L.off_nbuf);
     float *misc = reinterpret_cast<float *>(smem + L.off_misc);
     float *red = misc, *s_val = misc + 8;
-    float *sq = sm, *sk = sm + HS, *so = sm + 2 * HS, *att = sm + 3 * HS;
+    float *sq = sm, *sk = sm + HS, *so = sm + 2 * HS;
+    float *att = a.att_scratch ? a.att_scratch + (size_t)h * a.ctx : sm + 3 * HS;
     const int lane = tid & 31, warp = tid >> 5;
     constexpr int HALF = HS / 2;
     const int nt = pos + 1;
@@ -379,7 +535,7 @@ __device__ __forceinline__ void pd_attention_head(const PdArgs &a, const PdLayer
         int i0, i1;
         if (a.arch == 1) { i0 = p; i1 = p + HALF; } else { i0 = 2 * p; i1 = 2 * p + 1; }
         float v0 = ldcg_f32c(src + i0), v1 = ldcg_f32c(src + i1); // written by other CTAs in this kernel: bypass L1
-        if (a.arch == 1) {
+        if (a.arch == 1) { // Qwen3 per-head RMSNorm: literal sequential sum over the head (InferenceCore.java:594-600)
             float *sqr = is_q ? so : sk;
             sqr[i0] = __fmul_rn(v0, v0);
             sqr[i1] = __fmul_rn(v1, v1);
@@ -404,7 +560,7 @@ __device__ __forceinline__ void pd_attention_head(const PdArgs &a, const PdLayer
         float *dst = is_q ? sq : sk;
         dst[i0] = r0;
         dst[i1] = r1;
-        if (h % kv_mul == 0 && !is_q) {
+        if (h % kv_mul == 0 && !is_q) { // first query head of the KV group owns the cache write (InferenceCore.java:92-93)
             const size_t o = (size_t)pos * kvd + kvh * HS;
             kc[o + i0] = r0;
             kc[o + i1] = r1;
@@ -448,16 +604,21 @@ __device__ __forceinline__ void pd_attention_head(const PdArgs &a, const PdLayer
     for (int w = 1; w < SMV_CONSUMER_WARPS; w++) mx = fmaxf(mx, red[w]);
     for (int t = tid; t < nt; t += PD_CT) att[t] = (float)exp((double)__fsub_rn(att[t], mx));
     consumer_bar_sync();
-    if (tid == 0) {
+    if (tid == 0) { // sequential float sum (FloatTensor.softmaxInPlace, FloatTensor.java:211-219)
         float sum = 0.0f;
-        for (int t = 0; t < nt; t++) sum = __fadd_rn(sum, att[t]);
+        int t = 0;
+        for (; t + 4 <= nt; t += 4) {
+            const float a0 = att[t], a1 = att[t + 1], a2 = att[t + 2], a3 = att[t + 3];
+            sum = __fadd_rn(sum, a0); sum = __fadd_rn(sum, a1); sum = __fadd_rn(sum, a2); sum = __fadd_rn(sum, a3);
+        }
+        for (; t < nt; t++) sum = __fadd_rn(sum, att[t]);
         s_val[0] = sum;
     }
     consumer_bar_sync();
     const float sum = s_val[0];
     for (int t = tid; t < nt; t += PD_CT) att[t] = __fdiv_rn(att[t], sum);
     consumer_bar_sync();
-    if (tid < HS) {
+    if (tid < HS) { // xb = sum_t a_t * v_t, sequentially over t per element (saxpyInPlace, FloatTensor.java:221-227)
         const float *v = vc + kvh * HS + tid;
         float acc = 0.0f;
         int t = 0;
@@ -473,11 +634,19 @@ __device__ __forceinline__ void pd_attention_head(const PdArgs &a, const PdLayer
         so[tid] = acc;
     }
     consumer_bar_sync();
+    const int gh = a.head_base + h;
     for (int b = warp; b < HS / 32; b += SMV_CONSUMER_WARPS) {
         float as;
         const int q = quant_block_lane(so[b * 32 + lane], as);
-        a.attq[h * HS + b * 32 + lane] = (int8_t)q;
-        if (lane == 0) a.atts[(h * HS) / 32 + b] = as;
+        if (a.tp.n > 1) { // all-gather: this head's quantised output goes straight into every rank's buffer
+            for (int k = 0; k < a.tp.n; k++) {
+                tp_ptr<int8_t>(a.tp, k, a.tp.off_attq)[gh * HS + b * 32 + lane] = (int8_t)q;
+                if (lane == 0) tp_ptr<float>(a.tp, k, a.tp.off_atts)[(gh * HS) / 32 + b] = as;
+            }
+        } else {
+            a.attq[gh * HS + b * 32 + lane] = (int8_t)q;
+            if (lane == 0) a.atts[(gh * HS) / 32 + b] = as;
+        }
     }
 }
 
@@ -500,17 +669,7 @@ __global__ void __launch_bounds__(SMV_THREADS, 1) k_decode_persistent(PdArgs a, 
     __syncthreads();
 
     if (warp == SMV_CONSUMER_WARPS) { // ===== producer =====
-        if (lane == 0) {
-            unsigned seq = 0;
-            for (int l = 0; l < a.n_layers; l++) {
-                const PdLayer &Ly = a.layers[l];
-                pd_produce_matrix(Ly.qkv, smem, L, bar0, seq);
-                pd_produce_matrix(Ly.wo, smem, L, bar0, seq);
-                pd_produce_matrix(Ly.gu, smem, L, bar0, seq);
-                pd_produce_matrix(Ly.w2, smem, L, bar0, seq);
-            }
-            if (a.with_logits) pd_produce_matrix(a.lm_head, smem, L, bar0, seq);
-        }
+        if (lane == 0) pd_produce(a, smem, L, bar0);
         return;
     }
 
@@ -518,41 +677,55 @@ __global__ void __launch_bounds__(SMV_THREADS, 1) k_decode_persistent(PdArgs a, 
     const int token = a.st->token, pos = a.st->pos;
     const unsigned tick = *reinterpret_cast<volatile unsigned *>(a.sync + PD_S_TICK);
     const unsigned lmtick = *reinterpret_cast<volatile unsigned *>(a.sync + PD_S_LMTICK);
-    const unsigned nC = gridDim.x, nL = (unsigned)a.n_layers;
+    const unsigned nC = gridDim.x, nL = (unsigned)a.n_layers, nH = (unsigned)a.n_heads;
     unsigned seq_base = 0;
     for (int l = 0; l < a.n_layers; l++) {
         const PdLayer &Ly = a.layers[l];
         const unsigned e = tick * nL + (unsigned)l + 1u; // this layer's epoch
+        pd_stamp(a, l, 0, tid);
         pd_norm_to_smem(a, Ly.attn_norm, l == 0, token, smem, L, tid);
-        pd_consume_matrix<SMV_STORE>(Ly.qkv, a, smem, L, bar0, rel, seq_base, a.qkv, false, false, token, tid);
-        pd_arrive(a.sync + PD_S_QKV, tid);
-        if ((int)blockIdx.x < a.n_heads) { // attention: the first n_heads CTAs, one head each
-            pd_wait(a.sync + PD_S_QKV, e * nC, tid);
+        pd_stamp(a, l, 1, tid);
+        pd_consume_matrix<SMV_STORE>(Ly.qkv, a, smem, L, bar0, rel, seq_base, a.qkv, false, false, token, 0, tid);
+        pd_stamp(a, l, 2, tid);
+        pd_arrive(a, PD_S_QKV, e * nC, e, false, tid); // q/k/v of this rank's heads stay on this rank
+        if (blockIdx.x < nH) { // attention: the first n_heads CTAs, one head each
+            pd_wait(a, PD_S_QKV, e * nC, e, false, tid);
             pd_attention_head<HS>(a, Ly, blockIdx.x, pos, smem, L, tid);
-            pd_arrive(a.sync + PD_S_ATT, tid);
+            pd_arrive(a, PD_S_ATT, e * nH, e, true, tid);
         }
-        pd_wait(a.sync + PD_S_ATT, e * (unsigned)a.n_heads, tid);
+        pd_wait(a, PD_S_ATT, e * nH, e, true, tid);
+        pd_stamp(a, l, 3, tid);
         pd_load_act(a.attq, a.atts, a.qd, smem, L, tid);
-        pd_consume_matrix<SMV_RESID>(Ly.wo, a, smem, L, bar0, rel, seq_base, a.x, false, l == 0, token, tid);
-        pd_arrive(a.sync + PD_S_WO, tid);
-        pd_wait(a.sync + PD_S_WO, e * nC, tid);
+        pd_consume_matrix<SMV_RESID>(Ly.wo, a, smem, L, bar0, rel, seq_base, a.x, false, l == 0, token, a.dim_base, tid);
+        pd_stamp(a, l, 4, tid);
+        pd_arrive(a, PD_S_WO, e * nC, e, true, tid);
+        pd_wait(a, PD_S_WO, e * nC, e, true, tid);
+        pd_stamp(a, l, 5, tid);
         pd_norm_to_smem(a, Ly.ffn_norm, false, token, smem, L, tid);
-        pd_consume_matrix<SMV_GATEUP>(Ly.gu, a, smem, L, bar0, rel, seq_base, a.hb, false, false, token, tid);
-        pd_arrive(a.sync + PD_S_GU, tid);
-        pd_wait(a.sync + PD_S_GU, e * nC, tid);
+        pd_stamp(a, l, 6, tid);
+        pd_consume_matrix<SMV_GATEUP>(Ly.gu, a, smem, L, bar0, rel, seq_base, a.hb, false, false, token, a.hid_base, tid);
+        pd_stamp(a, l, 7, tid);
+        pd_arrive(a, PD_S_GU, e * nC, e, true, tid);
+        pd_wait(a, PD_S_GU, e * nC, e, true, tid);
         pd_load_act(a.hq, a.hs, a.hidden, smem, L, tid);
-        pd_consume_matrix<SMV_RESID>(Ly.w2, a, smem, L, bar0, rel, seq_base, a.x, false, false, token, tid);
-        pd_arrive(a.sync + PD_S_W2, tid);
-        pd_wait(a.sync + PD_S_W2, e * nC, tid);
+        pd_stamp(a, l, 8, tid);
+        pd_consume_matrix<SMV_RESID>(Ly.w2, a, smem, L, bar0, rel, seq_base, a.x, false, false, token, a.dim_base, tid);
+        pd_stamp(a, l, 9, tid);
+        pd_arrive(a, PD_S_W2, e * nC, e, true, tid);
+        pd_wait(a, PD_S_W2, e * nC, e, true, tid);
     }
     int best_i = 0;
     if (a.with_logits) {
+        const unsigned le = lmtick + 1u;
+        pd_stamp(a, a.n_layers, 0, tid);
         pd_norm_to_smem(a, a.out_norm, false, token, smem, L, tid);
-        pd_consume_matrix<SMV_STORE>(a.lm_head, a, smem, L, bar0, rel, seq_base, a.logits, true, false, token, tid);
-        pd_arrive(a.sync + PD_S_LM, tid);
+        pd_stamp(a, a.n_layers, 1, tid);
+        pd_consume_matrix<SMV_STORE>(a.lm_head, a, smem, L, bar0, rel, seq_base, a.logits, true, false, token, a.voc_base, tid);
+        pd_stamp(a, a.n_layers, 2, tid);
+        pd_arrive(a, PD_S_LM, le * nC, le, false, tid);
         if (blockIdx.x != 0) return;
-        pd_wait(a.sync + PD_S_LM, (lmtick + 1u) * nC, tid);
-        // FloatTensor.argmax over the per-CTA (max, first index) pairs: copy of k_argmax_advance
+        pd_wait(a, PD_S_LM, le * nC, le, false, tid);
+        // FloatTensor.argmax over the per-CTA (max, first index) pairs: k_argmax_advance
         float best = -INFINITY;
         best_i = 0x7fffffff;
         for (int i = tid; i < (int)nC; i += PD_CT) argmax_merge(best, best_i, ldcg_f32c(a.part_val + i), __ldcg(a.part_idx + i));
@@ -569,6 +742,23 @@ __global__ void __launch_bounds__(SMV_THREADS, 1) k_decode_persistent(PdArgs a, 
         if (tid == 0) {
             best = sv[0]; best_i = si[0];
             for (int w = 1; w < SMV_CONSUMER_WARPS; w++) argmax_merge(best, best_i, sv[w], si[w]);
+            if (a.tp.n > 1) { // exchange every rank's (max, lowest global index) and merge identically everywhere
+                for (int k = 0; k < a.tp.n; k++) {
+                    tp_ptr<float>(a.tp, k, a.tp.off_pv)[a.tp.rank] = best;
+                    tp_ptr<int>(a.tp, k, a.tp.off_pi)[a.tp.rank] = best_i;
+                }
+                __threadfence_system();
+                for (int k = 0; k < a.tp.n; k++) {
+                    unsigned *f = reinterpret_cast<unsigned *>(a.tp.peer[k] + a.pd_flags_off) + PD_S_ARG * TP_MAX + a.tp.rank;
+                    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(f), "r"(le) : "memory");
+                }
+                const unsigned *f = reinterpret_cast<const unsigned *>(a.tp.peer[a.tp.rank] + a.pd_flags_off) + PD_S_ARG * TP_MAX;
+                for (int k = 0; k < a.tp.n; k++) pd_spin<true>(f + k, le, a.sync + PD_S_ERR, a.host_err, 1u + PD_S_ARG);
+                best = -INFINITY; best_i = 0x7fffffff;
+                for (int k = 0; k < a.tp.n; k++)
+                    argmax_merge(best, best_i, ldcg_f32c(tp_ptr<float>(a.tp, a.tp.rank, a.tp.off_pv) + k),
+                                 __float_as_int(ldcg_f32c(reinterpret_cast<const float *>(tp_ptr<int>(a.tp, a.tp.rank, a.tp.off_pi)) + k)));
+            }
             if (best_i == 0x7fffffff) best_i = 0;
         }
     } else if (blockIdx.x != 0) {
@@ -585,5 +775,6 @@ __global__ void __launch_bounds__(SMV_THREADS, 1) k_decode_persistent(PdArgs a, 
         st->pos = st->pos + 1;
         *reinterpret_cast<volatile unsigned *>(a.sync + PD_S_TICK) = tick + 1u;
         if (a.with_logits) *reinterpret_cast<volatile unsigned *>(a.sync + PD_S_LMTICK) = lmtick + 1u;
+        pd_stamp(a, a.n_layers, 3, tid);
     }
 }

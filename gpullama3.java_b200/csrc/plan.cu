@@ -6,12 +6,7 @@
 #include "decode_kernels.cuh"
 #include "prefill.cuh"
 #include "stream_matvec.cuh"
-#ifdef B200_PERSISTENT_DECODE // opt-in build: one persistent kernel per token (experimental/decode_persistent.cuh; needs B200_SEQSUM_V2)
-#ifndef B200_SEQSUM_V2
-#error "B200_PERSISTENT_DECODE needs B200_SEQSUM_V2 (the 256-thread exact accumulator)"
-#endif
-#include "experimental/decode_persistent.cuh"
-#endif
+#include "decode_persistent.cuh"
 
 #include <math.h>
 #include <stdarg.h>
@@ -67,8 +62,16 @@ struct b200_plan {
     StepState *h_st = nullptr; // pinned
     int *h_ids = nullptr;      // pinned, seq_cap
 
-    cudaGraphExec_t g_decode = nullptr, g_prefill = nullptr, g_trace = nullptr;
+    cudaGraphExec_t g_decode = nullptr, g_prefill = nullptr, g_trace = nullptr; // the multi-kernel decode graph (round 1)
+    cudaGraphExec_t g_pdecode = nullptr, g_pprefill = nullptr, g_ptrace = nullptr; // one persistent kernel per token (decode_persistent.cuh)
     unsigned long long *trace_rec = nullptr;
+    int decode_mode = B200_DECODE_GRAPH; // which of the two the forward entry points launch
+    bool norm_v2 = false;                // k_rmsnorm_quant's accumulator: seqsum2.cuh instead of seqsum.cuh
+    // knobs read once at creation (never inside a launch helper)
+    size_t smv_budget = 96 * 1024;
+    int smv_budget_cols = 0;
+    unsigned l2_window = 0, pd_l2_ahead = 0;
+    float *att_scratch = nullptr; // [heads][ctx] score rows when the context does not fit shared memory
 
     // tensor parallelism (tp.n == 1: single GPU).  *_l = this rank's share.
     TpCtx tp{};
@@ -84,10 +87,17 @@ struct b200_plan {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
     PrefillCtx prefill;
-#ifdef B200_PERSISTENT_DECODE
-    PdLayer *pd_layers = nullptr; // device copies of the per-layer descriptors of the persistent decode kernel
-    unsigned *pd_sync = nullptr;  // its epoch counters
-#endif
+    // persistent decode kernel
+    bool pd_ok = false;           // the plan fits the kernel's restrictions
+    std::string pd_why;           // ... or why not
+    PdSmem pd_L{};
+    PdLayer *pd_layers = nullptr; // device copies of the per-layer descriptors
+    unsigned *pd_sync = nullptr;  // epoch counters, ticks, error word
+    unsigned *h_err = nullptr;    // mapped pinned host word written by a timed-out wait
+    unsigned *d_err = nullptr;    // its device alias
+    unsigned long long *pd_trace = nullptr;
+    unsigned pd_flags_off = 0;
+    bool pd_coop = true;          // launched with the cooperative attribute (co-residency guaranteed by the driver)
 };
 
 namespace {
@@ -295,20 +305,32 @@ int launch_k(b200_plan *p, bool pdl, void (*kern)(KA...), dim3 grid, dim3 block,
 }
 
 const size_t SMV_SMEM_BUDGET_MAX = 96 * 1024;
-static size_t smv_budget(int cols = 0) {
-    const char *e = getenv("B200_SMV_BUDGET_KB"); // debug: force a shallow ring
-    const char *m = getenv("B200_SMV_BUDGET_COLS"); // debug: ... only for matrices with this many columns
+// Debug/tuning knobs, read ONCE per plan (b200_plan_create), never inside a launch helper.
+void read_knobs(b200_plan *p) {
+    const char *e = getenv("B200_SMV_BUDGET_KB");   // force a shallow ring
+    const char *m = getenv("B200_SMV_BUDGET_COLS"); // ... only for matrices with this many columns
     size_t b = e ? (size_t)atoi(e) * 1024 : SMV_SMEM_BUDGET_MAX;
-    if (m && cols && atoi(m) != cols) b = SMV_SMEM_BUDGET_MAX;
-    return b > SMV_SMEM_BUDGET_MAX ? SMV_SMEM_BUDGET_MAX : b;
+    p->smv_budget = b > SMV_SMEM_BUDGET_MAX ? SMV_SMEM_BUDGET_MAX : b;
+    p->smv_budget_cols = m ? atoi(m) : 0;
+    const char *w = getenv("B200_L2_WINDOW_KB"); // experimental: measured slower on B200 (profiles/), off by default
+    p->l2_window = (unsigned)((w ? atoi(w) : 0) * 1024);
+    const char *a = getenv("B200_PD_L2_AHEAD"); // persistent kernel: tiles of L2 look-ahead while the ring is full
+    p->pd_l2_ahead = a ? (unsigned)atoi(a) : 0u;
+    const char *v = getenv("B200_NORM_V2");
+    p->norm_v2 = !(v && v[0] == '0');
+    const char *d = getenv("B200_DECODE");
+    p->decode_mode = (d && !strcmp(d, "graph")) ? B200_DECODE_GRAPH : B200_DECODE_PERSISTENT;
 }
-#define SMV_SMEM_BUDGET smv_budget()
+size_t smv_budget(const b200_plan *p, int cols) {
+    if (p->smv_budget_cols && cols && p->smv_budget_cols != cols) return SMV_SMEM_BUDGET_MAX;
+    return p->smv_budget;
+}
 
 template <int MODE>
 int launch_stream(b200_plan *p, const TileMat &W, const int8_t *xq, const float *xs, float *out, int8_t *hq, float *hs, bool argmax = false,
                   TraceBuf tr = TraceBuf{nullptr, 0, 0}, int wait_slot = -1, unsigned wait_op = 0, int out_slot = -1, unsigned out_op = 0,
                   int row_base = 0) {
-    SmvSmem L = smv_layout(W.cols, W.seg, smv_budget(W.cols));
+    SmvSmem L = smv_layout(W.cols, W.seg, smv_budget(p, W.cols));
     SmvArgs a;
     a.W = W; a.xq = xq; a.xs = xs; a.out = out; a.hq = hq; a.hs = hs; a.blk_cnt = p->blk_cnt;
     a.part_val = argmax ? p->part_val : nullptr;
@@ -316,10 +338,7 @@ int launch_stream(b200_plan *p, const TileMat &W, const int8_t *xq, const float 
     a.tr = tr;
     a.tp = p->tp;
     a.wait_slot = wait_slot; a.wait_op = wait_op; a.out_slot = out_slot; a.out_op = out_op; a.row_base = row_base;
-    {
-        const char *e = getenv("B200_L2_WINDOW_KB");
-        a.l2_window = (unsigned)((e ? atoi(e) : 0) * 1024); // experimental: measured slower on B200 (profiles/), off by default
-    }
+    a.l2_window = p->l2_window;
     return launch_k(p, p->use_pdl, k_stream_matvec_q8<MODE>, dim3(p->n_sms), dim3(SMV_THREADS), L.total, a, L);
 }
 
@@ -327,7 +346,7 @@ bool stream_shape_ok(int rows, int cols) {
     if (rows % 4 || cols % 32) return false;
     int nseg = smv_pick_nseg(cols);
     if (!nseg) return false;
-    return smv_layout(cols, cols / nseg, SMV_SMEM_BUDGET).stages >= 3;
+    return smv_layout(cols, cols / nseg, SMV_SMEM_BUDGET_MAX).stages >= 3;
 }
 
 bool gateup_fits(int hidden, int n_sms) { // epilogue buffer holds this CTA's hidden units
@@ -343,15 +362,18 @@ int enqueue_forward(b200_plan *p, bool with_logits, int *launches, bool trace = 
     const bool tpar = p->tp.n > 1;
     int n = 0;
     auto TR = [&](int id) { return TraceBuf{trace ? p->trace_rec : nullptr, n, id}; };
-    const size_t norm_smem = norm_smem_bytes(c.dim);
+    const size_t norm_smem = norm_smem_bytes(c.dim, p->norm_v2);
     int8_t *xq = q8 ? p->xq : nullptr;
     float *xs = q8 ? p->xs : nullptr;
     float *xbf = q8 ? nullptr : p->xb;
     const size_t ctx_kv = (size_t)c.context_length * p->kvd_l;
     const int rank = p->tp.rank;
     auto norm = [&](bool embed, const float *w, int wait_op) {
-        if (embed) return launch_k(p, pdl, k_rmsnorm_quant<true>, dim3(1), dim3(NORM_THREADS), norm_smem, p->x, (const StepState *)p->st, p->emb, w, c.rms_norm_eps, c.dim, xq, xs, xbf, (long long *)nullptr, TR(1), p->tp, wait_op);
-        return launch_k(p, pdl, k_rmsnorm_quant<false>, dim3(1), dim3(NORM_THREADS), norm_smem, p->x, (const StepState *)p->st, p->emb, w, c.rms_norm_eps, c.dim, xq, xs, xbf, (long long *)nullptr, TR(1), p->tp, wait_op);
+        auto go = [&](auto kern) {
+            return launch_k(p, pdl, kern, dim3(1), dim3(NORM_THREADS), norm_smem, p->x, (const StepState *)p->st, p->emb, w, c.rms_norm_eps, c.dim, xq, xs, xbf, (long long *)nullptr, TR(1), p->tp, wait_op);
+        };
+        if (p->norm_v2) return embed ? go(k_rmsnorm_quant<true, true>) : go(k_rmsnorm_quant<false, true>);
+        return embed ? go(k_rmsnorm_quant<true, false>) : go(k_rmsnorm_quant<false, false>);
     };
     for (int l = 0; l < c.n_layers; l++) {
         LayerW &L = p->layers[l];
@@ -365,12 +387,12 @@ int enqueue_forward(b200_plan *p, bool with_logits, int *launches, bool trace = 
         if (rc) return rc; n++;
         float *kc = p->key_cache + (size_t)l * ctx_kv, *vc = p->value_cache + (size_t)l * ctx_kv;
         {
-            const size_t att_smem = (size_t)(3 * c.head_size + c.context_length) * 4;
+            const size_t att_smem = (size_t)(3 * c.head_size + (p->att_scratch ? 0 : c.context_length)) * 4;
             auto att = [&](auto kern) {
                 return launch_k(p, pdl, kern, dim3(p->nh_l), dim3(ATT_THREADS), att_smem, p->qkv, kc, vc, (const StepState *)p->st,
                                 (const float *)p->rope_cr, (const float *)p->rope_ci, p->nh_l, p->nkv_l, c.arch, (const float *)L.q_norm,
                                 (const float *)L.k_norm, c.rms_norm_eps, (float)sqrt((double)c.head_size), q8 ? p->attq : nullptr, q8 ? p->atts : nullptr, xbf, TR(4),
-                                p->tp, (unsigned)(4 * l + 0), rank * p->nh_l);
+                                p->tp, (unsigned)(4 * l + 0), rank * p->nh_l, p->att_scratch, c.context_length);
             };
             if (c.head_size == 128) rc = att(k_attention<128>);
             else if (c.head_size == 64) rc = att(k_attention<64>);
@@ -422,25 +444,30 @@ int enqueue_forward(b200_plan *p, bool with_logits, int *launches, bool trace = 
     return B200_OK;
 }
 
-#ifdef B200_PERSISTENT_DECODE
-// One launch per token (experimental/decode_persistent.cuh).  Returns B200_ERR_UNSUPPORTED when the plan does not fit the
-// draft's restrictions, in which case the caller falls back to the multi-kernel graph.
-int pd_prepare(b200_plan *p, PdSmem *layout) { // checks + allocations only (never launches: the KV cache must stay zero-initialised)
+// ---- one persistent kernel per token (decode_persistent.cuh) ---------------------------------------------------------------
+// Checks the kernel's restrictions and allocates its descriptors; never launches (the KV cache must stay zero-initialised).
+// Leaves p->pd_ok / p->pd_why; a plan that does not fit simply keeps the multi-kernel graph.
+int pd_prepare(b200_plan *p) {
     const b200_config &c = p->cfg;
-    if (!p->use_stream || p->tp.n > 1 || c.tp_size > 1) return B200_ERR_UNSUPPORTED;
-    const int seg = p->layers[0].tqkv.seg;
-    for (const LayerW &L : p->layers)
-        if (L.tqkv.seg != seg || L.two.seg != seg || L.tgu.seg != seg || L.tw2.seg != seg) return B200_ERR_UNSUPPORTED;
-    if (p->tout.seg != seg) return B200_ERR_UNSUPPORTED;
-    if (c.head_size != 64 && c.head_size != 128) return B200_ERR_UNSUPPORTED;
-    if (c.n_heads > p->n_sms) return B200_ERR_UNSUPPORTED;
+    p->pd_ok = false;
+    if (!p->use_stream) { p->pd_why = "the persistent decode kernel needs the Q8_0 streaming layout"; return B200_OK; }
+    if (c.head_size != 64 && c.head_size != 128) { p->pd_why = "the persistent decode kernel supports head sizes 64 and 128"; return B200_OK; }
+    if (p->nh_l > p->n_sms) { p->pd_why = "more attention heads than SMs"; return B200_OK; }
+    if (!gateup_fits(p->hid_l, p->n_sms)) { p->pd_why = "hidden slice per CTA exceeds the epilogue buffer"; return B200_OK; }
+    int max_seg = p->tout.seg;
+    for (const LayerW &L : p->layers) {
+        const int segs[4] = {L.tqkv.seg, L.two.seg, L.tgu.seg, L.tw2.seg};
+        for (int k = 0; k < 4; k++) if (segs[k] > max_seg) max_seg = segs[k];
+    }
     int maxdyn = 0;
     CK(cudaDeviceGetAttribute(&maxdyn, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device));
-    const PdSmem L = pd_layout(c.dim, p->qd, c.hidden_dim, c.head_size, c.context_length, seg, (size_t)maxdyn);
-    if (L.stages < 4) return B200_ERR_UNSUPPORTED;
+    const int att_floats = 3 * c.head_size + (p->att_scratch ? 0 : c.context_length);
+    const PdSmem L = pd_layout(c.dim, p->qd, c.hidden_dim, att_floats, max_seg, (size_t)maxdyn);
+    if (L.stages < 4) { p->pd_why = "shape leaves fewer than 4 ring stages of shared memory"; return B200_OK; }
+    int rc;
     if (!p->pd_layers) {
         std::vector<PdLayer> h(c.n_layers);
-        const size_t ctx_kv = (size_t)c.context_length * p->kvd;
+        const size_t ctx_kv = (size_t)c.context_length * p->kvd_l;
         for (int l = 0; l < c.n_layers; l++) {
             const LayerW &W = p->layers[l];
             h[l].qkv = W.tqkv; h[l].wo = W.two; h[l].gu = W.tgu; h[l].w2 = W.tw2;
@@ -448,55 +475,62 @@ int pd_prepare(b200_plan *p, PdSmem *layout) { // checks + allocations only (nev
             h[l].kc = p->key_cache + (size_t)l * ctx_kv;
             h[l].vc = p->value_cache + (size_t)l * ctx_kv;
         }
-        int rc;
         if ((rc = dalloc(p, &p->pd_layers, h.size() * sizeof(PdLayer)))) return rc;
         CK(cudaMemcpy(p->pd_layers, h.data(), h.size() * sizeof(PdLayer), cudaMemcpyHostToDevice));
         if ((rc = dalloc(p, &p->pd_sync, PD_S_WORDS * 4))) return rc;
         CK(cudaMemset(p->pd_sync, 0, PD_S_WORDS * 4));
+        CK(cudaHostAlloc(&p->h_err, 64, cudaHostAllocMapped));
+        *p->h_err = 0u;
+        CK(cudaHostGetDevicePointer((void **)&p->d_err, p->h_err, 0));
+        if ((rc = dalloc(p, &p->pd_trace, (size_t)p->n_sms * (c.n_layers + 1) * PD_STAMPS * 8))) return rc;
+        CK(cudaMemset(p->pd_trace, 0, (size_t)p->n_sms * (c.n_layers + 1) * PD_STAMPS * 8));
     }
-    if (c.head_size == 128) CK(cudaFuncSetAttribute(k_decode_persistent<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-    else CK(cudaFuncSetAttribute(k_decode_persistent<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-    *layout = L;
+    CK(cudaFuncSetAttribute(k_decode_persistent<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxdyn));
+    CK(cudaFuncSetAttribute(k_decode_persistent<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxdyn));
+    p->pd_L = L;
+    p->pd_ok = true;
+    p->pd_why = "";
     return B200_OK;
 }
 
-int enqueue_persistent(b200_plan *p, bool with_logits, int *launches, const PdSmem &L) {
+int enqueue_persistent(b200_plan *p, bool with_logits, int *launches, bool trace) {
     const b200_config &c = p->cfg;
     PdArgs a;
+    memset(&a, 0, sizeof a);
     a.layers = p->pd_layers; a.n_layers = c.n_layers; a.lm_head = p->tout; a.out_norm = p->out_norm; a.emb = p->emb;
-    a.dim = c.dim; a.hidden = c.hidden_dim; a.qd = p->qd; a.kvd = p->kvd; a.n_heads = c.n_heads; a.n_kv_heads = c.n_kv_heads;
-    a.head_size = c.head_size; a.arch = c.arch; a.vocab = c.vocab_size; a.ctx = c.context_length;
+    a.dim = c.dim; a.hidden = c.hidden_dim; a.qd = p->qd; a.n_heads = p->nh_l; a.n_kv_heads = p->nkv_l;
+    a.head_size = c.head_size; a.arch = c.arch; a.ctx = c.context_length;
     a.eps = c.rms_norm_eps; a.sqrt_hs = (float)sqrt((double)c.head_size);
     a.rope_cr = p->rope_cr; a.rope_ci = p->rope_ci;
     a.st = p->st; a.seq_tokens = p->seq_tokens; a.out_ids = p->out_ids;
     a.x = p->x; a.qkv = p->qkv; a.hb = p->hb; a.logits = p->logits;
     a.attq = p->attq; a.atts = p->atts; a.hq = p->hq; a.hs = p->hs; a.blk_cnt = p->blk_cnt;
-    a.part_val = p->part_val; a.part_idx = p->part_idx; a.sync = p->pd_sync; a.with_logits = with_logits ? 1 : 0;
-    if (c.head_size == 128) k_decode_persistent<128><<<p->n_sms, SMV_THREADS, L.total, p->stream>>>(a, L);
-    else k_decode_persistent<64><<<p->n_sms, SMV_THREADS, L.total, p->stream>>>(a, L);
-    CK(cudaGetLastError());
+    a.part_val = p->part_val; a.part_idx = p->part_idx; a.sync = p->pd_sync; a.host_err = p->d_err;
+    a.att_scratch = p->att_scratch; a.trace = trace ? p->pd_trace : nullptr;
+    a.with_logits = with_logits ? 1 : 0;
+    a.l2_ahead = p->pd_l2_ahead;
+    a.tp = p->tp; a.pd_flags_off = p->pd_flags_off;
+    a.head_base = p->tp.rank * p->nh_l; a.dim_base = p->tp.rank * p->dim_l; a.hid_base = p->tp.rank * p->hid_l; a.voc_base = p->tp.rank * p->voc_l;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(p->n_sms);
+    cfg.blockDim = dim3(SMV_THREADS);
+    cfg.dynamicSmemBytes = p->pd_L.total;
+    cfg.stream = p->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative; // every CTA spins on its peers: the driver must guarantee co-residency
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = p->pd_coop ? 1 : 0;
+    if (c.head_size == 128) CK(cudaLaunchKernelEx(&cfg, k_decode_persistent<128>, a, p->pd_L));
+    else CK(cudaLaunchKernelEx(&cfg, k_decode_persistent<64>, a, p->pd_L));
     if (launches) *launches = 1;
     return B200_OK;
 }
-#endif
 
-int capture(b200_plan *p, bool with_logits, cudaGraphExec_t *exec, int *launches, bool trace = false) {
+int capture(b200_plan *p, bool with_logits, cudaGraphExec_t *exec, int *launches, bool trace = false, bool persistent = false) {
     cudaGraph_t g = nullptr;
-#ifdef B200_PERSISTENT_DECODE
-    bool persistent = !trace && !getenv("B200_NO_PERSISTENT") && p->use_stream && p->tp.n == 1 && p->cfg.tp_size == 1;
-    PdSmem pd_L{};
-    if (persistent) { // allocations cannot happen inside a capture
-        const int rc0 = pd_prepare(p, &pd_L);
-        if (rc0 == B200_ERR_UNSUPPORTED) persistent = false;
-        else if (rc0) return rc0;
-    }
-#endif
     CK(cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal));
-#ifdef B200_PERSISTENT_DECODE
-    int rc = persistent ? enqueue_persistent(p, with_logits, launches, pd_L) : enqueue_forward(p, with_logits, launches, trace);
-#else
-    int rc = enqueue_forward(p, with_logits, launches, trace);
-#endif
+    int rc = persistent ? enqueue_persistent(p, with_logits, launches, trace) : enqueue_forward(p, with_logits, launches, trace);
     cudaError_t e = cudaStreamEndCapture(p->stream, &g);
     if (rc) { if (g) cudaGraphDestroy(g); return rc; }
     if (e != cudaSuccess) return fail(p, B200_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
@@ -506,13 +540,46 @@ int capture(b200_plan *p, bool with_logits, cudaGraphExec_t *exec, int *launches
     return B200_OK;
 }
 
+// Both decode implementations are captured; b200_set_decode_mode picks which one the forward calls launch.
+int capture_all(b200_plan *p) {
+    int rc;
+    if ((rc = capture(p, true, &p->g_decode, &p->launches_decode))) return rc;
+    if ((rc = capture(p, false, &p->g_prefill, nullptr))) return rc;
+    if (p->use_stream) {
+        if ((rc = dalloc(p, &p->trace_rec, (size_t)(p->launches_decode + 8) * 32))) return rc;
+        if ((rc = capture(p, true, &p->g_trace, nullptr, true))) return rc;
+    }
+    if ((rc = pd_prepare(p))) return rc;
+    if (p->pd_ok) {
+        // grid = one CTA per SM with (almost) all of its shared memory: co-resident on an idle GPU either way; the cooperative
+        // attribute makes the driver check it.  Should a driver refuse cooperative kernel nodes in a graph, retry without.
+        for (int attempt = 0; attempt < 2; attempt++) {
+            p->pd_coop = attempt == 0 && !getenv("B200_PD_NO_COOP");
+            rc = capture(p, true, &p->g_pdecode, nullptr, false, true);
+            if (!rc) rc = capture(p, false, &p->g_pprefill, nullptr, false, true);
+            if (!rc) rc = capture(p, true, &p->g_ptrace, nullptr, true, true);
+            if (!rc) break;
+            cudaGetLastError();
+            for (cudaGraphExec_t *g : {&p->g_pdecode, &p->g_pprefill, &p->g_ptrace})
+                if (*g) { cudaGraphExecDestroy(*g); *g = nullptr; }
+        }
+        if (rc) { p->pd_ok = false; p->pd_why = "persistent decode kernel could not be captured: " + p->err; }
+    }
+    if (!p->pd_ok && p->decode_mode == B200_DECODE_PERSISTENT) p->decode_mode = B200_DECODE_GRAPH;
+    return B200_OK;
+}
+
+// cudaFuncSetAttribute is per function and process-wide: every kernel gets the device opt-in maximum ONCE, so a later plan
+// with a smaller context never lowers the limit under an earlier plan's instantiated graphs.
+const int ATT_SMEM_FLOATS_MAX = 4096; // q|k|out|scores beyond this: the score row goes to a global scratch row
+
 int set_smem_attrs(b200_plan *p) {
     const b200_config &c = p->cfg;
     int maxdyn = 0;
     CK(cudaDeviceGetAttribute(&maxdyn, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device));
-    size_t need_norm = norm_smem_bytes(c.dim);
     if (c.dim > 8192) return fail(p, B200_ERR_UNSUPPORTED, "dim > 8192 not supported by the RMSNorm kernel");
-    size_t need_att = (size_t)(3 * c.head_size + c.context_length) * 4;
+    size_t need_norm = norm_smem_bytes(c.dim, p->norm_v2);
+    size_t need_att = (size_t)(3 * c.head_size + (p->att_scratch ? 0 : c.context_length)) * 4;
     int maxcols = c.hidden_dim > c.dim ? c.hidden_dim : c.dim;
     if (p->qd > maxcols) maxcols = p->qd;
     size_t need_mv = q8_smem_bytes(maxcols, 4, 8);
@@ -520,24 +587,29 @@ int set_smem_attrs(b200_plan *p) {
     if (need_norm > (size_t)maxdyn || need_att > (size_t)maxdyn || (p->wtype == B200_GGML_Q8_0 && need_mv > (size_t)maxdyn) ||
         (p->wtype == B200_GGML_F16 && need_f16 > (size_t)maxdyn))
         return fail(p, B200_ERR_UNSUPPORTED, "shape needs more shared memory than the device offers (%d bytes)", maxdyn);
-    CK(cudaFuncSetAttribute(k_rmsnorm_quant<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_norm));
-    CK(cudaFuncSetAttribute(k_rmsnorm_quant<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_norm));
-    CK(cudaFuncSetAttribute(k_attention<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_att));
-    CK(cudaFuncSetAttribute(k_attention<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_att));
-    CK(cudaFuncSetAttribute(k_attention<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_att));
-    CK(cudaFuncSetAttribute(k_attention<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_att));
-    CK(cudaFuncSetAttribute(k_matvec_q8<1, MODE_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_mv));
-    CK(cudaFuncSetAttribute(k_matvec_q8<2, MODE_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_mv));
-    CK(cudaFuncSetAttribute(k_matvec_q8<4, MODE_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_mv));
-    CK(cudaFuncSetAttribute(k_matvec_q8<1, MODE_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_mv));
-    CK(cudaFuncSetAttribute(k_matvec_q8<2, MODE_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_mv));
-    CK(cudaFuncSetAttribute(k_matvec_q8<4, MODE_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_mv));
-    CK(cudaFuncSetAttribute(k_gateup_q8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_mv));
+    static bool done = false; // process-wide, like the attribute itself (plans are created from one thread at a time per process)
+    if (done) return B200_OK;
+    CK(cudaFuncSetAttribute(k_rmsnorm_quant<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxdyn));
+    CK(cudaFuncSetAttribute(k_rmsnorm_quant<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxdyn));
+    CK(cudaFuncSetAttribute(k_rmsnorm_quant<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxdyn));
+    CK(cudaFuncSetAttribute(k_rmsnorm_quant<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxdyn));
+    CK(cudaFuncSetAttribute(k_attention<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxdyn));
+    CK(cudaFuncSetAttribute(k_attention<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxdyn));
+    CK(cudaFuncSetAttribute(k_attention<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxdyn));
+    CK(cudaFuncSetAttribute(k_attention<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxdyn));
+    CK(cudaFuncSetAttribute(k_matvec_q8<1, MODE_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxdyn));
+    CK(cudaFuncSetAttribute(k_matvec_q8<2, MODE_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxdyn));
+    CK(cudaFuncSetAttribute(k_matvec_q8<4, MODE_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxdyn));
+    CK(cudaFuncSetAttribute(k_matvec_q8<1, MODE_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxdyn));
+    CK(cudaFuncSetAttribute(k_matvec_q8<2, MODE_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxdyn));
+    CK(cudaFuncSetAttribute(k_matvec_q8<4, MODE_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxdyn));
+    CK(cudaFuncSetAttribute(k_gateup_q8, cudaFuncAttributeMaxDynamicSharedMemorySize, maxdyn));
     CK(cudaFuncSetAttribute(k_stream_matvec_q8<SMV_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMV_SMEM_BUDGET_MAX));
     CK(cudaFuncSetAttribute(k_stream_matvec_q8<SMV_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMV_SMEM_BUDGET_MAX));
     CK(cudaFuncSetAttribute(k_stream_matvec_q8<SMV_GATEUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMV_SMEM_BUDGET_MAX));
-    CK(cudaFuncSetAttribute(k_matvec_f16<MODE_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_f16));
-    CK(cudaFuncSetAttribute(k_matvec_f16<MODE_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_f16));
+    CK(cudaFuncSetAttribute(k_matvec_f16<MODE_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxdyn));
+    CK(cudaFuncSetAttribute(k_matvec_f16<MODE_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxdyn));
+    done = true;
     return B200_OK;
 }
 
@@ -575,6 +647,7 @@ int build(b200_plan *p, const b200_tensor *tensors, int n_tensors) {
         return fail(p, B200_ERR_UNSUPPORTED, "Type: %d currently not supported for B200 weights (Q8_0 and F16 only)", p->wtype);
 
     CK(cudaSetDevice(p->device));
+    read_knobs(p);
     CK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&p->ev0));
     CK(cudaEventCreate(&p->ev1));
@@ -699,6 +772,7 @@ int build(b200_plan *p, const b200_tensor *tensors, int n_tensors) {
         p->tp.off_flags = (unsigned)o; o = al(o + TP_SLOTS * TP_MAX * 4);
         p->tp.off_tick = (unsigned)o; o = al(o + 4);
         p->tp.off_done = (unsigned)o; o = al(o + TP_SLOTS * 4);
+        p->pd_flags_off = (unsigned)o; o = al(o + PD_S_SLOTS * TP_MAX * 4); // epoch flags of the persistent decode kernel
         p->comm_bytes = o;
         if ((rc = dalloc(p, &p->comm, o))) return rc;
         CK(cudaMemset(p->comm, 0, o));
@@ -737,14 +811,12 @@ int build(b200_plan *p, const b200_tensor *tensors, int n_tensors) {
     CK(cudaMallocHost(&p->h_st, sizeof(StepState)));
     CK(cudaMallocHost(&p->h_ids, (size_t)p->seq_cap * 4));
 
+    if (3 * c.head_size + c.context_length > ATT_SMEM_FLOATS_MAX) { // long context: score rows in global memory
+        if ((rc = dalloc(p, &p->att_scratch, (size_t)p->nh_l * c.context_length * 4))) return rc;
+    }
     if ((rc = set_smem_attrs(p))) return rc;
     if (c.tp_size > 1) { CK(cudaStreamSynchronize(p->stream)); return B200_OK; } // graphs are captured by b200_tp_attach
-    if ((rc = capture(p, true, &p->g_decode, &p->launches_decode))) return rc;
-    if ((rc = capture(p, false, &p->g_prefill, nullptr))) return rc;
-    if (p->use_stream) {
-        if ((rc = dalloc(p, &p->trace_rec, (size_t)(p->launches_decode + 8) * 32))) return rc;
-        if ((rc = capture(p, true, &p->g_trace, nullptr, true))) return rc;
-    }
+    if ((rc = capture_all(p))) return rc;
     if (p->prefill_batch > 1)
         if ((rc = prefill_init(p))) return rc;
     CK(cudaStreamSynchronize(p->stream));
@@ -942,6 +1014,19 @@ int prefill_forward(b200_plan *p, int n, int start_pos, int *launches) {
     return B200_OK;
 }
 
+cudaGraphExec_t decode_graph(b200_plan *p) { return p->decode_mode == B200_DECODE_PERSISTENT && p->g_pdecode ? p->g_pdecode : p->g_decode; }
+cudaGraphExec_t prefill_graph(b200_plan *p) { return p->decode_mode == B200_DECODE_PERSISTENT && p->g_pprefill ? p->g_pprefill : p->g_prefill; }
+
+// After a synchronize: did a device-side wait of the persistent kernel (or a tensor-parallel flag wait) give up?
+int check_device_error(b200_plan *p) {
+    if (p->h_err && *reinterpret_cast<volatile unsigned *>(p->h_err)) {
+        const unsigned code = *reinterpret_cast<volatile unsigned *>(p->h_err);
+        return fail(p, B200_ERR_STATE, "device-side wait timed out in the persistent decode kernel (phase %u): a peer rank is missing or the ranks' call "
+                                       "sequences diverged; the plan must be freed", code - 1u);
+    }
+    return B200_OK;
+}
+
 int set_state(b200_plan *p, int token, int pos, int n_seq, int feedback) {
     StepState *h = p->h_st;
     h->token = token; h->pos = pos; h->step = 0; h->n_seq = n_seq; h->feedback = feedback;
@@ -989,10 +1074,11 @@ int b200_forward_decode(b200_plan *p, int32_t token, int32_t position, float *lo
     if ((rc = check_pos(p, token, position))) return rc;
     CK(cudaSetDevice(p->device));
     if ((rc = set_state(p, token, position, 0, 0))) return rc;
-    CK(cudaGraphLaunch(p->g_decode, p->stream));
+    CK(cudaGraphLaunch(decode_graph(p), p->stream));
     if (argmax) CK(cudaMemcpyAsync(p->h_ids, p->out_ids, 4, cudaMemcpyDeviceToHost, p->stream));
     if (logits) CK(cudaMemcpyAsync(logits, p->logits, (size_t)p->cfg.vocab_size * 4, cudaMemcpyDeviceToHost, p->stream));
     CK(cudaStreamSynchronize(p->stream));
+    if ((rc = check_device_error(p))) return rc;
     if (argmax) *argmax = p->h_ids[0];
     return B200_OK;
 }
@@ -1004,9 +1090,9 @@ int b200_forward_prefill(b200_plan *p, int32_t token, int32_t position) {
     if ((rc = check_pos(p, token, position))) return rc;
     CK(cudaSetDevice(p->device));
     if ((rc = set_state(p, token, position, 0, 0))) return rc;
-    CK(cudaGraphLaunch(p->g_prefill, p->stream));
+    CK(cudaGraphLaunch(prefill_graph(p), p->stream));
     CK(cudaStreamSynchronize(p->stream));
-    return B200_OK;
+    return check_device_error(p);
 }
 
 int b200_forward_batch_prefill(b200_plan *p, const int32_t *tokens, int32_t n, int32_t start_pos) {
@@ -1036,9 +1122,9 @@ int b200_forward_batch_prefill(b200_plan *p, const int32_t *tokens, int32_t n, i
     CK(cudaMemcpyAsync(p->seq_tokens, p->h_ids, (size_t)n * 4, cudaMemcpyHostToDevice, p->stream));
     int rc;
     if ((rc = set_state(p, tokens[0], start_pos, n, 0))) return rc;
-    for (int i = 0; i < n; i++) CK(cudaGraphLaunch(p->g_prefill, p->stream));
+    for (int i = 0; i < n; i++) CK(cudaGraphLaunch(prefill_graph(p), p->stream));
     CK(cudaStreamSynchronize(p->stream));
-    return B200_OK;
+    return check_device_error(p);
 }
 
 int b200_decode_sequence(b200_plan *p, const int32_t *tokens, int32_t n, int32_t start_pos, int32_t feedback,
@@ -1057,12 +1143,51 @@ int b200_decode_sequence(b200_plan *p, const int32_t *tokens, int32_t n, int32_t
     int rc;
     if ((rc = set_state(p, tokens[0], start_pos, nt, feedback))) return rc;
     CK(cudaEventRecord(p->ev0, p->stream));
-    for (int i = 0; i < n; i++) CK(cudaGraphLaunch(p->g_decode, p->stream));
+    for (int i = 0; i < n; i++) CK(cudaGraphLaunch(decode_graph(p), p->stream));
     CK(cudaEventRecord(p->ev1, p->stream));
     if (out_ids) CK(cudaMemcpyAsync(p->h_ids, p->out_ids, (size_t)n * 4, cudaMemcpyDeviceToHost, p->stream));
     CK(cudaStreamSynchronize(p->stream));
+    if ((rc = check_device_error(p))) return rc;
     if (out_ids) memcpy(out_ids, p->h_ids, (size_t)n * 4);
     if (device_ms) CK(cudaEventElapsedTime(device_ms, p->ev0, p->ev1));
+    return B200_OK;
+}
+
+int b200_set_decode_mode(b200_plan *p, int32_t mode) {
+    if (!p || (mode != B200_DECODE_GRAPH && mode != B200_DECODE_PERSISTENT)) return B200_ERR_BAD_ARG;
+    if (!p->g_decode) return fail(p, B200_ERR_STATE, "tensor-parallel plan: call b200_tp_attach on every rank first");
+    if (mode == B200_DECODE_PERSISTENT && !p->pd_ok) return fail(p, B200_ERR_UNSUPPORTED, "%s", p->pd_why.c_str());
+    p->decode_mode = mode;
+    return B200_OK;
+}
+
+int b200_decode_info(b200_plan *p, int32_t *mode, int32_t *launches, int32_t *ring_stages, int32_t *smem_bytes) {
+    if (!p) return B200_ERR_BAD_ARG;
+    const bool pers = p->decode_mode == B200_DECODE_PERSISTENT && p->g_pdecode;
+    if (mode) *mode = pers ? B200_DECODE_PERSISTENT : B200_DECODE_GRAPH;
+    if (launches) *launches = pers ? 1 : p->launches_decode;
+    if (ring_stages) *ring_stages = p->pd_ok ? p->pd_L.stages : 0;
+    if (smem_bytes) *smem_bytes = p->pd_ok ? (int32_t)p->pd_L.total : 0;
+    return B200_OK;
+}
+
+int b200_trace_persistent(b200_plan *p, int32_t token, int32_t position, uint64_t *stamps, int64_t cap, int32_t *n_ctas, int32_t *n_rows, int32_t *n_stamps) {
+    if (!p || !stamps) return B200_ERR_BAD_ARG;
+    if (!p->g_ptrace) return fail(p, B200_ERR_UNSUPPORTED, "%s", p->pd_ok ? "no traced persistent graph" : p->pd_why.c_str());
+    int rc;
+    if ((rc = check_pos(p, token, position))) return rc;
+    CK(cudaSetDevice(p->device));
+    const size_t words = (size_t)p->n_sms * (p->cfg.n_layers + 1) * PD_STAMPS;
+    if ((size_t)cap < words) return fail(p, B200_ERR_BAD_ARG, "stamp buffer too small: need %zu uint64", words);
+    CK(cudaMemsetAsync(p->pd_trace, 0, words * 8, p->stream));
+    if ((rc = set_state(p, token, position, 0, 0))) return rc;
+    CK(cudaGraphLaunch(p->g_ptrace, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    if ((rc = check_device_error(p))) return rc;
+    CK(cudaMemcpy(stamps, p->pd_trace, words * 8, cudaMemcpyDeviceToHost));
+    if (n_ctas) *n_ctas = p->n_sms;
+    if (n_rows) *n_rows = p->cfg.n_layers + 1;
+    if (n_stamps) *n_stamps = PD_STAMPS;
     return B200_OK;
 }
 
@@ -1239,10 +1364,7 @@ int b200_tp_attach(b200_plan *p, const void *handles, int32_t n) {
     p->tp.n = n;
     p->attached = true;
     int rc;
-    if ((rc = capture(p, true, &p->g_decode, &p->launches_decode))) return rc;
-    if ((rc = capture(p, false, &p->g_prefill, nullptr))) return rc;
-    if ((rc = dalloc(p, &p->trace_rec, (size_t)(p->launches_decode + 8) * 32))) return rc;
-    if ((rc = capture(p, true, &p->g_trace, nullptr, true))) return rc;
+    if ((rc = capture_all(p))) return rc;
     CK(cudaStreamSynchronize(p->stream));
     return B200_OK;
 }
@@ -1272,10 +1394,12 @@ int b200_profile_norm(b200_plan *p, int64_t *cycles4) {
     long long *d = nullptr;
     CK(cudaMalloc(&d, 128));
     const b200_config &c = p->cfg;
-    const size_t norm_smem = norm_smem_bytes(c.dim);
+    const size_t norm_smem = norm_smem_bytes(c.dim, p->norm_v2);
     const bool q8 = p->wtype == B200_GGML_Q8_0;
     for (int i = 0; i < 3; i++)
-        k_rmsnorm_quant<false><<<1, NORM_THREADS, norm_smem, p->stream>>>(p->x, p->st, p->emb, p->layers[0].attn_norm, c.rms_norm_eps, c.dim,
+        if (p->norm_v2) k_rmsnorm_quant<false, true><<<1, NORM_THREADS, norm_smem, p->stream>>>(p->x, p->st, p->emb, p->layers[0].attn_norm, c.rms_norm_eps, c.dim,
+                                                                 q8 ? p->xq : nullptr, q8 ? p->xs : nullptr, q8 ? nullptr : p->xb, d, TraceBuf{nullptr, 0, 0}, p->tp, -1);
+        else k_rmsnorm_quant<false, false><<<1, NORM_THREADS, norm_smem, p->stream>>>(p->x, p->st, p->emb, p->layers[0].attn_norm, c.rms_norm_eps, c.dim,
                                                                  q8 ? p->xq : nullptr, q8 ? p->xs : nullptr, q8 ? nullptr : p->xb, d, TraceBuf{nullptr, 0, 0}, p->tp, -1);
     cudaError_t e = cudaStreamSynchronize(p->stream);
     long long h[16] = {0};
@@ -1286,19 +1410,30 @@ int b200_profile_norm(b200_plan *p, int64_t *cycles4) {
     return e == cudaSuccess ? B200_OK : B200_ERR_CUDA;
 }
 
-int b200_test_seqsum(const float *terms, int32_t n, float *out, int32_t *info) {
+static int run_seqsum_hook(const float *terms, int32_t n, int threads, float *out, int32_t *info) {
     if (!terms || !out || n <= 0 || n > 8192) return B200_ERR_BAD_ARG;
+    if (threads != 0 && threads != 256 && threads != 1024) return B200_ERR_BAD_ARG;
     float *d = nullptr, *o = nullptr;
-    if (cudaMalloc(&d, (size_t)n * 4) != cudaSuccess || cudaMalloc(&o, 16) != cudaSuccess) return B200_ERR_OOM;
-#ifdef B200_SEQSUM_V2
-    size_t smem = norm_smem_bytes(n);
-#else
-    size_t smem = (size_t)((n + 31) & ~31) * 4 + seqsum_scratch_bytes((n + 31) & ~31);
-#endif
-    cudaFuncSetAttribute(k_test_seqsum, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaMemcpy(d, terms, (size_t)n * 4, cudaMemcpyHostToDevice);
-    k_test_seqsum<<<1, NORM_THREADS, smem>>>(d, n, o, reinterpret_cast<int *>(o) + 1);
-    cudaError_t e = cudaDeviceSynchronize();
+    if (cudaMalloc(&d, (size_t)n * 4) != cudaSuccess) return B200_ERR_OOM;
+    if (cudaMalloc(&o, 16) != cudaSuccess) { cudaFree(d); return B200_ERR_OOM; }
+    cudaError_t e = cudaMemcpy(d, terms, (size_t)n * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        if (threads == 0) { // round-1 accumulator (seqsum.cuh)
+            const size_t smem = (size_t)((n + 31) & ~31) * 4 + seqsum_scratch_bytes((n + 31) & ~31);
+            e = cudaFuncSetAttribute(k_test_seqsum, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) k_test_seqsum<<<1, NORM_THREADS, smem>>>(d, n, o, reinterpret_cast<int *>(o) + 1);
+        } else if (threads == 1024) {
+            const size_t smem = (size_t)1024 * ((n + 1023) / 1024) * 4 + seqsum2_scratch_bytes(1024);
+            e = cudaFuncSetAttribute(k_test_seqsum2<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) k_test_seqsum2<1024><<<1, 1024, smem>>>(d, n, o, reinterpret_cast<int *>(o) + 1);
+        } else {
+            const size_t smem = (size_t)256 * ((n + 255) / 256) * 4 + seqsum2_scratch_bytes(256);
+            e = cudaFuncSetAttribute(k_test_seqsum2<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) k_test_seqsum2<256><<<1, 256, smem>>>(d, n, o, reinterpret_cast<int *>(o) + 1);
+        }
+    }
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
     int32_t host[3] = {0, 0, 0};
     if (e == cudaSuccess) e = cudaMemcpy(host, o, 12, cudaMemcpyDeviceToHost);
     memcpy(out, host, 4);
@@ -1306,6 +1441,12 @@ int b200_test_seqsum(const float *terms, int32_t n, float *out, int32_t *info) {
     cudaFree(d);
     cudaFree(o);
     return e == cudaSuccess ? B200_OK : B200_ERR_CUDA;
+}
+
+int b200_test_seqsum(const float *terms, int32_t n, float *out, int32_t *info) { return run_seqsum_hook(terms, n, 0, out, info); }
+int b200_test_seqsum2(const float *terms, int32_t n, int32_t threads, float *out, int32_t *info) {
+    if (threads != 256 && threads != 1024) return B200_ERR_BAD_ARG;
+    return run_seqsum_hook(terms, n, threads, out, info);
 }
 
 int b200_gemm_f16(const uint16_t *a, const uint16_t *b, float *c, int32_t m, int32_t n, int32_t k, int32_t iters, float *ms) {
@@ -1348,7 +1489,10 @@ int b200_gemm_f16(const uint16_t *a, const uint16_t *b, float *c, int32_t m, int
     return e == cudaSuccess ? B200_OK : B200_ERR_CUDA;
 }
 
-int b200_launches_per_decode(b200_plan *p) { return p ? p->launches_decode : 0; }
+int b200_launches_per_decode(b200_plan *p) {
+    if (!p) return 0;
+    return (p->decode_mode == B200_DECODE_PERSISTENT && p->g_pdecode) ? 1 : p->launches_decode;
+}
 int64_t b200_device_bytes(b200_plan *p) { return p ? p->bytes : 0; }
 
 void b200_plan_free(b200_plan *p) {
@@ -1359,6 +1503,10 @@ void b200_plan_free(b200_plan *p) {
     if (p->g_decode) cudaGraphExecDestroy(p->g_decode);
     if (p->g_prefill) cudaGraphExecDestroy(p->g_prefill);
     if (p->g_trace) cudaGraphExecDestroy(p->g_trace);
+    if (p->g_pdecode) cudaGraphExecDestroy(p->g_pdecode);
+    if (p->g_pprefill) cudaGraphExecDestroy(p->g_pprefill);
+    if (p->g_ptrace) cudaGraphExecDestroy(p->g_ptrace);
+    if (p->h_err) cudaFreeHost(p->h_err);
     for (int k = 0; k < TP_MAX; k++) if (p->peer_open[k]) cudaIpcCloseMemHandle(p->peer_open[k]);
     for (void *d : p->allocs) cudaFree(d);
     if (p->h_st) cudaFreeHost(p->h_st);

@@ -1,6 +1,5 @@
-// seqsum2.cuh -- ROUND-2 CANDIDATE, not compiled into libb200llama.so yet (GPU budget of round 1 was spent; the algorithm is
-// validated on the CPU by tools/seqsum2/proto.c, this CUDA version is compile-checked only: tools/seqsum2/harness.cu runs it
-// against the literal loop on a GPU).
+// seqsum2.cuh -- the exact sequential-sum accumulator of the decode path's RMSNorms (round 2; the algorithm is validated on
+// the CPU by tools/seqsum2/proto.c, on the GPU by tools/seqsum2/harness.cu and tests/test_gpu_parity.py).
 //
 // Same contract as block_seqsum_exact (seqsum.cuh): the bit-exact value of  s = 0; for (i) s = s + t[i]  for non-negative
 // float terms (InferenceCore.rmsnorm's accumulator, InferenceCore.java:39-48), evaluated by one CTA.  Where the round-1
@@ -15,10 +14,9 @@
 //      exit) and add the integer; a failed check replays the run literally.  Predictions decide speed, never the result.
 // CPU model (20000 adversarial cases, n = 2048/4096/8192): 0 mismatches, ~3 head threads + ~24 items per sum.
 #pragma once
-#include "../seqsum.cuh"
+#include "seqsum.cuh"
 
 #define SEQSUM2_THREADS 1024
-#define SEQSUM2_MAXE 8           // terms per thread: n <= 8192
 #define SEQSUM2_LITERAL INT_MIN
 
 struct SeqItem {
@@ -39,14 +37,14 @@ struct SeqSum2Scratch {
     float *result;    // [1]
     int *info;        // [2] {items, fallbacks}
 };
-__host__ __device__ inline size_t seqsum2_scratch_bytes() {
-    return 32 * 4 + 32 * sizeof(SeqPair) + 4 * 32 * 4 + SEQSUM2_THREADS * 4 + SEQSUM2_THREADS * sizeof(SeqItem) + 16 + 16;
+__host__ __device__ inline size_t seqsum2_scratch_bytes(int T = SEQSUM2_THREADS) { // T = threads that run the accumulator
+    return 32 * 4 + 32 * sizeof(SeqPair) + 4 * 32 * 4 + (size_t)T * 4 + (size_t)T * sizeof(SeqItem) + 16 + 16;
 }
-__device__ __forceinline__ SeqSum2Scratch seqsum2_carve(unsigned char *p) { // p 16-byte aligned
+__device__ __forceinline__ SeqSum2Scratch seqsum2_carve(unsigned char *p, int T = SEQSUM2_THREADS) { // p 16-byte aligned
     SeqSum2Scratch s;
-    s.items = reinterpret_cast<SeqItem *>(p); p += SEQSUM2_THREADS * sizeof(SeqItem);
+    s.items = reinterpret_cast<SeqItem *>(p); p += (size_t)T * sizeof(SeqItem);
     s.wtail = reinterpret_cast<SeqPair *>(p); p += 32 * sizeof(SeqPair);
-    s.cls = reinterpret_cast<int *>(p); p += SEQSUM2_THREADS * 4;
+    s.cls = reinterpret_cast<int *>(p); p += (size_t)T * 4;
     s.wsum = reinterpret_cast<float *>(p); p += 32 * 4;
     s.wtail_f = reinterpret_cast<int *>(p); p += 32 * 4;
     s.wcls_last = reinterpret_cast<int *>(p); p += 32 * 4;

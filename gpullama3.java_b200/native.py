@@ -40,6 +40,7 @@ class Tensor(C.Structure):
 
 
 EXPORTS = ["b200_plan_create", "b200_forward_decode", "b200_forward_prefill", "b200_forward_batch_prefill", "b200_set_prefill_mode", "b200_prefill_info",
+           "b200_set_decode_mode", "b200_decode_info", "b200_trace_persistent", "b200_test_seqsum2",
            "b200_decode_sequence", "b200_time_kernel", "b200_tp_handle", "b200_tp_attach", "b200_trace_decode", "b200_profile_norm", "b200_test_seqsum", "b200_gemm_f16", "b200_kv_reset", "b200_read_buffer", "b200_launches_per_decode",
            "b200_device_bytes", "b200_plan_free", "b200_last_error", "b200_version"]
 
@@ -67,6 +68,10 @@ def lib() -> C.CDLL:
     L.b200_tp_attach.argtypes = [vp, vp, i32]
     L.b200_test_seqsum.argtypes = [vp, i32, C.POINTER(C.c_float), C.POINTER(i32)]
     L.b200_set_prefill_mode.argtypes = [vp, i32]
+    L.b200_set_decode_mode.argtypes = [vp, i32]
+    L.b200_decode_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    L.b200_trace_persistent.argtypes = [vp, i32, i32, vp, C.c_int64, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    L.b200_test_seqsum2.argtypes = [vp, i32, i32, C.POINTER(C.c_float), C.POINTER(i32)]
     L.b200_prefill_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_float)]
     L.b200_gemm_f16.argtypes = [vp, vp, vp, i32, i32, i32, i32, C.POINTER(C.c_float)]
     L.b200_time_kernel.argtypes = [vp, i32, i32, C.POINTER(C.c_float), C.POINTER(C.c_int64)]
@@ -89,11 +94,15 @@ def _raise(code: int, msg: str):
     raise B200Error(code, msg)
 
 
-def test_seqsum(terms, want_info: bool = False):
+def test_seqsum(terms, want_info: bool = False, threads: int = 0):
+    """threads = 0: the round-1 accumulator (seqsum.cuh); 1024 / 256: seqsum2.cuh in the norm kernel's / persistent kernel's form."""
     t = np.ascontiguousarray(terms, dtype=np.float32)
     out = C.c_float(0)
     info = (C.c_int32 * 2)()
-    rc = lib().b200_test_seqsum(t.ctypes.data, len(t), C.byref(out), info)
+    if threads:
+        rc = lib().b200_test_seqsum2(t.ctypes.data, len(t), threads, C.byref(out), info)
+    else:
+        rc = lib().b200_test_seqsum(t.ctypes.data, len(t), C.byref(out), info)
     if rc != B200_OK:
         _raise(rc, "b200_test_seqsum failed")
     return (out.value, info[0], info[1]) if want_info else out.value
@@ -156,6 +165,23 @@ class NativePlan:
 
     def set_prefill_mode(self, mode: int):
         self._ck(lib().b200_set_prefill_mode(self._p, mode))
+
+    def set_decode_mode(self, mode: int):
+        self._ck(lib().b200_set_decode_mode(self._p, mode))
+
+    def decode_info(self):
+        """(mode, kernels per decode step, ring stages, shared-memory bytes of the persistent kernel)."""
+        a, b, c, d = C.c_int32(0), C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        self._ck(lib().b200_decode_info(self._p, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return a.value, b.value, c.value, d.value
+
+    def trace_persistent(self, token: int, position: int) -> np.ndarray:
+        """uint64 %globaltimer stamps [cta][row][k] of one traced step of the persistent decode kernel."""
+        cap = 200 * (self.cfg.n_layers + 1) * 16
+        buf = np.zeros(cap, dtype=np.uint64)
+        a, b, c = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        self._ck(lib().b200_trace_persistent(self._p, token, position, buf.ctypes.data, cap, C.byref(a), C.byref(b), C.byref(c)))
+        return buf[: a.value * b.value * c.value].reshape(a.value, b.value, c.value)
 
     def prefill_info(self):
         mode, launches, ms = C.c_int32(0), C.c_int32(0), C.c_float(0)

@@ -125,6 +125,21 @@ class B200MasterPlan:
         """(active mode, kernels launched, device ms) of the last tensor-core prefill chunk."""
         return self._native.prefill_info()
 
+    # -Dllama.cudaGraphs-style switch of the decode implementation (both bit-identical): "graph" = one CUDA graph of
+    # ~7 kernels per layer, "persistent" = one persistent kernel per token (csrc/decode_persistent.cuh)
+    DECODE_GRAPH, DECODE_PERSISTENT = 0, 1
+
+    def set_decode_mode(self, mode):
+        if isinstance(mode, str):
+            mode = {"graph": 0, "persistent": 1}[mode]
+        self._native.set_decode_mode(int(mode))
+
+    def decode_info(self):
+        return self._native.decode_info()
+
+    def trace_persistent(self, token: int, position: int):
+        return self._native.trace_persistent(token, position)
+
     def decode_sequence(self, tokens, n: int, start_pos: int, feedback: bool = False):
         return self._native.decode_sequence(tokens, n, start_pos, feedback)
 

@@ -55,6 +55,10 @@ SHAPES = {
     "small-llama": Shape("llama", 1536, 4096, 3, 12, 4, 128, 4096, False, 500000.0, 1e-5),
     # the real Llama-3-8B layer geometry (7 column segments in the down projection, 4 KB rows) with 2 layers / small vocab
     "mid-llama": Shape("llama", 4096, 14336, 2, 32, 8, 128, 8192, False, 500000.0, 1e-5),
+    # 2-layer cuts of the other BASELINE geometries (parity tests at the real row/segment shapes, small vocabulary)
+    "mid-qwen3-4b": Shape("qwen3", 2560, 9728, 2, 32, 8, 128, 8192, True, 1000000.0, 1e-6, 40960),
+    "mid-llama-1b": Shape("llama", 2048, 8192, 2, 32, 8, 64, 8192, True, 500000.0, 1e-5, 131072),
+    "mid-llama-70b": Shape("llama", 8192, 28672, 2, 64, 8, 128, 8192, False, 500000.0, 1e-5),
     # BASELINE.json shapes
     "llama-3.2-1b": Shape("llama", 2048, 8192, 16, 32, 8, 64, 128256, True, 500000.0, 1e-5, 131072),
     "llama-3-8b": Shape("llama", 4096, 14336, 32, 32, 8, 128, 128256, False, 500000.0, 1e-5),

@@ -121,6 +121,23 @@ int b200_set_prefill_mode(b200_plan *plan, int32_t mode);
 /* Active mode, kernels launched and device milliseconds of the last tensor-core chunk (any pointer may be NULL). */
 int b200_prefill_info(b200_plan *plan, int32_t *mode, int32_t *launches, float *device_ms);
 
+/* How the single-token forwards (b200_forward_decode / _prefill / b200_decode_sequence) run.  Both replace
+ * TornadoVMMasterPlanSingleToken.tornadoVMForwardDecode's N+2 TaskGraph executions
+ * (TornadoVMMasterPlanSingleToken.java:68-95) and produce bit-identical results:
+ *   B200_DECODE_GRAPH       one CUDA graph of ~7 kernels per layer with programmatic-dependent-launch edges;
+ *   B200_DECODE_PERSISTENT  ONE persistent kernel per token (csrc/decode_persistent.cuh): one CTA per SM streams the
+ *                           weights of every matrix through a shared-memory ring while epoch counters order the phases.
+ *                           Default when the plan fits (Q8_0 streaming layout, head size 64/128); the environment
+ *                           variable B200_DECODE=graph selects the graph at creation.
+ * Returns B200_ERR_UNSUPPORTED with the reason in b200_last_error when the plan cannot run the requested mode.
+ * Under tensor parallelism every rank must switch at the same point of the call sequence. */
+#define B200_DECODE_GRAPH 0
+#define B200_DECODE_PERSISTENT 1
+int b200_set_decode_mode(b200_plan *plan, int32_t mode);
+
+/* Active decode mode, kernels per decode step, and the persistent kernel's ring depth / shared memory (0 if unsupported). */
+int b200_decode_info(b200_plan *plan, int32_t *mode, int32_t *launches, int32_t *ring_stages, int32_t *smem_bytes);
+
 /* Device-resident token loop (what LlamaBench.runTest times, LlamaBench.java:234-254, and the
  * greedy generation loop InferenceEngine.java:96-145 with the sampler on the device):
  * runs n single-token forwards at positions start_pos..start_pos+n-1 without host round trips.
@@ -169,6 +186,12 @@ int b200_tp_attach(b200_plan *plan, const void *handles, int32_t n);
  * 7 down, 8 lm_head, 9 argmax/advance.  records holds 4*cap uint64. */
 int b200_trace_decode(b200_plan *plan, int32_t token, int32_t position, uint64_t *records, int32_t cap, int32_t *n_out);
 
+/* Diagnostic: ONE decode step through the persistent kernel with phase stamps: stamps[cta][row][k] (uint64, %globaltimer ns),
+ * rows 0..n_layers-1 = layers with k = {0 layer start, 1 attn norm done, 2 QKV rows done, 3 attention gathered, 4 Wo rows done,
+ * 5 x gathered, 6 ffn norm done, 7 gate/up done, 8 hidden activation gathered+staged, 9 W2 rows done}; row n_layers = lm_head
+ * {0 start, 1 final norm done, 2 lm_head rows done, 3 (CTA 0) step advanced}.  cap = capacity of stamps in uint64. */
+int b200_trace_persistent(b200_plan *plan, int32_t token, int32_t position, uint64_t *stamps, int64_t cap, int32_t *n_ctas, int32_t *n_rows, int32_t *n_stamps);
+
 /* Diagnostic: SM-clock cycles of the RMSNorm kernel's phases {launch->dependency wait, load+square,
  * exact sequential sum, normalise+quantise+store} followed by {entries, first fallback element or -1,
  * overflow flag} of the sequential-sum emulation, then at [8..12] the cycles of its phases
@@ -179,6 +202,9 @@ int b200_profile_norm(b200_plan *plan, int64_t *cycles);
  * (csrc/seqsum.cuh; the RMSNorm accumulator of InferenceCore.java:39-48): sums n <= 8192
  * non-negative host floats on the device exactly as `for (i) s += t[i]` would. */
 int b200_test_seqsum(const float *terms, int32_t n, float *out, int32_t *info /* nullable: {entries, first fallback element or -1} */);
+/* Same contract for the round-2 accumulator (csrc/seqsum2.cuh) run by `threads` = 1024 (the RMSNorm kernel's form) or 256
+ * (the persistent decode kernel's form) threads; info = {items walked, fallbacks}. */
+int b200_test_seqsum2(const float *terms, int32_t n, int32_t threads, float *out, int32_t *info /* nullable */);
 
 /* Batched-prefill GEMM building block (csrc/prefill_gemm.cuh; replaces the reference's mma.sync GEMMs
  * gemmMMA / gemmMMAQKV / gemmMMAGateUp, TransformerBatchPrefillKernels.java:792-1132) exposed for

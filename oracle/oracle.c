@@ -433,6 +433,17 @@ void oracle_quantize_q8_0(const float *x, int64_t n, uint8_t *out) {
     }
 }
 
+/* torchrun exports OMP_NUM_THREADS=1: the bench's CPU legs set the thread count explicitly (all host cores, like
+ * Parallel.parallelFor's ForkJoin common pool, Parallel.java:9-11). */
+void oracle_set_threads(int n) {
+#ifdef _OPENMP
+    extern void omp_set_num_threads(int);
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int oracle_omp_threads(void) {
 #ifdef _OPENMP
     extern int omp_get_max_threads(void);

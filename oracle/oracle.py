@@ -72,8 +72,19 @@ def lib() -> C.CDLL:
         L.oracle_f16_to_f32_daz.argtypes = [C.c_uint16]
         L.oracle_f16_to_f32_daz.restype = f32
         L.oracle_omp_threads.restype = i32
+        L.oracle_set_threads.argtypes = [i32]
         _lib = L
     return _lib
+
+
+def use_all_cores() -> int:
+    """Row-parallel over every host core this process may run on, whatever OMP_NUM_THREADS says (torchrun sets it to 1)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    lib().oracle_set_threads(n)
+    return int(lib().oracle_omp_threads())
 
 
 def _ot(entry) -> OTensor:

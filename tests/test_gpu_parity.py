@@ -21,8 +21,22 @@ def assert_bit_equal(a, b, what):
                              f"max|d|={np.abs(a - b).max():.3e}")
 
 
-def run_stream(pkg, orc, model, lanes, n, check_kv=True, prefill_first=0):
+MODES = ["graph", "persistent"]  # the CUDA graph of ~7 kernels per layer / one persistent kernel per token
+
+
+def set_mode(pkg, plan, mode):
+    """Select the decode implementation; a plan that cannot run the persistent kernel (FP16 weights) skips that case."""
+    try:
+        plan.set_decode_mode(mode)
+    except pkg.native.UnsupportedOperation as e:
+        plan.free()
+        pytest.skip(str(e))
+    assert plan.decode_info()[0] == {"graph": 0, "persistent": 1}[mode]
+
+
+def run_stream(pkg, orc, model, lanes, n, check_kv=True, prefill_first=0, mode="graph"):
     plan = pkg.B200MasterPlan.initialize_plan(model, fp16_lanes=lanes)
+    set_mode(pkg, plan, mode)
     om = orc.OracleModel(model, lanes=lanes)
     c = model.configuration
     stream = orc.bench_tokens(c.vocab_size, n)
@@ -47,10 +61,11 @@ def run_stream(pkg, orc, model, lanes, n, check_kv=True, prefill_first=0):
         om.close()
 
 
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("shape", ["tiny-llama", "tiny-llama-tied", "tiny-qwen3"])
-def test_decode_q8_bit_exact(pkg, orc, make_model, shape):
+def test_decode_q8_bit_exact(pkg, orc, make_model, shape, mode):
     m = make_model(shape, pkg.gguf.GGMLType.Q8_0, 24)
-    run_stream(pkg, orc, m, 16, 20)
+    run_stream(pkg, orc, m, 16, 20, mode=mode)
 
 
 @pytest.mark.parametrize("shape,lanes", [("tiny-llama", 16), ("tiny-llama-tied", 8), ("tiny-llama", 0), ("tiny-qwen3", 16)])
@@ -59,30 +74,47 @@ def test_decode_f16_bit_exact(pkg, orc, make_model, shape, lanes):
     run_stream(pkg, orc, m, lanes, 12)
 
 
-def test_decode_small_llama_q8(pkg, orc, make_model):
+@pytest.mark.parametrize("mode", MODES)
+def test_decode_small_llama_q8(pkg, orc, make_model, mode):
     """dim 1536 (not a multiple of 512: exercises the column tail), 12 heads / 4 KV heads, 3 layers."""
     m = make_model("small-llama", pkg.gguf.GGMLType.Q8_0, 40)
-    run_stream(pkg, orc, m, 16, 36, check_kv=False)
+    run_stream(pkg, orc, m, 16, 36, check_kv=False, mode=mode)
 
 
-def test_decode_mid_llama_q8(pkg, orc):
-    """The real Llama-3-8B layer geometry (dim 4096, hidden 14336 = 7 column segments, 32/8 heads)
-    with 2 layers: the streaming kernel's ring laps many times per matvec here."""
-    sh = pkg.synth.SHAPES["mid-llama"]
-    m = pkg.loader.model_from_tensors(sh, pkg.gguf.GGMLType.Q8_0, pkg.synth.build_tensors_fast(sh, pkg.gguf.GGMLType.Q8_0, seed=5), 16)
-    run_stream(pkg, orc, m, 16, 6, check_kv=True)
+_mid_cache = {}
 
 
-def test_prefill_graph_then_decode(pkg, orc, make_model):
+def mid_model(pkg, name, ctx):
+    if name not in _mid_cache:
+        sh = pkg.synth.SHAPES[name]
+        _mid_cache[name] = (sh, pkg.synth.build_tensors_fast(sh, pkg.gguf.GGMLType.Q8_0, seed=5))
+    sh, tensors = _mid_cache[name]
+    return pkg.loader.model_from_tensors(sh, pkg.gguf.GGMLType.Q8_0, tensors, ctx)
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("shape", ["mid-llama", "mid-qwen3-4b", "mid-llama-1b", "mid-llama-70b"])
+def test_decode_mid_geometries_q8(pkg, orc, shape, mode):
+    """2-layer cuts of the BASELINE geometries, bit-exact vs the oracle: Llama-3-8B (dim 4096, hidden 14336 = 7 column segments,
+    32/8 heads), Qwen3-4B (dim 2560 / hidden 9728 / q width 4096: three different segment widths, q/k norm, NeoX rope),
+    Llama-3.2-1B (head 64, tied classifier), Llama-3-70B (dim 8192 / hidden 28672 / 64 heads).  The ring laps many times per matvec."""
+    m = mid_model(pkg, shape, 16)
+    run_stream(pkg, orc, m, 16, 5, check_kv=True, mode=mode)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_prefill_graph_then_decode(pkg, orc, make_model, mode):
     """forward_prefill (no logits) fills the same KV cache as a full forward."""
     m = make_model("tiny-llama", pkg.gguf.GGMLType.Q8_0, 24)
-    run_stream(pkg, orc, m, 16, 16, prefill_first=9)
+    run_stream(pkg, orc, m, 16, 16, prefill_first=9, mode=mode)
 
 
-def test_batch_prefill_matches_oracle(pkg, orc, make_model):
+@pytest.mark.parametrize("mode", MODES)
+def test_batch_prefill_matches_oracle(pkg, orc, make_model, mode):
     m = make_model("tiny-llama", pkg.gguf.GGMLType.Q8_0, 32)
     c = m.configuration
     plan = pkg.B200MasterPlan.initialize_plan(m, prefill_batch_size=8)
+    set_mode(pkg, plan, mode)
     plan.set_prefill_mode("exact")  # the token-by-token graph; the tensor-core mode is covered by test_gpu_prefill.py
     om = orc.OracleModel(m)
     stream = orc.bench_tokens(c.vocab_size, 20)
@@ -99,12 +131,14 @@ def test_batch_prefill_matches_oracle(pkg, orc, make_model):
     plan.free()
 
 
-def test_decode_sequence_device_loop(pkg, orc, make_model):
+@pytest.mark.parametrize("mode", MODES)
+def test_decode_sequence_device_loop(pkg, orc, make_model, mode):
     """The device-resident loop (tokens and argmax never leave the GPU) equals step-by-step calls,
     in both teacher-forced (LlamaBench) and greedy-feedback modes."""
     m = make_model("tiny-llama", pkg.gguf.GGMLType.Q8_0, 40)
     c = m.configuration
     plan = pkg.B200MasterPlan.initialize_plan(m)
+    set_mode(pkg, plan, mode)
     om = orc.OracleModel(m)
     stream = orc.bench_tokens(c.vocab_size, 24)
     ids, ms = plan.decode_sequence(stream, 24, 0, feedback=False)
@@ -121,12 +155,14 @@ def test_decode_sequence_device_loop(pkg, orc, make_model):
     plan.free()
 
 
-def test_generation_loops_match_oracle(pkg, orc, make_model):
+@pytest.mark.parametrize("mode", MODES)
+def test_generation_loops_match_oracle(pkg, orc, make_model, mode):
     """The reference's loop conventions end to end: Llama (BOS at pos 0 and 1) and Qwen3 (skipped
     position, which reads the zero-initialised KV row)."""
     for shape, loop in (("tiny-llama", "llama"), ("tiny-qwen3", "qwen3")):
         m = make_model(shape, pkg.gguf.GGMLType.Q8_0, 32)
         plan = pkg.B200MasterPlan.initialize_plan(m)
+        set_mode(pkg, plan, mode)
         om = orc.OracleModel(m)
         prompt = [int(t) for t in orc.bench_tokens(m.configuration.vocab_size, 6)]
         fn = pkg.engine.generate_tokens_llama if loop == "llama" else pkg.engine.generate_tokens_qwen3
@@ -148,9 +184,31 @@ def test_batch_prefill_generation_loop(pkg, orc, make_model):
     plan.free()
 
 
-def test_kv_reset_and_determinism(pkg, orc, make_model):
+def test_modes_interleave(pkg, orc, make_model):
+    """Both decode implementations share the KV cache and the step state: switching between them mid-stream changes nothing."""
+    m = make_model("tiny-llama", pkg.gguf.GGMLType.Q8_0, 24)
+    plan = pkg.B200MasterPlan.initialize_plan(m)
+    om = orc.OracleModel(m)
+    stream = orc.bench_tokens(m.configuration.vocab_size, 16)
+    for pos in range(16):
+        plan.set_decode_mode("persistent" if (pos // 3) % 2 == 0 else "graph")
+        lg, am = plan.forward_decode(int(stream[pos]), pos)
+        assert_bit_equal(lg, om.forward(int(stream[pos]), pos), f"logits pos {pos}")
+    plan.free()
+
+
+def test_long_context_score_row_in_global_memory(pkg, orc, make_model):
+    """A context too long for the shared-memory score row (real checkpoints default to 131072) builds a plan and stays bit-exact."""
+    m = make_model("tiny-llama", pkg.gguf.GGMLType.Q8_0, 20000)
+    for mode in MODES:
+        run_stream(pkg, orc, m, 16, 6, check_kv=False, mode=mode)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_kv_reset_and_determinism(pkg, orc, make_model, mode):
     m = make_model("tiny-qwen3", pkg.gguf.GGMLType.Q8_0, 24)
     plan = pkg.B200MasterPlan.initialize_plan(m)
+    set_mode(pkg, plan, mode)
     stream = orc.bench_tokens(m.configuration.vocab_size, 10)
     a = [plan.forward_decode(int(stream[p]), p)[0] for p in range(10)]
     plan.kv_reset()
@@ -181,8 +239,10 @@ def _seq(t):
     return np.add.accumulate(np.asarray(t, dtype=np.float32), dtype=np.float32)[-1]
 
 
-def test_exact_parallel_sequential_sum(pkg):
-    """csrc/seqsum.cuh: the parallel emulation of `for (i) s += t[i]` in float32 must equal the
+@pytest.mark.parametrize("threads", [0, 1024, 256])
+def test_exact_parallel_sequential_sum(pkg, threads):
+    """csrc/seqsum.cuh (threads = 0) and csrc/seqsum2.cuh (1024 = the norm kernel's form, 256 = the persistent decode kernel's
+    form): the parallel emulation of `for (i) s += t[i]` in float32 must equal the
     literal chain bit for bit, on benign and adversarial inputs (ties, binade edges, zeros,
     huge dynamic range, sums parked next to a power of two, forced fallbacks)."""
     rng = np.random.default_rng(0)
@@ -214,6 +274,6 @@ def test_exact_parallel_sequential_sum(pkg):
     cases.append((4.0 ** (np.arange(300) % 150 - 75)).astype(np.float32))
     cases.append(np.array([1.0] * 40 + [np.inf] + [1.0] * 40, dtype=np.float32))
     for t in cases:
-        got = np.float32(pkg.native.test_seqsum(t))
+        got = np.float32(pkg.native.test_seqsum(t, threads=threads))
         ref = _seq(t)
         assert got.view(np.uint32) == ref.view(np.uint32) or (np.isnan(got) and np.isnan(ref)), (len(t), got, ref)
