@@ -41,7 +41,10 @@ struct TpCtx {
     unsigned ops_per_fwd;          // 4 * layers + 1
     unsigned char *peer[TP_MAX];   // base of each rank's communication buffer (peer[rank] = own)
     unsigned off_x, off_attq, off_atts, off_hq, off_hs, off_pv, off_pi, off_flags, off_tick, off_done;
+    unsigned *err;      // device word: != 0 once any wait of this plan gave up (every later wait returns at once)
+    unsigned *host_err; // mapped pinned host alias the host checks after each synchronize
 };
+#define TP_TIMEOUT_NS 4000000000ull // a peer that has not signalled after 4 s is gone (or the ranks' call sequences diverged)
 template <typename T> __device__ __forceinline__ T *tp_ptr(const TpCtx &t, int k, unsigned off) {
     return reinterpret_cast<T *>(t.peer[k] + off);
 }
@@ -49,11 +52,32 @@ __device__ __forceinline__ unsigned tp_seq(const TpCtx &t, unsigned op) {
     const unsigned tick = *reinterpret_cast<volatile unsigned *>(t.peer[t.rank] + t.off_tick);
     return tick * t.ops_per_fwd + op + 1u;
 }
-__device__ __forceinline__ void tp_wait(const TpCtx &t, int slot, unsigned seq) { // one thread
+__device__ __forceinline__ unsigned long long gtime_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// one thread; bounded: a rank that errored out or died must not leave the others spinning inside a captured graph
+__device__ __noinline__ void tp_wait(const TpCtx &t, int slot, unsigned seq) {
     const unsigned *f = reinterpret_cast<const unsigned *>(t.peer[t.rank] + t.off_flags) + slot * TP_MAX;
+    unsigned it = 0;
+    unsigned long long t0 = 0;
     for (int k = 0; k < t.n; k++) {
-        unsigned v;
-        do { asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f + k) : "memory"); } while ((int)(v - seq) < 0);
+        for (;;) {
+            unsigned v;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f + k) : "memory");
+            if ((int)(v - seq) >= 0) break;
+            if ((++it & 255u) == 0u && t.err) {
+                if (*reinterpret_cast<volatile unsigned *>(t.err)) return;
+                const unsigned long long now = gtime_ns();
+                if (!t0) t0 = now;
+                else if (now - t0 > TP_TIMEOUT_NS) {
+                    atomicCAS(t.err, 0u, 100u + (unsigned)slot);
+                    *reinterpret_cast<volatile unsigned *>(t.host_err) = 100u + (unsigned)slot;
+                    return;
+                }
+            }
+        }
     }
 }
 __device__ __forceinline__ void tp_signal(const TpCtx &t, int slot, unsigned seq) { // one thread, after the data stores

@@ -120,6 +120,14 @@ int fail(b200_plan *p, int code, const char *fmt, ...) {
                         cudaGetErrorString(e_), __FILE__, __LINE__);                                 \
     } while (0)
 
+// Largest dynamic shared memory a kernel may ask for = the device opt-in limit minus the kernel's own static shared memory.
+template <typename K> cudaError_t set_max_dyn(K kern, int maxdyn) {
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, kern);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, maxdyn - (int)fa.sharedSizeBytes);
+}
+
 template <typename T> int dalloc(b200_plan *p, T **ptr, size_t n_bytes) {
     void *d = nullptr;
     if (n_bytes == 0) n_bytes = 16;
@@ -477,16 +485,11 @@ int pd_prepare(b200_plan *p) {
         }
         if ((rc = dalloc(p, &p->pd_layers, h.size() * sizeof(PdLayer)))) return rc;
         CK(cudaMemcpy(p->pd_layers, h.data(), h.size() * sizeof(PdLayer), cudaMemcpyHostToDevice));
-        if ((rc = dalloc(p, &p->pd_sync, PD_S_WORDS * 4))) return rc;
-        CK(cudaMemset(p->pd_sync, 0, PD_S_WORDS * 4));
-        CK(cudaHostAlloc(&p->h_err, 64, cudaHostAllocMapped));
-        *p->h_err = 0u;
-        CK(cudaHostGetDevicePointer((void **)&p->d_err, p->h_err, 0));
         if ((rc = dalloc(p, &p->pd_trace, (size_t)p->n_sms * (c.n_layers + 1) * PD_STAMPS * 8))) return rc;
         CK(cudaMemset(p->pd_trace, 0, (size_t)p->n_sms * (c.n_layers + 1) * PD_STAMPS * 8));
     }
-    CK(cudaFuncSetAttribute(k_decode_persistent<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxdyn));
-    CK(cudaFuncSetAttribute(k_decode_persistent<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxdyn));
+    CK(set_max_dyn(k_decode_persistent<128>, maxdyn));
+    CK(set_max_dyn(k_decode_persistent<64>, maxdyn));
     p->pd_L = L;
     p->pd_ok = true;
     p->pd_why = "";
@@ -589,26 +592,26 @@ int set_smem_attrs(b200_plan *p) {
         return fail(p, B200_ERR_UNSUPPORTED, "shape needs more shared memory than the device offers (%d bytes)", maxdyn);
     static bool done = false; // process-wide, like the attribute itself (plans are created from one thread at a time per process)
     if (done) return B200_OK;
-    CK(cudaFuncSetAttribute(k_rmsnorm_quant<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxdyn));
-    CK(cudaFuncSetAttribute(k_rmsnorm_quant<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxdyn));
-    CK(cudaFuncSetAttribute(k_rmsnorm_quant<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxdyn));
-    CK(cudaFuncSetAttribute(k_rmsnorm_quant<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxdyn));
-    CK(cudaFuncSetAttribute(k_attention<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxdyn));
-    CK(cudaFuncSetAttribute(k_attention<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxdyn));
-    CK(cudaFuncSetAttribute(k_attention<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxdyn));
-    CK(cudaFuncSetAttribute(k_attention<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxdyn));
-    CK(cudaFuncSetAttribute(k_matvec_q8<1, MODE_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxdyn));
-    CK(cudaFuncSetAttribute(k_matvec_q8<2, MODE_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxdyn));
-    CK(cudaFuncSetAttribute(k_matvec_q8<4, MODE_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxdyn));
-    CK(cudaFuncSetAttribute(k_matvec_q8<1, MODE_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxdyn));
-    CK(cudaFuncSetAttribute(k_matvec_q8<2, MODE_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxdyn));
-    CK(cudaFuncSetAttribute(k_matvec_q8<4, MODE_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxdyn));
-    CK(cudaFuncSetAttribute(k_gateup_q8, cudaFuncAttributeMaxDynamicSharedMemorySize, maxdyn));
+    CK(set_max_dyn(k_rmsnorm_quant<true, false>, maxdyn));
+    CK(set_max_dyn(k_rmsnorm_quant<false, false>, maxdyn));
+    CK(set_max_dyn(k_rmsnorm_quant<true, true>, maxdyn));
+    CK(set_max_dyn(k_rmsnorm_quant<false, true>, maxdyn));
+    CK(set_max_dyn(k_attention<32>, maxdyn));
+    CK(set_max_dyn(k_attention<64>, maxdyn));
+    CK(set_max_dyn(k_attention<128>, maxdyn));
+    CK(set_max_dyn(k_attention<256>, maxdyn));
+    CK(set_max_dyn(k_matvec_q8<1, MODE_STORE>, maxdyn));
+    CK(set_max_dyn(k_matvec_q8<2, MODE_STORE>, maxdyn));
+    CK(set_max_dyn(k_matvec_q8<4, MODE_STORE>, maxdyn));
+    CK(set_max_dyn(k_matvec_q8<1, MODE_RESID>, maxdyn));
+    CK(set_max_dyn(k_matvec_q8<2, MODE_RESID>, maxdyn));
+    CK(set_max_dyn(k_matvec_q8<4, MODE_RESID>, maxdyn));
+    CK(set_max_dyn(k_gateup_q8, maxdyn));
     CK(cudaFuncSetAttribute(k_stream_matvec_q8<SMV_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMV_SMEM_BUDGET_MAX));
     CK(cudaFuncSetAttribute(k_stream_matvec_q8<SMV_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMV_SMEM_BUDGET_MAX));
     CK(cudaFuncSetAttribute(k_stream_matvec_q8<SMV_GATEUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMV_SMEM_BUDGET_MAX));
-    CK(cudaFuncSetAttribute(k_matvec_f16<MODE_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxdyn));
-    CK(cudaFuncSetAttribute(k_matvec_f16<MODE_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxdyn));
+    CK(set_max_dyn(k_matvec_f16<MODE_STORE>, maxdyn));
+    CK(set_max_dyn(k_matvec_f16<MODE_RESID>, maxdyn));
     done = true;
     return B200_OK;
 }
@@ -811,6 +814,14 @@ int build(b200_plan *p, const b200_tensor *tensors, int n_tensors) {
     CK(cudaMallocHost(&p->h_st, sizeof(StepState)));
     CK(cudaMallocHost(&p->h_ids, (size_t)p->seq_cap * 4));
 
+    // epoch counters of the persistent kernel + the error word every bounded device-side wait reports through
+    if ((rc = dalloc(p, &p->pd_sync, PD_S_WORDS * 4))) return rc;
+    CK(cudaMemset(p->pd_sync, 0, PD_S_WORDS * 4));
+    CK(cudaHostAlloc(&p->h_err, 64, cudaHostAllocMapped));
+    *p->h_err = 0u;
+    CK(cudaHostGetDevicePointer((void **)&p->d_err, p->h_err, 0));
+    p->tp.err = p->pd_sync + PD_S_ERR;
+    p->tp.host_err = p->d_err;
     if (3 * c.head_size + c.context_length > ATT_SMEM_FLOATS_MAX) { // long context: score rows in global memory
         if ((rc = dalloc(p, &p->att_scratch, (size_t)p->nh_l * c.context_length * 4))) return rc;
     }
@@ -1021,8 +1032,8 @@ cudaGraphExec_t prefill_graph(b200_plan *p) { return p->decode_mode == B200_DECO
 int check_device_error(b200_plan *p) {
     if (p->h_err && *reinterpret_cast<volatile unsigned *>(p->h_err)) {
         const unsigned code = *reinterpret_cast<volatile unsigned *>(p->h_err);
-        return fail(p, B200_ERR_STATE, "device-side wait timed out in the persistent decode kernel (phase %u): a peer rank is missing or the ranks' call "
-                                       "sequences diverged; the plan must be freed", code - 1u);
+        return fail(p, B200_ERR_STATE, "a device-side wait timed out (code %u: 1+phase of the persistent decode kernel, 100+slot of a tensor-parallel flag): a peer "
+                                       "rank is missing or the ranks' call sequences diverged; the plan must be freed", code);
     }
     return B200_OK;
 }

@@ -67,19 +67,26 @@ def generate_tokens_qwen3(forward: Forward, latest_token: int, start_position: i
     return generated
 
 
-def generate_tokens_llama_batch_prefill(plan, latest_token: int, prompt_tokens: list[int], stop_tokens: Iterable[int],
-                                        max_tokens: int, context_length: int, batch_size: int) -> list[int]:
-    """prefillSeq = [latestToken, prompt[0..N-2]] in chunks of B through the batched prefill,
-    then decode from the last prompt token (InferenceEngineWithBatchPrefillDecode.java:163-251)."""
+def generate_tokens_llama_batch_prefill(plan, latest_token: int, start_position: int, prompt_tokens: list[int],
+                                        stop_tokens: Iterable[int], max_tokens: int, context_length: int, batch_size: int) -> list[int]:
+    """prefillSeq = [latestToken, prompt[0..N-2]] at positions startPosition.. in chunks of B through the batched
+    prefill, clamped to the token budget, then decode from the last prompt token at startPosition+N
+    (InferenceEngineWithBatchPrefillDecode.java:163-251; the chunk clamp is :204-205)."""
     if max_tokens < 0 or context_length < max_tokens:
         max_tokens = context_length
     stop = set(stop_tokens)
     n = len(prompt_tokens)
+    if n == 0:
+        raise IndexError("empty prompt (the reference's promptTokens.get(N - 1) throws as well)")
     seq = [latest_token] + list(prompt_tokens[: n - 1])
-    for off in range(0, len(seq), batch_size):
-        plan.forward_batch_prefill(seq[off:off + batch_size], off)
+    pos = start_position
+    chunk_start = 0
+    while chunk_start < n and pos + chunk_start < max_tokens:
+        chunk_end = min(chunk_start + batch_size, n, max_tokens - pos)
+        plan.forward_batch_prefill(seq[chunk_start:chunk_end], pos + chunk_start)
+        chunk_start += batch_size
     generated: list[int] = []
-    current, pos = prompt_tokens[n - 1], n
+    current, pos = prompt_tokens[n - 1], start_position + n
     while pos < max_tokens:
         _, nxt = plan.forward_decode(current, pos, logits=False)
         generated.append(nxt)

@@ -98,18 +98,22 @@ def load_model(path: str, context_length: int = -1) -> Model:
     typ = detect_model_type(md)
     q = _quantization(md)
     if typ == "LLAMA_3" or typ == "MISTRAL":
-        a = "llama"
+        # Mistral runs the same forward as Llama (Mistral.java -> InferenceCore.forwardJava; weights in the same
+        # LlamaStandardWeights slots, MistralModelLoader.java:92-113).  Differences are host-side only: the context is
+        # clamped to the model's (MistralModelLoader.java:45-46) and the vocabulary size may come from the token list.
         vocab = md.get("llama.vocab_size")
         if vocab is None:
             vocab = len(md["tokenizer.ggml.tokens"])
         model_ctx = int(md["llama.context_length"])
         n_heads = int(md["llama.attention.head_count"])
         dim = int(md["llama.embedding_length"])
+        if typ == "MISTRAL":
+            ctx = model_ctx if (context_length < 0 or model_ctx < context_length) else context_length
+        else:  # withContextLength(contextLength): LlamaConfiguration keeps the requested length when >= 0
+            ctx = model_ctx if context_length < 0 else context_length
         cfg = Configuration(
             ARCH_LLAMA, q, dim, int(md["llama.feed_forward_length"]), int(md["llama.block_count"]), n_heads,
-            int(md.get("llama.attention.head_count_kv", n_heads)), dim // n_heads, int(vocab),
-            # withContextLength(contextLength): LlamaConfiguration keeps the requested length when >= 0
-            model_ctx if context_length < 0 else context_length,
+            int(md.get("llama.attention.head_count_kv", n_heads)), dim // n_heads, int(vocab), ctx,
             float(md.get("llama.attention.layer_norm_rms_epsilon", 1e-5)), float(md.get("llama.rope.freq_base", 10000.0)))
     elif typ == "QWEN_3":
         model_ctx = int(md["qwen3.context_length"])
@@ -126,7 +130,7 @@ def load_model(path: str, context_length: int = -1) -> Model:
             int(md["qwen3.attention.key_length"]), int(vocab), ctx,
             float(md["qwen3.attention.layer_norm_rms_epsilon"]), float(md["qwen3.rope.freq_base"]))
     else:
-        raise UnsupportedModel(f"model type {typ} is outside the B200 hot-path scope (Llama/Qwen3 only)")
+        raise UnsupportedModel(f"model type {typ} is outside the B200 hot-path scope (Llama / Mistral / Qwen3 forward passes only)")
     return Model(g, cfg, typ)
 
 

@@ -98,7 +98,11 @@ class Tokenizer:
         missing = [s for s in allowed_special if s not in self.special_tokens]
         if missing:
             raise TokenizerError(f"not special tokens: {missing}")
-        parts = re.split("(" + "|".join(re.escape(s) for s in allowed_special) + ")", mapped_text)
+        # Java's String.split never returns the delimiters, capturing group or not (unlike Python's re.split), and drops
+        # trailing empty strings: the reference's encode(text, allowedSpecial) therefore DROPS the special tokens it splits at
+        # (its `special.contains(part)` branch is dead code, LlamaTokenizer.java:164-176).  Mirrored as is: chat formats add
+        # special tokens by id (LlamaChatFormat.java), never through this path.
+        parts = re.split("(?:" + "|".join(re.escape(s) for s in allowed_special) + ")", mapped_text)
         while parts and parts[-1] == "":
             parts.pop()
         ids = []
@@ -172,8 +176,17 @@ class Qwen3Tokenizer(Tokenizer):
         return self.token_types[token] in (1, 4, 6)
 
 
+class UnsupportedTokenizer(Exception):
+    """The model's tokenizer family is outside this package's scope (maps to UnsupportedOperationException)."""
+
+
 def from_metadata(metadata: dict, model_type: str) -> Tokenizer:
     """ModelLoader: Vocabulary.loadLlamaVocabulary / loadQwen3Vocabulary + the tokenizer constructors."""
+    if model_type.upper() in ("MISTRAL", "DEVSTRAL_2") or "tokenizer.ggml.merges" not in metadata:
+        # MistralTokenizer (tokenizer/MistralTokenizer.java) is a SentencePiece-style scorer over a 32k vocabulary, not the
+        # byte-level BPE implemented here: reject up front instead of mis-tokenising (the forward pass itself is supported).
+        raise UnsupportedTokenizer(f"no tokenizer for model type {model_type}: only the byte-level BPE vocabularies of Llama-3 and Qwen3 are "
+                                   "implemented; drive the plan with token ids")
     tokens = list(metadata["tokenizer.ggml.tokens"])
     merges = list(metadata["tokenizer.ggml.merges"])
     if model_type.upper().startswith("QWEN"):

@@ -106,7 +106,8 @@ class OracleTokenizer:
         if not allowed_special:
             return self.encode_ordinary(mapped_text)
         assert all(s in self.special_tokens for s in allowed_special)
-        pat = "(" + "|".join(regex.escape(s) for s in allowed_special) + ")"
+        # String.split(regex) never returns the delimiters, even for a capturing group: the specials are dropped (:164)
+        pat = "(?:" + "|".join(regex.escape(s) for s in allowed_special) + ")"
         ids = []
         parts = regex.split(pat, mapped_text)
         while parts and parts[-1] == "":  # String.split drops trailing empty strings

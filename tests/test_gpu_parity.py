@@ -178,10 +178,20 @@ def test_batch_prefill_generation_loop(pkg, orc, make_model):
     plan.set_prefill_mode("exact")
     om = orc.OracleModel(m)
     prompt = [int(t) for t in orc.bench_tokens(m.configuration.vocab_size, 7)]
-    got = pkg.engine.generate_tokens_llama_batch_prefill(plan, prompt[0], prompt, [], 20, 32, 4)
+    got = pkg.engine.generate_tokens_llama_batch_prefill(plan, prompt[0], 0, prompt, [], 20, 32, 4)
     ref = pkg.engine.generate_tokens_llama(lambda t, p: om.forward_argmax(t, p), prompt[0], 0, prompt, [], 20, 32)
     assert got == ref
     plan.free()
+
+
+def test_mistral_named_model_runs_the_llama_path(pkg, orc, tmp_path):
+    """Mistral = the Llama forward through the same kernels (Mistral.java -> InferenceCore.forwardJava)."""
+    path = str(tmp_path / "mistral.gguf")
+    pkg.synth.write_model(path, "tiny-llama", pkg.gguf.GGMLType.Q8_0, seed=11, display_name="Mistral-7B-Instruct synthetic")
+    m = pkg.load_model(path, 24)
+    assert m.model_type == "MISTRAL"
+    for mode in MODES:
+        run_stream(pkg, orc, m, 16, 12, mode=mode)
 
 
 def test_modes_interleave(pkg, orc, make_model):

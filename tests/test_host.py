@@ -88,6 +88,49 @@ def test_generation_loop_conventions(pkg):
     assert out == [101] and calls[-1] == (7, 1)  # stop token ends the loop, included in the output
 
 
+def test_mistral_loads_for_the_forward_pass_only(pkg, tmp_path):
+    """a Mistral GGUF uses the Llama forward and weight slots (MistralModelLoader.java:92-113); its context is clamped
+    to the model's (:45-46).  Its tokenizer family is NOT implemented and must be rejected up front, not mis-tokenised."""
+    path = str(tmp_path / "mistral.gguf")
+    pkg.synth.write_model(path, "tiny-llama", pkg.gguf.GGMLType.Q8_0, seed=3, display_name="Mistral-7B-Instruct synthetic")
+    m = pkg.load_model(path, 10 ** 6)
+    assert m.model_type == "MISTRAL" and m.configuration.arch == 0
+    assert m.configuration.context_length == pkg.synth.SHAPES["tiny-llama"].model_ctx  # clamped, unlike Llama
+    assert pkg.load_model(path, 48).configuration.context_length == 48
+    with pytest.raises(pkg.tokenizer.UnsupportedTokenizer):
+        pkg.tokenizer.from_metadata(m.gguf.metadata, m.model_type)
+
+
+def test_batch_prefill_loop_conventions(pkg):
+    """InferenceEngineWithBatchPrefillDecode.generateTokensGPULlama (:163-251): chunks are written at startPosition+chunkStart,
+    clamped to the token budget, and decode starts at startPosition+N -- also for a continuation (startPosition > 0)."""
+    class FakePlan:
+        def __init__(self):
+            self.prefill, self.decode = [], []
+
+        def forward_batch_prefill(self, toks, start):
+            self.prefill.append((list(toks), start))
+
+        def forward_decode(self, tok, pos, logits=False):
+            self.decode.append((tok, pos))
+            return None, 1000 + pos
+
+    fp = FakePlan()
+    out = pkg.engine.generate_tokens_llama_batch_prefill(fp, 7, 10, [21, 22, 23, 24, 25], [], 20, 64, 2)
+    assert fp.prefill == [([7, 21], 10), ([22, 23], 12), ([24], 14)]
+    assert fp.decode[0] == (25, 15) and fp.decode[-1][1] == 19 and out == [1015, 1016, 1017, 1018, 1019]
+    # prompt longer than the budget: the last chunk is truncated instead of overrunning the KV cache
+    fp = FakePlan()
+    out = pkg.engine.generate_tokens_llama_batch_prefill(fp, 7, 0, list(range(30, 40)), [], 5, 64, 4)
+    assert fp.prefill == [([7, 30, 31, 32], 0), ([33], 4)] and out == [] and fp.decode == []
+    with pytest.raises(IndexError):
+        pkg.engine.generate_tokens_llama_batch_prefill(FakePlan(), 7, 0, [], [], 5, 64, 4)
+    # equals the token-by-token loop on the same fake forward (which ignores history)
+    calls = []
+    ref = pkg.engine.generate_tokens_llama(lambda t, p: (calls.append((t, p)), 1000 + p)[1], 7, 10, [21, 22, 23, 24, 25], [], 20, 64)
+    assert ref == [1015, 1016, 1017, 1018, 1019]
+
+
 def test_abi_exports_every_declared_symbol(pkg):
     hdr = open(os.path.join(ROOT, "include", "b200llama.h")).read()
     declared = set(re.findall(r"\b(b200_[a-z_0-9]+)\s*\(", hdr))

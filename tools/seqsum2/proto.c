@@ -69,7 +69,7 @@ static float seqsum_v2(const float *t, int n, int T) {
     for (int j = 0; j < T; j++) {
         cls[j] = INT32_MIN;
         const float lo = P[j], hi = P[j + 1];
-        if (!(lo > 0.f) || fexp(lo) != fexp(hi) || fexp(lo) < -100) continue;
+        if (!(lo > 0.f) || fexp(lo) != fexp(hi) || fexp(lo) < -100 || fexp(lo) >= 128) continue; /* inf/nan prefix: literal adds */
         const int e = fexp(lo);
         const float b = ldexpf(1.0f, e);
         /* margin 2^-9: the sequential sum deviates from the exact prefix by < n * 2^-24 relative (n <= 8192 -> 2^-11) */
