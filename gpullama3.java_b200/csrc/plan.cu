@@ -7,6 +7,7 @@
 #include "prefill.cuh"
 #include "stream_matvec.cuh"
 #include "decode_persistent.cuh"
+#include "sampler.cuh"
 
 #include <math.h>
 #include <stdarg.h>
@@ -72,6 +73,7 @@ struct b200_plan {
     int smv_budget_cols = 0;
     unsigned l2_window = 0, pd_l2_ahead = 0;
     float *att_scratch = nullptr; // [heads][ctx] score rows when the context does not fit shared memory
+    int *smp_indices = nullptr, *smp_out = nullptr; // device-side sampler scratch (sampler.cuh): candidate list, {id, info[4]}
 
     // tensor parallelism (tp.n == 1: single GPU).  *_l = this rank's share.
     TpCtx tp{};
@@ -785,7 +787,7 @@ int build(b200_plan *p, const b200_tensor *tensors, int n_tensors) {
     if ((rc = dalloc(p, &p->qkv, (size_t)(p->qd_l + 2 * p->kvd_l) * 4))) return rc;
     if ((rc = dalloc(p, &p->hb, (size_t)c.hidden_dim * 4))) return rc;
     if ((rc = dalloc(p, &p->hb2, (size_t)c.hidden_dim * 4))) return rc;
-    if ((rc = dalloc(p, &p->logits, (size_t)c.vocab_size * 4))) return rc;
+    if ((rc = dalloc(p, &p->logits, (size_t)sampler_padded(c.vocab_size) * 4))) return rc; // zero pad: the sampler's exact sum runs over whole thread chunks
     if ((rc = dalloc(p, &p->xq, (size_t)big))) return rc;
     if ((rc = dalloc(p, &p->xs, (size_t)(big / 32) * 4))) return rc;
     if (c.tp_size > 1) {
@@ -804,7 +806,9 @@ int build(b200_plan *p, const b200_tensor *tensors, int n_tensors) {
     if ((rc = dalloc(p, &p->value_cache, kv_bytes))) return rc;
     CK(cudaMemset(p->key_cache, 0, kv_bytes));
     CK(cudaMemset(p->value_cache, 0, kv_bytes));
-    CK(cudaMemset(p->logits, 0, (size_t)c.vocab_size * 4));
+    CK(cudaMemset(p->logits, 0, (size_t)sampler_padded(c.vocab_size) * 4));
+    if ((rc = dalloc(p, &p->smp_indices, (size_t)c.vocab_size * 4))) return rc;
+    if ((rc = dalloc(p, &p->smp_out, 8 * 4))) return rc;
     p->seq_cap = c.context_length + 8;
     if ((rc = dalloc(p, &p->st, sizeof(StepState)))) return rc;
     if ((rc = dalloc(p, &p->seq_tokens, (size_t)p->seq_cap * 4))) return rc;
@@ -1091,6 +1095,34 @@ int b200_forward_decode(b200_plan *p, int32_t token, int32_t position, float *lo
     CK(cudaStreamSynchronize(p->stream));
     if ((rc = check_device_error(p))) return rc;
     if (argmax) *argmax = p->h_ids[0];
+    return B200_OK;
+}
+
+int b200_forward_decode_sample(b200_plan *p, int32_t token, int32_t position, float temperature, float topp, float uniform01, int32_t *token_out, int32_t *info) {
+    if (!p || !token_out) return B200_ERR_BAD_ARG;
+    if (!p->g_decode) return fail(p, B200_ERR_STATE, "tensor-parallel plan: call b200_tp_attach on every rank first");
+    if (p->tp.n > 1) return fail(p, B200_ERR_UNSUPPORTED, "the device-side temperature/top-p sampler needs the whole logits row on one GPU (tensor-parallel plans sample greedily)");
+    if (!(temperature >= 0.0f) || !(uniform01 >= 0.0f && uniform01 < 1.0f)) return fail(p, B200_ERR_BAD_ARG, "temperature must be >= 0 and the uniform number in [0, 1)");
+    int rc;
+    if ((rc = check_pos(p, token, position))) return rc;
+    CK(cudaSetDevice(p->device));
+    if ((rc = set_state(p, token, position, 0, 0))) return rc;
+    CK(cudaGraphLaunch(decode_graph(p), p->stream));
+    const bool greedy = temperature == 0.0f; // Sampler.selectSampler: temperature 0 -> FloatTensor.argmax, already computed by the forward
+    if (!greedy) {
+        static bool attr = false;
+        if (!attr) { CK(cudaFuncSetAttribute(k_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sampler_smem_bytes())); attr = true; }
+        SamplerArgs a;
+        a.logits = p->logits; a.n = p->cfg.vocab_size; a.temperature = temperature; a.topp = topp; a.r01 = uniform01;
+        a.indices = p->smp_indices; a.out_id = p->smp_out; a.info = p->smp_out + 1;
+        k_sample<<<1, SAMPLER_THREADS, sampler_smem_bytes(), p->stream>>>(a);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(p->h_ids, p->smp_out, 5 * 4, cudaMemcpyDeviceToHost, p->stream));
+    } else CK(cudaMemcpyAsync(p->h_ids, p->out_ids, 4, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    if ((rc = check_device_error(p))) return rc;
+    *token_out = p->h_ids[0];
+    if (info) for (int k = 0; k < 4; k++) info[k] = greedy ? 0 : p->h_ids[1 + k];
     return B200_OK;
 }
 

@@ -93,6 +93,16 @@ int b200_plan_create(const b200_config *cfg, const b200_tensor *tensors, int32_t
  * (first strict maximum, FloatTensor.java:138-151), computed on the device. */
 int b200_forward_decode(b200_plan *plan, int32_t token, int32_t position, float *logits, int32_t *argmax);
 
+/* b200_forward_decode + Sampler.sampleToken on the DEVICE (inference/sampler/Sampler.java:74-122, CategoricalSampler.java:28-40,
+ * ToppSampler.java:62-156): the reference copies the whole logits row to the host whenever temperature > 0; here 4 bytes go in
+ * (the uniform number the host-side Java RNG produced for this token, in [0,1)) and 4 bytes come out.  temperature == 0 is
+ * FloatTensor.argmax; otherwise logits/temperature, softmax, then categorical sampling (topp <= 0 or >= 1) or top-p.  Every
+ * float is evaluated in the reference's order (csrc/sampler.cuh), so the same uniform number yields the same token id.
+ * info (nullable, 4 ints): {top-p candidates after the cutoff, tokens kept, items / fallbacks of the exact softmax sum}.
+ * Single-GPU plans only (B200_ERR_UNSUPPORTED under tensor parallelism). */
+int b200_forward_decode_sample(b200_plan *plan, int32_t token, int32_t position, float temperature, float topp, float uniform01,
+                               int32_t *token_out, int32_t *info);
+
 /* TornadoVMMasterPlanPrefillDecode.tornadoVMForwardPrefill(position)
  * (TornadoVMMasterPlanPrefillDecode.java:116): single-token forward that only fills the KV
  * cache -- final norm, lm_head and argmax are skipped. */

@@ -433,6 +433,96 @@ void oracle_quantize_q8_0(const float *x, int64_t n, uint8_t *out) {
     }
 }
 
+/* ================================================================================================================
+ * Sampler: Sampler.selectSampler (inference/sampler/Sampler.java:74-122), CategoricalSampler.java:28-40,
+ * ToppSampler.java:26-156.  Temperature 0 -> FloatTensor.argmax; otherwise logits / temperature, softmaxInPlace, then
+ * either the categorical walk or the top-p heap.  PARITY UNPINNED (no JDK here): the uniform numbers come from
+ * RandomGeneratorFactory.getDefault() = L32X64MixRandom, restated below from the published LXM algorithm (Steele & Vigna,
+ * OOPSLA 2021) and the JDK 17 description of its seeding; its output stream could not be compared with a JVM's.  Everything
+ * after the uniform number is plain float arithmetic restated line by line (including the top-p loop's siftDown(..., i - 1)).
+ * ================================================================================================================ */
+typedef struct { uint32_t a, s, x0, x1; } lxm32;
+
+static inline uint32_t mix_murmur32(uint32_t z) { z = (z ^ (z >> 16)) * 0x85ebca6bu; z = (z ^ (z >> 13)) * 0xc2b2ae35u; return z ^ (z >> 16); }
+static inline uint32_t mix_lea32(uint32_t z) { z = (z ^ (z >> 16)) * 0xd36d884bu; z = (z ^ (z >> 16)) * 0xd36d884bu; return z ^ (z >> 16); }
+static inline uint32_t rotl32(uint32_t v, int k) { return (v << k) | (v >> (32 - k)); }
+
+/* new L32X64MixRandom(long seed): a = mixMurmur32(high half of seed ^ SILVER_RATIO_64) | 1, s = 1,
+ * x0 = mixLea32(low half), x1 = mixLea32(low half + GOLDEN_RATIO_32) */
+void oracle_lxm_seed(lxm32 *r, int64_t seed) {
+    uint64_t sd = (uint64_t)seed ^ 0x6A09E667F3BCC909ULL;
+    r->a = mix_murmur32((uint32_t)(sd >> 32)) | 1u;
+    r->s = 1u;
+    r->x0 = mix_lea32((uint32_t)sd);
+    r->x1 = mix_lea32((uint32_t)sd + 0x9e3779b9u);
+    if ((r->x0 | r->x1) == 0u) { r->x0 = 0x9e3779b9u; r->x1 = 0x3c6ef372u; } /* never all-zero xoroshiro state */
+}
+uint32_t oracle_lxm_next_int(lxm32 *r) {
+    const uint32_t z = r->s + r->x0;
+    const uint32_t result = mix_lea32(z);
+    r->s = 0xadb4a92du * r->s + r->a;                 /* LCG */
+    uint32_t q0 = r->x0, q1 = r->x1;                  /* xoroshiro64 */
+    q1 ^= q0; q0 = rotl32(q0, 26); q0 = q0 ^ q1 ^ (q1 << 9); q1 = rotl32(q1, 13);
+    r->x0 = q0; r->x1 = q1;
+    return result;
+}
+/* RandomGenerator.nextFloat(1f): (nextInt() >>> 8) * 2^-24, times the bound, clamped below the bound */
+float oracle_lxm_next_float1(lxm32 *r) {
+    float f = (float)(oracle_lxm_next_int(r) >> 8) * 0x1.0p-24f;
+    f = f * 1.0f;
+    if (f >= 1.0f) f = 0x1.fffffep-1f;
+    return f;
+}
+
+/* CategoricalSampler.sampleFromFloatTensor (:28-40) on probabilities p[0..n) */
+int oracle_sample_categorical(const float *p, int n, float r01) {
+    float cdf = 0.0f;
+    for (int i = 0; i < n; i++) { cdf += p[i]; if (r01 < cdf) return i; }
+    return n - 1;
+}
+
+/* Comparator.comparingDouble(logits::getFloat).reversed(): negative when value(a) > value(b) */
+static inline int topp_cmp(const float *p, int a, int b) { const double va = p[a], vb = p[b]; return vb < va ? -1 : (vb > va ? 1 : 0); }
+static void topp_sift_down(int *arr, int from, int n, const float *p) { /* ToppSampler.siftDown :32-46 */
+    int prev = from, next;
+    while ((next = 2 * prev + 1) < n) {
+        int r = 2 * prev + 2;
+        if (r < n && topp_cmp(p, arr[r], arr[next]) < 0) next = r;
+        if (topp_cmp(p, arr[next], arr[prev]) < 0) { int t = arr[prev]; arr[prev] = arr[next]; arr[next] = t; prev = next; }
+        else break;
+    }
+}
+/* ToppSampler.sampleFromFloatTensor + processTopP (:62-156); indices = scratch of n ints */
+int oracle_sample_topp(const float *p, int n, float topp, float r01, int *indices) {
+    int head = 0, tail = n - 1;
+    const float cutoff = (1.0f - topp) / (float)(n - 1);
+    for (int i = 0; i < n; i++) { if (p[i] >= cutoff) indices[head++] = i; else indices[tail--] = i; }
+    const int n0 = head;
+    for (int i = n0 / 2 - 1; i >= 0; --i) topp_sift_down(indices, i, n0, p);
+    float cumulative = 0.0f;
+    int last = 0;
+    for (int i = n0 - 1; i >= 0; i--) {
+        int t = indices[0]; indices[0] = indices[i]; indices[i] = t;
+        cumulative += p[indices[i]];
+        if (cumulative > topp) { last = i; break; }
+        topp_sift_down(indices, 0, i - 1, p); /* i - 1, as in the reference (:131) */
+    }
+    const float r = r01 * cumulative;
+    float cdf = 0.0f;
+    for (int i = n0 - 1; i >= last; i--) { cdf += p[indices[i]]; if (r < cdf) return indices[i]; }
+    return indices[last];
+}
+
+/* Sampler.selectSampler's lambda (:97-118): logits are modified in place exactly as the reference does.
+ * r01 = the uniform number the RNG produced for this token (ignored for temperature 0). */
+int oracle_sample(float *logits, int n, float temperature, float topp, float r01, int *indices) {
+    if (temperature == 0.0f) return oracle_argmax(logits, n);
+    for (int i = 0; i < n; i++) logits[i] = logits[i] / temperature; /* divideInPlace, FloatTensor.java:203-205 */
+    softmax(logits, n);
+    if (topp <= 0.0f || topp >= 1.0f) return oracle_sample_categorical(logits, n, r01);
+    return oracle_sample_topp(logits, n, topp, r01, indices);
+}
+
 /* torchrun exports OMP_NUM_THREADS=1: the bench's CPU legs set the thread count explicitly (all host cores, like
  * Parallel.parallelFor's ForkJoin common pool, Parallel.java:9-11). */
 void oracle_set_threads(int n) {

@@ -73,8 +73,63 @@ def lib() -> C.CDLL:
         L.oracle_f16_to_f32_daz.restype = f32
         L.oracle_omp_threads.restype = i32
         L.oracle_set_threads.argtypes = [i32]
+        L.oracle_lxm_seed.argtypes = [vp, C.c_int64]
+        L.oracle_lxm_next_int.argtypes = [vp]
+        L.oracle_lxm_next_int.restype = C.c_uint32
+        L.oracle_lxm_next_float1.argtypes = [vp]
+        L.oracle_lxm_next_float1.restype = f32
+        L.oracle_sample.argtypes = [vp, i32, f32, f32, f32, vp]
+        L.oracle_sample_categorical.argtypes = [vp, i32, f32]
+        L.oracle_sample_topp.argtypes = [vp, i32, f32, f32, vp]
         _lib = L
     return _lib
+
+
+class JavaLXM:
+    """RandomGeneratorFactory.getDefault().create(seed) = L32X64MixRandom (Sampler.java:84), restated in oracle.c."""
+
+    def __init__(self, seed: int):
+        self._st = (C.c_uint32 * 4)()
+        lib().oracle_lxm_seed(self._st, seed)
+
+    def next_int(self) -> int:
+        return int(lib().oracle_lxm_next_int(self._st))
+
+    def next_float1(self) -> float:
+        return float(lib().oracle_lxm_next_float1(self._st))
+
+
+def sample(logits: np.ndarray, temperature: float, topp: float, r01: float) -> int:
+    """Sampler.selectSampler's lambda on a COPY of the logits (the reference modifies them in place)."""
+    lg = np.ascontiguousarray(logits, dtype=np.float32).copy()
+    idx = np.empty(len(lg), dtype=np.int32)
+    return int(lib().oracle_sample(lg.ctypes.data, len(lg), temperature, topp, r01, idx.ctypes.data))
+
+
+def np_sample(logits: np.ndarray, temperature: float, topp: float, r01: float) -> int:
+    """Independent numpy restatement of the same lines (cross-check of the C code): sequential float32 sums via
+    np.add.accumulate, the top-p set via a stable argsort -- valid whenever the kept probabilities are distinct."""
+    lg = np.asarray(logits, dtype=np.float32)
+    if temperature == 0.0:
+        return int(np.argmax(lg))
+    x = (lg / np.float32(temperature)).astype(np.float32)
+    e = np.exp((x - x.max()).astype(np.float64)).astype(np.float32)
+    p = (e / np.add.accumulate(e, dtype=np.float32)[-1]).astype(np.float32)
+    n = len(p)
+    if topp <= 0 or topp >= 1:
+        cdf = np.add.accumulate(p, dtype=np.float32)
+        hit = np.flatnonzero(np.float32(r01) < cdf)
+        return int(hit[0]) if len(hit) else n - 1
+    cutoff = (np.float32(1.0) - np.float32(topp)) / np.float32(n - 1)
+    cand = np.flatnonzero(p >= cutoff)
+    order = cand[np.argsort(-p[cand].astype(np.float64), kind="stable")]
+    cum = np.add.accumulate(p[order], dtype=np.float32)
+    over = np.flatnonzero(cum > np.float32(topp))
+    k = int(over[0]) + 1 if len(over) else len(order)
+    total = cum[k - 1]
+    r = np.float32(r01) * total
+    hit = np.flatnonzero(r < cum[:k])
+    return int(order[hit[0]]) if len(hit) else int(order[k - 1])
 
 
 def use_all_cores() -> int:
