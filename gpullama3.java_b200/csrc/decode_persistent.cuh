@@ -32,7 +32,7 @@
 #define PD_CT (SMV_CONSUMER_WARPS * 32) // consumer threads
 #define PD_MAX_STAGES 32
 #define PD_TIMEOUT_NS 4000000000ull    // 4 s: far beyond any legitimate wait, well under gpurun's limits
-#define PD_STAMPS 10                    // trace stamps per layer and CTA
+#define PD_STAMPS 16                    // trace stamps per layer and CTA (0-9 phases, 10-15 inside the attn norm / the attention)
 
 enum { PD_S_QKV = 0, PD_S_ATT = 1, PD_S_WO = 2, PD_S_GU = 3, PD_S_W2 = 4, PD_S_LM = 5, PD_S_ARG = 6, PD_S_SLOTS = 8,
        PD_S_TICK = 8, PD_S_LMTICK = 9, PD_S_ERR = 10, PD_S_WORDS = 16 };
@@ -80,9 +80,10 @@ struct PdArgs {
 };
 
 struct PdSmem {
-    size_t off_bar, off_xq, off_xs, off_nbuf, off_xbuf, off_seq, off_terms, off_hvals, off_misc, off_ring, total;
-    int stages, stage_bytes, nbs_pad, nbuf_floats;
+    size_t off_bar, off_xq, off_xs, off_nbuf, off_seq, off_terms, off_hvals, off_misc, off_ring, total;
+    int stages, stage_bytes, tstride, nbuf_floats;
 };
+#define PD_NORM_U 8 // float4 slots per consumer thread in the norm: dim <= 4 * PD_CT * PD_NORM_U = 8192
 
 // max_seg = widest column segment of any matrix of the plan; att_floats = 3*head_size + ctx when the score row lives in
 // shared memory, 3*head_size otherwise.
@@ -90,11 +91,12 @@ __host__ __device__ inline PdSmem pd_layout(int dim, int qd, int hidden, int att
     PdSmem L;
     const int unit = smv_unit_bytes(max_seg);
     L.stage_bytes = (4 * unit + 127) & ~127;
-    L.nbs_pad = (max_seg / 32) | 1;
+    L.tstride = ((max_seg / 32 + 3) & ~3) + 4; // per-row stride of the term buffer: 16-byte aligned rows, the four walker lanes on distinct banks
     int maxc = dim > qd ? dim : qd;
     if (hidden > maxc) maxc = hidden;
-    const int dim_pad = (dim + PD_CT - 1) / PD_CT * PD_CT;
-    L.nbuf_floats = dim_pad > att_floats ? dim_pad : att_floats;
+    const int E = (dim + PD_CT - 1) / PD_CT;
+    const int sq_floats = PD_CT * seqsum2_stride(E); // squares of the norm in the accumulator's bank-conflict-free chunk layout
+    L.nbuf_floats = sq_floats > att_floats ? sq_floats : att_floats;
     size_t o = 0;
     L.off_bar = o; o += 2 * PD_MAX_STAGES * 8 + PD_MAX_STAGES * 4;
     o = (o + 15) & ~(size_t)15;
@@ -103,11 +105,9 @@ __host__ __device__ inline PdSmem pd_layout(int dim, int qd, int hidden, int att
     o = (o + 15) & ~(size_t)15;
     L.off_nbuf = o; o += (size_t)L.nbuf_floats * 4; // squares of the norm | q,k,out,att of the attention (time-disjoint)
     o = (o + 15) & ~(size_t)15;
-    L.off_xbuf = o; o += (size_t)dim * 4; // the residual stream, kept between the two passes of the norm
-    o = (o + 15) & ~(size_t)15;
     L.off_seq = o; o += seqsum2_scratch_bytes(PD_CT);
     o = (o + 15) & ~(size_t)15;
-    L.off_terms = o; o += (size_t)SMV_CONSUMER_WARPS * 4 * L.nbs_pad * 4;
+    L.off_terms = o; o += (size_t)SMV_CONSUMER_WARPS * 4 * L.tstride * 4;
     L.off_hvals = o; o += SMV_HVALS * 4;
     L.off_misc = o; o += 64 * 4; // red[8], s_val[2], scale, argmax merge scratch
     o = (o + 127) & ~(size_t)127;
@@ -289,7 +289,7 @@ __device__ __forceinline__ void pd_consume_matrix(const TileMat &W, const PdArgs
     const int ngroups = W.rows >> 2;
     const int g0 = (int)(((long long)blockIdx.x * ngroups) / gridDim.x), g1 = (int)(((long long)(blockIdx.x + 1) * ngroups) / gridDim.x);
     const int nseg = W.nseg, nbs = W.seg >> 5;
-    float *terms = reinterpret_cast<float *>(smem + L.off_terms) + (size_t)warp * 4 * L.nbs_pad;
+    float *terms = reinterpret_cast<float *>(smem + L.off_terms) + (size_t)warp * 4 * L.tstride;
     const unsigned char *sact = smem + L.off_xq;
     const float *sxs = reinterpret_cast<const float *>(smem + L.off_xs);
     float *hvals = reinterpret_cast<float *>(smem + L.off_hvals);
@@ -329,7 +329,7 @@ __device__ __forceinline__ void pd_consume_matrix(const TileMat &W, const PdArgs
                         isum = __dp4a(w1.y, a1.y, isum);
                         isum = __dp4a(w1.z, a1.z, isum);
                         isum = __dp4a(w1.w, a1.w, isum);
-                        terms[r * L.nbs_pad + b] = __fmul_rn((float)isum, __fmul_rn(__half2float(sc), as));
+                        terms[r * L.tstride + b] = __fmul_rn((float)isum, __fmul_rn(__half2float(sc), as));
                     }
                 }
                 __syncwarp();
@@ -337,10 +337,7 @@ __device__ __forceinline__ void pd_consume_matrix(const TileMat &W, const PdArgs
                     rel[st] = lap + 1u;
                     mbar_arrive(bar0 + 8 * (PD_MAX_STAGES + st));
                 }
-                if (lane < 4) {
-                    const float *t = terms + lane * L.nbs_pad;
-                    for (int b = 0; b < nbs; b++) acc = __fadd_rn(acc, t[b]); // strictly in block order
-                }
+                if (lane < 4) acc = pd_walk_terms(acc, terms + lane * L.tstride, nbs); // strictly in block order
                 __syncwarp();
             }
             if (MODE == SMV_GATEUP) {
@@ -434,41 +431,47 @@ __device__ __forceinline__ float4 pd_ldcg128(const float *p) {
     return v;
 }
 
-__device__ __forceinline__ void pd_norm_to_smem(const PdArgs &a, const float *w, bool from_emb, int token, unsigned char *smem, const PdSmem &L, int tid) {
-    const int lane = tid & 31, warp = tid >> 5, dim = a.dim;
+// Thread t owns the 16-byte slots i4 = u * PD_CT + t (u < PD_NORM_U) of the vector: x and the norm weights stay in REGISTERS
+// between the two passes; a 32-element quantisation block is eight consecutive slots = eight consecutive lanes, so its amax
+// is three shuffles.  Only the squares go through shared memory (the exact accumulator's chunk layout).
+__device__ __forceinline__ void pd_norm_to_smem(const PdArgs &a, const float *w, bool from_emb, int token, unsigned char *smem, const PdSmem &L, int tid, int stamp_layer = -1) {
+    const int dim = a.dim, n4 = dim >> 2;
     float *sq = reinterpret_cast<float *>(smem + L.off_nbuf);
-    float *xb = reinterpret_cast<float *>(smem + L.off_xbuf);
     float *misc = reinterpret_cast<float *>(smem + L.off_misc);
     SeqSum2Scratch scratch = seqsum2_carve(smem + L.off_seq, PD_CT);
-    const int dim_pad = (dim + PD_CT - 1) / PD_CT * PD_CT;
-    if (from_emb) { // first layer: the embedding row (quantised table: element-wise)
-        for (int i = tid; i < dim; i += PD_CT) {
-            const float v = emb_get(a.emb, token, i);
-            xb[i] = v;
-            sq[i] = __fmul_rn(v, v);
+    const int E = (dim + PD_CT - 1) / PD_CT, S = seqsum2_stride(E);
+    float4 xv[PD_NORM_U], wv[PD_NORM_U];
+#pragma unroll
+    for (int u = 0; u < PD_NORM_U; u++) { // every load of this thread in flight at once: one L2 round trip
+        const int i4 = u * PD_CT + tid;
+        xv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        wv[u] = xv[u];
+        if (i4 < n4) {
+            if (from_emb) { // first layer: the embedding row (quantised table: element-wise, FloatTensor.copyTo)
+                xv[u] = make_float4(emb_get(a.emb, token, 4 * i4), emb_get(a.emb, token, 4 * i4 + 1), emb_get(a.emb, token, 4 * i4 + 2), emb_get(a.emb, token, 4 * i4 + 3));
+            } else xv[u] = pd_ldcg128(a.x + 4 * i4);
+            wv[u] = __ldg(reinterpret_cast<const float4 *>(w) + i4);
         }
-    } else { // x from L2: four independent 16-byte loads in flight per thread, one round trip for dim <= 4096
-        const int n4 = dim >> 2;
-        for (int base = 0; base < n4; base += 4 * PD_CT) {
-            float4 v[4];
+    }
+    // squares -> chunk layout: element i belongs to accumulator thread i / E at offset i % E of its S-float chunk
+    for (int i = dim + tid; i < PD_CT * E; i += PD_CT) sq[(i / E) * S + (i % E)] = 0.0f; // zero padding of the last chunks
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int i4 = base + u * PD_CT + tid;
-                v[u] = i4 < n4 ? pd_ldcg128(a.x + 4 * i4) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int i4 = base + u * PD_CT + tid;
-                if (i4 < n4) {
-                    reinterpret_cast<float4 *>(xb)[i4] = v[u];
-                    reinterpret_cast<float4 *>(sq)[i4] = make_float4(__fmul_rn(v[u].x, v[u].x), __fmul_rn(v[u].y, v[u].y), __fmul_rn(v[u].z, v[u].z), __fmul_rn(v[u].w, v[u].w));
-                }
+    for (int u = 0; u < PD_NORM_U; u++) {
+        const int i4 = u * PD_CT + tid;
+        if (i4 < n4) {
+            const int i = 4 * i4;
+            const float4 q = make_float4(__fmul_rn(xv[u].x, xv[u].x), __fmul_rn(xv[u].y, xv[u].y), __fmul_rn(xv[u].z, xv[u].z), __fmul_rn(xv[u].w, xv[u].w));
+            if ((E & 3) == 0) *reinterpret_cast<float4 *>(sq + (i / E) * S + (i % E)) = q; // the four elements share a chunk
+            else {
+                sq[(i / E) * S + (i % E)] = q.x; sq[((i + 1) / E) * S + ((i + 1) % E)] = q.y;
+                sq[((i + 2) / E) * S + ((i + 2) % E)] = q.z; sq[((i + 3) / E) * S + ((i + 3) % E)] = q.w;
             }
         }
     }
-    for (int i = dim + tid; i < dim_pad; i += PD_CT) sq[i] = 0.0f;
     consumer_bar_sync();
-    float ss = block_seqsum_exact_v2_t<PD_CT>(sq, dim, scratch, tid, PdConsumerSync());
+    if (stamp_layer >= 0) pd_stamp(a, stamp_layer, 10, tid);
+    float ss = block_seqsum_exact_v2_t<PD_CT>(sq, dim, scratch, tid, PdConsumerSync(), S);
+    if (stamp_layer >= 0) pd_stamp(a, stamp_layer, 11, tid);
     if (tid == 0) {
         ss = __fdiv_rn(ss, (float)dim);
         ss = __fadd_rn(ss, a.eps);
@@ -476,26 +479,30 @@ __device__ __forceinline__ void pd_norm_to_smem(const PdArgs &a, const float *w,
     }
     consumer_bar_sync();
     ss = misc[16];
-    int8_t *sxq = reinterpret_cast<int8_t *>(smem + L.off_xq);
+    unsigned *sxq = reinterpret_cast<unsigned *>(smem + L.off_xq);
     float *sxs = reinterpret_cast<float *>(smem + L.off_xs);
-    const int nb = dim / 32;
-#pragma unroll 1
-    for (int b0 = warp; b0 < nb; b0 += 8 * SMV_CONSUMER_WARPS) { // 8 norm-weight loads in flight per lane; x comes from shared memory
-        float wv[8];
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
-            const int b = b0 + u * SMV_CONSUMER_WARPS;
-            wv[u] = b < nb ? __ldg(w + b * 32 + lane) : 0.0f;
-        }
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-            const int b = b0 + u * SMV_CONSUMER_WARPS;
-            if (b < nb) {
-                const float v = __fmul_rn(wv[u], __fmul_rn(ss, xb[b * 32 + lane]));
-                float as;
-                const int q = quant_block_lane(v, as);
-                sxq[b * 32 + lane] = (int8_t)q;
-                if (lane == 0) sxs[b] = as;
+    for (int u = 0; u < PD_NORM_U; u++) { // out = w * (ss * x) (InferenceCore.java:45-47), then Q8_0FloatTensor.java:100-117 per 32-block
+        const int i4 = u * PD_CT + tid;
+        if (u * PD_CT < n4) { // warp-uniform (n4 is a multiple of 8 and whole 8-lane groups are in or out)
+            float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+            if (i4 < n4) {
+                v0 = __fmul_rn(wv[u].x, __fmul_rn(ss, xv[u].x)); v1 = __fmul_rn(wv[u].y, __fmul_rn(ss, xv[u].y));
+                v2 = __fmul_rn(wv[u].z, __fmul_rn(ss, xv[u].z)); v3 = __fmul_rn(wv[u].w, __fmul_rn(ss, xv[u].w));
+            }
+            float amax = fmaxf(fmaxf(fabsf(v0), fabsf(v1)), fmaxf(fabsf(v2), fabsf(v3)));
+            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
+            const float qs = __fdiv_rn(amax, 127.0f);
+            const float ascale = __half2float(__float2half_rn(qs));
+            const float ainv = qs != 0.0f ? __fdiv_rn(1.0f, qs) : 0.0f;
+            const float s0 = __fmul_rn(v0, ainv), s1 = __fmul_rn(v1, ainv), s2 = __fmul_rn(v2, ainv), s3 = __fmul_rn(v3, ainv);
+            const int q0 = __float2int_rz(__fadd_rn(s0, copysignf(0.5f, s0))), q1 = __float2int_rz(__fadd_rn(s1, copysignf(0.5f, s1)));
+            const int q2 = __float2int_rz(__fadd_rn(s2, copysignf(0.5f, s2))), q3 = __float2int_rz(__fadd_rn(s3, copysignf(0.5f, s3)));
+            if (i4 < n4) {
+                sxq[i4] = (unsigned)(q0 & 0xff) | ((unsigned)(q1 & 0xff) << 8) | ((unsigned)(q2 & 0xff) << 16) | ((unsigned)(q3 & 0xff) << 24);
+                if ((tid & 7) == 0) sxs[i4 >> 3] = ascale;
             }
         }
     }
@@ -507,20 +514,44 @@ __device__ __forceinline__ void pd_load_act(const int8_t *q, const float *s, int
     int4 *sxq = reinterpret_cast<int4 *>(smem + L.off_xq);
     float *sxs = reinterpret_cast<float *>(smem + L.off_xs);
     const int4 *src = reinterpret_cast<const int4 *>(q);
-    for (int c = tid; c < cols / 16; c += PD_CT) sxq[c] = __ldcg(src + c);
-    for (int b = tid; b < cols / 32; b += PD_CT) sxs[b] = __ldcg(s + b);
+    const int n16 = cols >> 4, nb = cols >> 5;
+    for (int c0 = 0; c0 < n16; c0 += 4 * PD_CT) { // four 16-byte loads + one scale load in flight per thread: one L2 round trip for 16 K columns
+        int4 v[4];
+        float sc[2];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int c = c0 + u * PD_CT + tid;
+            v[u] = c < n16 ? __ldcg(src + c) : make_int4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int b = (c0 >> 1) + u * PD_CT + tid;
+            sc[u] = b < nb ? __ldcg(s + b) : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int c = c0 + u * PD_CT + tid;
+            if (c < n16) sxq[c] = v[u];
+        }
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int b = (c0 >> 1) + u * PD_CT + tid;
+            if (b < nb) sxs[b] = sc[u];
+        }
+    }
     consumer_bar_sync();
 }
 
 // ---- one attention head with the consumer warps: k_attention's body (exact CPU order, InferenceCore.java:98-137) -------------
 // h = local head index on this rank.
 template <int HS>
-__device__ __forceinline__ void pd_attention_head(const PdArgs &a, const PdLayer &Ly, int h, int pos, unsigned char *smem, const PdSmem &L, int tid) {
+__device__ __forceinline__ void pd_attention_head(const PdArgs &a, const PdLayer &Ly, int h, int pos, unsigned char *smem, const PdSmem &L, int tid, int layer) {
     float *sm = reinterpret_cast<float *>(smem + L.off_nbuf);
     float *misc = reinterpret_cast<float *>(smem + L.off_misc);
     float *red = misc, *s_val = misc + 8;
     float *sq = sm, *sk = sm + HS, *so = sm + 2 * HS;
-    float *att = a.att_scratch ? a.att_scratch + (size_t)h * a.ctx : sm + 3 * HS;
+    const int ctx_pad = (a.ctx + PD_CT - 1) / PD_CT * PD_CT; // score rows are padded to whole accumulator chunks
+    float *att = a.att_scratch ? a.att_scratch + (size_t)h * ctx_pad : sm + 3 * HS;
     const int lane = tid & 31, warp = tid >> 5;
     constexpr int HALF = HS / 2;
     const int nt = pos + 1;
@@ -535,6 +566,10 @@ __device__ __forceinline__ void pd_attention_head(const PdArgs &a, const PdLayer
         int i0, i1;
         if (a.arch == 1) { i0 = p; i1 = p + HALF; } else { i0 = 2 * p; i1 = 2 * p + 1; }
         float v0 = ldcg_f32c(src + i0), v1 = ldcg_f32c(src + i1); // written by other CTAs in this kernel: bypass L1
+        const float fcr = __ldg(a.rope_cr + (size_t)pos * HALF + p), fci = __ldg(a.rope_ci + (size_t)pos * HALF + p); // same round trip as q/k
+        float cv0 = 0.f, cv1 = 0.f;
+        const bool owner = (h % kv_mul == 0) && !is_q; // first query head of the KV group owns the cache write (InferenceCore.java:92-93)
+        if (owner) { cv0 = ldcg_f32c(vsrc + i0); cv1 = ldcg_f32c(vsrc + i1); }
         if (a.arch == 1) { // Qwen3 per-head RMSNorm: literal sequential sum over the head (InferenceCore.java:594-600)
             float *sqr = is_q ? so : sk;
             sqr[i0] = __fmul_rn(v0, v0);
@@ -554,18 +589,17 @@ __device__ __forceinline__ void pd_attention_head(const PdArgs &a, const PdLayer
             v1 = __fmul_rn(nw[i1], __fmul_rn(ss, v1));
             asm volatile("bar.sync 3, %0;" ::"n"(HS) : "memory");
         }
-        const float fcr = a.rope_cr[(size_t)pos * HALF + p], fci = a.rope_ci[(size_t)pos * HALF + p];
         const float r0 = __fsub_rn(__fmul_rn(v0, fcr), __fmul_rn(v1, fci));
         const float r1 = __fadd_rn(__fmul_rn(v0, fci), __fmul_rn(v1, fcr));
         float *dst = is_q ? sq : sk;
         dst[i0] = r0;
         dst[i1] = r1;
-        if (h % kv_mul == 0 && !is_q) { // first query head of the KV group owns the cache write (InferenceCore.java:92-93)
+        if (owner) {
             const size_t o = (size_t)pos * kvd + kvh * HS;
             kc[o + i0] = r0;
             kc[o + i1] = r1;
-            vc[o + i0] = ldcg_f32c(vsrc + i0);
-            vc[o + i1] = ldcg_f32c(vsrc + i1);
+            vc[o + i0] = cv0;
+            vc[o + i1] = cv1;
         }
     }
     consumer_bar_sync();
@@ -578,12 +612,12 @@ __device__ __forceinline__ void pd_attention_head(const PdArgs &a, const PdLayer
         } else {
             const float4 *k = reinterpret_cast<const float4 *>(kc + (size_t)t * kvd + kvh * HS);
 #pragma unroll
-            for (int j0 = 0; j0 < HS / 4; j0 += 8) {
-                float4 kk[8];
+            for (int j0 = 0; j0 < HS / 4; j0 += 16) { // 16 x 16 bytes in flight per thread: two L2 round trips per key at head size 128
+                float4 kk[16];
 #pragma unroll
-                for (int u = 0; u < 8; u++) kk[u] = __ldcg(k + j0 + u); // rows of earlier tokens: written by earlier launches
+                for (int u = 0; u < 16; u++) kk[u] = __ldcg(k + j0 + u); // rows of earlier tokens: written by earlier launches
 #pragma unroll
-                for (int u = 0; u < 8; u++) {
+                for (int u = 0; u < 16; u++) {
                     const int j = 4 * (j0 + u);
                     acc = __fadd_rn(acc, __fmul_rn(sq[j + 0], kk[u].x));
                     acc = __fadd_rn(acc, __fmul_rn(sq[j + 1], kk[u].y));
@@ -599,38 +633,58 @@ __device__ __forceinline__ void pd_attention_head(const PdArgs &a, const PdLayer
     lmax = warp_max_f(lmax);
     if (lane == 0) red[warp] = lmax;
     consumer_bar_sync();
+    pd_stamp(a, layer, 13, tid);
     float mx = red[0];
 #pragma unroll
     for (int w = 1; w < SMV_CONSUMER_WARPS; w++) mx = fmaxf(mx, red[w]);
     for (int t = tid; t < nt; t += PD_CT) att[t] = (float)exp((double)__fsub_rn(att[t], mx));
     consumer_bar_sync();
-    if (tid == 0) { // sequential float sum (FloatTensor.softmaxInPlace, FloatTensor.java:211-219)
-        float sum = 0.0f;
-        int t = 0;
-        for (; t + 4 <= nt; t += 4) {
-            const float a0 = att[t], a1 = att[t + 1], a2 = att[t + 2], a3 = att[t + 3];
-            sum = __fadd_rn(sum, a0); sum = __fadd_rn(sum, a1); sum = __fadd_rn(sum, a2); sum = __fadd_rn(sum, a3);
-        }
-        for (; t < nt; t++) sum = __fadd_rn(sum, att[t]);
-        s_val[0] = sum;
+    // sequential float sum (FloatTensor.softmaxInPlace, FloatTensor.java:211-219): short rows by one thread (16-byte loads ahead of
+    // the add chain), long rows with the exact parallel accumulator (the terms are non-negative)
+    float sum;
+    if (nt >= 512) {
+        const int E = (nt + PD_CT - 1) / PD_CT;
+        for (int t = nt + tid; t < PD_CT * E; t += PD_CT) att[t] = 0.0f;
+        consumer_bar_sync();
+        SeqSum2Scratch scratch = seqsum2_carve(smem + L.off_seq, PD_CT);
+        sum = block_seqsum_exact_v2_t<PD_CT>(att, nt, scratch, tid, PdConsumerSync());
+    } else {
+        if (tid == 0) s_val[0] = seq2_literal(0.0f, att, nt, (reinterpret_cast<uintptr_t>(att) & 15) == 0);
+        consumer_bar_sync();
+        sum = s_val[0];
     }
-    consumer_bar_sync();
-    const float sum = s_val[0];
     for (int t = tid; t < nt; t += PD_CT) att[t] = __fdiv_rn(att[t], sum);
     consumer_bar_sync();
+    pd_stamp(a, layer, 14, tid);
     if (tid < HS) { // xb = sum_t a_t * v_t, sequentially over t per element (saxpyInPlace, FloatTensor.java:221-227)
         const float *v = vc + kvh * HS + tid;
         float acc = 0.0f;
         int t = 0;
-        for (; t + 16 <= pos; t += 16) {
+        const float vcur = ldcg_f32c(vsrc + tid); // the current position's v, straight from the packed q|k|v vector
+        if (pos >= 16) { // the next 16 rows are in flight while the current 16 are being added (the add chain is the floor: 4 cycles per key)
             float vv[16];
 #pragma unroll
-            for (int u = 0; u < 16; u++) vv[u] = __ldcg(v + (size_t)(t + u) * kvd);
+            for (int u = 0; u < 16; u++) vv[u] = __ldcg(v + (size_t)u * kvd);
+            for (; t + 16 <= pos; t += 16) {
+                float nv[16];
+                const bool more = t + 32 <= pos;
 #pragma unroll
-            for (int u = 0; u < 16; u++) acc = __fadd_rn(__fmul_rn(att[t + u], vv[u]), acc);
+                for (int u = 0; u < 16; u++) nv[u] = more ? __ldcg(v + (size_t)(t + 16 + u) * kvd) : 0.0f;
+#pragma unroll
+                for (int u = 0; u < 16; u++) acc = __fadd_rn(__fmul_rn(att[t + u], vv[u]), acc);
+#pragma unroll
+                for (int u = 0; u < 16; u++) vv[u] = nv[u];
+            }
         }
-        for (; t < pos; t++) acc = __fadd_rn(__fmul_rn(att[t], __ldcg(v + (size_t)t * kvd)), acc);
-        acc = __fadd_rn(__fmul_rn(att[pos], ldcg_f32c(vsrc + tid)), acc);
+        {
+            float vv[16]; // tail: up to 15 rows, all loads first
+#pragma unroll
+            for (int u = 0; u < 16; u++) vv[u] = t + u < pos ? __ldcg(v + (size_t)(t + u) * kvd) : 0.0f;
+#pragma unroll
+            for (int u = 0; u < 16; u++)
+                if (t + u < pos) acc = __fadd_rn(__fmul_rn(att[t + u], vv[u]), acc);
+        }
+        acc = __fadd_rn(__fmul_rn(att[pos], vcur), acc);
         so[tid] = acc;
     }
     consumer_bar_sync();
@@ -648,6 +702,7 @@ __device__ __forceinline__ void pd_attention_head(const PdArgs &a, const PdLayer
             if (lane == 0) a.atts[(gh * HS) / 32 + b] = as;
         }
     }
+    pd_stamp(a, layer, 15, tid);
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------------------------------
@@ -683,14 +738,15 @@ __global__ void __launch_bounds__(SMV_THREADS, 1) k_decode_persistent(PdArgs a, 
         const PdLayer &Ly = a.layers[l];
         const unsigned e = tick * nL + (unsigned)l + 1u; // this layer's epoch
         pd_stamp(a, l, 0, tid);
-        pd_norm_to_smem(a, Ly.attn_norm, l == 0, token, smem, L, tid);
+        pd_norm_to_smem(a, Ly.attn_norm, l == 0, token, smem, L, tid, l);
         pd_stamp(a, l, 1, tid);
         pd_consume_matrix<SMV_STORE>(Ly.qkv, a, smem, L, bar0, rel, seq_base, a.qkv, false, false, token, 0, tid);
         pd_stamp(a, l, 2, tid);
         pd_arrive(a, PD_S_QKV, e * nC, e, false, tid); // q/k/v of this rank's heads stay on this rank
         if (blockIdx.x < nH) { // attention: the first n_heads CTAs, one head each
             pd_wait(a, PD_S_QKV, e * nC, e, false, tid);
-            pd_attention_head<HS>(a, Ly, blockIdx.x, pos, smem, L, tid);
+            pd_stamp(a, l, 12, tid);
+            pd_attention_head<HS>(a, Ly, blockIdx.x, pos, smem, L, tid, l);
             pd_arrive(a, PD_S_ATT, e * nH, e, true, tid);
         }
         pd_wait(a, PD_S_ATT, e * nH, e, true, tid);

@@ -471,7 +471,7 @@ int pd_prepare(b200_plan *p) {
     }
     int maxdyn = 0;
     CK(cudaDeviceGetAttribute(&maxdyn, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device));
-    const int att_floats = 3 * c.head_size + (p->att_scratch ? 0 : c.context_length);
+    const int att_floats = 3 * c.head_size + (p->att_scratch ? 0 : (c.context_length + PD_CT - 1) / PD_CT * PD_CT); // score row padded to whole accumulator chunks
     const PdSmem L = pd_layout(c.dim, p->qd, c.hidden_dim, att_floats, max_seg, (size_t)maxdyn);
     if (L.stages < 4) { p->pd_why = "shape leaves fewer than 4 ring stages of shared memory"; return B200_OK; }
     int rc;
@@ -827,7 +827,7 @@ int build(b200_plan *p, const b200_tensor *tensors, int n_tensors) {
     p->tp.err = p->pd_sync + PD_S_ERR;
     p->tp.host_err = p->d_err;
     if (3 * c.head_size + c.context_length > ATT_SMEM_FLOATS_MAX) { // long context: score rows in global memory
-        if ((rc = dalloc(p, &p->att_scratch, (size_t)p->nh_l * c.context_length * 4))) return rc;
+        if ((rc = dalloc(p, &p->att_scratch, (size_t)p->nh_l * ((c.context_length + PD_CT - 1) / PD_CT * PD_CT) * 4))) return rc;
     }
     if ((rc = set_smem_attrs(p))) return rc;
     if (c.tp_size > 1) { CK(cudaStreamSynchronize(p->stream)); return B200_OK; } // graphs are captured by b200_tp_attach

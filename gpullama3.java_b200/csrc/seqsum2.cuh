@@ -74,20 +74,56 @@ struct SeqSum2BlockSync {
     __device__ __forceinline__ void operator()() const { __syncthreads(); }
 };
 
-// sq: n terms in shared memory, padded with zeros up to T * E (E = ceil(n / T)).  Exactly T threads (a multiple of 32, at most
-// SEQSUM2_THREADS) call this with tid in [0, T); `sync` is a barrier over those T threads (the whole CTA, or a named barrier
-// over a subset of its warps as in the persistent decode kernel).
+// Chunk stride that makes the 16-byte reads of consecutive threads hit distinct shared-memory banks (E = terms per thread):
+// thread t's terms live at sq[t * S .. t * S + E).  E = 16 -> 20, 8 -> 12, 32 -> 36, 4 -> 4.
+__host__ __device__ inline int seqsum2_stride(int E) { return (E % 4 == 0 && (E / 4) % 2 == 0) ? E + 4 : E; }
+
+// literal adds of one thread's E terms, 16-byte loads batched ahead of the dependent add chain
+__device__ __forceinline__ float seq2_literal(float s, const float *q, int E, bool vec) {
+    int k = 0;
+    if (vec) {
+        for (; k + 16 <= E; k += 16) {
+            const float4 v0 = *reinterpret_cast<const float4 *>(q + k), v1 = *reinterpret_cast<const float4 *>(q + k + 4);
+            const float4 v2 = *reinterpret_cast<const float4 *>(q + k + 8), v3 = *reinterpret_cast<const float4 *>(q + k + 12);
+            s = __fadd_rn(s, v0.x); s = __fadd_rn(s, v0.y); s = __fadd_rn(s, v0.z); s = __fadd_rn(s, v0.w);
+            s = __fadd_rn(s, v1.x); s = __fadd_rn(s, v1.y); s = __fadd_rn(s, v1.z); s = __fadd_rn(s, v1.w);
+            s = __fadd_rn(s, v2.x); s = __fadd_rn(s, v2.y); s = __fadd_rn(s, v2.z); s = __fadd_rn(s, v2.w);
+            s = __fadd_rn(s, v3.x); s = __fadd_rn(s, v3.y); s = __fadd_rn(s, v3.z); s = __fadd_rn(s, v3.w);
+        }
+        for (; k + 4 <= E; k += 4) {
+            const float4 v = *reinterpret_cast<const float4 *>(q + k);
+            s = __fadd_rn(s, v.x); s = __fadd_rn(s, v.y); s = __fadd_rn(s, v.z); s = __fadd_rn(s, v.w);
+        }
+    }
+    for (; k < E; k++) s = __fadd_rn(s, q[k]);
+    return s;
+}
+
+// sq: n terms, thread t's E = ceil(n / T) consecutive terms at sq[t * S + k] (S >= E; S = E is the plain contiguous layout),
+// zero-padded up to T whole chunks.  Exactly T threads (a multiple of 32, at most SEQSUM2_THREADS) call this with tid in
+// [0, T); `sync` is a barrier over those T threads (the whole CTA, or a named barrier over a subset of its warps as in the
+// persistent decode kernel).  When S and E are multiples of 4 and sq is 16-byte aligned the terms are read with 16-byte loads.
 template <int T, class Sync>
-__device__ float block_seqsum_exact_v2_t(const float *sq, int n, SeqSum2Scratch sc, int tid, Sync sync) {
+__device__ float block_seqsum_exact_v2_t(const float *sq, int n, SeqSum2Scratch sc, int tid, Sync sync, int S = 0) {
     static_assert(T % 32 == 0 && T <= SEQSUM2_THREADS, "T threads = T/32 whole warps");
     constexpr int NW = T / 32;
     const int lane = tid & 31, warp = tid >> 5;
     const int E = (n + T - 1) / T;
-    const float *mine = sq + tid * E;
+    if (S == 0) S = E;
+    const bool vec = ((E | S) & 3) == 0 && (reinterpret_cast<uintptr_t>(sq) & 15) == 0;
+    const float *mine = sq + tid * S;
 
     // ---- 1. float prefix over per-thread sums
     float loc = 0.0f;
-    for (int k = 0; k < E; k++) loc += mine[k];
+    {
+        int k = 0;
+        if (vec)
+            for (; k < E; k += 4) {
+                const float4 v = *reinterpret_cast<const float4 *>(mine + k);
+                loc += v.x; loc += v.y; loc += v.z; loc += v.w;
+            }
+        for (; k < E; k++) loc += mine[k];
+    }
     float inc = loc;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -121,7 +157,19 @@ __device__ float block_seqsum_exact_v2_t(const float *sq, int n, SeqSum2Scratch 
             // margin 2^-9: the sequential sum deviates from any exact prefix by < n * 2^-24 relative (n <= 8192 -> 2^-11)
             if (p_start >= b * (1.0f + 0x1p-9f) && p_end <= 2.0f * b * (1.0f - 0x1p-9f)) {
                 bool ok = true;
-                for (int k = 0; k < E; k++) {
+                int k = 0;
+                if (vec)
+                    for (; ok && k < E; k += 4) {
+                        const float4 v = *reinterpret_cast<const float4 *>(mine + k);
+                        const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int c = 0; c < 4; c++) {
+                            SeqPair q;
+                            if (!seq_pair(vv[c], e, q)) { ok = false; break; }
+                            pr = seq_compose(pr, q);
+                        }
+                    }
+                for (; ok && k < E; k++) {
                     SeqPair q;
                     if (!seq_pair(mine[k], e, q)) { ok = false; break; }
                     pr = seq_compose(pr, q);
@@ -185,11 +233,12 @@ __device__ float block_seqsum_exact_v2_t(const float *sq, int n, SeqSum2Scratch 
         const int n_items = sc.info[0];
         float s = 0.0f;
         int fallbacks = 0;
+        SeqItem nxt = sc.items[0];
         for (int i = 0; i < n_items; i++) {
-            const SeqItem it = sc.items[i];
+            const SeqItem it = nxt;
+            if (i + 1 < n_items) nxt = sc.items[i + 1]; // in flight while this item is resolved
             if (it.cls == SEQSUM2_LITERAL) {
-                const float *q = sq + it.last * E;
-                for (int k = 0; k < E; k++) s = __fadd_rn(s, q[k]);
+                s = seq2_literal(s, sq + it.last * S, E, vec);
                 continue;
             }
             const unsigned sb = __float_as_uint(s);
@@ -203,7 +252,7 @@ __device__ float block_seqsum_exact_v2_t(const float *sq, int n, SeqSum2Scratch 
             if (!ok) { // misprediction: replay the run literally (its first thread: walk back over equal classes)
                 int first = it.last;
                 while (first > 0 && sc.cls[first - 1] == it.cls) first--;
-                for (int k = first * E; k < (it.last + 1) * E; k++) s = __fadd_rn(s, sq[k]);
+                for (int j = first; j <= it.last; j++) s = seq2_literal(s, sq + j * S, E, vec);
                 fallbacks++;
             }
         }

@@ -49,7 +49,7 @@ __host__ __device__ inline SmvSmem smv_layout(int cols, int seg, size_t budget) 
     SmvSmem L;
     int unit = smv_unit_bytes(seg);
     L.stage_bytes = (4 * unit + 127) & ~127;
-    L.nbs_pad = (seg / 32) | 1;
+    L.nbs_pad = ((seg / 32 + 3) & ~3) + 4; // row stride of the term buffer: 16-byte aligned rows, the four walker lanes on distinct banks
     size_t o = 0;
     L.off_bar = o; o += 2 * SMV_MAX_STAGES * 8 + SMV_MAX_STAGES * 4; // full[], empty[] mbarriers + release counters
     L.off_xq = o; o += (size_t)cols;
@@ -111,6 +111,35 @@ __device__ __forceinline__ float ldcg_f32(const float *p) {
 __device__ __forceinline__ float swiglu_exact(float g, float u) { // InferenceCore.java:150-158
     float s = __fdiv_rn(g, (float)(1.0 + exp((double)(-g))));
     return __fmul_rn(s, u);
+}
+
+// The ordered sum of one row's block terms (Q8_0FloatTensor.java:117-121: result += ..., block after block).  The add chain is
+// inherently serial (4 cycles per term); what can be taken off it is the shared-memory latency: 16 terms are fetched with four
+// 16-byte loads while the previous 16 are being added.
+__device__ __forceinline__ float pd_walk_terms(float acc, const float *t, int nbs) {
+    int b = 0;
+    if (nbs >= 16) {
+        float4 c0 = *reinterpret_cast<const float4 *>(t), c1 = *reinterpret_cast<const float4 *>(t + 4);
+        float4 c2 = *reinterpret_cast<const float4 *>(t + 8), c3 = *reinterpret_cast<const float4 *>(t + 12);
+        for (; b + 16 <= nbs; b += 16) {
+            float4 n0 = c0, n1 = c1, n2 = c2, n3 = c3;
+            if (b + 32 <= nbs) {
+                n0 = *reinterpret_cast<const float4 *>(t + b + 16); n1 = *reinterpret_cast<const float4 *>(t + b + 20);
+                n2 = *reinterpret_cast<const float4 *>(t + b + 24); n3 = *reinterpret_cast<const float4 *>(t + b + 28);
+            }
+            acc = __fadd_rn(acc, c0.x); acc = __fadd_rn(acc, c0.y); acc = __fadd_rn(acc, c0.z); acc = __fadd_rn(acc, c0.w);
+            acc = __fadd_rn(acc, c1.x); acc = __fadd_rn(acc, c1.y); acc = __fadd_rn(acc, c1.z); acc = __fadd_rn(acc, c1.w);
+            acc = __fadd_rn(acc, c2.x); acc = __fadd_rn(acc, c2.y); acc = __fadd_rn(acc, c2.z); acc = __fadd_rn(acc, c2.w);
+            acc = __fadd_rn(acc, c3.x); acc = __fadd_rn(acc, c3.y); acc = __fadd_rn(acc, c3.z); acc = __fadd_rn(acc, c3.w);
+            c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        }
+    }
+    for (; b + 4 <= nbs; b += 4) {
+        const float4 v = *reinterpret_cast<const float4 *>(t + b);
+        acc = __fadd_rn(acc, v.x); acc = __fadd_rn(acc, v.y); acc = __fadd_rn(acc, v.z); acc = __fadd_rn(acc, v.w);
+    }
+    for (; b < nbs; b++) acc = __fadd_rn(acc, t[b]);
+    return acc;
 }
 
 struct SmvArgs {
@@ -266,10 +295,7 @@ __global__ void __launch_bounds__(SMV_THREADS, 1) k_stream_matvec_q8(SmvArgs a, 
                     rel[st] = lap + 1u;
                     mbar_arrive(bar0 + 8 * (SMV_MAX_STAGES + st));
                 }
-                if (lane < 4) {
-                    const float *t = terms + lane * L.nbs_pad;
-                    for (int b = 0; b < nbs; b++) acc = __fadd_rn(acc, t[b]); // strictly in block order
-                }
+                if (lane < 4) acc = pd_walk_terms(acc, terms + lane * L.nbs_pad, nbs); // strictly in block order
                 __syncwarp();
             }
             // rows 4G..4G+3 are complete in lanes 0..3

@@ -104,6 +104,10 @@ class B200MasterPlan:
         lg, am = self._native.forward_decode(token, position, want_logits=logits, want_argmax=True)
         return lg, am
 
+    # forward + Sampler.sampleToken on the device (Sampler.java:74-122): 4 bytes in (the uniform number), 4 bytes out
+    def forward_decode_sample(self, token: int, position: int, temperature: float, topp: float, uniform01: float, want_info: bool = False):
+        return self._native.forward_decode_sample(token, position, temperature, topp, uniform01, want_info)
+
     # void tornadoVMForwardPrefill(int position)  (TornadoVMMasterPlanPrefillDecode.java:116)
     def forward_prefill(self, token: int, position: int):
         self._native.forward_prefill(token, position)

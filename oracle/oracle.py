@@ -107,8 +107,8 @@ def sample(logits: np.ndarray, temperature: float, topp: float, r01: float) -> i
 
 
 def np_sample(logits: np.ndarray, temperature: float, topp: float, r01: float) -> int:
-    """Independent numpy restatement of the same lines (cross-check of the C code): sequential float32 sums via
-    np.add.accumulate, the top-p set via a stable argsort -- valid whenever the kept probabilities are distinct."""
+    """Second restatement of the same lines in numpy/Python (cross-check of the C code): sequential float32 sums via
+    np.add.accumulate for the categorical walk, a statement-by-statement port of the top-p heap."""
     lg = np.asarray(logits, dtype=np.float32)
     if temperature == 0.0:
         return int(np.argmax(lg))
@@ -120,16 +120,45 @@ def np_sample(logits: np.ndarray, temperature: float, topp: float, r01: float) -
         cdf = np.add.accumulate(p, dtype=np.float32)
         hit = np.flatnonzero(np.float32(r01) < cdf)
         return int(hit[0]) if len(hit) else n - 1
+    # ToppSampler.sampleFromFloatTensor + processTopP, ported statement by statement (the popped order is NOT a perfect sort:
+    # the reference sifts with heap size i - 1, ToppSampler.java:131, so the heap mechanics are part of the result)
     cutoff = (np.float32(1.0) - np.float32(topp)) / np.float32(n - 1)
-    cand = np.flatnonzero(p >= cutoff)
-    order = cand[np.argsort(-p[cand].astype(np.float64), kind="stable")]
-    cum = np.add.accumulate(p[order], dtype=np.float32)
-    over = np.flatnonzero(cum > np.float32(topp))
-    k = int(over[0]) + 1 if len(over) else len(order)
-    total = cum[k - 1]
-    r = np.float32(r01) * total
-    hit = np.flatnonzero(r < cum[:k])
-    return int(order[hit[0]]) if len(hit) else int(order[k - 1])
+    idx = [i for i in range(n) if p[i] >= cutoff]
+    n0 = len(idx)
+
+    def less(x, y):  # comparator.compare(x, y) < 0  <=>  value(x) > value(y)
+        return p[x] > p[y]
+
+    def sift_down(frm, size):
+        prev = frm
+        while 2 * prev + 1 < size:
+            nxt = 2 * prev + 1
+            r = 2 * prev + 2
+            if r < size and less(idx[r], idx[nxt]):
+                nxt = r
+            if less(idx[nxt], idx[prev]):
+                idx[prev], idx[nxt] = idx[nxt], idx[prev]
+                prev = nxt
+            else:
+                break
+
+    for i in range(n0 // 2 - 1, -1, -1):
+        sift_down(i, n0)
+    cum, last = np.float32(0.0), 0
+    for i in range(n0 - 1, -1, -1):
+        idx[0], idx[i] = idx[i], idx[0]
+        cum = np.float32(cum + p[idx[i]])
+        if cum > np.float32(topp):
+            last = i
+            break
+        sift_down(0, i - 1)
+    r = np.float32(np.float32(r01) * cum)
+    cdf = np.float32(0.0)
+    for i in range(n0 - 1, last - 1, -1):
+        cdf = np.float32(cdf + p[idx[i]])
+        if r < cdf:
+            return int(idx[i])
+    return int(idx[last])
 
 
 def use_all_cores() -> int:

@@ -189,3 +189,23 @@ def test_golden_fixture(orc, pkg, make_model):
         key = f"{shape}/{pkg.gguf.GGMLType.NAMES[quant]}/lanes{lanes}"
         got = golden_run(orc, pkg, make_model, shape, quant, lanes)
         assert got == gold[key], key
+
+
+def test_sampler_restatements_agree(pkg, orc):
+    """SURVEY 8(f) N3 (parity unpinned: no JDK): the product's Python restatement of L32X64MixRandom equals the oracle's C
+    restatement, and the oracle's C sampler (Sampler.java / CategoricalSampler.java / ToppSampler.java line by line, heap
+    included) equals an independent numpy formulation on random logits."""
+    for seed in (0, 1, 42, -7, 2 ** 40 + 3):
+        a, b = pkg.sampler.L32X64MixRandom(seed), orc.JavaLXM(seed)
+        assert [a.next_int() for _ in range(50)] == [b.next_int() for _ in range(50)]
+        assert abs(a.next_float1() - b.next_float1()) == 0.0
+    rng = np.random.default_rng(3)
+    for t in range(200):
+        n = int(rng.choice([17, 512, 4096]))
+        lg = (rng.standard_normal(n) * 3).astype(np.float32)
+        temp = float(rng.choice([0.0, 0.5, 1.0, 1.5]))
+        topp = float(rng.choice([0.0, 0.3, 0.9, 0.95, 1.0]))
+        r = float(np.float32(rng.random()))
+        assert orc.sample(lg, temp, topp, r) == orc.np_sample(lg, temp, topp, r), (n, temp, topp, r)
+    # first strict maximum for temperature 0 (FloatTensor.argmax)
+    assert orc.sample(np.array([1.0, 3.0, 3.0, 2.0], dtype=np.float32), 0.0, 0.9, 0.5) == 1

@@ -39,13 +39,25 @@ def main():
     lay = st[:, :nL, :]  # [cta][layer][10]
     print(f"# {workload} Q8_0, persistent decode kernel, position {depth + 2}; decode_info = {plan.decode_info()}")
     nxt = np.concatenate([lay[:, 1:, 0], st[:, nL:nL + 1, 0]], axis=1)  # start of the next layer (or of the lm_head row)
-    ends = np.concatenate([lay[:, :, 1:], nxt[:, :, None]], axis=2)     # end stamp of phase k = stamp k+1
-    dur = ends - lay                                                     # [cta][layer][10]
+    ends = np.concatenate([lay[:, :, 1:10], nxt[:, :, None]], axis=2)   # end stamp of phase k = stamp k+1
+    dur = ends - lay[:, :, :10]                                          # [cta][layer][10]
     sel = slice(1, nL) if nL > 1 else slice(0, 1)
     print(f"{'phase':44s} {'mean us':>9s} {'slowest CTA':>12s}")
     for k, name in enumerate(PHASES):
         d = dur[:, sel, k]
         print(f"{name:44s} {d.mean():9.2f} {d.max(axis=0).mean():12.2f}")
+    # inside the attn norm (every CTA) and the attention (head CTAs only: stamps 12-15 are zero elsewhere)
+    print(f"{'  attn norm: load x,w + squares':44s} {(lay[:, sel, 10] - lay[:, sel, 0]).mean():9.2f}")
+    print(f"{'  attn norm: exact sequential sum':44s} {(lay[:, sel, 11] - lay[:, sel, 10]).mean():9.2f}")
+    print(f"{'  attn norm: scale + normalise + quantise':44s} {(lay[:, sel, 1] - lay[:, sel, 11]).mean():9.2f}")
+    heads = np.flatnonzero(st[:, 1 if nL > 1 else 0, 12] > -1e6)  # unstamped slots are zero, i.e. hugely negative after the shift
+    if len(heads):
+        hl = lay[heads][:, sel, :]
+        print(f"{'  attention: QKV barrier (arrive -> all in)':44s} {(hl[:, :, 12] - hl[:, :, 2]).mean():9.2f}")
+        print(f"{'  attention: rope + scores + max':44s} {(hl[:, :, 13] - hl[:, :, 12]).mean():9.2f}")
+        print(f"{'  attention: exp + sum + normalise':44s} {(hl[:, :, 14] - hl[:, :, 13]).mean():9.2f}")
+        print(f"{'  attention: weighted value sum + quantise':44s} {(hl[:, :, 15] - hl[:, :, 14]).mean():9.2f}")
+        print(f"{'  attention: ATT barrier (head done -> gathered)':44s} {(hl[:, :, 3] - hl[:, :, 15]).mean():9.2f}")
     per_layer = (nxt[:, sel] - lay[:, sel, 0])
     print(f"{'layer total (CTA mean)':44s} {per_layer.mean():9.2f}")
     # exposed barrier latency: last arrival -> first departure, per dependency
