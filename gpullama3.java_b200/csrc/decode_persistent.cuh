@@ -73,6 +73,9 @@ struct PdArgs {
     unsigned long long *trace; // [gridDim.x][n_layers + 1][PD_STAMPS] %globaltimer stamps, or NULL
     int with_logits;
     unsigned l2_ahead;         // tiles the producer may prefetch into L2 beyond the ring while the ring is full
+    unsigned max_fly;          // bulk copies one CTA keeps IN FLIGHT (issued, not landed); 0 = no limit but the ring.  A deep DRAM queue
+                               // delays every latency-critical access of the dependent phases (barrier polls, x / KV loads, instruction
+                               // fetches) by the time the queue takes to drain; ~6 tiles per SM keep HBM saturated with a ~1 us queue
     // tensor parallelism (tp.n == 1: everything below unused)
     TpCtx tp;
     unsigned pd_flags_off;     // offset of the persistent kernel's epoch flags [PD_S_SLOTS][TP_MAX] in every rank's comm buffer
@@ -80,14 +83,13 @@ struct PdArgs {
 };
 
 struct PdSmem {
-    size_t off_bar, off_xq, off_xs, off_nbuf, off_seq, off_terms, off_hvals, off_misc, off_ring, total;
+    size_t off_bar, off_xq, off_xs, off_nbuf, off_wbuf, off_rope, off_seq, off_terms, off_hvals, off_misc, off_ring, total;
     int stages, stage_bytes, tstride, nbuf_floats;
 };
-#define PD_NORM_U 8 // float4 slots per consumer thread in the norm: dim <= 4 * PD_CT * PD_NORM_U = 8192
 
 // max_seg = widest column segment of any matrix of the plan; att_floats = 3*head_size + ctx when the score row lives in
 // shared memory, 3*head_size otherwise.
-__host__ __device__ inline PdSmem pd_layout(int dim, int qd, int hidden, int att_floats, int max_seg, size_t budget) {
+__host__ __device__ inline PdSmem pd_layout(int dim, int qd, int hidden, int head_size, int att_floats, int max_seg, size_t budget, int max_stages = PD_MAX_STAGES) {
     PdSmem L;
     const int unit = smv_unit_bytes(max_seg);
     L.stage_bytes = (4 * unit + 127) & ~127;
@@ -105,6 +107,9 @@ __host__ __device__ inline PdSmem pd_layout(int dim, int qd, int hidden, int att
     o = (o + 15) & ~(size_t)15;
     L.off_nbuf = o; o += (size_t)L.nbuf_floats * 4; // squares of the norm | q,k,out,att of the attention (time-disjoint)
     o = (o + 15) & ~(size_t)15;
+    L.off_wbuf = o; o += (size_t)2 * dim * 4; // norm weights of the next attn norm / ffn norm, fetched one phase ahead (cp.async)
+    L.off_rope = o; o += (size_t)head_size * 4; // this position's rope row: cos | sin
+    o = (o + 15) & ~(size_t)15;
     L.off_seq = o; o += seqsum2_scratch_bytes(PD_CT);
     o = (o + 15) & ~(size_t)15;
     L.off_terms = o; o += (size_t)SMV_CONSUMER_WARPS * 4 * L.tstride * 4;
@@ -115,6 +120,7 @@ __host__ __device__ inline PdSmem pd_layout(int dim, int qd, int hidden, int att
     long room = (long)budget - (long)o;
     int s = room > 0 ? (int)(room / L.stage_bytes) : 0;
     if (s > PD_MAX_STAGES) s = PD_MAX_STAGES;
+    if (max_stages > 0 && s > max_stages) s = max_stages;
     L.stages = s;
     L.total = o + (size_t)s * L.stage_bytes;
     return L;
@@ -255,6 +261,7 @@ __device__ __forceinline__ void pd_produce(const PdArgs &a, unsigned char *smem,
     cur.init(&a);
     pf = cur;
     unsigned seq = 0, pf_seq = 0; // tiles issued into the ring / tiles covered by the L2 prefetch cursor
+    unsigned landed = 0;          // tiles known to have landed (their full barrier completed)
     for (; cur.valid(); cur.next(), seq++) {
         const int st = seq % S;
         const unsigned ph = (seq / S) & 1u;
@@ -273,6 +280,11 @@ __device__ __forceinline__ void pd_produce(const PdArgs &a, unsigned char *smem,
                 }
             }
         } else mbar_wait(empty, ph ^ 1u);
+        if (a.max_fly) // in-flight throttle: wait for the oldest outstanding copy (its stage cannot have been re-armed: max_fly <= S)
+            while (seq - landed >= a.max_fly) {
+                mbar_wait(bar0 + 8 * (landed % S), (landed / S) & 1u);
+                landed++;
+            }
         const unsigned full = bar0 + 8 * st;
         mbar_expect_tx(full, cur.tile_bytes);
         bulk_g2s(smem_u32(smem + L.off_ring + (size_t)st * L.stage_bytes), cur.addr(), cur.tile_bytes, full);
@@ -283,7 +295,7 @@ __device__ __forceinline__ void pd_produce(const PdArgs &a, unsigned char *smem,
 // l0_emb: layer 0's Wo writes x = embedding + acc (the embedding row is never copied into x beforehand).
 // row_base: global index of this rank's first output row (RESID, STORE/argmax) or hidden unit (GATEUP).
 template <int MODE>
-__device__ __forceinline__ void pd_consume_matrix(const TileMat &W, const PdArgs &a, unsigned char *smem, const PdSmem &L, unsigned bar0, volatile unsigned *rel,
+__device__ __noinline__ void pd_consume_matrix(const TileMat &W, const PdArgs &a, unsigned char *smem, const PdSmem &L, unsigned bar0, volatile unsigned *rel,
                                                   unsigned &seq_base, float *out, bool argmax, bool l0_emb, int token, int row_base, int tid) {
     const int lane = tid & 31, warp = tid >> 5, S = L.stages;
     const int ngroups = W.rows >> 2;
@@ -296,11 +308,13 @@ __device__ __forceinline__ void pd_consume_matrix(const TileMat &W, const PdArgs
     const int hsel = (lane >> 2) & 1;
     float best = -INFINITY;
     int best_i = 0x7fffffff;
+#pragma unroll 1
     for (int gb = g0; gb < g1; gb += SMV_CONSUMER_WARPS) {
         const int nw = min(SMV_CONSUMER_WARPS, g1 - gb);
         if (warp < nw) {
             const int G = gb + warp;
             float acc = 0.0f;
+#pragma unroll 1
             for (int s = 0; s < nseg; s++) {
                 const unsigned seq = seq_base + (unsigned)(s * nw + warp);
                 const int st = seq % S;
@@ -310,6 +324,7 @@ __device__ __forceinline__ void pd_consume_matrix(const TileMat &W, const PdArgs
                 __syncwarp();
                 mbar_wait(bar0 + 8 * st, lap & 1u);
                 const unsigned char *tile = smem + L.off_ring + (size_t)st * L.stage_bytes;
+#pragma unroll 1
                 for (int b = lane; b < nbs; b += 32) {
                     const unsigned char *ab = sact + ((size_t)(s * nbs + b) << 5);
                     const int4 a0 = *reinterpret_cast<const int4 *>(ab + 16 * hsel);
@@ -431,32 +446,47 @@ __device__ __forceinline__ float4 pd_ldcg128(const float *p) {
     return v;
 }
 
-// Thread t owns the 16-byte slots i4 = u * PD_CT + t (u < PD_NORM_U) of the vector: x and the norm weights stay in REGISTERS
-// between the two passes; a 32-element quantisation block is eight consecutive slots = eight consecutive lanes, so its amax
-// is three shuffles.  Only the squares go through shared memory (the exact accumulator's chunk layout).
-__device__ __forceinline__ void pd_norm_to_smem(const PdArgs &a, const float *w, bool from_emb, int token, unsigned char *smem, const PdSmem &L, int tid, int stamp_layer = -1) {
+// One out-of-line copy of the exact accumulator for every caller (attn norm, ffn norm, final norm, long softmax rows): the
+// kernel's code must stay inside the instruction cache, every cold fetch queues behind the weight stream.
+__device__ __noinline__ float pd_seqsum(const float *sq, int n, int S, unsigned char *smem, const PdSmem &L, int tid) {
+    SeqSum2Scratch scratch = seqsum2_carve(smem + L.off_seq, PD_CT);
+    return block_seqsum_exact_v2_t<PD_CT>(sq, n, scratch, tid, PdConsumerSync(), S);
+}
+
+// Norm weights are fetched with cp.async one phase ahead into their shared-memory buffer (slot i4 by the thread that will
+// read slot i4: no barrier needed, only that thread's own wait_group).
+__device__ __forceinline__ void pd_prefetch_w(const float *w, float *sbuf, int dim, int tid) {
+    const int n4 = dim >> 2;
+    for (int i4 = tid; i4 < n4; i4 += PD_CT)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sbuf + 4 * i4)), "l"(w + 4 * i4) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// Thread t owns the 16-byte slots i4 = u * PD_CT + t (u < U) of the vector: x and the norm weights stay in REGISTERS between
+// the two passes; a 32-element quantisation block is eight consecutive slots = eight consecutive lanes, so its amax is three
+// shuffles.  Only the squares go through shared memory (the exact accumulator's chunk layout).  wbuf: this norm's weights,
+// already on their way into shared memory (pd_prefetch_w).
+template <int U>
+__device__ __noinline__ void pd_norm_u(const PdArgs &a, const float *wbuf, bool from_emb, int token, unsigned char *smem, const PdSmem &L, int tid, int stamp_layer) {
     const int dim = a.dim, n4 = dim >> 2;
     float *sq = reinterpret_cast<float *>(smem + L.off_nbuf);
     float *misc = reinterpret_cast<float *>(smem + L.off_misc);
-    SeqSum2Scratch scratch = seqsum2_carve(smem + L.off_seq, PD_CT);
     const int E = (dim + PD_CT - 1) / PD_CT, S = seqsum2_stride(E);
-    float4 xv[PD_NORM_U], wv[PD_NORM_U];
+    float4 xv[U];
 #pragma unroll
-    for (int u = 0; u < PD_NORM_U; u++) { // every load of this thread in flight at once: one L2 round trip
+    for (int u = 0; u < U; u++) { // every load of this thread in flight at once: one L2 round trip
         const int i4 = u * PD_CT + tid;
         xv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        wv[u] = xv[u];
         if (i4 < n4) {
             if (from_emb) { // first layer: the embedding row (quantised table: element-wise, FloatTensor.copyTo)
                 xv[u] = make_float4(emb_get(a.emb, token, 4 * i4), emb_get(a.emb, token, 4 * i4 + 1), emb_get(a.emb, token, 4 * i4 + 2), emb_get(a.emb, token, 4 * i4 + 3));
             } else xv[u] = pd_ldcg128(a.x + 4 * i4);
-            wv[u] = __ldg(reinterpret_cast<const float4 *>(w) + i4);
         }
     }
     // squares -> chunk layout: element i belongs to accumulator thread i / E at offset i % E of its S-float chunk
     for (int i = dim + tid; i < PD_CT * E; i += PD_CT) sq[(i / E) * S + (i % E)] = 0.0f; // zero padding of the last chunks
 #pragma unroll
-    for (int u = 0; u < PD_NORM_U; u++) {
+    for (int u = 0; u < U; u++) {
         const int i4 = u * PD_CT + tid;
         if (i4 < n4) {
             const int i = 4 * i4;
@@ -470,25 +500,27 @@ __device__ __forceinline__ void pd_norm_to_smem(const PdArgs &a, const float *w,
     }
     consumer_bar_sync();
     if (stamp_layer >= 0) pd_stamp(a, stamp_layer, 10, tid);
-    float ss = block_seqsum_exact_v2_t<PD_CT>(sq, dim, scratch, tid, PdConsumerSync(), S);
+    float ss = pd_seqsum(sq, dim, S, smem, L, tid);
     if (stamp_layer >= 0) pd_stamp(a, stamp_layer, 11, tid);
     if (tid == 0) {
         ss = __fdiv_rn(ss, (float)dim);
         ss = __fadd_rn(ss, a.eps);
         misc[16] = (float)(1.0 / sqrt((double)ss));
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory"); // this thread's slots of the norm weights have landed
     consumer_bar_sync();
     ss = misc[16];
     unsigned *sxq = reinterpret_cast<unsigned *>(smem + L.off_xq);
     float *sxs = reinterpret_cast<float *>(smem + L.off_xs);
 #pragma unroll
-    for (int u = 0; u < PD_NORM_U; u++) { // out = w * (ss * x) (InferenceCore.java:45-47), then Q8_0FloatTensor.java:100-117 per 32-block
+    for (int u = 0; u < U; u++) { // out = w * (ss * x) (InferenceCore.java:45-47), then Q8_0FloatTensor.java:100-117 per 32-block
         const int i4 = u * PD_CT + tid;
         if (u * PD_CT < n4) { // warp-uniform (n4 is a multiple of 8 and whole 8-lane groups are in or out)
             float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
             if (i4 < n4) {
-                v0 = __fmul_rn(wv[u].x, __fmul_rn(ss, xv[u].x)); v1 = __fmul_rn(wv[u].y, __fmul_rn(ss, xv[u].y));
-                v2 = __fmul_rn(wv[u].z, __fmul_rn(ss, xv[u].z)); v3 = __fmul_rn(wv[u].w, __fmul_rn(ss, xv[u].w));
+                const float4 wv = *reinterpret_cast<const float4 *>(wbuf + 4 * i4);
+                v0 = __fmul_rn(wv.x, __fmul_rn(ss, xv[u].x)); v1 = __fmul_rn(wv.y, __fmul_rn(ss, xv[u].y));
+                v2 = __fmul_rn(wv.z, __fmul_rn(ss, xv[u].z)); v3 = __fmul_rn(wv.w, __fmul_rn(ss, xv[u].w));
             }
             float amax = fmaxf(fmaxf(fabsf(v0), fabsf(v1)), fmaxf(fabsf(v2), fabsf(v3)));
             amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
@@ -509,8 +541,17 @@ __device__ __forceinline__ void pd_norm_to_smem(const PdArgs &a, const float *w,
     consumer_bar_sync();
 }
 
+// U = 16-byte slots per consumer thread = ceil(dim / 1024): only the instantiation the model needs ever executes
+__device__ __forceinline__ void pd_norm_to_smem(const PdArgs &a, const float *wbuf, bool from_emb, int token, unsigned char *smem, const PdSmem &L, int tid, int stamp_layer = -1) {
+    const int U = ((a.dim >> 2) + PD_CT - 1) / PD_CT;
+    if (U <= 1) pd_norm_u<1>(a, wbuf, from_emb, token, smem, L, tid, stamp_layer);
+    else if (U == 2) pd_norm_u<2>(a, wbuf, from_emb, token, smem, L, tid, stamp_layer);
+    else if (U <= 4) pd_norm_u<4>(a, wbuf, from_emb, token, smem, L, tid, stamp_layer);
+    else pd_norm_u<8>(a, wbuf, from_emb, token, smem, L, tid, stamp_layer);
+}
+
 // a quantised activation vector produced by other CTAs / ranks (attention output, hidden activation) -> shared memory
-__device__ __forceinline__ void pd_load_act(const int8_t *q, const float *s, int cols, unsigned char *smem, const PdSmem &L, int tid) {
+__device__ __noinline__ void pd_load_act(const int8_t *q, const float *s, int cols, unsigned char *smem, const PdSmem &L, int tid) {
     int4 *sxq = reinterpret_cast<int4 *>(smem + L.off_xq);
     float *sxs = reinterpret_cast<float *>(smem + L.off_xs);
     const int4 *src = reinterpret_cast<const int4 *>(q);
@@ -545,7 +586,7 @@ __device__ __forceinline__ void pd_load_act(const int8_t *q, const float *s, int
 // ---- one attention head with the consumer warps: k_attention's body (exact CPU order, InferenceCore.java:98-137) -------------
 // h = local head index on this rank.
 template <int HS>
-__device__ __forceinline__ void pd_attention_head(const PdArgs &a, const PdLayer &Ly, int h, int pos, unsigned char *smem, const PdSmem &L, int tid, int layer) {
+__device__ __noinline__ void pd_attention_head(const PdArgs &a, const PdLayer &Ly, int h, int pos, unsigned char *smem, const PdSmem &L, int tid, int layer) {
     float *sm = reinterpret_cast<float *>(smem + L.off_nbuf);
     float *misc = reinterpret_cast<float *>(smem + L.off_misc);
     float *red = misc, *s_val = misc + 8;
@@ -566,7 +607,8 @@ __device__ __forceinline__ void pd_attention_head(const PdArgs &a, const PdLayer
         int i0, i1;
         if (a.arch == 1) { i0 = p; i1 = p + HALF; } else { i0 = 2 * p; i1 = 2 * p + 1; }
         float v0 = ldcg_f32c(src + i0), v1 = ldcg_f32c(src + i1); // written by other CTAs in this kernel: bypass L1
-        const float fcr = __ldg(a.rope_cr + (size_t)pos * HALF + p), fci = __ldg(a.rope_ci + (size_t)pos * HALF + p); // same round trip as q/k
+        const float *srope = reinterpret_cast<const float *>(smem + L.off_rope); // this position's rope row, staged at kernel start
+        const float fcr = srope[p], fci = srope[HALF + p];
         float cv0 = 0.f, cv1 = 0.f;
         const bool owner = (h % kv_mul == 0) && !is_q; // first query head of the KV group owns the cache write (InferenceCore.java:92-93)
         if (owner) { cv0 = ldcg_f32c(vsrc + i0); cv1 = ldcg_f32c(vsrc + i1); }
@@ -646,8 +688,7 @@ __device__ __forceinline__ void pd_attention_head(const PdArgs &a, const PdLayer
         const int E = (nt + PD_CT - 1) / PD_CT;
         for (int t = nt + tid; t < PD_CT * E; t += PD_CT) att[t] = 0.0f;
         consumer_bar_sync();
-        SeqSum2Scratch scratch = seqsum2_carve(smem + L.off_seq, PD_CT);
-        sum = block_seqsum_exact_v2_t<PD_CT>(att, nt, scratch, tid, PdConsumerSync());
+        sum = pd_seqsum(att, nt, 0, smem, L, tid);
     } else {
         if (tid == 0) s_val[0] = seq2_literal(0.0f, att, nt, (reinterpret_cast<uintptr_t>(att) & 15) == 0);
         consumer_bar_sync();
@@ -707,7 +748,7 @@ __device__ __forceinline__ void pd_attention_head(const PdArgs &a, const PdLayer
 
 // ---- the kernel -----------------------------------------------------------------------------------------------------------
 template <int HS>
-__global__ void __launch_bounds__(SMV_THREADS, 1) k_decode_persistent(PdArgs a, PdSmem L) {
+__global__ void __launch_bounds__(SMV_THREADS, 1) k_decode_persistent(const __grid_constant__ PdArgs a, const __grid_constant__ PdSmem L) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int S = L.stages;
@@ -733,12 +774,28 @@ __global__ void __launch_bounds__(SMV_THREADS, 1) k_decode_persistent(PdArgs a, 
     const unsigned tick = *reinterpret_cast<volatile unsigned *>(a.sync + PD_S_TICK);
     const unsigned lmtick = *reinterpret_cast<volatile unsigned *>(a.sync + PD_S_LMTICK);
     const unsigned nC = gridDim.x, nL = (unsigned)a.n_layers, nH = (unsigned)a.n_heads;
+    float *wbufA = reinterpret_cast<float *>(smem + L.off_wbuf), *wbufF = wbufA + a.dim; // norm weights: attn (and final) / ffn
+    pd_prefetch_w(a.n_layers ? a.layers[0].attn_norm : a.out_norm, wbufA, a.dim, tid);
+    if (tid < a.head_size) { // this position's rope row (RoPE.precomputeFreqsCis table), the same for every layer
+        const int half = a.head_size >> 1;
+        float *srope = reinterpret_cast<float *>(smem + L.off_rope);
+        srope[tid] = tid < half ? __ldg(a.rope_cr + (size_t)pos * half + tid) : __ldg(a.rope_ci + (size_t)pos * half + (tid - half));
+    }
     unsigned seq_base = 0;
+#pragma unroll 1
     for (int l = 0; l < a.n_layers; l++) {
         const PdLayer &Ly = a.layers[l];
         const unsigned e = tick * nL + (unsigned)l + 1u; // this layer's epoch
         pd_stamp(a, l, 0, tid);
-        pd_norm_to_smem(a, Ly.attn_norm, l == 0, token, smem, L, tid, l);
+        if (blockIdx.x < nH) { // head CTAs: pull this layer's K/V rows of their KV head into L2 now, ~15 us before the scores need them
+            const int kvh = (int)blockIdx.x / (a.n_heads / a.n_kv_heads), kvd = a.n_kv_heads * a.head_size;
+            for (int t = tid; t < pos; t += PD_CT) {
+                bulk_prefetch_l2(Ly.kc + (size_t)t * kvd + kvh * a.head_size, (unsigned)a.head_size * 4u);
+                bulk_prefetch_l2(Ly.vc + (size_t)t * kvd + kvh * a.head_size, (unsigned)a.head_size * 4u);
+            }
+        }
+        pd_norm_to_smem(a, wbufA, l == 0, token, smem, L, tid, l);
+        pd_prefetch_w(Ly.ffn_norm, wbufF, a.dim, tid); // needed after the attention block
         pd_stamp(a, l, 1, tid);
         pd_consume_matrix<SMV_STORE>(Ly.qkv, a, smem, L, bar0, rel, seq_base, a.qkv, false, false, token, 0, tid);
         pd_stamp(a, l, 2, tid);
@@ -757,7 +814,8 @@ __global__ void __launch_bounds__(SMV_THREADS, 1) k_decode_persistent(PdArgs a, 
         pd_arrive(a, PD_S_WO, e * nC, e, true, tid);
         pd_wait(a, PD_S_WO, e * nC, e, true, tid);
         pd_stamp(a, l, 5, tid);
-        pd_norm_to_smem(a, Ly.ffn_norm, false, token, smem, L, tid);
+        pd_norm_to_smem(a, wbufF, false, token, smem, L, tid);
+        pd_prefetch_w(l + 1 < a.n_layers ? a.layers[l + 1].attn_norm : a.out_norm, wbufA, a.dim, tid); // the next attn norm (or the final norm)
         pd_stamp(a, l, 6, tid);
         pd_consume_matrix<SMV_GATEUP>(Ly.gu, a, smem, L, bar0, rel, seq_base, a.hb, false, false, token, a.hid_base, tid);
         pd_stamp(a, l, 7, tid);
@@ -774,7 +832,7 @@ __global__ void __launch_bounds__(SMV_THREADS, 1) k_decode_persistent(PdArgs a, 
     if (a.with_logits) {
         const unsigned le = lmtick + 1u;
         pd_stamp(a, a.n_layers, 0, tid);
-        pd_norm_to_smem(a, a.out_norm, false, token, smem, L, tid);
+        pd_norm_to_smem(a, wbufA, false, token, smem, L, tid);
         pd_stamp(a, a.n_layers, 1, tid);
         pd_consume_matrix<SMV_STORE>(a.lm_head, a, smem, L, bar0, rel, seq_base, a.logits, true, false, token, a.voc_base, tid);
         pd_stamp(a, a.n_layers, 2, tid);

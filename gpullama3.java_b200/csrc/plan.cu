@@ -71,7 +71,8 @@ struct b200_plan {
     // knobs read once at creation (never inside a launch helper)
     size_t smv_budget = 96 * 1024;
     int smv_budget_cols = 0;
-    unsigned l2_window = 0, pd_l2_ahead = 0;
+    unsigned l2_window = 0, pd_l2_ahead = 0, pd_max_fly = 6;
+    int pd_max_stages = 0; // 0 = as many as shared memory holds
     float *att_scratch = nullptr; // [heads][ctx] score rows when the context does not fit shared memory
     int *smp_indices = nullptr, *smp_out = nullptr; // device-side sampler scratch (sampler.cuh): candidate list, {id, info[4]}
 
@@ -326,6 +327,10 @@ void read_knobs(b200_plan *p) {
     p->l2_window = (unsigned)((w ? atoi(w) : 0) * 1024);
     const char *a = getenv("B200_PD_L2_AHEAD"); // persistent kernel: tiles of L2 look-ahead while the ring is full
     p->pd_l2_ahead = a ? (unsigned)atoi(a) : 0u;
+    const char *f = getenv("B200_PD_MAXFLY"); // persistent kernel: bulk copies in flight per CTA (0 = unlimited)
+    p->pd_max_fly = f ? (unsigned)atoi(f) : 6u;
+    const char *g = getenv("B200_PD_STAGES"); // persistent kernel: cap on the ring depth
+    p->pd_max_stages = g ? atoi(g) : 0;
     const char *v = getenv("B200_NORM_V2");
     p->norm_v2 = !(v && v[0] == '0');
     const char *d = getenv("B200_DECODE");
@@ -472,7 +477,7 @@ int pd_prepare(b200_plan *p) {
     int maxdyn = 0;
     CK(cudaDeviceGetAttribute(&maxdyn, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device));
     const int att_floats = 3 * c.head_size + (p->att_scratch ? 0 : (c.context_length + PD_CT - 1) / PD_CT * PD_CT); // score row padded to whole accumulator chunks
-    const PdSmem L = pd_layout(c.dim, p->qd, c.hidden_dim, att_floats, max_seg, (size_t)maxdyn);
+    const PdSmem L = pd_layout(c.dim, p->qd, c.hidden_dim, c.head_size, att_floats, max_seg, (size_t)maxdyn, p->pd_max_stages);
     if (L.stages < 4) { p->pd_why = "shape leaves fewer than 4 ring stages of shared memory"; return B200_OK; }
     int rc;
     if (!p->pd_layers) {
@@ -514,6 +519,7 @@ int enqueue_persistent(b200_plan *p, bool with_logits, int *launches, bool trace
     a.att_scratch = p->att_scratch; a.trace = trace ? p->pd_trace : nullptr;
     a.with_logits = with_logits ? 1 : 0;
     a.l2_ahead = p->pd_l2_ahead;
+    a.max_fly = p->pd_max_fly > (unsigned)p->pd_L.stages ? (unsigned)p->pd_L.stages : p->pd_max_fly;
     a.tp = p->tp; a.pd_flags_off = p->pd_flags_off;
     a.head_base = p->tp.rank * p->nh_l; a.dim_base = p->tp.rank * p->dim_l; a.hid_base = p->tp.rank * p->hid_l; a.voc_base = p->tp.rank * p->voc_l;
     cudaLaunchConfig_t cfg = {};
