@@ -73,9 +73,8 @@ struct PdArgs {
     unsigned long long *trace; // [gridDim.x][n_layers + 1][PD_STAMPS] %globaltimer stamps, or NULL
     int with_logits;
     unsigned l2_ahead;         // tiles the producer may prefetch into L2 beyond the ring while the ring is full
-    unsigned max_fly;          // bulk copies one CTA keeps IN FLIGHT (issued, not landed); 0 = no limit but the ring.  A deep DRAM queue
-                               // delays every latency-critical access of the dependent phases (barrier polls, x / KV loads, instruction
-                               // fetches) by the time the queue takes to drain; ~6 tiles per SM keep HBM saturated with a ~1 us queue
+    unsigned max_fly;          // experiment knob (B200_PD_MAXFLY): bulk copies one CTA keeps in flight; 0 = no limit but the ring (default:
+                               // limiting it never helped the dependent phases and always slowed the stream, profiles/r2_run3_knob_sweep.log)
     // tensor parallelism (tp.n == 1: everything below unused)
     TpCtx tp;
     unsigned pd_flags_off;     // offset of the persistent kernel's epoch flags [PD_S_SLOTS][TP_MAX] in every rank's comm buffer

@@ -71,7 +71,7 @@ struct b200_plan {
     // knobs read once at creation (never inside a launch helper)
     size_t smv_budget = 96 * 1024;
     int smv_budget_cols = 0;
-    unsigned l2_window = 0, pd_l2_ahead = 0, pd_max_fly = 6;
+    unsigned l2_window = 0, pd_l2_ahead = 0, pd_max_fly = 0;
     int pd_max_stages = 0; // 0 = as many as shared memory holds
     float *att_scratch = nullptr; // [heads][ctx] score rows when the context does not fit shared memory
     int *smp_indices = nullptr, *smp_out = nullptr; // device-side sampler scratch (sampler.cuh): candidate list, {id, info[4]}
@@ -328,7 +328,7 @@ void read_knobs(b200_plan *p) {
     const char *a = getenv("B200_PD_L2_AHEAD"); // persistent kernel: tiles of L2 look-ahead while the ring is full
     p->pd_l2_ahead = a ? (unsigned)atoi(a) : 0u;
     const char *f = getenv("B200_PD_MAXFLY"); // persistent kernel: bulk copies in flight per CTA (0 = unlimited)
-    p->pd_max_fly = f ? (unsigned)atoi(f) : 6u;
+    p->pd_max_fly = f ? (unsigned)atoi(f) : 0u; // measured (profiles/r2_run3_knob_sweep.log): any limit below the ring depth only slows the stream
     const char *g = getenv("B200_PD_STAGES"); // persistent kernel: cap on the ring depth
     p->pd_max_stages = g ? atoi(g) : 0;
     const char *v = getenv("B200_NORM_V2");
@@ -893,8 +893,8 @@ int prefill_init(b200_plan *p) {
     {
         const char *e = getenv("B200_GEMM_2CTA");
         c.pair = !(e && e[0] == '0') && nqkv % 256 == 0 && g.dim % 256 == 0 && g.hidden_dim % 128 == 0;
-        const char *e2 = getenv("B200_GEMM_PERSIST"); // round-2 candidate: persistent CTA-pair kernel for QKV and gate/up (compile-checked only)
-        c.persist = e2 && e2[0] == '1';
+        const char *e2 = getenv("B200_GEMM_PERSIST"); // persistent CTA-pair kernel (double-buffered TMEM) for QKV and gate/up: validated on the
+        c.persist = !(e2 && e2[0] == '0');            // GPU in round 2 (tests/test_gpu_prefill.py, profiles/r2_run1_first_green.log); =0 selects the one-tile kernels
     }
     if (!ok) { c.why = "cuTensorMapEncodeTiled rejected a tensor map"; return B200_OK; }
     if (g.head_size == 128) {

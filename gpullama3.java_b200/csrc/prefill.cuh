@@ -34,7 +34,7 @@ struct PrefillCtx {
     bool ready = false; // tensor-core path usable for this plan
     int mode = 0;       // 0 = exact token-by-token graph, 1 = tensor-core GEMMs
     bool pair = true;      // CTA-pair (cta_group::2) GEMMs; B200_GEMM_2CTA=0 selects the single-CTA kernels
-    bool persist = false;  // B200_GEMM_PERSIST=1: persistent CTA-pair GEMM for QKV and gate/up (round-2 candidate, untested)
+    bool persist = true;   // persistent CTA-pair GEMM (double-buffered TMEM accumulators) for QKV and gate/up; B200_GEMM_PERSIST=0 turns it off
     bool att_simt = false; // debug: FP32 SIMT attention instead of the mma.sync kernel (B200_PF_ATT=simt)
     float *X = nullptr, *QKV = nullptr;
     __half *A16 = nullptr, *ATT16 = nullptr, *H16 = nullptr;

@@ -413,8 +413,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
 }
 
 // =====================================================================================================
-// ROUND-2 CANDIDATE (compile-checked only; selected by B200_GEMM_PERSIST=1, never by default): the CTA-pair GEMM as a
-// PERSISTENT kernel.  One cluster per TPC walks tiles t = cluster + i * clusters (M pair tiles fastest, so neighbouring
+// The CTA-pair GEMM as a PERSISTENT kernel (default for the QKV and gate/up GEMMs since round 2; B200_GEMM_PERSIST=0 disables).  One cluster per TPC walks tiles t = cluster + i * clusters (M pair tiles fastest, so neighbouring
 // clusters share a weight tile in L2); the accumulator is double buffered in TMEM (2 x BN columns), so while the four
 // epilogue warps drain tile i the MMA thread already accumulates tile i+1 and the producers are loading tile i+2 --
 // prologue, pipeline fill and epilogue no longer sit on the critical path of every tile (they are ~25 % of a K = 4096 tile

@@ -53,6 +53,9 @@ public final class B200MasterPlan implements AutoCloseable {
     private static final MethodHandle PREFILL = fn("b200_forward_prefill", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT));
     private static final MethodHandle BATCH_PREFILL = fn("b200_forward_batch_prefill", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT));
     private static final MethodHandle SET_PREFILL_MODE = fn("b200_set_prefill_mode", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT));
+    private static final MethodHandle SET_DECODE_MODE = fn("b200_set_decode_mode", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT));
+    private static final MethodHandle DECODE_SAMPLE = fn("b200_forward_decode_sample",
+            FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, JAVA_FLOAT, JAVA_FLOAT, JAVA_FLOAT, ADDRESS, ADDRESS));
     private static final MethodHandle DECODE_SEQUENCE = fn("b200_decode_sequence",
             FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT, JAVA_INT, ADDRESS, ADDRESS));
     private static final MethodHandle TP_HANDLE = fn("b200_tp_handle", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
@@ -143,6 +146,20 @@ public final class B200MasterPlan implements AutoCloseable {
             int rc = (int) BATCH_PREFILL.invokeExact(plan, a.allocateFrom(JAVA_INT, tokens), tokens.length, startPos);
             if (rc != 0) check(rc, lastError());
         }
+    }
+
+    /** Forward + Sampler.sampleToken on the device (Sampler.java:74-122): the caller draws uniform01 = rng.nextFloat(1f) from the
+     *  sampler's own RandomGenerator (Sampler.java:84) and gets the token id back; the logits row never crosses PCIe. */
+    public int forwardDecodeSample(int token, int position, float temperature, float topp, float uniform01) throws Throwable {
+        int rc = (int) DECODE_SAMPLE.invokeExact(plan, token, position, temperature, topp, uniform01, argmax, MemorySegment.NULL);
+        if (rc != 0) check(rc, lastError());
+        return argmax.get(JAVA_INT, 0);
+    }
+
+    /** 0 = CUDA graph of ~7 kernels per layer, 1 = one persistent kernel per token (default when the plan supports it); bit-identical. */
+    public void setDecodeMode(int mode) throws Throwable {
+        int rc = (int) SET_DECODE_MODE.invokeExact(plan, mode);
+        if (rc != 0) check(rc, lastError());
     }
 
     /** TensorCoreSupport.java's switch: 0 = exact token-by-token prefill (bit-identical KV cache), 1 = TMA + tcgen05 GEMMs. */
