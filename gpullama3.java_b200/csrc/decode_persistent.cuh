@@ -29,7 +29,10 @@
 #include "seqsum2.cuh"
 #include "stream_matvec.cuh"
 
-#define PD_CT (SMV_CONSUMER_WARPS * 32) // consumer threads
+#define PD_WARPS 16                     // consumer warps: 4 per SM sub-partition -- every phase of this kernel is a chain of dependent instructions,
+                                        // and the ncu samples (profiles/r2_pd_full_v2.summary.txt) show warps waiting on their own previous result
+#define PD_CT (PD_WARPS * 32)           // consumer threads
+#define PD_THREADS (PD_CT + 32)         // + the producer warp
 #define PD_MAX_STAGES 32
 #define PD_TIMEOUT_NS 4000000000ull    // 4 s: far beyond any legitimate wait, well under gpurun's limits
 #define PD_STAMPS 16                    // trace stamps per layer and CTA (0-9 phases, 10-15 inside the attn norm / the attention)
@@ -111,9 +114,9 @@ __host__ __device__ inline PdSmem pd_layout(int dim, int qd, int hidden, int hea
     o = (o + 15) & ~(size_t)15;
     L.off_seq = o; o += seqsum2_scratch_bytes(PD_CT);
     o = (o + 15) & ~(size_t)15;
-    L.off_terms = o; o += (size_t)SMV_CONSUMER_WARPS * 4 * L.tstride * 4;
+    L.off_terms = o; o += (size_t)PD_WARPS * 4 * L.tstride * 4;
     L.off_hvals = o; o += SMV_HVALS * 4;
-    L.off_misc = o; o += 64 * 4; // red[8], s_val[2], scale, argmax merge scratch
+    L.off_misc = o; o += 96 * 4; // red[16], s_val[2] @16, scale @20, argmax merge scratch @32 (16 floats) / @48 (16 ints)
     o = (o + 127) & ~(size_t)127;
     L.off_ring = o;
     long room = (long)budget - (long)o;
@@ -126,14 +129,16 @@ __host__ __device__ inline PdSmem pd_layout(int dim, int qd, int hidden, int hea
 }
 
 // ---- bounded waits ----------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned pd_ld_acquire_gpu(const unsigned *p) {
+// Polls are RELAXED loads; one acquire fence follows the successful one.  (ld.acquire in the loop compiles to a load plus
+// CCTL.IVALL: every poll of thread 0 threw away the whole L1 of its SM -- norm weights, tile descriptors, rope rows.)
+__device__ __forceinline__ unsigned pd_ld_relaxed_gpu(const unsigned *p) {
     unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ unsigned pd_ld_acquire_sys(const unsigned *p) {
+__device__ __forceinline__ unsigned pd_ld_relaxed_sys(const unsigned *p) {
     unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 // one thread: spin until *p >= target (wrap-safe); gives up after PD_TIMEOUT_NS or as soon as another waiter gave up
@@ -141,8 +146,12 @@ template <bool SYS> __device__ __noinline__ void pd_spin(const unsigned *p, unsi
     unsigned it = 0;
     unsigned long long t0 = 0;
     for (;;) {
-        const unsigned v = SYS ? pd_ld_acquire_sys(p) : pd_ld_acquire_gpu(p);
-        if ((int)(v - target) >= 0) return;
+        const unsigned v = SYS ? pd_ld_relaxed_sys(p) : pd_ld_relaxed_gpu(p);
+        if ((int)(v - target) >= 0) {
+            if (SYS) asm volatile("fence.acq_rel.sys;" ::: "memory");
+            else asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            return;
+        }
         if ((++it & 255u) == 0u) {
             if (*reinterpret_cast<volatile unsigned *>(err)) return;
             const unsigned long long now = gtime();
@@ -156,15 +165,17 @@ template <bool SYS> __device__ __noinline__ void pd_spin(const unsigned *p, unsi
     }
 }
 
+__device__ __forceinline__ void pd_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(PD_CT) : "memory"); }
+
 struct PdConsumerSync {
-    __device__ __forceinline__ void operator()() const { consumer_bar_sync(); }
+    __device__ __forceinline__ void operator()() const { pd_bar_sync(); }
 };
 
 // Every consumer thread calls these.  `cross`: the phase's outputs are consumed by other ranks too (tensor parallelism):
 // the CTA's peer stores (made before the barrier) are published by thread 0's system-scope fence, and the LAST local
 // arriver raises this rank's epoch flag on every rank.
 __device__ __forceinline__ void pd_arrive(const PdArgs &a, int slot, unsigned target, unsigned epoch, bool cross, int tid) {
-    consumer_bar_sync();
+    pd_bar_sync();
     if (tid == 0) {
         const bool x = cross && a.tp.n > 1;
         if (x) __threadfence_system();
@@ -186,7 +197,7 @@ __device__ __forceinline__ void pd_wait(const PdArgs &a, int slot, unsigned targ
             for (int k = 0; k < a.tp.n; k++) pd_spin<true>(f + k, epoch, a.sync + PD_S_ERR, a.host_err, 1u + (unsigned)slot);
         } else pd_spin<false>(a.sync + slot, target, a.sync + PD_S_ERR, a.host_err, 1u + (unsigned)slot);
     }
-    consumer_bar_sync();
+    pd_bar_sync();
 }
 
 __device__ __forceinline__ void pd_stamp(const PdArgs &a, int layer, int k, int tid) {
@@ -213,7 +224,7 @@ struct PdWalk {
             gb = (int)(((long long)blockIdx.x * ngroups) / gridDim.x);
             g1 = (int)(((long long)(blockIdx.x + 1) * ngroups) / gridDim.x);
             if (gb < g1) {
-                nw = min(SMV_CONSUMER_WARPS, g1 - gb);
+                nw = min(PD_WARPS, g1 - gb);
                 s = 0; w = 0;
                 tile_bytes = 4u * (unsigned)W.unit_bytes;
                 return;
@@ -233,8 +244,8 @@ struct PdWalk {
         w = 0;
         if (++s < W.nseg) return;
         s = 0;
-        gb += SMV_CONSUMER_WARPS;
-        if (gb < g1) { nw = min(SMV_CONSUMER_WARPS, g1 - gb); return; }
+        gb += PD_WARPS;
+        if (gb < g1) { nw = min(PD_WARPS, g1 - gb); return; }
         mi++;
         open();
     }
@@ -296,11 +307,16 @@ __device__ __forceinline__ void pd_produce(const PdArgs &a, unsigned char *smem,
 template <int MODE>
 __device__ __noinline__ void pd_consume_matrix(const TileMat &W, const PdArgs &a, unsigned char *smem, const PdSmem &L, unsigned bar0, volatile unsigned *rel,
                                                   unsigned &seq_base, float *out, bool argmax, bool l0_emb, int token, int row_base, int tid) {
-    const int lane = tid & 31, warp = tid >> 5, S = L.stages;
+    // every descriptor field into a register once: the waits below are asm with a memory clobber, after which the compiler would
+    // otherwise re-read W.* (global memory) and L.* on every use inside the tile loop
+    const int lane = tid & 31, warp = tid >> 5, S = L.stages, tstride = L.tstride, stage_bytes = L.stage_bytes;
+    const int w_unit = W.unit_bytes, w_seg = W.seg;
     const int ngroups = W.rows >> 2;
     const int g0 = (int)(((long long)blockIdx.x * ngroups) / gridDim.x), g1 = (int)(((long long)(blockIdx.x + 1) * ngroups) / gridDim.x);
-    const int nseg = W.nseg, nbs = W.seg >> 5;
-    float *terms = reinterpret_cast<float *>(smem + L.off_terms) + (size_t)warp * 4 * L.tstride;
+    const int nseg = W.nseg, nbs = w_seg >> 5;
+    const unsigned char *ring = smem + L.off_ring;
+    const int tp_n = a.tp.n;
+    float *terms = reinterpret_cast<float *>(smem + L.off_terms) + (size_t)warp * 4 * tstride;
     const unsigned char *sact = smem + L.off_xq;
     const float *sxs = reinterpret_cast<const float *>(smem + L.off_xs);
     float *hvals = reinterpret_cast<float *>(smem + L.off_hvals);
@@ -308,8 +324,8 @@ __device__ __noinline__ void pd_consume_matrix(const TileMat &W, const PdArgs &a
     float best = -INFINITY;
     int best_i = 0x7fffffff;
 #pragma unroll 1
-    for (int gb = g0; gb < g1; gb += SMV_CONSUMER_WARPS) {
-        const int nw = min(SMV_CONSUMER_WARPS, g1 - gb);
+    for (int gb = g0; gb < g1; gb += PD_WARPS) {
+        const int nw = min(PD_WARPS, g1 - gb);
         if (warp < nw) {
             const int G = gb + warp;
             float acc = 0.0f;
@@ -322,8 +338,8 @@ __device__ __noinline__ void pd_consume_matrix(const TileMat &W, const PdArgs &a
                     while (rel[st] != lap) {}
                 __syncwarp();
                 mbar_wait(bar0 + 8 * st, lap & 1u);
-                const unsigned char *tile = smem + L.off_ring + (size_t)st * L.stage_bytes;
-#pragma unroll 1
+                const unsigned char *tile = ring + (size_t)st * stage_bytes;
+#pragma unroll 2
                 for (int b = lane; b < nbs; b += 32) {
                     const unsigned char *ab = sact + ((size_t)(s * nbs + b) << 5);
                     const int4 a0 = *reinterpret_cast<const int4 *>(ab + 16 * hsel);
@@ -331,10 +347,10 @@ __device__ __noinline__ void pd_consume_matrix(const TileMat &W, const PdArgs &a
                     const float as = sxs[s * nbs + b];
 #pragma unroll
                     for (int r = 0; r < 4; r++) {
-                        const unsigned char *wb = tile + (size_t)r * W.unit_bytes + ((size_t)b << 5);
+                        const unsigned char *wb = tile + (size_t)r * w_unit + ((size_t)b << 5);
                         const int4 w0 = *reinterpret_cast<const int4 *>(wb + 16 * hsel);
                         const int4 w1 = *reinterpret_cast<const int4 *>(wb + 16 * (hsel ^ 1));
-                        const __half sc = *reinterpret_cast<const __half *>(tile + (size_t)r * W.unit_bytes + W.seg + 2 * b);
+                        const __half sc = *reinterpret_cast<const __half *>(tile + (size_t)r * w_unit + w_seg + 2 * b);
                         int isum = __dp4a(w0.x, a0.x, 0);
                         isum = __dp4a(w0.y, a0.y, isum);
                         isum = __dp4a(w0.z, a0.z, isum);
@@ -343,7 +359,7 @@ __device__ __noinline__ void pd_consume_matrix(const TileMat &W, const PdArgs &a
                         isum = __dp4a(w1.y, a1.y, isum);
                         isum = __dp4a(w1.z, a1.z, isum);
                         isum = __dp4a(w1.w, a1.w, isum);
-                        terms[r * L.tstride + b] = __fmul_rn((float)isum, __fmul_rn(__half2float(sc), as));
+                        terms[r * tstride + b] = __fmul_rn((float)isum, __fmul_rn(__half2float(sc), as));
                     }
                 }
                 __syncwarp();
@@ -351,7 +367,7 @@ __device__ __noinline__ void pd_consume_matrix(const TileMat &W, const PdArgs &a
                     rel[st] = lap + 1u;
                     mbar_arrive(bar0 + 8 * (PD_MAX_STAGES + st));
                 }
-                if (lane < 4) acc = pd_walk_terms(acc, terms + lane * L.tstride, nbs); // strictly in block order
+                if (lane < 4) acc = pd_walk_terms(acc, terms + lane * tstride, nbs); // strictly in block order
                 __syncwarp();
             }
             if (MODE == SMV_GATEUP) {
@@ -368,8 +384,8 @@ __device__ __noinline__ void pd_consume_matrix(const TileMat &W, const PdArgs &a
                     const size_t grow = (size_t)row_base + row;
                     const float base = l0_emb ? emb_get(a.emb, token, (int)grow) : out[grow];
                     const float v = __fadd_rn(base, acc); // x[i] = x[i] + xb2[i]
-                    if (a.tp.n > 1) { // all-gather of the residual stream: this rank's rows go to every rank
-                        for (int k = 0; k < a.tp.n; k++) tp_ptr<float>(a.tp, k, a.tp.off_x)[grow] = v;
+                    if (tp_n > 1) { // all-gather of the residual stream: this rank's rows go to every rank
+                        for (int k = 0; k < tp_n; k++) tp_ptr<float>(a.tp, k, a.tp.off_x)[grow] = v;
                     } else out[grow] = v;
                 } else {
                     out[row] = acc;
@@ -381,10 +397,10 @@ __device__ __noinline__ void pd_consume_matrix(const TileMat &W, const PdArgs &a
         seq_base += (unsigned)(nseg * nw);
     }
     if (MODE == SMV_GATEUP) { // Q8_0 quantisation of the hidden activation: k_stream_matvec_q8's epilogue
-        consumer_bar_sync();
+        pd_bar_sync();
         const int u0 = 2 * g0, u1 = 2 * g1;
         if (u1 > u0) {
-            for (int blk = (u0 >> 5) + warp; blk <= ((u1 - 1) >> 5); blk += SMV_CONSUMER_WARPS) {
+            for (int blk = (u0 >> 5) + warp; blk <= ((u1 - 1) >> 5); blk += PD_WARPS) {
                 const int lo = max(blk << 5, u0), hi = min((blk << 5) + 32, u1);
                 float v = 0.0f;
                 bool mine = true;
@@ -421,13 +437,13 @@ __device__ __noinline__ void pd_consume_matrix(const TileMat &W, const PdArgs &a
         }
     } else if (MODE == SMV_STORE && argmax) {
         int *cand_i = reinterpret_cast<int *>(hvals + 64);
-        consumer_bar_sync(); // hvals may still be read by a previous phase
+        pd_bar_sync(); // hvals may still be read by a previous phase
         if (lane < 4) { hvals[warp * 4 + lane] = best; cand_i[warp * 4 + lane] = best_i; }
-        consumer_bar_sync();
+        pd_bar_sync();
         if (tid == 0) {
             float bv = -INFINITY;
             int bi = 0x7fffffff;
-            for (int k = 0; k < SMV_CONSUMER_WARPS * 4; k++) {
+            for (int k = 0; k < PD_WARPS * 4; k++) {
                 const float v = hvals[k];
                 const int ix = cand_i[k];
                 if (v > bv || (v == bv && ix < bi)) { bv = v; bi = ix; }
@@ -497,18 +513,18 @@ __device__ __noinline__ void pd_norm_u(const PdArgs &a, const float *wbuf, bool 
             }
         }
     }
-    consumer_bar_sync();
+    pd_bar_sync();
     if (stamp_layer >= 0) pd_stamp(a, stamp_layer, 10, tid);
     float ss = pd_seqsum(sq, dim, S, smem, L, tid);
     if (stamp_layer >= 0) pd_stamp(a, stamp_layer, 11, tid);
     if (tid == 0) {
         ss = __fdiv_rn(ss, (float)dim);
         ss = __fadd_rn(ss, a.eps);
-        misc[16] = (float)(1.0 / sqrt((double)ss));
+        misc[20] = (float)(1.0 / sqrt((double)ss));
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory"); // this thread's slots of the norm weights have landed
-    consumer_bar_sync();
-    ss = misc[16];
+    pd_bar_sync();
+    ss = misc[20];
     unsigned *sxq = reinterpret_cast<unsigned *>(smem + L.off_xq);
     float *sxs = reinterpret_cast<float *>(smem + L.off_xs);
 #pragma unroll
@@ -537,16 +553,15 @@ __device__ __noinline__ void pd_norm_u(const PdArgs &a, const float *wbuf, bool 
             }
         }
     }
-    consumer_bar_sync();
+    pd_bar_sync();
 }
 
-// U = 16-byte slots per consumer thread = ceil(dim / 1024): only the instantiation the model needs ever executes
+// U = 16-byte slots per consumer thread = ceil(dim / (4 * PD_CT)): only the instantiation the model needs ever executes
 __device__ __forceinline__ void pd_norm_to_smem(const PdArgs &a, const float *wbuf, bool from_emb, int token, unsigned char *smem, const PdSmem &L, int tid, int stamp_layer = -1) {
     const int U = ((a.dim >> 2) + PD_CT - 1) / PD_CT;
     if (U <= 1) pd_norm_u<1>(a, wbuf, from_emb, token, smem, L, tid, stamp_layer);
     else if (U == 2) pd_norm_u<2>(a, wbuf, from_emb, token, smem, L, tid, stamp_layer);
-    else if (U <= 4) pd_norm_u<4>(a, wbuf, from_emb, token, smem, L, tid, stamp_layer);
-    else pd_norm_u<8>(a, wbuf, from_emb, token, smem, L, tid, stamp_layer);
+    else pd_norm_u<4>(a, wbuf, from_emb, token, smem, L, tid, stamp_layer); // dim <= 4 * PD_CT * 4 = 8192 (checked at plan creation)
 }
 
 // a quantised activation vector produced by other CTAs / ranks (attention output, hidden activation) -> shared memory
@@ -579,7 +594,7 @@ __device__ __noinline__ void pd_load_act(const int8_t *q, const float *s, int co
             if (b < nb) sxs[b] = sc[u];
         }
     }
-    consumer_bar_sync();
+    pd_bar_sync();
 }
 
 // ---- one attention head with the consumer warps: k_attention's body (exact CPU order, InferenceCore.java:98-137) -------------
@@ -588,7 +603,7 @@ template <int HS>
 __device__ __noinline__ void pd_attention_head(const PdArgs &a, const PdLayer &Ly, int h, int pos, unsigned char *smem, const PdSmem &L, int tid, int layer) {
     float *sm = reinterpret_cast<float *>(smem + L.off_nbuf);
     float *misc = reinterpret_cast<float *>(smem + L.off_misc);
-    float *red = misc, *s_val = misc + 8;
+    float *red = misc, *s_val = misc + 16;
     float *sq = sm, *sk = sm + HS, *so = sm + 2 * HS;
     const int ctx_pad = (a.ctx + PD_CT - 1) / PD_CT * PD_CT; // score rows are padded to whole accumulator chunks
     float *att = a.att_scratch ? a.att_scratch + (size_t)h * ctx_pad : sm + 3 * HS;
@@ -643,7 +658,7 @@ __device__ __noinline__ void pd_attention_head(const PdArgs &a, const PdLayer &L
             vc[o + i1] = cv1;
         }
     }
-    consumer_bar_sync();
+    pd_bar_sync();
     float lmax = -INFINITY;
     for (int t = tid; t < nt; t += PD_CT) {
         float acc = 0.0f;
@@ -673,63 +688,48 @@ __device__ __noinline__ void pd_attention_head(const PdArgs &a, const PdLayer &L
     }
     lmax = warp_max_f(lmax);
     if (lane == 0) red[warp] = lmax;
-    consumer_bar_sync();
+    pd_bar_sync();
     pd_stamp(a, layer, 13, tid);
     float mx = red[0];
 #pragma unroll
-    for (int w = 1; w < SMV_CONSUMER_WARPS; w++) mx = fmaxf(mx, red[w]);
+    for (int w = 1; w < PD_WARPS; w++) mx = fmaxf(mx, red[w]);
     for (int t = tid; t < nt; t += PD_CT) att[t] = (float)exp((double)__fsub_rn(att[t], mx));
-    consumer_bar_sync();
+    pd_bar_sync();
     // sequential float sum (FloatTensor.softmaxInPlace, FloatTensor.java:211-219): short rows by one thread (16-byte loads ahead of
     // the add chain), long rows with the exact parallel accumulator (the terms are non-negative)
     float sum;
     if (nt >= 512) {
         const int E = (nt + PD_CT - 1) / PD_CT;
         for (int t = nt + tid; t < PD_CT * E; t += PD_CT) att[t] = 0.0f;
-        consumer_bar_sync();
+        pd_bar_sync();
         sum = pd_seqsum(att, nt, 0, smem, L, tid);
     } else {
         if (tid == 0) s_val[0] = seq2_literal(0.0f, att, nt, (reinterpret_cast<uintptr_t>(att) & 15) == 0);
-        consumer_bar_sync();
+        pd_bar_sync();
         sum = s_val[0];
     }
     for (int t = tid; t < nt; t += PD_CT) att[t] = __fdiv_rn(att[t], sum);
-    consumer_bar_sync();
+    pd_bar_sync();
     pd_stamp(a, layer, 14, tid);
     if (tid < HS) { // xb = sum_t a_t * v_t, sequentially over t per element (saxpyInPlace, FloatTensor.java:221-227)
         const float *v = vc + kvh * HS + tid;
         float acc = 0.0f;
-        int t = 0;
         const float vcur = ldcg_f32c(vsrc + tid); // the current position's v, straight from the packed q|k|v vector
-        if (pos >= 16) { // the next 16 rows are in flight while the current 16 are being added (the add chain is the floor: 4 cycles per key)
-            float vv[16];
+#pragma unroll 1
+        for (int t0 = 0; t0 < pos; t0 += 32) { // 32 rows in flight per thread: one L2 round trip per 32 keys (the add chain itself is 4 cycles per key)
+            float vv[32];
 #pragma unroll
-            for (int u = 0; u < 16; u++) vv[u] = __ldcg(v + (size_t)u * kvd);
-            for (; t + 16 <= pos; t += 16) {
-                float nv[16];
-                const bool more = t + 32 <= pos;
+            for (int u = 0; u < 32; u++) vv[u] = t0 + u < pos ? __ldcg(v + (size_t)(t0 + u) * kvd) : 0.0f;
 #pragma unroll
-                for (int u = 0; u < 16; u++) nv[u] = more ? __ldcg(v + (size_t)(t + 16 + u) * kvd) : 0.0f;
-#pragma unroll
-                for (int u = 0; u < 16; u++) acc = __fadd_rn(__fmul_rn(att[t + u], vv[u]), acc);
-#pragma unroll
-                for (int u = 0; u < 16; u++) vv[u] = nv[u];
-            }
-        }
-        {
-            float vv[16]; // tail: up to 15 rows, all loads first
-#pragma unroll
-            for (int u = 0; u < 16; u++) vv[u] = t + u < pos ? __ldcg(v + (size_t)(t + u) * kvd) : 0.0f;
-#pragma unroll
-            for (int u = 0; u < 16; u++)
-                if (t + u < pos) acc = __fadd_rn(__fmul_rn(att[t + u], vv[u]), acc);
+            for (int u = 0; u < 32; u++)
+                if (t0 + u < pos) acc = __fadd_rn(__fmul_rn(att[t0 + u], vv[u]), acc);
         }
         acc = __fadd_rn(__fmul_rn(att[pos], vcur), acc);
         so[tid] = acc;
     }
-    consumer_bar_sync();
+    pd_bar_sync();
     const int gh = a.head_base + h;
-    for (int b = warp; b < HS / 32; b += SMV_CONSUMER_WARPS) {
+    for (int b = warp; b < HS / 32; b += PD_WARPS) {
         float as;
         const int q = quant_block_lane(so[b * 32 + lane], as);
         if (a.tp.n > 1) { // all-gather: this head's quantised output goes straight into every rank's buffer
@@ -747,7 +747,7 @@ __device__ __noinline__ void pd_attention_head(const PdArgs &a, const PdLayer &L
 
 // ---- the kernel -----------------------------------------------------------------------------------------------------------
 template <int HS>
-__global__ void __launch_bounds__(SMV_THREADS, 1) k_decode_persistent(const __grid_constant__ PdArgs a, const __grid_constant__ PdSmem L) {
+__global__ void __launch_bounds__(PD_THREADS, 1) k_decode_persistent(const __grid_constant__ PdArgs a, const __grid_constant__ PdSmem L) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int S = L.stages;
@@ -763,7 +763,7 @@ __global__ void __launch_bounds__(SMV_THREADS, 1) k_decode_persistent(const __gr
     }
     __syncthreads();
 
-    if (warp == SMV_CONSUMER_WARPS) { // ===== producer =====
+    if (warp == PD_WARPS) { // ===== producer =====
         if (lane == 0) pd_produce(a, smem, L, bar0);
         return;
     }
@@ -848,13 +848,13 @@ __global__ void __launch_bounds__(SMV_THREADS, 1) k_decode_persistent(const __gr
             const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
             argmax_merge(best, best_i, ov, oi);
         }
-        float *sv = reinterpret_cast<float *>(smem + L.off_misc) + 24;
-        int *si = reinterpret_cast<int *>(sv + 8);
+        float *sv = reinterpret_cast<float *>(smem + L.off_misc) + 32;
+        int *si = reinterpret_cast<int *>(sv + 16);
         if (lane == 0) { sv[warp] = best; si[warp] = best_i; }
-        consumer_bar_sync();
+        pd_bar_sync();
         if (tid == 0) {
             best = sv[0]; best_i = si[0];
-            for (int w = 1; w < SMV_CONSUMER_WARPS; w++) argmax_merge(best, best_i, sv[w], si[w]);
+            for (int w = 1; w < PD_WARPS; w++) argmax_merge(best, best_i, sv[w], si[w]);
             if (a.tp.n > 1) { // exchange every rank's (max, lowest global index) and merge identically everywhere
                 for (int k = 0; k < a.tp.n; k++) {
                     tp_ptr<float>(a.tp, k, a.tp.off_pv)[a.tp.rank] = best;

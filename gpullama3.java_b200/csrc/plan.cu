@@ -524,7 +524,7 @@ int enqueue_persistent(b200_plan *p, bool with_logits, int *launches, bool trace
     a.head_base = p->tp.rank * p->nh_l; a.dim_base = p->tp.rank * p->dim_l; a.hid_base = p->tp.rank * p->hid_l; a.voc_base = p->tp.rank * p->voc_l;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(p->n_sms);
-    cfg.blockDim = dim3(SMV_THREADS);
+    cfg.blockDim = dim3(PD_THREADS);
     cfg.dynamicSmemBytes = p->pd_L.total;
     cfg.stream = p->stream;
     cudaLaunchAttribute attr[1];
@@ -1461,7 +1461,7 @@ int b200_profile_norm(b200_plan *p, int64_t *cycles4) {
 
 static int run_seqsum_hook(const float *terms, int32_t n, int threads, float *out, int32_t *info) {
     if (!terms || !out || n <= 0 || n > 8192) return B200_ERR_BAD_ARG;
-    if (threads != 0 && threads != 256 && threads != 1024) return B200_ERR_BAD_ARG;
+    if (threads != 0 && threads != 256 && threads != 512 && threads != 1024) return B200_ERR_BAD_ARG;
     float *d = nullptr, *o = nullptr;
     if (cudaMalloc(&d, (size_t)n * 4) != cudaSuccess) return B200_ERR_OOM;
     if (cudaMalloc(&o, 16) != cudaSuccess) { cudaFree(d); return B200_ERR_OOM; }
@@ -1475,6 +1475,10 @@ static int run_seqsum_hook(const float *terms, int32_t n, int threads, float *ou
             const size_t smem = (size_t)1024 * ((n + 1023) / 1024) * 4 + seqsum2_scratch_bytes(1024);
             e = cudaFuncSetAttribute(k_test_seqsum2<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e == cudaSuccess) k_test_seqsum2<1024><<<1, 1024, smem>>>(d, n, o, reinterpret_cast<int *>(o) + 1);
+        } else if (threads == 512) {
+            const size_t smem = (size_t)512 * ((n + 511) / 512) * 4 + seqsum2_scratch_bytes(512);
+            e = cudaFuncSetAttribute(k_test_seqsum2<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) k_test_seqsum2<512><<<1, 512, smem>>>(d, n, o, reinterpret_cast<int *>(o) + 1);
         } else {
             const size_t smem = (size_t)256 * ((n + 255) / 256) * 4 + seqsum2_scratch_bytes(256);
             e = cudaFuncSetAttribute(k_test_seqsum2<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1494,7 +1498,7 @@ static int run_seqsum_hook(const float *terms, int32_t n, int threads, float *ou
 
 int b200_test_seqsum(const float *terms, int32_t n, float *out, int32_t *info) { return run_seqsum_hook(terms, n, 0, out, info); }
 int b200_test_seqsum2(const float *terms, int32_t n, int32_t threads, float *out, int32_t *info) {
-    if (threads != 256 && threads != 1024) return B200_ERR_BAD_ARG;
+    if (threads != 256 && threads != 512 && threads != 1024) return B200_ERR_BAD_ARG;
     return run_seqsum_hook(terms, n, threads, out, info);
 }
 

@@ -159,15 +159,12 @@ __device__ float block_seqsum_exact_v2_t(const float *sq, int n, SeqSum2Scratch 
                 bool ok = true;
                 int k = 0;
                 if (vec)
-                    for (; ok && k < E; k += 4) {
+                    for (; k < E; k += 4) { // four independent pair evaluations, composed as a tree: the dependent chain is E/4 + 2 composes, not E
                         const float4 v = *reinterpret_cast<const float4 *>(mine + k);
-                        const float vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                        for (int c = 0; c < 4; c++) {
-                            SeqPair q;
-                            if (!seq_pair(vv[c], e, q)) { ok = false; break; }
-                            pr = seq_compose(pr, q);
-                        }
+                        SeqPair q0, q1, q2, q3;
+                        const bool o0 = seq_pair(v.x, e, q0), o1 = seq_pair(v.y, e, q1), o2 = seq_pair(v.z, e, q2), o3 = seq_pair(v.w, e, q3);
+                        ok = ok && o0 && o1 && o2 && o3; // composing an invalid pair is harmless: the result is discarded
+                        pr = seq_compose(pr, seq_compose(seq_compose(q0, q1), seq_compose(q2, q3)));
                     }
                 for (; ok && k < E; k++) {
                     SeqPair q;

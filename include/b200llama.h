@@ -213,8 +213,8 @@ int b200_profile_norm(b200_plan *plan, int64_t *cycles);
  * (csrc/seqsum.cuh; the RMSNorm accumulator of InferenceCore.java:39-48): sums n <= 8192
  * non-negative host floats on the device exactly as `for (i) s += t[i]` would. */
 int b200_test_seqsum(const float *terms, int32_t n, float *out, int32_t *info /* nullable: {entries, first fallback element or -1} */);
-/* Same contract for the round-2 accumulator (csrc/seqsum2.cuh) run by `threads` = 1024 (the RMSNorm kernel's form) or 256
- * (the persistent decode kernel's form) threads; info = {items walked, fallbacks}. */
+/* Same contract for the round-2 accumulator (csrc/seqsum2.cuh) run by `threads` = 1024 (the RMSNorm kernel's form), 512
+ * (the persistent decode kernel's form) or 256 threads; info = {items walked, fallbacks}. */
 int b200_test_seqsum2(const float *terms, int32_t n, int32_t threads, float *out, int32_t *info /* nullable */);
 
 /* Batched-prefill GEMM building block (csrc/prefill_gemm.cuh; replaces the reference's mma.sync GEMMs
