@@ -344,7 +344,7 @@ def main():
                      "algorithmic_bytes_per_token": ab, "traffic": traffic,
                      "persistent_kernel": {"ring_stages": ring_stages, "smem_bytes": pd_smem} if persistent else None,
                      "other_kernels": per_kernel},
-        "load": {"synthesise_s": gen_s, "upload_repack_s": load_s, "device_bytes": plan.device_bytes},
+        "load": {"synthesise_s": gen_s, "upload_repack_s": load_s, "device_bytes": plan.device_bytes, "pipeline": plan.upload_info()},
     }
     if not args.no_cpu:
         orc = ge.import_oracle()

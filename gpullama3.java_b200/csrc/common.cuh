@@ -64,8 +64,8 @@ __device__ __noinline__ void tp_wait(const TpCtx &t, int slot, unsigned seq) {
     unsigned long long t0 = 0;
     for (int k = 0; k < t.n; k++) {
         for (;;) {
-            unsigned v;
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f + k) : "memory");
+            unsigned v; // relaxed polls, ONE acquire fence after the last flag: ld.acquire in the loop is a load + CCTL.IVALL (an L1 flush per poll)
+            asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f + k) : "memory");
             if ((int)(v - seq) >= 0) break;
             if ((++it & 255u) == 0u && t.err) {
                 if (*reinterpret_cast<volatile unsigned *>(t.err)) return;
@@ -79,6 +79,7 @@ __device__ __noinline__ void tp_wait(const TpCtx &t, int slot, unsigned seq) {
             }
         }
     }
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
 }
 __device__ __forceinline__ void tp_signal(const TpCtx &t, int slot, unsigned seq) { // one thread, after the data stores
     __threadfence_system();

@@ -15,7 +15,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <chrono>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -29,8 +31,31 @@ struct LayerW {
 
 } // namespace
 
+// Weight upload pipeline (replaces the reference's lazy FIRST_EXECUTION copy-in, LlamaQ8_0FFNLayers.java:122-132,
+// timed by TornadoVMMasterPlanSingleToken.java:51-54): pageable/mmapped host bytes -> pinned double buffer (several host
+// threads) -> async H2D on a copy stream -> device staging (double buffered) -> repack kernel on the plan's stream.  The host
+// copy of chunk i+1, the DMA of chunk i and the repack of the previous matrix overlap; nothing synchronises per matrix.
+struct Uploader {
+    bool on = false;
+    cudaStream_t copy = nullptr;
+    unsigned char *pin[2] = {nullptr, nullptr};
+    size_t pin_bytes = 0;
+    cudaEvent_t pin_done[2] = {nullptr, nullptr};
+    bool pin_used[2] = {false, false};
+    int pi = 0;
+    unsigned char *dst[2] = {nullptr, nullptr};
+    size_t dst_bytes = 0;
+    cudaEvent_t d_ready[2] = {nullptr, nullptr}, d_free[2] = {nullptr, nullptr};
+    bool d_used[2] = {false, false};
+    int di = 0;
+    int threads = 4;
+    double host_copy_s = 0.0, total_s = 0.0;
+    int64_t h2d_bytes = 0;
+};
+
 struct b200_plan {
     b200_config cfg{};
+    Uploader up;
     int device = 0;
     int wtype = 0; // B200_GGML_Q8_0 or B200_GGML_F16 (matrix type)
     int qd = 0, kvd = 0;
@@ -141,6 +166,96 @@ template <typename T> int dalloc(b200_plan *p, T **ptr, size_t n_bytes) {
     return B200_OK;
 }
 
+void par_memcpy(void *dst, const void *src, size_t n, int threads) {
+    if (threads <= 1 || n < (size_t)(4u << 20)) { memcpy(dst, src, n); return; }
+    std::vector<std::thread> th;
+    const size_t per = ((n + threads - 1) / threads + 4095) & ~(size_t)4095;
+    for (int i = 0; i < threads; i++) {
+        const size_t o = (size_t)i * per;
+        if (o >= n) break;
+        const size_t m = n - o < per ? n - o : per;
+        th.emplace_back([=] { memcpy((unsigned char *)dst + o, (const unsigned char *)src + o, m); });
+    }
+    for (auto &t : th) t.join();
+}
+
+int up_init(b200_plan *p, size_t dst_bytes) {
+    Uploader &u = p->up;
+    const char *e = getenv("B200_UPLOAD_SYNC"); // =1: the round-1 path (one blocking copy + synchronize per matrix)
+    if (e && e[0] == '1') return B200_OK;
+    const char *t = getenv("B200_UPLOAD_THREADS");
+    u.threads = t ? atoi(t) : 4;
+    u.pin_bytes = (size_t)64 << 20;
+    u.dst_bytes = dst_bytes;
+    CK(cudaStreamCreateWithFlags(&u.copy, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        CK(cudaHostAlloc((void **)&u.pin[i], u.pin_bytes, cudaHostAllocDefault));
+        CK(cudaMalloc((void **)&u.dst[i], dst_bytes));
+        CK(cudaEventCreateWithFlags(&u.pin_done[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&u.d_ready[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&u.d_free[i], cudaEventDisableTiming));
+    }
+    u.on = true;
+    return B200_OK;
+}
+
+void up_destroy(b200_plan *p) {
+    Uploader &u = p->up;
+    if (u.copy) cudaStreamSynchronize(u.copy);
+    for (int i = 0; i < 2; i++) {
+        if (u.pin[i]) cudaFreeHost(u.pin[i]);
+        if (u.dst[i]) cudaFree(u.dst[i]);
+        if (u.pin_done[i]) cudaEventDestroy(u.pin_done[i]);
+        if (u.d_ready[i]) cudaEventDestroy(u.d_ready[i]);
+        if (u.d_free[i]) cudaEventDestroy(u.d_free[i]);
+        u.pin[i] = nullptr; u.dst[i] = nullptr; u.pin_done[i] = u.d_ready[i] = u.d_free[i] = nullptr;
+    }
+    if (u.copy) cudaStreamDestroy(u.copy);
+    u.copy = nullptr;
+    u.on = false;
+}
+
+// host bytes -> device, through the pinned double buffer, on the copy stream (asynchronous with respect to the caller except
+// for the wait on a pinned buffer still in flight)
+int up_h2d(b200_plan *p, void *dst, const void *src, size_t bytes) {
+    Uploader &u = p->up;
+    for (size_t o = 0; o < bytes; o += u.pin_bytes) {
+        const size_t n = bytes - o < u.pin_bytes ? bytes - o : u.pin_bytes;
+        const int i = u.pi;
+        if (u.pin_used[i]) CK(cudaEventSynchronize(u.pin_done[i]));
+        const auto t0 = std::chrono::steady_clock::now();
+        par_memcpy(u.pin[i], (const unsigned char *)src + o, n, u.threads);
+        u.host_copy_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        CK(cudaMemcpyAsync((unsigned char *)dst + o, u.pin[i], n, cudaMemcpyHostToDevice, u.copy));
+        CK(cudaEventRecord(u.pin_done[i], u.copy));
+        u.pin_used[i] = true;
+        u.pi ^= 1;
+        u.h2d_bytes += (int64_t)n;
+    }
+    return B200_OK;
+}
+// device staging buffer protocol: begin (copy stream waits until the repack that last read this buffer is done) -> h2d... ->
+// ready (plan stream waits for the copies) -> [repack kernel on the plan stream] -> release
+int up_stage_begin(b200_plan *p, unsigned char **stage) {
+    Uploader &u = p->up;
+    if (u.d_used[u.di]) CK(cudaStreamWaitEvent(u.copy, u.d_free[u.di], 0));
+    *stage = u.dst[u.di];
+    return B200_OK;
+}
+int up_stage_ready(b200_plan *p) {
+    Uploader &u = p->up;
+    CK(cudaEventRecord(u.d_ready[u.di], u.copy));
+    CK(cudaStreamWaitEvent(p->stream, u.d_ready[u.di], 0));
+    return B200_OK;
+}
+int up_stage_release(b200_plan *p) {
+    Uploader &u = p->up;
+    CK(cudaEventRecord(u.d_free[u.di], p->stream));
+    u.d_used[u.di] = true;
+    u.di ^= 1;
+    return B200_OK;
+}
+
 // GGUF Q8_0 blocks (f16 scale + 32 int8, 34 bytes, GGMLType.java:13) -> split planes.
 // One thread per 16-bit word of the raw stream: word 0 of each block is the scale.
 __global__ void k_repack_q8(const uint16_t *__restrict__ raw, uint16_t *__restrict__ qs, uint16_t *__restrict__ sc,
@@ -181,18 +296,28 @@ int upload_matrix(b200_plan *p, const b200_tensor *t, int rows, int cols, DevMat
         int8_t *qs = (int8_t *)dst.qs + (size_t)row_off * cols;
         __half *sc = (__half *)dst.sc + (size_t)row_off * (cols / 32);
         // chunked through the staging buffer (multiple of 34 bytes)
+        if (p->up.on) stage_bytes = p->up.dst_bytes;
         size_t blk_per_chunk = stage_bytes / 34;
         for (size_t b0 = 0; b0 < nblk; b0 += blk_per_chunk) {
             size_t nb = nblk - b0 < blk_per_chunk ? nblk - b0 : blk_per_chunk;
-            CK(cudaMemcpyAsync(stage, (const uint8_t *)t->data + b0 * 34, nb * 34, cudaMemcpyHostToDevice, p->stream));
+            int rc;
+            if (p->up.on) {
+                unsigned char *stg = nullptr;
+                if ((rc = up_stage_begin(p, &stg))) return rc;
+                if ((rc = up_h2d(p, stg, (const uint8_t *)t->data + b0 * 34, nb * 34))) return rc;
+                if ((rc = up_stage_ready(p))) return rc;
+                stage = stg;
+            } else CK(cudaMemcpyAsync(stage, (const uint8_t *)t->data + b0 * 34, nb * 34, cudaMemcpyHostToDevice, p->stream));
             size_t words = nb * 17;
             k_repack_q8<<<(unsigned)((words + 255) / 256), 256, 0, p->stream>>>((const uint16_t *)stage, (uint16_t *)(qs + b0 * 32),
                                                                                   (uint16_t *)(sc + b0), words);
             CK(cudaGetLastError());
-            CK(cudaStreamSynchronize(p->stream)); // staging buffer is reused
+            if (p->up.on) { if ((rc = up_stage_release(p))) return rc; }
+            else CK(cudaStreamSynchronize(p->stream)); // staging buffer is reused
         }
     } else {
         size_t esz = dst.type == B200_GGML_F16 ? 2 : 4;
+        if (p->up.on) return up_h2d(p, (uint8_t *)dst.qs + (size_t)row_off * cols * esz, t->data, (size_t)rows * cols * esz); // ordered by the final synchronize
         CK(cudaMemcpy((uint8_t *)dst.qs + (size_t)row_off * cols * esz, t->data, (size_t)rows * cols * esz, cudaMemcpyHostToDevice));
     }
     return B200_OK;
@@ -205,22 +330,34 @@ int upload_tiles(b200_plan *p, const b200_tensor *t0, const b200_tensor *t1, con
     int rs[3] = {r0, r1, r2};
     RepackSrc src;
     size_t off = 0;
+    int rc;
+    if (p->up.on) {
+        unsigned char *stg = nullptr;
+        if ((rc = up_stage_begin(p, &stg))) return rc;
+        stage = stg;
+        stage_bytes = p->up.dst_bytes;
+    }
     for (int k = 0; k < 3; k++) {
         src.raw[k] = nullptr;
         src.rows[k] = rs[k];
-        src.row0[k] = row0 ? row0[k] : 0;
+        src.row0[k] = 0; // only this rank's row range [row0, row0 + rows) crosses PCIe (rows are contiguous in GGUF)
         if (rs[k] == 0) continue;
         const int full_rows = full ? full[k] : rs[k];
+        const int first = row0 ? row0[k] : 0;
         const b200_tensor *t = ts[k];
         if (!t) return fail(p, B200_ERR_BAD_ARG, "missing tensor");
         if (t->ggml_type != B200_GGML_Q8_0) return fail(p, B200_ERR_UNSUPPORTED, "tensor %s has ggml type %d, plan weight type is Q8_0", t->name, t->ggml_type);
         if (n_elems(t) != (int64_t)full_rows * cols) return fail(p, B200_ERR_BAD_ARG, "tensor %s has %lld elements, expected %lld", t->name, (long long)n_elems(t), (long long)full_rows * cols);
-        size_t nbytes = (size_t)full_rows * cols / 32 * 34;
+        if (first < 0 || first + rs[k] > full_rows) return fail(p, B200_ERR_BAD_ARG, "row range of tensor %s out of bounds", t->name);
+        const size_t row_bytes = (size_t)cols / 32 * 34, nbytes = (size_t)rs[k] * row_bytes;
+        const unsigned char *hsrc = (const unsigned char *)t->data + (size_t)first * row_bytes;
         if (off + nbytes > stage_bytes) return fail(p, B200_ERR_STATE, "staging buffer too small");
-        CK(cudaMemcpyAsync((unsigned char *)stage + off, t->data, nbytes, cudaMemcpyHostToDevice, p->stream));
+        if (p->up.on) { if ((rc = up_h2d(p, (unsigned char *)stage + off, hsrc, nbytes))) return rc; }
+        else CK(cudaMemcpyAsync((unsigned char *)stage + off, hsrc, nbytes, cudaMemcpyHostToDevice, p->stream));
         src.raw[k] = (const unsigned char *)stage + off;
         off += (nbytes + 255) & ~(size_t)255;
     }
+    if (p->up.on && (rc = up_stage_ready(p))) return rc;
     src.gateup = gateup ? 1 : 0;
     const int rows = gateup ? r0 + r1 : r0 + r1 + r2;
     out.rows = rows;
@@ -230,11 +367,12 @@ int upload_tiles(b200_plan *p, const b200_tensor *t0, const b200_tensor *t1, con
     out.unit_bytes = smv_unit_bytes(out.seg);
     size_t total = (size_t)rows * out.nseg * out.unit_bytes;
     unsigned char *d;
-    int rc = dalloc(p, &d, total);
+    rc = dalloc(p, &d, total);
     if (rc) return rc;
     out.base = d;
     k_repack_tiles<<<(unsigned)((size_t)rows * out.nseg), 128, 0, p->stream>>>(src, d, rows, cols, out.seg, out.nseg, out.unit_bytes);
     CK(cudaGetLastError());
+    if (p->up.on) return up_stage_release(p);
     CK(cudaStreamSynchronize(p->stream));
     return B200_OK;
 }
@@ -683,8 +821,10 @@ int build(b200_plan *p, const b200_tensor *tensors, int n_tensors) {
         size_t need = mx / 32 * 34 + 4096;
         if (need > stage_bytes) stage_bytes = need;
     }
-    if (p->wtype == B200_GGML_Q8_0 || emb->ggml_type == B200_GGML_Q8_0) CK(cudaMalloc(&stage, stage_bytes));
-    struct StageGuard { void *s; ~StageGuard() { if (s) cudaFree(s); } } guard{stage};
+    const auto t_up0 = std::chrono::steady_clock::now();
+    if ((rc = up_init(p, stage_bytes))) return rc; // pipelined upload (B200_UPLOAD_SYNC=1: the blocking round-1 path)
+    if (!p->up.on && (p->wtype == B200_GGML_Q8_0 || emb->ggml_type == B200_GGML_Q8_0)) CK(cudaMalloc(&stage, stage_bytes));
+    struct StageGuard { void *s; b200_plan *pl; ~StageGuard() { if (s) cudaFree(s); up_destroy(pl); } } guard{stage, p};
 
     // embedding table (+ tied classifier: AbstractModelLoader.java:186-195)
     if ((rc = alloc_matrix(p, p->emb, c.vocab_size, c.dim, emb->ggml_type))) return rc;
@@ -747,6 +887,19 @@ int build(b200_plan *p, const b200_tensor *tensors, int n_tensors) {
         if ((rc = upload_matrix(p, T("ffn_down.weight"), c.dim, c.hidden_dim, L.w2, 0, stage, stage_bytes))) return rc;
     }
 
+    if (p->up.on) { // drain the pipeline: every copy and every repack has finished before the first forward
+        CK(cudaStreamSynchronize(p->up.copy));
+        CK(cudaStreamSynchronize(p->stream));
+    }
+    p->up.total_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_up0).count();
+    {
+        const double hs = p->up.host_copy_s, ts = p->up.total_s;
+        const int64_t hb = p->up.h2d_bytes;
+        const bool was_on = p->up.on;
+        up_destroy(p); // pinned buffers and device staging are not needed any more
+        p->up.host_copy_s = hs; p->up.total_s = ts; p->up.h2d_bytes = hb; p->up.on = false;
+        (void)was_on;
+    }
     // RoPE table exactly as RoPE.precomputeFreqsCis (RoPE.java:6-37, ropeScaling=false):
     // freq = (float)(1.0 / Math.pow(theta, i / (double) headSize)); val = pos * freq (float);
     // cos/sin evaluated in double and narrowed.
@@ -1509,37 +1662,38 @@ int b200_gemm_f16(const uint16_t *a, const uint16_t *b, float *c, int32_t m, int
     if (!a || !b || !c || m <= 0 || n <= 0 || k <= 0 || m % 128 || n % 128 || k % 64) return B200_ERR_BAD_ARG;
     __half *da = nullptr, *db = nullptr;
     float *dc = nullptr;
-    if (cudaMalloc(&da, (size_t)m * k * 2) != cudaSuccess || cudaMalloc(&db, (size_t)n * k * 2) != cudaSuccess ||
-        cudaMalloc(&dc, (size_t)m * n * 4) != cudaSuccess) {
-        cudaFree(da); cudaFree(db); cudaFree(dc);
-        return B200_ERR_OOM;
-    }
-    cudaMemcpy(da, a, (size_t)m * k * 2, cudaMemcpyHostToDevice);
-    cudaMemcpy(db, b, (size_t)n * k * 2, cudaMemcpyHostToDevice);
-    cudaMemset(dc, resid ? 0 : 0xFF, (size_t)m * n * 4);
-    int rc = pg::gemm_f16(da, db, dc, m, n, k, stages, resid, two_cta, 0);
-    cudaError_t e = cudaDeviceSynchronize();
-    if (rc == 0 && e == cudaSuccess && iters > 0 && ms) {
-        cudaEvent_t e0, e1;
-        cudaEventCreate(&e0); cudaEventCreate(&e1);
-        cudaEventRecord(e0, 0);
-        for (int i = 0; i < iters; i++) pg::gemm_f16(da, db, dc, m, n, k, stages, resid, two_cta, 0);
-        cudaEventRecord(e1, 0);
-        e = cudaEventSynchronize(e1);
-        float t = 0.f;
-        cudaEventElapsedTime(&t, e0, e1);
-        *ms = t / iters;
-        cudaEventDestroy(e0); cudaEventDestroy(e1);
-        if (resid) { // C accumulated 1 + iters products: return exactly one
-            cudaMemset(dc, 0, (size_t)m * n * 4);
-            pg::gemm_f16(da, db, dc, m, n, k, stages, resid, two_cta, 0);
-            e = cudaDeviceSynchronize();
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int rc = B200_OK;
+    auto ok = [&](cudaError_t e) { if (e != cudaSuccess && rc == B200_OK) rc = e == cudaErrorMemoryAllocation ? B200_ERR_OOM : B200_ERR_CUDA; return rc == B200_OK; }; // first failure wins
+    if (ok(cudaMalloc(&da, (size_t)m * k * 2)) && ok(cudaMalloc(&db, (size_t)n * k * 2)) && ok(cudaMalloc(&dc, (size_t)m * n * 4)) &&
+        ok(cudaMemcpy(da, a, (size_t)m * k * 2, cudaMemcpyHostToDevice)) && ok(cudaMemcpy(db, b, (size_t)n * k * 2, cudaMemcpyHostToDevice)) &&
+        ok(cudaMemset(dc, resid ? 0 : 0xFF, (size_t)m * n * 4))) {
+        if (pg::gemm_f16(da, db, dc, m, n, k, stages, resid, two_cta, 0)) rc = B200_ERR_CUDA;
+        ok(cudaDeviceSynchronize());
+        if (rc == B200_OK && iters > 0 && ms && ok(cudaEventCreate(&e0)) && ok(cudaEventCreate(&e1)) && ok(cudaEventRecord(e0, 0))) {
+            for (int i = 0; i < iters && rc == B200_OK; i++)
+                if (pg::gemm_f16(da, db, dc, m, n, k, stages, resid, two_cta, 0)) rc = B200_ERR_CUDA;
+            float t = 0.f;
+            if (ok(cudaEventRecord(e1, 0)) && ok(cudaEventSynchronize(e1)) && ok(cudaEventElapsedTime(&t, e0, e1))) *ms = t / iters;
+            if (rc == B200_OK && resid) { // C accumulated 1 + iters products: return exactly one
+                if (ok(cudaMemset(dc, 0, (size_t)m * n * 4)) && pg::gemm_f16(da, db, dc, m, n, k, stages, resid, two_cta, 0)) rc = B200_ERR_CUDA;
+                ok(cudaDeviceSynchronize());
+            }
         }
+        if (rc == B200_OK) ok(cudaMemcpy(c, dc, (size_t)m * n * 4, cudaMemcpyDeviceToHost));
     }
-    if (rc == 0 && e == cudaSuccess) e = cudaMemcpy(c, dc, (size_t)m * n * 4, cudaMemcpyDeviceToHost);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
     cudaFree(da); cudaFree(db); cudaFree(dc);
-    if (rc) return B200_ERR_CUDA;
-    return e == cudaSuccess ? B200_OK : B200_ERR_CUDA;
+    return rc;
+}
+
+int b200_upload_info(b200_plan *p, double *seconds, double *host_copy_seconds, int64_t *h2d_bytes) {
+    if (!p) return B200_ERR_BAD_ARG;
+    if (seconds) *seconds = p->up.total_s;
+    if (host_copy_seconds) *host_copy_seconds = p->up.host_copy_s;
+    if (h2d_bytes) *h2d_bytes = p->up.h2d_bytes;
+    return B200_OK;
 }
 
 int b200_launches_per_decode(b200_plan *p) {

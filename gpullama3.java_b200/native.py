@@ -40,7 +40,7 @@ class Tensor(C.Structure):
 
 
 EXPORTS = ["b200_plan_create", "b200_forward_decode", "b200_forward_prefill", "b200_forward_batch_prefill", "b200_set_prefill_mode", "b200_prefill_info",
-           "b200_set_decode_mode", "b200_decode_info", "b200_trace_persistent", "b200_test_seqsum2", "b200_forward_decode_sample",
+           "b200_set_decode_mode", "b200_decode_info", "b200_trace_persistent", "b200_test_seqsum2", "b200_forward_decode_sample", "b200_upload_info",
            "b200_decode_sequence", "b200_time_kernel", "b200_tp_handle", "b200_tp_attach", "b200_trace_decode", "b200_profile_norm", "b200_test_seqsum", "b200_gemm_f16", "b200_kv_reset", "b200_read_buffer", "b200_launches_per_decode",
            "b200_device_bytes", "b200_plan_free", "b200_last_error", "b200_version"]
 
@@ -77,6 +77,7 @@ def lib() -> C.CDLL:
     L.b200_gemm_f16.argtypes = [vp, vp, vp, i32, i32, i32, i32, C.POINTER(C.c_float)]
     L.b200_time_kernel.argtypes = [vp, i32, i32, C.POINTER(C.c_float), C.POINTER(C.c_int64)]
     L.b200_read_buffer.argtypes = [vp, C.c_char_p, i32, vp, C.c_size_t]
+    L.b200_upload_info.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     L.b200_launches_per_decode.argtypes = [vp]
     L.b200_device_bytes.argtypes = [vp]
     L.b200_device_bytes.restype = C.c_int64
@@ -239,6 +240,12 @@ class NativePlan:
         out = np.empty(n, dtype=dtype)
         self._ck(lib().b200_read_buffer(self._p, name.encode(), layer, out.ctypes.data, out.nbytes))
         return out
+
+    def upload_info(self) -> dict:
+        a, b, c = C.c_double(0), C.c_double(0), C.c_int64(0)
+        self._ck(lib().b200_upload_info(self._p, C.byref(a), C.byref(b), C.byref(c)))
+        return {"seconds": a.value, "host_copy_seconds": b.value, "h2d_bytes": c.value,
+                "GB/s": (c.value / a.value / 1e9) if a.value > 0 else None}
 
     @property
     def launches_per_decode(self) -> int:

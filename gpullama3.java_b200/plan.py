@@ -156,6 +156,10 @@ class B200MasterPlan:
     def read_buffer(self, *a, **kw):
         return self._native.read_buffer(*a, **kw)
 
+    def upload_info(self):
+        """Seconds / bytes of the weight upload pipeline of plan creation (load-time metric, ModelLoader.java:102-106)."""
+        return self._native.upload_info()
+
     @property
     def launches_per_decode(self):
         return self._native.launches_per_decode

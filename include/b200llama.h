@@ -224,6 +224,13 @@ int b200_test_seqsum2(const float *terms, int32_t n, int32_t threads, float *out
  * iters > 0 additionally times `iters` back-to-back launches (device events) into *ms. */
 int b200_gemm_f16(const uint16_t *a, const uint16_t *b, float *c, int32_t m, int32_t n, int32_t k, int32_t iters, float *ms /* nullable */);
 
+/* Weight upload of b200_plan_create (the counterpart of the reference's load-time metrics, ModelLoader.java:102-106 and the
+ * copy-in timing of TornadoVMMasterPlanSingleToken.java:51-54): wall seconds from the first tensor to the last repack kernel,
+ * seconds the host spent copying mapped/pageable bytes into the pinned double buffer, and bytes sent over PCIe (a tensor-parallel
+ * rank sends only its row ranges).  The pipeline: pinned double buffer filled by several host threads -> async H2D on a copy
+ * stream -> double-buffered device staging -> repack kernel on the plan's stream; B200_UPLOAD_SYNC=1 selects blocking copies. */
+int b200_upload_info(b200_plan *plan, double *seconds, double *host_copy_seconds, int64_t *h2d_bytes);
+
 /* Number of kernels one decode step launches (bench.py's gpu_launches). */
 int b200_launches_per_decode(b200_plan *plan);
 

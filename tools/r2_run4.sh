@@ -16,6 +16,10 @@ except Exception as e:
 }
 {
   nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader
+  echo "== 0. upload pipeline smoke (falls back to B200_UPLOAD_SYNC=1 for the rest of this script if it fails)"
+  if ! timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -k "q8_bit_exact and tiny-llama-graph" 2>&1 | tail -3 | grep -q "1 passed"; then
+    echo "UPLOAD PIPELINE FAILED -> B200_UPLOAD_SYNC=1"; export B200_UPLOAD_SYNC=1
+  fi
   echo "== 1. parity file (both decode modes)"
   timeout 1200 python -m pytest tests/test_gpu_parity.py -x -q 2>&1 | tail -4
   echo "== 2. bench"
