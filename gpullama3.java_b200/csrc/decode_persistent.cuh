@@ -35,7 +35,7 @@
 #define PD_THREADS (PD_CT + 32)         // + the producer warp
 #define PD_MAX_STAGES 32
 #define PD_TIMEOUT_NS 4000000000ull    // 4 s: far beyond any legitimate wait, well under gpurun's limits
-#define PD_STAMPS 16                    // trace stamps per layer and CTA (0-9 phases, 10-15 inside the attn norm / the attention)
+#define PD_STAMPS 20                    // trace stamps per layer and CTA (0-9 phases, 10-15 inside the attn norm / the attention)
 
 enum { PD_S_QKV = 0, PD_S_ATT = 1, PD_S_WO = 2, PD_S_GU = 3, PD_S_W2 = 4, PD_S_LM = 5, PD_S_ARG = 6, PD_S_SLOTS = 8,
        PD_S_TICK = 8, PD_S_LMTICK = 9, PD_S_ERR = 10, PD_S_WORDS = 16 };
@@ -174,7 +174,7 @@ struct PdConsumerSync {
 // Every consumer thread calls these.  `cross`: the phase's outputs are consumed by other ranks too (tensor parallelism):
 // the CTA's peer stores (made before the barrier) are published by thread 0's system-scope fence, and the LAST local
 // arriver raises this rank's epoch flag on every rank.
-__device__ __forceinline__ void pd_arrive(const PdArgs &a, int slot, unsigned target, unsigned epoch, bool cross, int tid) {
+__device__ __noinline__ void pd_arrive(const PdArgs &a, int slot, unsigned target, unsigned epoch, bool cross, int tid) {
     pd_bar_sync();
     if (tid == 0) {
         const bool x = cross && a.tp.n > 1;
@@ -190,7 +190,7 @@ __device__ __forceinline__ void pd_arrive(const PdArgs &a, int slot, unsigned ta
         }
     }
 }
-__device__ __forceinline__ void pd_wait(const PdArgs &a, int slot, unsigned target, unsigned epoch, bool cross, int tid) {
+__device__ __noinline__ void pd_wait(const PdArgs &a, int slot, unsigned target, unsigned epoch, bool cross, int tid) {
     if (tid == 0) {
         if (cross && a.tp.n > 1) {
             const unsigned *f = reinterpret_cast<const unsigned *>(a.tp.peer[a.tp.rank] + a.pd_flags_off) + slot * TP_MAX;
@@ -301,6 +301,34 @@ __device__ __forceinline__ void pd_produce(const PdArgs &a, unsigned char *smem,
     }
 }
 
+// Fat scalar helpers kept OUT OF LINE: the kernel's phases execute on a cold instruction cache every layer (the loop body of a
+// layer is several times the cache), so static code size and taken branches cost more than call overhead.
+__device__ __noinline__ float pd_walk_rolled(float acc, const float *t, int nbs) { // strictly in block order (Q8_0FloatTensor.java:117-121)
+    int b = 0;
+    if (nbs >= 4) {
+        float4 c = *reinterpret_cast<const float4 *>(t);
+#pragma unroll 1
+        for (; b + 4 <= nbs; b += 4) {
+            float4 n = c;
+            if (b + 8 <= nbs) n = *reinterpret_cast<const float4 *>(t + b + 4); // next four terms in flight during the adds
+            acc = __fadd_rn(acc, c.x); acc = __fadd_rn(acc, c.y); acc = __fadd_rn(acc, c.z); acc = __fadd_rn(acc, c.w);
+            c = n;
+        }
+    }
+#pragma unroll 1
+    for (; b < nbs; b++) acc = __fadd_rn(acc, t[b]);
+    return acc;
+}
+__device__ __noinline__ float pd_swiglu(float g, float u) { return swiglu_exact(g, u); }
+__device__ __noinline__ int pd_quant_block(float v, float *ascale) {
+    float as;
+    const int q = quant_block_lane(v, as);
+    *ascale = as;
+    return q;
+}
+__device__ __noinline__ float pd_emb_get(const DevMat &e, int token, int i) { return emb_get(e, token, i); }
+__device__ __noinline__ float pd_exp_narrow(float x) { return (float)exp((double)x); } // (float) Math.exp(double)
+
 // ---- consumers: one matrix (the loop of k_stream_matvec_q8, activation already in shared memory) --------------------------
 // l0_emb: layer 0's Wo writes x = embedding + acc (the embedding row is never copied into x beforehand).
 // row_base: global index of this rank's first output row (RESID, STORE/argmax) or hidden unit (GATEUP).
@@ -339,7 +367,7 @@ __device__ __noinline__ void pd_consume_matrix(const TileMat &W, const PdArgs &a
                 __syncwarp();
                 mbar_wait(bar0 + 8 * st, lap & 1u);
                 const unsigned char *tile = ring + (size_t)st * stage_bytes;
-#pragma unroll 2
+#pragma unroll 1
                 for (int b = lane; b < nbs; b += 32) {
                     const unsigned char *ab = sact + ((size_t)(s * nbs + b) << 5);
                     const int4 a0 = *reinterpret_cast<const int4 *>(ab + 16 * hsel);
@@ -367,14 +395,14 @@ __device__ __noinline__ void pd_consume_matrix(const TileMat &W, const PdArgs &a
                     rel[st] = lap + 1u;
                     mbar_arrive(bar0 + 8 * (PD_MAX_STAGES + st));
                 }
-                if (lane < 4) acc = pd_walk_terms(acc, terms + lane * tstride, nbs); // strictly in block order
+                if (lane < 4) acc = pd_walk_rolled(acc, terms + lane * tstride, nbs);
                 __syncwarp();
             }
             if (MODE == SMV_GATEUP) {
                 const float up = __shfl_down_sync(0xffffffffu, acc, 2);
                 if (lane < 2) {
                     const int unit = 2 * G + lane;
-                    const float hval = swiglu_exact(acc, up);
+                    const float hval = pd_swiglu(acc, up);
                     out[unit] = hval;
                     hvals[unit - 2 * g0] = hval;
                 }
@@ -382,7 +410,7 @@ __device__ __noinline__ void pd_consume_matrix(const TileMat &W, const PdArgs &a
                 const size_t row = (size_t)4 * G + lane;
                 if (MODE == SMV_RESID) {
                     const size_t grow = (size_t)row_base + row;
-                    const float base = l0_emb ? emb_get(a.emb, token, (int)grow) : out[grow];
+                    const float base = l0_emb ? pd_emb_get(a.emb, token, (int)grow) : out[grow];
                     const float v = __fadd_rn(base, acc); // x[i] = x[i] + xb2[i]
                     if (tp_n > 1) { // all-gather of the residual stream: this rank's rows go to every rank
                         for (int k = 0; k < tp_n; k++) tp_ptr<float>(a.tp, k, a.tp.off_x)[grow] = v;
@@ -421,7 +449,7 @@ __device__ __noinline__ void pd_consume_matrix(const TileMat &W, const PdArgs &a
                 }
                 if (mine) {
                     float as;
-                    const int q = quant_block_lane(v, as);
+                    const int q = pd_quant_block(v, &as);
                     const int gblk = (row_base >> 5) + blk;
                     if (a.tp.n > 1) {
                         for (int k = 0; k < a.tp.n; k++) {
@@ -494,7 +522,7 @@ __device__ __noinline__ void pd_norm_u(const PdArgs &a, const float *wbuf, bool 
         xv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (i4 < n4) {
             if (from_emb) { // first layer: the embedding row (quantised table: element-wise, FloatTensor.copyTo)
-                xv[u] = make_float4(emb_get(a.emb, token, 4 * i4), emb_get(a.emb, token, 4 * i4 + 1), emb_get(a.emb, token, 4 * i4 + 2), emb_get(a.emb, token, 4 * i4 + 3));
+                xv[u] = make_float4(pd_emb_get(a.emb, token, 4 * i4), pd_emb_get(a.emb, token, 4 * i4 + 1), pd_emb_get(a.emb, token, 4 * i4 + 2), pd_emb_get(a.emb, token, 4 * i4 + 3));
             } else xv[u] = pd_ldcg128(a.x + 4 * i4);
         }
     }
@@ -667,7 +695,7 @@ __device__ __noinline__ void pd_attention_head(const PdArgs &a, const PdLayer &L
             for (int j = 0; j < HS; j++) acc = __fadd_rn(acc, __fmul_rn(sq[j], sk[j]));
         } else {
             const float4 *k = reinterpret_cast<const float4 *>(kc + (size_t)t * kvd + kvh * HS);
-#pragma unroll
+#pragma unroll 1
             for (int j0 = 0; j0 < HS / 4; j0 += 16) { // 16 x 16 bytes in flight per thread: two L2 round trips per key at head size 128
                 float4 kk[16];
 #pragma unroll
@@ -693,7 +721,7 @@ __device__ __noinline__ void pd_attention_head(const PdArgs &a, const PdLayer &L
     float mx = red[0];
 #pragma unroll
     for (int w = 1; w < PD_WARPS; w++) mx = fmaxf(mx, red[w]);
-    for (int t = tid; t < nt; t += PD_CT) att[t] = (float)exp((double)__fsub_rn(att[t], mx));
+    for (int t = tid; t < nt; t += PD_CT) att[t] = pd_exp_narrow(__fsub_rn(att[t], mx));
     pd_bar_sync();
     // sequential float sum (FloatTensor.softmaxInPlace, FloatTensor.java:211-219): short rows by one thread (16-byte loads ahead of
     // the add chain), long rows with the exact parallel accumulator (the terms are non-negative)
@@ -716,12 +744,12 @@ __device__ __noinline__ void pd_attention_head(const PdArgs &a, const PdLayer &L
         float acc = 0.0f;
         const float vcur = ldcg_f32c(vsrc + tid); // the current position's v, straight from the packed q|k|v vector
 #pragma unroll 1
-        for (int t0 = 0; t0 < pos; t0 += 32) { // 32 rows in flight per thread: one L2 round trip per 32 keys (the add chain itself is 4 cycles per key)
-            float vv[32];
+        for (int t0 = 0; t0 < pos; t0 += 16) { // 16 rows in flight per thread (the add chain itself is 4 cycles per key)
+            float vv[16];
 #pragma unroll
-            for (int u = 0; u < 32; u++) vv[u] = t0 + u < pos ? __ldcg(v + (size_t)(t0 + u) * kvd) : 0.0f;
+            for (int u = 0; u < 16; u++) vv[u] = t0 + u < pos ? __ldcg(v + (size_t)(t0 + u) * kvd) : 0.0f;
 #pragma unroll
-            for (int u = 0; u < 32; u++)
+            for (int u = 0; u < 16; u++)
                 if (t0 + u < pos) acc = __fadd_rn(__fmul_rn(att[t0 + u], vv[u]), acc);
         }
         acc = __fadd_rn(__fmul_rn(att[pos], vcur), acc);
@@ -731,7 +759,7 @@ __device__ __noinline__ void pd_attention_head(const PdArgs &a, const PdLayer &L
     const int gh = a.head_base + h;
     for (int b = warp; b < HS / 32; b += PD_WARPS) {
         float as;
-        const int q = quant_block_lane(so[b * 32 + lane], as);
+        const int q = pd_quant_block(so[b * 32 + lane], &as);
         if (a.tp.n > 1) { // all-gather: this head's quantised output goes straight into every rank's buffer
             for (int k = 0; k < a.tp.n; k++) {
                 tp_ptr<int8_t>(a.tp, k, a.tp.off_attq)[gh * HS + b * 32 + lane] = (int8_t)q;
@@ -794,6 +822,13 @@ __global__ void __launch_bounds__(PD_THREADS, 1) k_decode_persistent(const __gri
             }
         }
         pd_norm_to_smem(a, wbufA, l == 0, token, smem, L, tid, l);
+        if (a.trace && l == 1) { // diagnostic (traced launch only): the same exact sum again, instruction cache warm -- stamps 16 -> 17 vs 10 -> 11
+            const int E = (a.dim + PD_CT - 1) / PD_CT;
+            pd_stamp(a, l, 16, tid);
+            const float again = pd_seqsum(reinterpret_cast<const float *>(smem + L.off_nbuf), a.dim, seqsum2_stride(E), smem, L, tid);
+            if (tid == 0) reinterpret_cast<float *>(smem + L.off_misc)[30] = again;
+            pd_stamp(a, l, 17, tid);
+        }
         pd_prefetch_w(Ly.ffn_norm, wbufF, a.dim, tid); // needed after the attention block
         pd_stamp(a, l, 1, tid);
         pd_consume_matrix<SMV_STORE>(Ly.qkv, a, smem, L, bar0, rel, seq_base, a.qkv, false, false, token, 0, tid);

@@ -56,8 +56,10 @@ __device__ __forceinline__ SeqSum2Scratch seqsum2_carve(unsigned char *p, int T 
 }
 
 // Segmented inclusive scan step set over one warp: f = 1 when the run containing this lane starts inside the covered range.
-__device__ __forceinline__ void seq2_warp_segscan(SeqPair &p, int &f, int lane) {
-#pragma unroll
+// (Code size matters more than instruction count here: these phases run once per call on a cold instruction cache, so every
+// loop is kept rolled and the helpers out of line -- a taken branch into code that is not cached costs more than the loop.)
+__device__ __noinline__ void seq2_warp_segscan(SeqPair &p, int &f, int lane) {
+#pragma unroll 1
     for (int d = 1; d < 32; d <<= 1) {
         const unsigned u0 = __shfl_up_sync(0xffffffffu, p.a0, d), u1 = __shfl_up_sync(0xffffffffu, p.a1, d);
         const int fu = __shfl_up_sync(0xffffffffu, f, d);
@@ -78,25 +80,29 @@ struct SeqSum2BlockSync {
 // thread t's terms live at sq[t * S .. t * S + E).  E = 16 -> 20, 8 -> 12, 32 -> 36, 4 -> 4.
 __host__ __device__ inline int seqsum2_stride(int E) { return (E % 4 == 0 && (E / 4) % 2 == 0) ? E + 4 : E; }
 
-// literal adds of one thread's E terms, 16-byte loads batched ahead of the dependent add chain
-__device__ __forceinline__ float seq2_literal(float s, const float *q, int E, bool vec) {
+// literal adds of one thread's E terms (16-byte loads when the layout allows)
+__device__ __noinline__ float seq2_literal(float s, const float *q, int E, bool vec) {
     int k = 0;
     if (vec) {
-        for (; k + 16 <= E; k += 16) {
-            const float4 v0 = *reinterpret_cast<const float4 *>(q + k), v1 = *reinterpret_cast<const float4 *>(q + k + 4);
-            const float4 v2 = *reinterpret_cast<const float4 *>(q + k + 8), v3 = *reinterpret_cast<const float4 *>(q + k + 12);
-            s = __fadd_rn(s, v0.x); s = __fadd_rn(s, v0.y); s = __fadd_rn(s, v0.z); s = __fadd_rn(s, v0.w);
-            s = __fadd_rn(s, v1.x); s = __fadd_rn(s, v1.y); s = __fadd_rn(s, v1.z); s = __fadd_rn(s, v1.w);
-            s = __fadd_rn(s, v2.x); s = __fadd_rn(s, v2.y); s = __fadd_rn(s, v2.z); s = __fadd_rn(s, v2.w);
-            s = __fadd_rn(s, v3.x); s = __fadd_rn(s, v3.y); s = __fadd_rn(s, v3.z); s = __fadd_rn(s, v3.w);
-        }
+#pragma unroll 1
         for (; k + 4 <= E; k += 4) {
             const float4 v = *reinterpret_cast<const float4 *>(q + k);
             s = __fadd_rn(s, v.x); s = __fadd_rn(s, v.y); s = __fadd_rn(s, v.z); s = __fadd_rn(s, v.w);
         }
     }
+#pragma unroll 1
     for (; k < E; k++) s = __fadd_rn(s, q[k]);
     return s;
+}
+
+// inclusive float prefix over the 32 lanes of a warp (predictor only: plain adds)
+__device__ __noinline__ float seq2_warp_scan_f(float v, int lane) {
+#pragma unroll 1
+    for (int d = 1; d < 32; d <<= 1) {
+        const float u = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += u;
+    }
+    return v;
 }
 
 // sq: n terms, thread t's E = ceil(n / T) consecutive terms at sq[t * S + k] (S >= E; S = E is the plain contiguous layout),
@@ -117,29 +123,22 @@ __device__ float block_seqsum_exact_v2_t(const float *sq, int n, SeqSum2Scratch 
     float loc = 0.0f;
     {
         int k = 0;
-        if (vec)
+        if (vec) {
+#pragma unroll 1
             for (; k < E; k += 4) {
                 const float4 v = *reinterpret_cast<const float4 *>(mine + k);
                 loc += v.x; loc += v.y; loc += v.z; loc += v.w;
             }
+        }
+#pragma unroll 1
         for (; k < E; k++) loc += mine[k];
     }
-    float inc = loc;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const float u = __shfl_up_sync(0xffffffffu, inc, d);
-        if (lane >= d) inc += u;
-    }
+    const float inc = seq2_warp_scan_f(loc, lane);
     if (lane == 31) sc.wsum[warp] = inc;
     sync();
     if (warp == 0) {
         const float w = lane < NW ? sc.wsum[lane] : 0.0f;
-        float v = w;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const float u = __shfl_up_sync(0xffffffffu, v, d);
-            if (lane >= d) v += u;
-        }
+        const float v = seq2_warp_scan_f(w, lane);
         if (lane < NW) sc.wsum[lane] = v - w; // exclusive
     }
     sync();
@@ -159,6 +158,7 @@ __device__ float block_seqsum_exact_v2_t(const float *sq, int n, SeqSum2Scratch 
                 bool ok = true;
                 int k = 0;
                 if (vec)
+#pragma unroll 1
                     for (; k < E; k += 4) { // four independent pair evaluations, composed as a tree: the dependent chain is E/4 + 2 composes, not E
                         const float4 v = *reinterpret_cast<const float4 *>(mine + k);
                         SeqPair q0, q1, q2, q3;
@@ -166,6 +166,7 @@ __device__ float block_seqsum_exact_v2_t(const float *sq, int n, SeqSum2Scratch 
                         ok = ok && o0 && o1 && o2 && o3; // composing an invalid pair is harmless: the result is discarded
                         pr = seq_compose(pr, seq_compose(seq_compose(q0, q1), seq_compose(q2, q3)));
                     }
+#pragma unroll 1
                 for (; ok && k < E; k++) {
                     SeqPair q;
                     if (!seq_pair(mine[k], e, q)) { ok = false; break; }
@@ -209,7 +210,7 @@ __device__ float block_seqsum_exact_v2_t(const float *sq, int n, SeqSum2Scratch 
     if (warp == 0) {
         const int c = lane < NW ? sc.wcnt[lane] : 0;
         int v = c;
-#pragma unroll
+#pragma unroll 1
         for (int d = 1; d < 32; d <<= 1) {
             const int u = __shfl_up_sync(0xffffffffu, v, d);
             if (lane >= d) v += u;
@@ -231,6 +232,7 @@ __device__ float block_seqsum_exact_v2_t(const float *sq, int n, SeqSum2Scratch 
         float s = 0.0f;
         int fallbacks = 0;
         SeqItem nxt = sc.items[0];
+#pragma unroll 1
         for (int i = 0; i < n_items; i++) {
             const SeqItem it = nxt;
             if (i + 1 < n_items) nxt = sc.items[i + 1]; // in flight while this item is resolved
@@ -249,6 +251,7 @@ __device__ float block_seqsum_exact_v2_t(const float *sq, int n, SeqSum2Scratch 
             if (!ok) { // misprediction: replay the run literally (its first thread: walk back over equal classes)
                 int first = it.last;
                 while (first > 0 && sc.cls[first - 1] == it.cls) first--;
+#pragma unroll 1
                 for (int j = first; j <= it.last; j++) s = seq2_literal(s, sq + j * S, E, vec);
                 fallbacks++;
             }

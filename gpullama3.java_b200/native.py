@@ -185,7 +185,7 @@ class NativePlan:
 
     def trace_persistent(self, token: int, position: int) -> np.ndarray:
         """uint64 %globaltimer stamps [cta][row][k] of one traced step of the persistent decode kernel."""
-        cap = 200 * (self.cfg.n_layers + 1) * 16
+        cap = 200 * (self.cfg.n_layers + 1) * 32
         buf = np.zeros(cap, dtype=np.uint64)
         a, b, c = C.c_int32(0), C.c_int32(0), C.c_int32(0)
         self._ck(lib().b200_trace_persistent(self._p, token, position, buf.ctypes.data, cap, C.byref(a), C.byref(b), C.byref(c)))

@@ -58,6 +58,10 @@ def main():
         print(f"{'  attention: exp + sum + normalise':44s} {(hl[:, :, 14] - hl[:, :, 13]).mean():9.2f}")
         print(f"{'  attention: weighted value sum + quantise':44s} {(hl[:, :, 15] - hl[:, :, 14]).mean():9.2f}")
         print(f"{'  attention: ATT barrier (head done -> gathered)':44s} {(hl[:, :, 3] - hl[:, :, 15]).mean():9.2f}")
+    if st.shape[2] > 17 and nL > 1:
+        cold = (lay[:, 1, 11] - lay[:, 1, 10]).mean()
+        warm = (lay[:, 1, 17] - lay[:, 1, 16]).mean()
+        print(f"{'  exact sum of layer 1: first run / immediate re-run':52s} {cold:6.2f} / {warm:5.2f}   (same code, same data: the difference is instruction fetch)")
     per_layer = (nxt[:, sel] - lay[:, sel, 0])
     print(f"{'layer total (CTA mean)':44s} {per_layer.mean():9.2f}")
     # exposed barrier latency: last arrival -> first departure, per dependency
