@@ -814,13 +814,6 @@ __global__ void __launch_bounds__(PD_THREADS, 1) k_decode_persistent(const __gri
         const PdLayer &Ly = a.layers[l];
         const unsigned e = tick * nL + (unsigned)l + 1u; // this layer's epoch
         pd_stamp(a, l, 0, tid);
-        if (blockIdx.x < nH) { // head CTAs: pull this layer's K/V rows of their KV head into L2 now, ~15 us before the scores need them
-            const int kvh = (int)blockIdx.x / (a.n_heads / a.n_kv_heads), kvd = a.n_kv_heads * a.head_size;
-            for (int t = tid; t < pos; t += PD_CT) {
-                bulk_prefetch_l2(Ly.kc + (size_t)t * kvd + kvh * a.head_size, (unsigned)a.head_size * 4u);
-                bulk_prefetch_l2(Ly.vc + (size_t)t * kvd + kvh * a.head_size, (unsigned)a.head_size * 4u);
-            }
-        }
         pd_norm_to_smem(a, wbufA, l == 0, token, smem, L, tid, l);
         if (a.trace && l == 1) { // diagnostic (traced launch only): the same exact sum again, instruction cache warm -- stamps 16 -> 17 vs 10 -> 11
             const int E = (a.dim + PD_CT - 1) / PD_CT;
@@ -833,6 +826,14 @@ __global__ void __launch_bounds__(PD_THREADS, 1) k_decode_persistent(const __gri
         pd_stamp(a, l, 1, tid);
         pd_consume_matrix<SMV_STORE>(Ly.qkv, a, smem, L, bar0, rel, seq_base, a.qkv, false, false, token, 0, tid);
         pd_stamp(a, l, 2, tid);
+        if (blockIdx.x < nH) { // head CTAs: pull this layer's K/V rows of their KV head into L2 NOW -- a line survives only ~20 us in L2 under
+            // the weight stream (126 MB at 5.6 TB/s), so the prefetch must sit just ahead of the scores, not at the top of the layer
+            const int kvh = (int)blockIdx.x / (a.n_heads / a.n_kv_heads), kvd = a.n_kv_heads * a.head_size;
+            for (int t = tid; t < pos; t += PD_CT) {
+                bulk_prefetch_l2(Ly.kc + (size_t)t * kvd + kvh * a.head_size, (unsigned)a.head_size * 4u);
+                bulk_prefetch_l2(Ly.vc + (size_t)t * kvd + kvh * a.head_size, (unsigned)a.head_size * 4u);
+            }
+        }
         pd_arrive(a, PD_S_QKV, e * nC, e, false, tid); // q/k/v of this rank's heads stay on this rank
         if (blockIdx.x < nH) { // attention: the first n_heads CTAs, one head each
             pd_wait(a, PD_S_QKV, e * nC, e, false, tid);

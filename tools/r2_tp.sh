@@ -15,7 +15,8 @@ TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr
   fi
   echo "== 2. bench $WL tp$N: persistent, graph"
   for m in persistent graph; do
-    timeout 900 $TR bench.py --gpus $N --workload $WL --no-pp --decode-mode $m > gpurun_out/bench_r2_tp${N}_${WL}_$m.json 2> gpurun_out/bench_r2_tp${N}_${WL}_$m.err
+    extra=""; [ "$m" = "graph" ] && extra="--no-cpu"   # the oracle-backed parity gate runs once (persistent mode)
+    timeout 1200 $TR bench.py --gpus $N --workload $WL --no-pp --steps 64 --decode-mode $m $extra > gpurun_out/bench_r2_tp${N}_${WL}_$m.json 2> gpurun_out/bench_r2_tp${N}_${WL}_$m.err
     python - <<PY
 import json
 try:
