@@ -79,7 +79,10 @@ __device__ __noinline__ void tp_wait(const TpCtx &t, int slot, unsigned seq) {
             }
         }
     }
-    asm volatile("fence.acq_rel.sys;" ::: "memory");
+    { // one acquire load after the relaxed polls (flags are monotone); a fence.acq_rel.sys here is a MEMBAR.SYS per wait
+        unsigned v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+    }
 }
 __device__ __forceinline__ void tp_signal(const TpCtx &t, int slot, unsigned seq) { // one thread, after the data stores
     __threadfence_system();

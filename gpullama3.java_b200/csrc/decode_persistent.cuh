@@ -129,8 +129,9 @@ __host__ __device__ inline PdSmem pd_layout(int dim, int qd, int hidden, int hea
 }
 
 // ---- bounded waits ----------------------------------------------------------------------------------------------------------
-// Polls are RELAXED loads; one acquire fence follows the successful one.  (ld.acquire in the loop compiles to a load plus
-// CCTL.IVALL: every poll of thread 0 threw away the whole L1 of its SM -- norm weights, tile descriptors, rope rows.)
+// Polls are RELAXED loads; ONE acquire load of the same word follows the successful one.  (ld.acquire in the loop compiles to a
+// load plus CCTL.IVALL: every poll of thread 0 threw away the whole L1 of its SM; a trailing fence.acq_rel.sys instead costs a
+// MEMBAR.SYS per wait, which made tensor-parallel steps ~20 % slower -- profiles/r2_tp2_fences.log.)
 __device__ __forceinline__ unsigned pd_ld_relaxed_gpu(const unsigned *p) {
     unsigned v;
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -147,9 +148,10 @@ template <bool SYS> __device__ __noinline__ void pd_spin(const unsigned *p, unsi
     unsigned long long t0 = 0;
     for (;;) {
         const unsigned v = SYS ? pd_ld_relaxed_sys(p) : pd_ld_relaxed_gpu(p);
-        if ((int)(v - target) >= 0) {
-            if (SYS) asm volatile("fence.acq_rel.sys;" ::: "memory");
-            else asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        if ((int)(v - target) >= 0) { // counters and flags are monotone: the acquire re-read observes a value >= the relaxed one
+            unsigned w;
+            if (SYS) asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(w) : "l"(p) : "memory");
+            else asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(w) : "l"(p) : "memory");
             return;
         }
         if ((++it & 255u) == 0u) {
@@ -178,8 +180,10 @@ __device__ __noinline__ void pd_arrive(const PdArgs &a, int slot, unsigned targe
     pd_bar_sync();
     if (tid == 0) {
         const bool x = cross && a.tp.n > 1;
-        if (x) __threadfence_system();
-        else __threadfence();
+        // gpu-scope fence per CTA, ONE system-scope fence by the last arriver below: the CTAs' peer stores reach system scope through the
+        // cumulativity of the fence chain (CTA store -> fence.gpu -> atomic -> last arriver's atomic -> fence.sys -> flag).  A per-CTA
+        // __threadfence_system() here cost ~7 us per exchange at tp2 (148 MEMBAR.SYS waiting on NVLink round trips).
+        __threadfence();
         const unsigned old = atomicAdd(a.sync + slot, 1u);
         if (x && old + 1u == target) {
             __threadfence_system();

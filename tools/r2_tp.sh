@@ -20,7 +20,7 @@ TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr
     python - <<PY
 import json
 try:
-    j = json.load(open("gpurun_out/bench_r2_tp${N}_${WL}_$m.json"))
+    j = json.loads([l for l in open("gpurun_out/bench_r2_tp${N}_${WL}_$m.json") if l.startswith("{")][-1])
     print("$m", "value", round(j["value"], 1), "e2e", round(j["e2e"]["value"], 1), "ms", round(j["ms_per_step"], 3), "by rank", [round(v, 3) for v in j["ms_per_step_by_rank"]],
           "roofline", round(j["roofline"]["frac"], 3), "parity", j.get("parity"))
 except Exception as e:
