@@ -143,11 +143,11 @@ def algorithmic_bytes_per_token(shape, quant_q8: bool, ctx_avg_pos: float) -> di
     return {"weights": w, "norms": norms, "kv": kv, "total": w + norms + kv}
 
 
-def build_model(pkg, ctx: int, device: str | None):
+def build_model(pkg, ctx: int, device: str | None, tp_rank: int = 0, tp_size: int = 1):
     shape = pkg.synth.SHAPES[WORKLOAD]
     quant = pkg.gguf.GGMLType.Q8_0
     t0 = time.time()
-    tensors = pkg.synth.build_tensors_fast(shape, quant, seed=1234, device=device)
+    tensors = pkg.synth.build_tensors_fast(shape, quant, seed=1234, device=device, tp_rank=tp_rank, tp_size=tp_size)
     model = pkg.loader.model_from_tensors(shape, quant, tensors, ctx)
     return shape, model, time.time() - t0
 
@@ -247,7 +247,9 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     torch.cuda.set_device(local)
-    shape, model, gen_s = build_model(pkg, ctx, f"cuda:{local}")
+    # a rank that never runs the oracle keeps only the rows it uploads on the host (70B: ~10 GB instead of 74 GB per rank)
+    shard_host = world > 1 and (rank != 0 or args.no_cpu)
+    shape, model, gen_s = build_model(pkg, ctx, f"cuda:{local}", rank if shard_host else 0, world if shard_host else 1)
     t0 = time.time()
     plan = pkg.B200MasterPlan.initialize_plan(model, device=local, tp_rank=rank, tp_size=world)
     load_s = time.time() - t0

@@ -76,6 +76,8 @@ struct PdArgs {
     unsigned long long *trace; // [gridDim.x][n_layers + 1][PD_STAMPS] %globaltimer stamps, or NULL
     int with_logits;
     unsigned l2_ahead;         // tiles the producer may prefetch into L2 beyond the ring while the ring is full
+    unsigned evict_first;      // 1: the weight stream's bulk copies carry an L2 evict_first policy -- 8 GB of single-use weights per token
+                               // otherwise churn the 126 MB L2 and push out the KV rows, x, the norm weights and the prefetched tiles
     unsigned max_fly;          // experiment knob (B200_PD_MAXFLY): bulk copies one CTA keeps in flight; 0 = no limit but the ring (default:
                                // limiting it never helped the dependent phases and always slowed the stream, profiles/r2_run3_knob_sweep.log)
     // tensor parallelism (tp.n == 1: everything below unused)
@@ -269,8 +271,20 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
     return ok != 0u;
 }
 
+__device__ __forceinline__ unsigned long long pd_policy_evict_first() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(unsigned dst, const void *src, unsigned bytes, unsigned bar, unsigned long long pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar), "l"(pol)
+                 : "memory");
+}
+
 __device__ __forceinline__ void pd_produce(const PdArgs &a, unsigned char *smem, const PdSmem &L, unsigned bar0) {
     const int S = L.stages;
+    const unsigned long long pol = pd_policy_evict_first();
     PdWalk cur, pf;
     cur.init(&a);
     pf = cur;
@@ -301,7 +315,8 @@ __device__ __forceinline__ void pd_produce(const PdArgs &a, unsigned char *smem,
             }
         const unsigned full = bar0 + 8 * st;
         mbar_expect_tx(full, cur.tile_bytes);
-        bulk_g2s(smem_u32(smem + L.off_ring + (size_t)st * L.stage_bytes), cur.addr(), cur.tile_bytes, full);
+        if (a.evict_first) bulk_g2s_hint(smem_u32(smem + L.off_ring + (size_t)st * L.stage_bytes), cur.addr(), cur.tile_bytes, full, pol);
+        else bulk_g2s(smem_u32(smem + L.off_ring + (size_t)st * L.stage_bytes), cur.addr(), cur.tile_bytes, full);
     }
 }
 

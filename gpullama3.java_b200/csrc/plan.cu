@@ -96,7 +96,7 @@ struct b200_plan {
     // knobs read once at creation (never inside a launch helper)
     size_t smv_budget = 96 * 1024;
     int smv_budget_cols = 0;
-    unsigned l2_window = 0, pd_l2_ahead = 0, pd_max_fly = 0;
+    unsigned l2_window = 0, pd_l2_ahead = 0, pd_max_fly = 0, pd_evict_first = 1;
     int pd_max_stages = 0; // 0 = as many as shared memory holds
     float *att_scratch = nullptr; // [heads][ctx] score rows when the context does not fit shared memory
     int *smp_indices = nullptr, *smp_out = nullptr; // device-side sampler scratch (sampler.cuh): candidate list, {id, info[4]}
@@ -467,6 +467,8 @@ void read_knobs(b200_plan *p) {
     p->pd_l2_ahead = a ? (unsigned)atoi(a) : 0u;
     const char *f = getenv("B200_PD_MAXFLY"); // persistent kernel: bulk copies in flight per CTA (0 = unlimited)
     p->pd_max_fly = f ? (unsigned)atoi(f) : 0u; // measured (profiles/r2_run3_knob_sweep.log): any limit below the ring depth only slows the stream
+    const char *ev = getenv("B200_PD_EVICT_FIRST"); // persistent kernel: L2 evict_first policy on the weight stream (default on)
+    p->pd_evict_first = ev ? (unsigned)atoi(ev) : 1u;
     const char *g = getenv("B200_PD_STAGES"); // persistent kernel: cap on the ring depth
     p->pd_max_stages = g ? atoi(g) : 0;
     const char *v = getenv("B200_NORM_V2");
@@ -657,6 +659,7 @@ int enqueue_persistent(b200_plan *p, bool with_logits, int *launches, bool trace
     a.att_scratch = p->att_scratch; a.trace = trace ? p->pd_trace : nullptr;
     a.with_logits = with_logits ? 1 : 0;
     a.l2_ahead = p->pd_l2_ahead;
+    a.evict_first = p->pd_evict_first;
     a.max_fly = p->pd_max_fly > (unsigned)p->pd_L.stages ? (unsigned)p->pd_L.stages : p->pd_max_fly;
     a.tp = p->tp; a.pd_flags_off = p->pd_flags_off;
     a.head_base = p->tp.rank * p->nh_l; a.dim_base = p->tp.rank * p->dim_l; a.hid_base = p->tp.rank * p->hid_l; a.voc_base = p->tp.rank * p->voc_l;

@@ -254,10 +254,36 @@ def write_model(path: str, shape_name: str, quant: int, seed: int = 1234, w_std:
     return shape
 
 
-def build_tensors_fast(shape: Shape, quant: int, seed: int = 1234, device: str | None = None):
+def tp_row_ranges(shape: Shape, tp_rank: int, tp_size: int) -> dict:
+    """Row range [r0, r1) of every sharded matrix that tensor-parallel rank `tp_rank` uploads (mirrors plan.tp_shard_plan /
+    csrc/plan.cu); tensors not listed (embedding table, norms) are needed whole."""
+    r, n = tp_rank, tp_size
+    qd_l, kvd_l = shape.q_dim // n, shape.kv_dim // n
+    hid_l, dim_l, voc_l = shape.hidden // n, shape.dim // n, shape.vocab // n
+    out = {}
+    for i in range(shape.n_layers):
+        p = f"blk.{i}."
+        out[p + "attn_q.weight"] = (r * qd_l, (r + 1) * qd_l)
+        out[p + "attn_k.weight"] = (r * kvd_l, (r + 1) * kvd_l)
+        out[p + "attn_v.weight"] = (r * kvd_l, (r + 1) * kvd_l)
+        out[p + "attn_output.weight"] = (r * dim_l, (r + 1) * dim_l)
+        out[p + "ffn_gate.weight"] = (r * hid_l, (r + 1) * hid_l)
+        out[p + "ffn_up.weight"] = (r * hid_l, (r + 1) * hid_l)
+        out[p + "ffn_down.weight"] = (r * dim_l, (r + 1) * dim_l)
+    if not shape.tied:
+        out["output.weight"] = (r * voc_l, (r + 1) * voc_l)
+    return out
+
+
+def build_tensors_fast(shape: Shape, quant: int, seed: int = 1234, device: str | None = None, tp_rank: int = 0, tp_size: int = 1):
     """Same tensor set as build_tensors, generated with torch (on the GPU when there is one) so an
     8B/70B-shaped model takes seconds, not minutes.  Data plumbing only -- not on the hot path.
-    Returns {name: (ggml_type, dims, uint8 ndarray in GGUF layout)} (host memory)."""
+    Returns {name: (ggml_type, dims, uint8 ndarray in GGUF layout)} (host memory).
+
+    tp_size > 1: every value is generated (same seeded stream, so the model is identical for every world size) but only the rows
+    this rank uploads are copied to the host; the arrays keep their full size (untouched pages are never committed), because the
+    C ABI takes whole-tensor descriptors and reads only the rank's row range.  A 70B-shaped model then costs each of 8 ranks
+    ~10 GB of host memory instead of 74 GB."""
     import torch
 
     dev = torch.device(device or ("cuda" if torch.cuda.is_available() else "cpu"))
@@ -265,6 +291,7 @@ def build_tensors_fast(shape: Shape, quant: int, seed: int = 1234, device: str |
     gen.manual_seed(seed)
     out = {}
     chunk = 1 << 26
+    ranges = tp_row_ranges(shape, tp_rank, tp_size) if tp_size > 1 else {}
     for name, tt, dims, kind in tensor_plan(shape, quant):
         n = int(np.prod(dims))
         if kind == "n":
@@ -274,27 +301,34 @@ def build_tensors_fast(shape: Shape, quant: int, seed: int = 1234, device: str |
         std = 1.0 / float(np.sqrt(dims[0]))
         nbytes = GGMLType.byte_size_for(tt, n)
         host = np.empty(nbytes, dtype=np.uint8)
+        cols = int(dims[0])
+        row_bytes = GGMLType.byte_size_for(tt, cols)
+        keep = ranges.get(name)  # None: the whole tensor
         ho = 0
         for o in range(0, n, chunk):
             m = min(chunk, n - o)
             x = torch.randn(m, device=dev, generator=gen) * std
-            if tt == GGMLType.F16:
-                b = x.half().view(torch.uint8)
-            elif tt == GGMLType.Q8_0:
-                xb = x.view(-1, 32)
-                d = xb.abs().amax(dim=1) / 127.0
-                inv = torch.where(d != 0, 1.0 / d, torch.zeros_like(d))
-                s = xb * inv[:, None]
-                q = torch.trunc(s + torch.copysign(torch.full_like(s, 0.5), s)).to(torch.int8)
-                blk = torch.empty((xb.shape[0], 34), dtype=torch.uint8, device=dev)
-                blk[:, 0:2] = d.half().view(torch.uint8).view(-1, 2)
-                blk[:, 2:] = q.view(torch.uint8)
-                b = blk.view(-1)
-            else:
-                b = x.float().view(torch.uint8)
-            hb = b.cpu().numpy().reshape(-1)
-            host[ho:ho + hb.size] = hb
-            ho += hb.size
+            cb = GGMLType.byte_size_for(tt, m)
+            lo, hi = ho, ho + cb  # byte range of this chunk in the tensor
+            if keep is not None:
+                lo, hi = max(lo, keep[0] * row_bytes), min(hi, keep[1] * row_bytes)
+            if lo < hi:
+                if tt == GGMLType.F16:
+                    b = x.half().view(torch.uint8)
+                elif tt == GGMLType.Q8_0:
+                    xb = x.view(-1, 32)
+                    d = xb.abs().amax(dim=1) / 127.0
+                    inv = torch.where(d != 0, 1.0 / d, torch.zeros_like(d))
+                    sc = xb * inv[:, None]
+                    q = torch.trunc(sc + torch.copysign(torch.full_like(sc, 0.5), sc)).to(torch.int8)
+                    blk = torch.empty((xb.shape[0], 34), dtype=torch.uint8, device=dev)
+                    blk[:, 0:2] = d.half().view(torch.uint8).view(-1, 2)
+                    blk[:, 2:] = q.view(torch.uint8)
+                    b = blk.view(-1)
+                else:
+                    b = x.float().view(torch.uint8)
+                host[lo:hi] = b[lo - ho:hi - ho].cpu().numpy().reshape(-1)
+            ho += cb
         assert ho == nbytes
         out[name] = (tt, dims, host)
     return out

@@ -61,3 +61,29 @@ def test_handle_exchange_gloo_world2():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res == [(0, [0, 1], True), (1, [0, 1], True)]  # every rank sees the handles in rank order
+
+
+def test_sharded_host_tensors_equal_the_full_model_on_the_ranks_rows(pkg):
+    """bench.py --gpus N keeps only each rank's rows on the host (70B: 74 GB -> ~10 GB per rank); the kept rows must be
+    byte-identical to the single-GPU model, whatever the world size (same seeded stream)."""
+    import numpy as np
+    sh = pkg.synth.SHAPES["tiny-qwen3"]
+    Q = pkg.gguf.GGMLType.Q8_0
+    full = pkg.synth.build_tensors_fast(sh, Q, seed=9, device="cpu")
+    for n in (2,):  # tiny-qwen3 has 2 KV heads
+        for r in range(n):
+            part = pkg.synth.build_tensors_fast(sh, Q, seed=9, device="cpu", tp_rank=r, tp_size=n)
+            rng = pkg.synth.tp_row_ranges(sh, r, n)
+            plan = pkg.plan.tp_shard_plan(type("C", (), dict(n_heads=sh.n_heads, n_kv_heads=sh.n_kv_heads, head_size=sh.head_size, dim=sh.dim,
+                                                            hidden_dim=sh.hidden, vocab_size=sh.vocab))(), n)[r]
+            assert rng["blk.0.attn_q.weight"] == plan["q_rows"] and rng["blk.0.ffn_gate.weight"] == plan["hidden_units"]
+            assert rng["blk.1.ffn_down.weight"] == plan["residual_rows"] and rng["blk.0.attn_v.weight"] == plan["kv_rows"]
+            for name, (tt, dims, raw) in full.items():
+                praw = part[name][2]
+                assert praw.shape == raw.shape
+                if name in rng:
+                    rb = pkg.gguf.GGMLType.byte_size_for(tt, int(dims[0]))
+                    lo, hi = rng[name][0] * rb, rng[name][1] * rb
+                    assert np.array_equal(praw[lo:hi], raw[lo:hi]), name
+                else:
+                    assert np.array_equal(praw, raw), name
