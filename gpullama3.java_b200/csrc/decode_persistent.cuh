@@ -706,32 +706,55 @@ __device__ __noinline__ void pd_attention_head(const PdArgs &a, const PdLayer &L
         }
     }
     pd_bar_sync();
+    // ---- scores (scalarDot, FloatTensor.java:86-92: one sequential unfused mul/add chain per key).  Four threads share a key: each
+    // loads ITS quarter of the K row at once (one L2 round trip per pass of PD_CT/4 keys instead of two dependent ones per key), then
+    // the chain runs through the quad in element order, handed on by shuffle.  The V rows this thread will need are requested
+    // here as well: they do not depend on the scores, so their round trip overlaps with everything up to the weighted sum.
+    constexpr int QE = HS / 4, QV = HS / 16; // elements / 16-byte loads per quarter row
+    const int quad = tid & 3, qbase = lane & ~3;
+    constexpr int VB = 32;                   // V rows per thread and round of the weighted sum (4 threads per output element -> 128 keys per round)
+    const int vd = tid >> 2;                 // output element of the weighted sum owned by this quad (HS <= PD_CT / 4)
+    const bool vlive = vd < HS;
+    float vv[VB];
+    {
+        const float *vcol = vc + kvh * HS + vd;
+        const int vt0 = quad * VB;           // rows [vt0, vt0 + VB) of round 0
+#pragma unroll
+        for (int u = 0; u < VB; u++) vv[u] = (vlive && vt0 + u < pos) ? __ldcg(vcol + (size_t)(vt0 + u) * kvd) : 0.0f;
+    }
     float lmax = -INFINITY;
-    for (int t = tid; t < nt; t += PD_CT) {
-        float acc = 0.0f;
-        if (t == pos) {
-#pragma unroll 8
-            for (int j = 0; j < HS; j++) acc = __fadd_rn(acc, __fmul_rn(sq[j], sk[j]));
-        } else {
-            const float4 *k = reinterpret_cast<const float4 *>(kc + (size_t)t * kvd + kvh * HS);
 #pragma unroll 1
-            for (int j0 = 0; j0 < HS / 4; j0 += 16) { // 16 x 16 bytes in flight per thread: two L2 round trips per key at head size 128
-                float4 kk[16];
+    for (int t0 = 0; t0 < nt; t0 += PD_CT / 4) {
+        const int t = t0 + (tid >> 2);
+        float4 kk[QV];
+        if (t < pos) { // rows of earlier tokens: written by earlier launches
+            const float4 *k = reinterpret_cast<const float4 *>(kc + (size_t)t * kvd + kvh * HS + quad * QE);
 #pragma unroll
-                for (int u = 0; u < 16; u++) kk[u] = __ldcg(k + j0 + u); // rows of earlier tokens: written by earlier launches
+            for (int u = 0; u < QV; u++) kk[u] = __ldcg(k + u);
+        } else { // t == pos: this step's rotated k (shared memory); t > pos: idle slot
 #pragma unroll
-                for (int u = 0; u < 16; u++) {
-                    const int j = 4 * (j0 + u);
-                    acc = __fadd_rn(acc, __fmul_rn(sq[j + 0], kk[u].x));
-                    acc = __fadd_rn(acc, __fmul_rn(sq[j + 1], kk[u].y));
-                    acc = __fadd_rn(acc, __fmul_rn(sq[j + 2], kk[u].z));
-                    acc = __fadd_rn(acc, __fmul_rn(sq[j + 3], kk[u].w));
+            for (int u = 0; u < QV; u++) kk[u] = t == pos ? *reinterpret_cast<const float4 *>(sk + quad * QE + 4 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float acc = 0.0f;
+#pragma unroll 1
+        for (int qd = 0; qd < 4; qd++) {
+            if (quad == qd) {
+                const float *qq = sq + qd * QE;
+#pragma unroll
+                for (int u = 0; u < QV; u++) {
+                    acc = __fadd_rn(acc, __fmul_rn(qq[4 * u + 0], kk[u].x));
+                    acc = __fadd_rn(acc, __fmul_rn(qq[4 * u + 1], kk[u].y));
+                    acc = __fadd_rn(acc, __fmul_rn(qq[4 * u + 2], kk[u].z));
+                    acc = __fadd_rn(acc, __fmul_rn(qq[4 * u + 3], kk[u].w));
                 }
             }
+            acc = __shfl_sync(0xffffffffu, acc, qbase + qd); // the chain so far, to the whole quad
         }
-        const float s = __fdiv_rn(acc, a.sqrt_hs);
-        att[t] = s;
-        lmax = fmaxf(lmax, s);
+        if (quad == 0 && t < nt) {
+            const float sc = __fdiv_rn(acc, a.sqrt_hs);
+            att[t] = sc;
+            lmax = fmaxf(lmax, sc);
+        }
     }
     lmax = warp_max_f(lmax);
     if (lane == 0) red[warp] = lmax;
@@ -758,21 +781,31 @@ __device__ __noinline__ void pd_attention_head(const PdArgs &a, const PdLayer &L
     for (int t = tid; t < nt; t += PD_CT) att[t] = __fdiv_rn(att[t], sum);
     pd_bar_sync();
     pd_stamp(a, layer, 14, tid);
-    if (tid < HS) { // xb = sum_t a_t * v_t, sequentially over t per element (saxpyInPlace, FloatTensor.java:221-227)
-        const float *v = vc + kvh * HS + tid;
+    { // xb = sum_t a_t * v_t, sequentially over t per element (saxpyInPlace, FloatTensor.java:221-227).  Four threads per element: thread
+      // `quad` holds rows [128 r + 32 quad, +32) of round r, all requested before the chain starts; the chain itself (4 cycles per key, the
+      // floor of this phase) runs through the quad in row order.
+        const float *vcol = vc + kvh * HS + vd;
+        const float vcur = vlive ? ldcg_f32c(vsrc + vd) : 0.0f; // the current position's v, straight from the packed q|k|v vector
         float acc = 0.0f;
-        const float vcur = ldcg_f32c(vsrc + tid); // the current position's v, straight from the packed q|k|v vector
 #pragma unroll 1
-        for (int t0 = 0; t0 < pos; t0 += 16) { // 16 rows in flight per thread (the add chain itself is 4 cycles per key)
-            float vv[16];
+        for (int r0 = 0; r0 < pos; r0 += 4 * VB) {
+            if (r0 > 0) { // round 0 was requested before the scores
+                const int vt0 = r0 + quad * VB;
 #pragma unroll
-            for (int u = 0; u < 16; u++) vv[u] = t0 + u < pos ? __ldcg(v + (size_t)(t0 + u) * kvd) : 0.0f;
+                for (int u = 0; u < VB; u++) vv[u] = (vlive && vt0 + u < pos) ? __ldcg(vcol + (size_t)(vt0 + u) * kvd) : 0.0f;
+            }
+#pragma unroll 1
+            for (int qd = 0; qd < 4; qd++) {
+                if (quad == qd) {
+                    const int vt0 = r0 + qd * VB;
 #pragma unroll
-            for (int u = 0; u < 16; u++)
-                if (t0 + u < pos) acc = __fadd_rn(__fmul_rn(att[t0 + u], vv[u]), acc);
+                    for (int u = 0; u < VB; u++)
+                        if (vt0 + u < pos) acc = __fadd_rn(__fmul_rn(att[vt0 + u], vv[u]), acc);
+                }
+                acc = __shfl_sync(0xffffffffu, acc, qbase + qd);
+            }
         }
-        acc = __fadd_rn(__fmul_rn(att[pos], vcur), acc);
-        so[tid] = acc;
+        if (vlive && quad == 0) so[vd] = __fadd_rn(__fmul_rn(att[pos], vcur), acc);
     }
     pd_bar_sync();
     const int gh = a.head_base + h;

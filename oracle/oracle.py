@@ -167,6 +167,12 @@ def use_all_cores() -> int:
         n = len(os.sched_getaffinity(0))
     except AttributeError:
         n = os.cpu_count() or 1
+    try:  # a container's CPU quota (cgroup v2 cpu.max = "<quota> <period>"): more OpenMP threads than that only fight each other
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = max(1, min(n, int(quota) // int(period)))
+    except (OSError, ValueError):
+        pass
     lib().oracle_set_threads(n)
     return int(lib().oracle_omp_threads())
 
