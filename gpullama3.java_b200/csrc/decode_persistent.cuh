@@ -111,7 +111,8 @@ __host__ __device__ inline PdSmem pd_layout(int dim, int qd, int hidden, int hea
     o = (o + 15) & ~(size_t)15;
     L.off_nbuf = o; o += (size_t)L.nbuf_floats * 4; // squares of the norm | q,k,out,att of the attention (time-disjoint)
     o = (o + 15) & ~(size_t)15;
-    L.off_wbuf = o; o += (size_t)2 * dim * 4; // norm weights of the next attn norm / ffn norm, fetched one phase ahead (cp.async)
+    L.off_wbuf = o; o += (size_t)dim * 4; // weights of the NEXT norm (attn, ffn or final), fetched one phase ahead (cp.async) as soon as
+                                          // the previous norm has read its own out of this buffer
     L.off_rope = o; o += (size_t)head_size * 4; // this position's rope row: cos | sin
     o = (o + 15) & ~(size_t)15;
     L.off_seq = o; o += seqsum2_scratch_bytes(PD_CT);
@@ -271,20 +272,9 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
     return ok != 0u;
 }
 
-__device__ __forceinline__ unsigned long long pd_policy_evict_first() {
-    unsigned long long pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ void bulk_g2s_hint(unsigned dst, const void *src, unsigned bytes, unsigned bar, unsigned long long pol) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst), "l"(src),
-                 "r"(bytes), "r"(bar), "l"(pol)
-                 : "memory");
-}
-
 __device__ __forceinline__ void pd_produce(const PdArgs &a, unsigned char *smem, const PdSmem &L, unsigned bar0) {
     const int S = L.stages;
-    const unsigned long long pol = pd_policy_evict_first();
+    const unsigned long long pol = l2_policy_evict_first();
     PdWalk cur, pf;
     cur.init(&a);
     pf = cur;
@@ -315,7 +305,7 @@ __device__ __forceinline__ void pd_produce(const PdArgs &a, unsigned char *smem,
             }
         const unsigned full = bar0 + 8 * st;
         mbar_expect_tx(full, cur.tile_bytes);
-        if (a.evict_first) bulk_g2s_hint(smem_u32(smem + L.off_ring + (size_t)st * L.stage_bytes), cur.addr(), cur.tile_bytes, full, pol);
+        if (a.evict_first) bulk_g2s_evict_first(smem_u32(smem + L.off_ring + (size_t)st * L.stage_bytes), cur.addr(), cur.tile_bytes, full, pol);
         else bulk_g2s(smem_u32(smem + L.off_ring + (size_t)st * L.stage_bytes), cur.addr(), cur.tile_bytes, full);
     }
 }
@@ -853,7 +843,7 @@ __global__ void __launch_bounds__(PD_THREADS, 1) k_decode_persistent(const __gri
     const unsigned tick = *reinterpret_cast<volatile unsigned *>(a.sync + PD_S_TICK);
     const unsigned lmtick = *reinterpret_cast<volatile unsigned *>(a.sync + PD_S_LMTICK);
     const unsigned nC = gridDim.x, nL = (unsigned)a.n_layers, nH = (unsigned)a.n_heads;
-    float *wbufA = reinterpret_cast<float *>(smem + L.off_wbuf), *wbufF = wbufA + a.dim; // norm weights: attn (and final) / ffn
+    float *wbufA = reinterpret_cast<float *>(smem + L.off_wbuf), *wbufF = wbufA; // one buffer: every thread re-fills exactly the slots it has just read
     pd_prefetch_w(a.n_layers ? a.layers[0].attn_norm : a.out_norm, wbufA, a.dim, tid);
     if (tid < a.head_size) { // this position's rope row (RoPE.precomputeFreqsCis table), the same for every layer
         const int half = a.head_size >> 1;
@@ -881,9 +871,11 @@ __global__ void __launch_bounds__(PD_THREADS, 1) k_decode_persistent(const __gri
         if (blockIdx.x < nH) { // head CTAs: pull this layer's K/V rows of their KV head into L2 NOW -- a line survives only ~20 us in L2 under
             // the weight stream (126 MB at 5.6 TB/s), so the prefetch must sit just ahead of the scores, not at the top of the layer
             const int kvh = (int)blockIdx.x / (a.n_heads / a.n_kv_heads), kvd = a.n_kv_heads * a.head_size;
-            for (int t = tid; t < pos; t += PD_CT) {
-                bulk_prefetch_l2(Ly.kc + (size_t)t * kvd + kvh * a.head_size, (unsigned)a.head_size * 4u);
-                bulk_prefetch_l2(Ly.vc + (size_t)t * kvd + kvh * a.head_size, (unsigned)a.head_size * 4u);
+            const int lines = a.head_size >> 5; // 128-byte lines per row of one KV head
+            for (int i = tid; i < pos * lines; i += PD_CT) { // plain L2 prefetches through the LSU: the TMA queue is busy refilling the ring right now
+                const size_t off = (size_t)(i / lines) * kvd + kvh * a.head_size + (i % lines) * 32;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(Ly.kc + off));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(Ly.vc + off));
             }
         }
         pd_arrive(a, PD_S_QKV, e * nC, e, false, tid); // q/k/v of this rank's heads stay on this rank
