@@ -36,6 +36,7 @@ sys.path.insert(0, ROOT)
 import __graft_entry__ as ge  # noqa: E402
 
 WORKLOAD = "llama-3-8b"
+QUANT = "q8_0"
 FALLBACK_HBM_GBS = 6650.0
 
 
@@ -145,7 +146,7 @@ def algorithmic_bytes_per_token(shape, quant_q8: bool, ctx_avg_pos: float) -> di
 
 def build_model(pkg, ctx: int, device: str | None, tp_rank: int = 0, tp_size: int = 1):
     shape = pkg.synth.SHAPES[WORKLOAD]
-    quant = pkg.gguf.GGMLType.Q8_0
+    quant = pkg.gguf.GGMLType.Q8_0 if QUANT == "q8_0" else pkg.gguf.GGMLType.F16
     t0 = time.time()
     tensors = pkg.synth.build_tensors_fast(shape, quant, seed=1234, device=device, tp_rank=tp_rank, tp_size=tp_size)
     model = pkg.loader.model_from_tensors(shape, quant, tensors, ctx)
@@ -192,7 +193,7 @@ def parity_gate(plan, tokens, ref, want_logits: bool):
 
 
 def main():
-    global WORKLOAD
+    global WORKLOAD, QUANT
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=128)
@@ -203,12 +204,14 @@ def main():
     ap.add_argument("--no-pp", action="store_true", help="skip the pp512 tensor-core prefill leg")
     ap.add_argument("--decode-mode", default="default", choices=["default", "persistent", "graph"],
                     help="decode implementation: one persistent kernel per token, or the round-1 CUDA graph of ~7 kernels per layer")
+    ap.add_argument("--quant", default="q8_0", choices=["q8_0", "f16"], help="weight type of the synthetic model (f16: the exact lane-order FP16 matvec path, graph mode)")
     ap.add_argument("--depth", type=int, default=-1, help="LlamaBench -d: KV positions filled before the timed steps (default: the warm-up steps)")
     ap.add_argument("--workload", default=WORKLOAD, choices=["llama-3-8b", "llama-3-70b", "llama-3.2-1b", "qwen3-4b"],
                     help="shape of the synthetic model (default: the BASELINE headline, Llama-3-8B; 70B is BASELINE config 5, meant for --gpus 2/4/8)")
     args = ap.parse_args()
     K, W = args.steps, max(args.warmup, 3)
     WORKLOAD = args.workload
+    QUANT = args.quant
     pretty = {"llama-3-8b": "Llama-3-8B", "llama-3-70b": "Llama-3-70B", "llama-3.2-1b": "Llama-3.2-1B", "qwen3-4b": "Qwen3-4B"}[WORKLOAD]
 
     rank = int(os.environ.get("RANK", "0"))
@@ -220,9 +223,10 @@ def main():
     D = max(W, args.depth)  # LlamaBench -d: positions filled before the timed steps; the fill doubles as the warm-up
     ctx = D + K + 8  # LlamaBench: depth + tokens + 8 (LlamaBench.java:174)
     tokens = np.asarray(lb.synthetic_tokens(shape.vocab, D + K), dtype=np.int32)
-    config = {"workload": f"{pretty}-shaped synthetic GGUF, Q8_0, tg{K} single-stream decode from depth {D}",
+    qname = "Q8_0" if QUANT == "q8_0" else "FP16"
+    config = {"workload": f"{pretty}-shaped synthetic GGUF, {qname}, tg{K} single-stream decode from depth {D}",
               "weights": "seeded N(0,1/sqrt(fan_in)) quantised with the ggml Q8_0 rule; tokens java.util.Random(42)",
-              "context": ctx, "l2": f"inputs larger than L2 ({shape.matmul_elements() // 32 * 34 / 1e9:.2f} GB of weights stream per step vs 126 MB L2)"}
+              "context": ctx, "l2": f"inputs larger than L2 ({(shape.matmul_elements() // 32 * 34 if QUANT == 'q8_0' else shape.matmul_elements() * 2) / 1e9:.2f} GB of weights stream per step vs 126 MB L2)"}
 
     if args.impl == "reference":
         if world > 1 and rank != 0:
@@ -315,7 +319,7 @@ def main():
 
     # ---- roofline: the whole decode step (in persistent mode it is ONE kernel launch) ------------------
     peak, peak_src = peaks()
-    ab = algorithmic_bytes_per_token(shape, True, D + (K - 1) / 2.0)
+    ab = algorithmic_bytes_per_token(shape, QUANT == "q8_0", D + (K - 1) / 2.0)
     step_bytes = ab["total"] / world                 # algorithmic bytes one GPU must read per token
     step_gbs = step_bytes * value / 1e9              # ... x tok/s
     per_kernel = {}
@@ -332,7 +336,7 @@ def main():
     line = {
         "metric": "decode_tokens_per_s", "value": value, "unit": "tok/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak" if world == 1 else "strong", "vs_baseline": None,
-        "dtype": "q8_0xq8_0->int32, f32 accumulate", "data": "synthetic", "config": config,
+        "dtype": "q8_0xq8_0->int32, f32 accumulate" if QUANT == "q8_0" else "f16 weights x f32 activations, f32 fma chains (16 lanes)", "data": "synthetic", "config": config,
         "parallelism": "single GPU" if world == 1 else f"tp{world}: row-sharded weights, in-kernel all-gather over NVLink peer memory (bit-exact with tp1)",
         "decode_mode": "persistent (1 kernel per token)" if persistent else f"graph ({launches_per_step} kernels per token)",
         "e2e": {"value": K / e2e_s, "unit": "tok/s", "h2d_bytes_per_step": 32, "d2h_bytes_per_step": 4},
@@ -359,7 +363,7 @@ def main():
             dist.broadcast_object_list([len(ref["ids"])], src=0)
         line["parity"] = parity_gate(plan, tokens, ref, want_logits=world == 1)
     plan.free()
-    if not args.no_pp and world == 1 and WORKLOAD == "llama-3-8b":  # BASELINE config 3 is the 8B FP16 model
+    if not args.no_pp and world == 1 and WORKLOAD == "llama-3-8b" and QUANT == "q8_0":  # BASELINE config 3 is the 8B FP16 model
         del model, plan
         line["pp512"] = prefill_leg(pkg, lb, local, 512, 5)
     print(json.dumps(line))

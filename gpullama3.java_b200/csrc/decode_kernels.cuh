@@ -405,7 +405,7 @@ __global__ void k_swiglu(float *__restrict__ hb, const float *__restrict__ hb2, 
 // The current position's k/v come from shared memory / the packed qkv vector, older ones from the
 // FP32 cache.  Output as floats (xb) and/or quantised to Q8_0 (activation of the Wo matvec).
 // ------------------------------------------------------------------------------------------
-#define ATT_THREADS 256
+#define ATT_THREADS 512 // four threads per key (scores) and per output element (weighted sum): head size <= ATT_THREADS / 4
 
 template <int HS>
 __global__ void __launch_bounds__(ATT_THREADS) k_attention(float *__restrict__ qkv, float *__restrict__ kc, float *__restrict__ vc,
@@ -424,11 +424,20 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attention(float *__restrict__ q
     constexpr int HALF = HS / 2;
     trace_entry(tr);
     pdl_launch_dependents();
+    const int kv_mul = n_heads / n_kv_heads, kvh = h / kv_mul;
+    const int qd = n_heads * HS, kvd = n_kv_heads * HS;
     pdl_wait();
     trace_mark(tr, 2);
     const int pos = st->pos, nt = pos + 1;
-    const int kv_mul = n_heads / n_kv_heads, kvh = h / kv_mul;
-    const int qd = n_heads * HS, kvd = n_kv_heads * HS;
+    { // K/V rows of the earlier positions -> L2, one 128-byte line per request, so the score loads below hit L2 (the weight stream carries an
+      // evict_first policy; without the prefetch these rows come from HBM every layer)
+        constexpr int LINES = HS / 32;
+        for (int i = tid; i < pos * LINES; i += ATT_THREADS) {
+            const size_t off = (size_t)(i / LINES) * kvd + kvh * HS + (i % LINES) * 32;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(kc + off));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(vc + off));
+        }
+    }
     const float *qsrc = qkv + h * HS, *ksrc = qkv + qd + kvh * HS, *vsrc = qkv + qd + kvd + kvh * HS;
     // ---- prologue: threads [0,HALF) rotate q pairs, threads [HALF,HS) rotate k pairs
     if (tid < HS) {
@@ -480,33 +489,51 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attention(float *__restrict__ q
         if (is_q) { qkv[h * HS + i0] = r0; qkv[h * HS + i1] = r1; }
     }
     __syncthreads();
-    // ---- scores: one thread per time step, 8 x 16-byte loads in flight
+    // ---- scores (scalarDot, FloatTensor.java:86-92: one sequential unfused mul/add chain per key).  Four threads share a key: each loads
+    // ITS quarter of the K row at once (one round trip per pass of ATT_THREADS/4 keys), then the chain runs through the quad in element
+    // order, handed on by shuffle.  The V rows of the first round of the weighted sum are requested here too (they do not depend on the scores).
+    constexpr int QE = HS / 4, QV = HS / 16, VB = 32;
+    const int quad = tid & 3, qbase = lane & ~3, vd = tid >> 2;
+    const bool vlive = vd < HS;
+    float vv[VB];
+    {
+        const float *vcol = vc + kvh * HS + vd;
+#pragma unroll
+        for (int u = 0; u < VB; u++) vv[u] = (vlive && quad * VB + u < pos) ? __ldg(vcol + (size_t)(quad * VB + u) * kvd) : 0.0f;
+    }
     float lmax = -INFINITY;
-    for (int t = tid; t < nt; t += ATT_THREADS) {
-        float acc = 0.0f;
-        if (t == pos) {
-#pragma unroll 8
-            for (int j = 0; j < HS; j++) acc = __fadd_rn(acc, __fmul_rn(sq[j], sk[j]));
+#pragma unroll 1
+    for (int t0 = 0; t0 < nt; t0 += ATT_THREADS / 4) {
+        const int t = t0 + (tid >> 2);
+        float4 kk[QV];
+        if (t < pos) {
+            const float4 *k = reinterpret_cast<const float4 *>(kc + (size_t)t * kvd + kvh * HS + quad * QE);
+#pragma unroll
+            for (int u = 0; u < QV; u++) kk[u] = __ldg(k + u);
         } else {
-            const float4 *k = reinterpret_cast<const float4 *>(kc + (size_t)t * kvd + kvh * HS);
 #pragma unroll
-            for (int j0 = 0; j0 < HS / 4; j0 += 8) {
-                float4 kk[8];
+            for (int u = 0; u < QV; u++) kk[u] = t == pos ? *reinterpret_cast<const float4 *>(sk + quad * QE + 4 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float acc = 0.0f;
+#pragma unroll 1
+        for (int qd4 = 0; qd4 < 4; qd4++) {
+            if (quad == qd4) {
+                const float *qq = sq + qd4 * QE;
 #pragma unroll
-                for (int u = 0; u < 8; u++) kk[u] = __ldg(k + j0 + u);
-#pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const int j = 4 * (j0 + u);
-                    acc = __fadd_rn(acc, __fmul_rn(sq[j + 0], kk[u].x));
-                    acc = __fadd_rn(acc, __fmul_rn(sq[j + 1], kk[u].y));
-                    acc = __fadd_rn(acc, __fmul_rn(sq[j + 2], kk[u].z));
-                    acc = __fadd_rn(acc, __fmul_rn(sq[j + 3], kk[u].w));
+                for (int u = 0; u < QV; u++) {
+                    acc = __fadd_rn(acc, __fmul_rn(qq[4 * u + 0], kk[u].x));
+                    acc = __fadd_rn(acc, __fmul_rn(qq[4 * u + 1], kk[u].y));
+                    acc = __fadd_rn(acc, __fmul_rn(qq[4 * u + 2], kk[u].z));
+                    acc = __fadd_rn(acc, __fmul_rn(qq[4 * u + 3], kk[u].w));
                 }
             }
+            acc = __shfl_sync(0xffffffffu, acc, qbase + qd4);
         }
-        const float s = __fdiv_rn(acc, sqrt_hs);
-        att[t] = s;
-        lmax = fmaxf(lmax, s);
+        if (quad == 0 && t < nt) {
+            const float s = __fdiv_rn(acc, sqrt_hs);
+            att[t] = s;
+            lmax = fmaxf(lmax, s);
+        }
     }
     lmax = warp_max_f(lmax);
     if (lane == 0) red[warp] = lmax;
@@ -530,22 +557,38 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attention(float *__restrict__ q
     const float sum = s_val[0];
     for (int t = tid; t < nt; t += ATT_THREADS) att[t] = __fdiv_rn(att[t], sum);
     __syncthreads();
-    // ---- output: one thread per element, sequential over t, 16 loads in flight
-    if (tid < HS) {
-        const float *v = vc + kvh * HS + tid;
+    // ---- output: xb = sum_t a_t * v_t sequentially over t per element (saxpyInPlace, FloatTensor.java:221-227); four threads per element, thread
+    // `quad` holds rows [128 r + 32 quad, +32) of round r, the chain runs through the quad in row order
+#pragma unroll 1
+    for (int vd0 = 0; vd0 < HS; vd0 += ATT_THREADS / 4) { // one pass for head sizes up to 128
+        const int d = vd0 + vd;
+        const bool live = d < HS;
+        const float *vcol = vc + kvh * HS + d;
+        const float vcur = live ? vsrc[d] : 0.0f; // current position: straight from the packed qkv vector
         float acc = 0.0f;
-        int t = 0;
-        for (; t + 16 <= pos; t += 16) {
-            float vv[16];
+#pragma unroll 1
+        for (int r0 = 0; r0 < pos; r0 += 4 * VB) {
+            if (r0 > 0 || vd0 > 0) { // (round 0 of the first pass was requested before the scores)
+                const int vt0 = r0 + quad * VB;
 #pragma unroll
-            for (int u = 0; u < 16; u++) vv[u] = __ldg(v + (size_t)(t + u) * kvd);
+                for (int u = 0; u < VB; u++) vv[u] = (live && vt0 + u < pos) ? __ldg(vcol + (size_t)(vt0 + u) * kvd) : 0.0f;
+            }
+#pragma unroll 1
+            for (int qd4 = 0; qd4 < 4; qd4++) {
+                if (quad == qd4) {
+                    const int vt0 = r0 + qd4 * VB;
 #pragma unroll
-            for (int u = 0; u < 16; u++) acc = __fadd_rn(__fmul_rn(att[t + u], vv[u]), acc);
+                    for (int u = 0; u < VB; u++)
+                        if (vt0 + u < pos) acc = __fadd_rn(__fmul_rn(att[vt0 + u], vv[u]), acc);
+                }
+                acc = __shfl_sync(0xffffffffu, acc, qbase + qd4);
+            }
         }
-        for (; t < pos; t++) acc = __fadd_rn(__fmul_rn(att[t], __ldg(v + (size_t)t * kvd)), acc);
-        acc = __fadd_rn(__fmul_rn(att[pos], vsrc[tid]), acc); // current position: straight from the packed qkv vector
-        so[tid] = acc;
-        if (xb) xb[h * HS + tid] = acc;
+        if (live && quad == 0) {
+            acc = __fadd_rn(__fmul_rn(att[pos], vcur), acc);
+            so[d] = acc;
+            if (xb) xb[h * HS + d] = acc;
+        }
     }
     __syncthreads();
     if (xq) {

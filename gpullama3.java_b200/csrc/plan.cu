@@ -1050,7 +1050,9 @@ int prefill_init(b200_plan *p) {
         const char *e = getenv("B200_GEMM_2CTA");
         c.pair = !(e && e[0] == '0') && nqkv % 256 == 0 && g.dim % 256 == 0 && g.hidden_dim % 128 == 0;
         const char *e2 = getenv("B200_GEMM_PERSIST"); // persistent CTA-pair kernel (double-buffered TMEM) for QKV and gate/up: validated on the
-        c.persist = !(e2 && e2[0] == '0');            // GPU in round 2 (tests/test_gpu_prefill.py, profiles/r2_run1_first_green.log); =0 selects the one-tile kernels
+        c.persist = !(e2 && e2[0] == '0');
+        const char *e3 = getenv("B200_GEMM_PERSIST_RESID"); // =1: Wo / W2 through the persistent kernel too (split-K folded into its work list); experimental
+        c.persist_resid = c.persist && e3 && e3[0] == '1';            // GPU in round 2 (tests/test_gpu_prefill.py, profiles/r2_run1_first_green.log); =0 selects the one-tile kernels
     }
     if (!ok) { c.why = "cuTensorMapEncodeTiled rejected a tensor map"; return B200_OK; }
     if (g.head_size == 128) {
@@ -1125,6 +1127,14 @@ int prefill_forward(b200_plan *p, int n, int start_pos, int *launches) {
         while (sp > 1 && nk / sp < 8) sp--;
         return sp < 1 ? 1 : sp;
     };
+    // persistent residual GEMMs: enough (tile, k-range) items for ~2 waves of the 74 clusters, at least 8 k-blocks per item
+    auto persist_splits = [&](int n_tiles, int K) {
+        const int tiles = (mt2 / 2) * n_tiles, nk = K / pg::BK, clusters = p->n_sms / 2;
+        int sp = (2 * clusters + tiles - 1) / tiles;
+        if (sp > 8) sp = 8;
+        while (sp > 1 && (nk / sp < 8 || (sp - 1) * ((nk + sp - 1) / sp) >= nk)) sp--;
+        return sp < 1 ? 1 : sp;
+    };
     k_pf_embed<<<n, 256, 0, s>>>(c.tok, p->emb, c.X, g.dim); nl++;
     for (int l = 0; l < g.n_layers; l++) {
         const LayerW &L = p->layers[l];
@@ -1157,7 +1167,10 @@ int prefill_forward(b200_plan *p, int n, int start_pos, int *launches) {
             else k_pf_attention_mma<64><<<ag, PM_THREADS, pm_smem_bytes<64>(), s>>>(c.QKV, nqkv, c.KH, c.VH, p->kvd, kv_mul, n, start_pos, inv_sqrt_hs, c.ATT16, p->qd);
         }
         nl += 2;
-        if (c.pair) {
+        if (c.pair && c.persist_resid) { // persistent CTA-pair kernel with the split-K ranges folded into its work list
+            if (pg::gemm2_persist_launch<pg::GEMM_RESID, 256, pg::GEMM2_PERSIST_STAGES_256>(c.mATT, m.wo, m.wo, c.mX, c.X, g.dim, n, mt2, g.dim / 256, p->qd, p->n_sms, s, persist_splits(g.dim / 256, p->qd)))
+                return fail(p, B200_ERR_CUDA, "Wo GEMM launch failed");
+        } else if (c.pair) {
             if (pg::gemm2_launch<pg::GEMM_RESID, 256, pg::GEMM2_STAGES_256>(c.mATT, m.wo, m.wo, c.mX, c.X, g.dim, n, mt2, g.dim / 256, p->qd, s, pair_splits(g.dim / 256, p->qd)))
                 return fail(p, B200_ERR_CUDA, "Wo GEMM launch failed");
         } else
@@ -1177,7 +1190,10 @@ int prefill_forward(b200_plan *p, int n, int start_pos, int *launches) {
                                                   : pg::gemm_launch<pg::GEMM_GATEUP, ST>(c.mA, m.w1, m.w3, c.mX, c.H16, g.hidden_dim, n, mt, g.hidden_dim / (pg::BN / 2), g.dim, s))
             return fail(p, B200_ERR_CUDA, "gate/up GEMM launch failed");
         nl++;
-        if (c.pair) {
+        if (c.pair && c.persist_resid) {
+            if (pg::gemm2_persist_launch<pg::GEMM_RESID, 256, pg::GEMM2_PERSIST_STAGES_256>(c.mH, m.w2, m.w2, c.mX, c.X, g.dim, n, mt2, g.dim / 256, g.hidden_dim, p->n_sms, s, persist_splits(g.dim / 256, g.hidden_dim)))
+                return fail(p, B200_ERR_CUDA, "W2 GEMM launch failed");
+        } else if (c.pair) {
             if (pg::gemm2_launch<pg::GEMM_RESID, 256, pg::GEMM2_STAGES_256>(c.mH, m.w2, m.w2, c.mX, c.X, g.dim, n, mt2, g.dim / 256, g.hidden_dim, s, pair_splits(g.dim / 256, g.hidden_dim)))
                 return fail(p, B200_ERR_CUDA, "W2 GEMM launch failed");
         } else

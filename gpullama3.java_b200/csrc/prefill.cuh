@@ -35,6 +35,7 @@ struct PrefillCtx {
     int mode = 0;       // 0 = exact token-by-token graph, 1 = tensor-core GEMMs
     bool pair = true;      // CTA-pair (cta_group::2) GEMMs; B200_GEMM_2CTA=0 selects the single-CTA kernels
     bool persist = true;   // persistent CTA-pair GEMM (double-buffered TMEM accumulators) for QKV and gate/up; B200_GEMM_PERSIST=0 turns it off
+    bool persist_resid = false; // B200_GEMM_PERSIST_RESID=1: the residual GEMMs (Wo, W2) through the persistent kernel with split-K work items
     bool att_simt = false; // debug: FP32 SIMT attention instead of the mma.sync kernel (B200_PF_ATT=simt)
     float *X = nullptr, *QKV = nullptr;
     __half *A16 = nullptr, *ATT16 = nullptr, *H16 = nullptr;

@@ -432,7 +432,7 @@ template <int BN, int STAGES> constexpr size_t smem_bytes_2cta_persist() {
 template <int MODE, int BN, int STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
     k_gemm_f16_2cta_persist(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_b2,
-                            const __grid_constant__ CUtensorMap tma_c, void *__restrict__ Cv, int ldc, int m_valid, int K, int m_pairs, int n_tiles) {
+                            const __grid_constant__ CUtensorMap tma_c, void *__restrict__ Cv, int ldc, int m_valid, int K, int m_pairs, int n_tiles, int splits) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     constexpr int A_BYTES = BM * BK * 2, B_BYTES = (BN / 2) * BK * 2, CST_BYTES = BM * 32 * 4;
@@ -457,24 +457,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
     cluster_sync_all();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
-    const int nk = (K + BK - 1) / BK;
-    const int n_clusters = (int)(gridDim.x >> 1), cid = (int)(blockIdx.x >> 1), total = m_pairs * n_tiles;
+    // split-K (GEMM_RESID only: every split reduce-adds its partial product): a work item is (pair tile, k-range); items of one tile are
+    // adjacent in the walk so the B tile of neighbouring clusters differs only in k
+    const int nk_all = (K + BK - 1) / BK, nk_split = (nk_all + splits - 1) / splits;
+    const int n_clusters = (int)(gridDim.x >> 1), cid = (int)(blockIdx.x >> 1), total = m_pairs * n_tiles * splits;
 
     if (warp == 0 && lane == 0) {
         // ===== TMA producer (both CTAs) =====
         const CUtensorMap *bmap = (MODE == GEMM_GATEUP && rank == 1) ? &tma_b2 : &tma_b;
         int it = 0; // running k-block counter across tiles: the ring never drains between tiles
         for (int t = cid; t < total; t += n_clusters) {
-            const int mp = t % m_pairs, nt = t / m_pairs;
+            const int ks = t % splits, tt = t / splits;
+            const int mp = tt % m_pairs, nt = tt / m_pairs;
             const int m0 = mp * 2 * BM + (int)rank * BM;
             const int n0 = nt * (MODE == GEMM_GATEUP ? BN / 2 : BN);
             const int brow = MODE == GEMM_GATEUP ? n0 : n0 + (int)rank * (BN / 2);
+            const int kb0 = ks * nk_split, nk = min(nk_split, nk_all - kb0);
             for (int kb = 0; kb < nk; kb++, it++) {
                 const int st = it % STAGES;
                 mbar_wait(empty0 + 8 * st, ((it / STAGES) & 1) ^ 1);
                 if (rank == 0) mbar_expect_tx(full0 + 8 * st, 2 * (A_BYTES + B_BYTES));
-                tma_load_2d_2sm(s32(sA + st * A_BYTES), &tma_a, kb * BK, m0, full0 + 8 * st);
-                tma_load_2d_2sm(s32(sB + st * B_BYTES), bmap, kb * BK, brow, full0 + 8 * st);
+                tma_load_2d_2sm(s32(sA + st * A_BYTES), &tma_a, (kb0 + kb) * BK, m0, full0 + 8 * st);
+                tma_load_2d_2sm(s32(sB + st * B_BYTES), bmap, (kb0 + kb) * BK, brow, full0 + 8 * st);
             }
         }
     } else if (warp == 1 && lane == 0 && rank == 0) {
@@ -483,6 +487,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
         int it = 0, i = 0;
         for (int t = cid; t < total; t += n_clusters, i++) {
             const int buf = i & 1;
+            const int kb0 = (t % splits) * nk_split, nk = min(nk_split, nk_all - kb0);
             mbar_wait(tempty0 + 8 * buf, ((i >> 1) & 1) ^ 1); // both CTAs' epilogues have drained this buffer (first two uses pass at once)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             for (int kb = 0; kb < nk; kb++, it++) {
@@ -502,7 +507,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
         int i = 0, chunk = 0;                         // chunk: running count of staged 32-column chunks (staging buffer = chunk & 1)
         for (int t = cid; t < total; t += n_clusters, i++) {
             const int buf = i & 1;
-            const int mp = t % m_pairs, nt = t / m_pairs;
+            const int tt = t / splits;
+            const int mp = tt % m_pairs, nt = tt / m_pairs;
             const int m0 = mp * 2 * BM + (int)rank * BM;
             const int n0 = nt * (MODE == GEMM_GATEUP ? BN / 2 : BN);
             const int row = m0 + q * 32 + lane;
@@ -660,7 +666,7 @@ constexpr int GEMM2_STAGES_256_M2 = 4;                    // 4 x (32 KB of A + 1
 // Persistent variant (round-2 candidate).  n_sms: SMs of the device; the grid is the largest even number of CTAs <= n_sms.
 template <int MODE, int BN, int STAGES>
 inline int gemm2_persist_launch(const CUtensorMap &a, const CUtensorMap &b, const CUtensorMap &b2, const CUtensorMap &c, void *C, int ldc, int m_valid, int m_tiles,
-                                int n_tiles, int K, int n_sms, cudaStream_t stream) {
+                                int n_tiles, int K, int n_sms, cudaStream_t stream, int splits = 1) {
     static bool attr = false;
     if (!attr) {
         if (cudaFuncSetAttribute(k_gemm_f16_2cta_persist<MODE, BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_2cta_persist<BN, STAGES>()) !=
@@ -668,12 +674,16 @@ inline int gemm2_persist_launch(const CUtensorMap &a, const CUtensorMap &b, cons
             return -4;
         attr = true;
     }
-    if (m_tiles & 1) return -6;
-    const int m_pairs = m_tiles / 2, total = m_pairs * n_tiles;
+    if (m_tiles & 1 || splits < 1 || (splits > 1 && MODE != GEMM_RESID)) return -6;
+    {
+        const int nk = (K + BK - 1) / BK, per = (nk + splits - 1) / splits;
+        if ((splits - 1) * per >= nk) return -6; // an empty split would publish an unwritten accumulator
+    }
+    const int m_pairs = m_tiles / 2, total = m_pairs * n_tiles * splits;
     int clusters = n_sms / 2;
     if (clusters > total) clusters = total;
     if (clusters < 1) return -6;
-    k_gemm_f16_2cta_persist<MODE, BN, STAGES><<<dim3(2 * clusters), 256, smem_bytes_2cta_persist<BN, STAGES>(), stream>>>(a, b, b2, c, C, ldc, m_valid, K, m_pairs, n_tiles);
+    k_gemm_f16_2cta_persist<MODE, BN, STAGES><<<dim3(2 * clusters), 256, smem_bytes_2cta_persist<BN, STAGES>(), stream>>>(a, b, b2, c, C, ldc, m_valid, K, m_pairs, n_tiles, splits);
     return cudaGetLastError() == cudaSuccess ? 0 : -5;
 }
 constexpr int GEMM2_PERSIST_STAGES_256 = 5; // 5 x 32 KB of operands + 2 x 16 KB of C staging
@@ -697,7 +707,7 @@ inline int gemm_f16(const __half *A, const __half *B, float *C, int M, int N, in
             int dev = 0, sms = 148;
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            return resid ? gemm2_persist_launch<GEMM_RESID, 256, GEMM2_PERSIST_STAGES_256>(ma, mb, mb, mc, C, N, M, M / BM, N / 256, K, sms, stream)
+            return resid ? gemm2_persist_launch<GEMM_RESID, 256, GEMM2_PERSIST_STAGES_256>(ma, mb, mb, mc, C, N, M, M / BM, N / 256, K, sms, stream, resid)
                          : gemm2_persist_launch<GEMM_F32, 256, GEMM2_PERSIST_STAGES_256>(ma, mb, mb, mc, C, N, M, M / BM, N / 256, K, sms, stream);
         }
         if (two_cta == 512) { // 256-wide pair tiles, two of them (512 rows) per CTA pair

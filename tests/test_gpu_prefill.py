@@ -14,7 +14,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 FP16_TOL = 2.0 ** -8
-Q8_TOL = 2.0 ** -4  # Q8_0 model: dominated by the CPU path's own int8 activation rounding, see test_tensor_core_prefill_q8_model
+Q8_NOISE_TOL = 0.03  # Q8_0 model vs the CPU path itself: the CPU path's own int8 activation rounding (measured 0.5-2.5 %), reported, not the parity bar
 
 
 @pytest.mark.parametrize("m,n,k", [(128, 128, 64), (256, 384, 512), (384, 1024, 2240)])
@@ -41,14 +41,11 @@ def test_gemm_rejects_ragged_shapes(pkg):
         pkg.native.gemm_f16(a, b)
 
 
-def _prefill_and_compare(pkg, orc, m, n_tok, batch, tol=FP16_TOL, opt_in=False):
+def _prefill_and_compare(pkg, orc, m, n_tok, batch, tol=FP16_TOL):
     c = m.configuration
     plan = pkg.B200MasterPlan.initialize_plan(m, prefill_batch_size=batch)
     om = orc.OracleModel(m)
     try:
-        if opt_in:  # Q8_0 plans default to the exact path; the tensor-core one builds f16 twins on request
-            assert plan.prefill_info()[0] == plan.PREFILL_EXACT
-            plan.set_prefill_mode("tensor_core")
         assert plan.prefill_info()[0] == plan.PREFILL_TENSOR_CORE  # default for FP16 plans created with a batch size
         toks = orc.bench_tokens(c.vocab_size, n_tok + 1)
         for off in range(0, n_tok, batch):
@@ -98,15 +95,71 @@ def test_tensor_core_prefill_mid_llama(pkg, orc):
     _prefill_and_compare(pkg, orc, m, 136, 128)
 
 
+def _dequantised_f16_twin(pkg, m):
+    """The model the Q8_0 tensor-core prefill actually computes with: every matrix replaced by f16(q * scale) (Q8_0FloatTensor.getFloat
+    rounded once, as k_tiles_to_f16 does on the device), norms untouched, embedding kept in Q8_0 (the gather dequantises in fp32)."""
+    G = pkg.gguf.GGMLType
+    tensors = {}
+    for name, (tt, dims, raw) in m.tensors.items():
+        if tt == G.Q8_0 and name != "token_embd.weight":
+            blocks = np.ascontiguousarray(raw).reshape(-1, 34)
+            d = blocks[:, :2].copy().view("<f2").astype(np.float32)
+            q = blocks[:, 2:].view(np.int8).astype(np.float32)
+            tensors[name] = (G.F16, dims, (q * d).astype(np.float16).view(np.uint8).reshape(-1))
+        else:
+            tensors[name] = (tt, dims, raw)
+    cfg = m.configuration
+    twin = pkg.loader.Model(None, type(cfg)(**{**cfg.__dict__, "quantization": "FP16"}), m.model_type, tensors)
+    return twin
+
+
 @pytest.mark.parametrize("shape", ["tiny-llama", "tiny-qwen3"])
 def test_tensor_core_prefill_q8_model(pkg, orc, make_model, shape):
-    """Opt-in on a Q8_0 plan: f16 twins of the matrices are dequantised on the device for the GEMMs.  The oracle
-    (CPU path) rounds activations to int8 per 32-block before every dot product, the tensor-core path does not
-    (nor does the reference's own GPU prefill), so what is measured here is mostly the CPU path's own
-    activation-quantisation noise (0.5-2 % of max|ref| on K/V, 2-3 % on the logits of these random models;
-    profiles/prefill_parity_q8_r1.json) -- which is why this mode is not the default for Q8_0 plans."""
+    """Opt-in on a Q8_0 plan: f16 twins of the matrices are dequantised on the device for the GEMMs (the reference's Q8_0 MMA prefill
+    feeds FP16 tiles the same way, TransformerBatchPrefillKernels.java:1563-1574).  PARITY BAR: the KV cache must agree at FP16
+    tolerance (2^-8) with the CPU oracle evaluated on exactly those dequantised FP16 weights -- that is what this path computes.
+    Against the CPU path of the Q8_0 model itself the difference is the CPU path's own int8 activation rounding, which the tensor-core
+    path (like the reference's GPU prefill) does not apply: percent-level, bounded loosely and reported, which is why this mode is not
+    the default for Q8_0 plans."""
     m = make_model(shape, pkg.gguf.GGMLType.Q8_0, 48)
-    _prefill_and_compare(pkg, orc, m, 40, 16, tol=Q8_TOL, opt_in=True)
+    c = m.configuration
+    n_tok, batch = 40, 16
+    plan = pkg.B200MasterPlan.initialize_plan(m, prefill_batch_size=batch)
+    om_twin = orc.OracleModel(_dequantised_f16_twin(pkg, m))
+    om_q8 = orc.OracleModel(m)
+    try:
+        assert plan.prefill_info()[0] == plan.PREFILL_EXACT  # Q8_0 plans default to the exact path
+        plan.set_prefill_mode("tensor_core")
+        toks = orc.bench_tokens(c.vocab_size, n_tok + 1)
+        for off in range(0, n_tok, batch):
+            plan.forward_batch_prefill(toks[off:min(off + batch, n_tok)], off)
+        for pos in range(n_tok):
+            om_twin.forward(int(toks[pos]), pos, want_logits=False)
+            om_q8.forward(int(toks[pos]), pos, want_logits=False)
+        nv = n_tok * c.kv_dim
+        worst_twin = worst_q8 = 0.0
+        for l in range(c.n_layers):
+            nkv = c.context_length * c.kv_dim
+            for name in ("key_cache", "value_cache"):
+                got = plan.read_buffer(name, nkv, layer=l)[:nv]
+                rt = (om_twin.key_cache(l) if name == "key_cache" else om_twin.value_cache(l))[:nv]
+                rq = (om_q8.key_cache(l) if name == "key_cache" else om_q8.value_cache(l))[:nv]
+                worst_twin = max(worst_twin, float(np.max(np.abs(got - rt)) / np.max(np.abs(rt))))
+                worst_q8 = max(worst_q8, float(np.max(np.abs(got - rq)) / np.max(np.abs(rq))))
+        assert worst_twin <= FP16_TOL, f"vs the oracle on the dequantised FP16 weights: rel err {worst_twin:.2e}"
+        assert worst_q8 <= Q8_NOISE_TOL, f"vs the CPU path of the Q8_0 model (its int8 activation rounding): rel err {worst_q8:.2e}"
+        print(f"q8 tensor-core prefill {shape}: {worst_twin:.2e} vs dequantised-FP16 oracle, {worst_q8:.2e} vs the Q8_0 CPU path")
+        # the exact mode of the same plan stays bit-identical to the CPU path of the Q8_0 model
+        plan.set_prefill_mode("exact")
+        plan.kv_reset()
+        for off in range(0, n_tok, batch):
+            plan.forward_batch_prefill(toks[off:min(off + batch, n_tok)], off)
+        k = plan.read_buffer("key_cache", c.context_length * c.kv_dim, layer=c.n_layers - 1)
+        assert np.array_equal(k.view(np.uint32)[:nv], om_q8.key_cache(c.n_layers - 1).view(np.uint32)[:nv])
+    finally:
+        plan.free()
+        om_twin.close()
+        om_q8.close()
 
 
 def test_tensor_core_prefill_unsupported_is_loud(pkg, make_model):
