@@ -6,6 +6,7 @@
 #include "decode_kernels.cuh"
 #include "prefill.cuh"
 #include "stream_matvec.cuh"
+#include "stream_matvec_f16.cuh"
 #include "decode_persistent.cuh"
 #include "sampler.cuh"
 
@@ -68,6 +69,7 @@ struct b200_plan {
     DevMat emb{}, out{};
     TileMat tout{};
     bool use_stream = false, use_pdl = false;
+    bool use_f16_stream = false; // FP16 plans: per-warp bulk-copy rings (stream_matvec_f16.cuh) instead of k_matvec_f16
     bool f16_copies = false; // Q8_0 plan that also holds f16 weight matrices for the tensor-core prefill
     int n_sms = 148;
     unsigned *blk_cnt = nullptr;
@@ -435,6 +437,22 @@ template <int MODE> int launch_matvec_f16(b200_plan *p, const DevMat &m, const f
     return B200_OK;
 }
 
+// FP16 plans on the streaming path (stream_matvec_f16.cuh); m2 = ffn_up for SF_GATEUP.
+template <typename... KA, typename... A> int launch_k(b200_plan *p, bool pdl, void (*kern)(KA...), dim3 grid, dim3 block, size_t smem, A... args);
+template <int MODE> int launch_stream_f16(b200_plan *p, const DevMat &m, const DevMat *m2, const float *x, float *out, TraceBuf tr = TraceBuf{nullptr, 0, 0}) {
+    const int lanes = p->cfg.fp16_lanes;
+    const SfLayout L = sf_layout(m.rows, m.cols, lanes, MODE == SF_GATEUP);
+    if (!L.ok) return fail(p, B200_ERR_STATE, "f16 streaming layout does not fit %d x %d", m.rows, m.cols);
+    SfArgs a;
+    a.w0 = (const __half *)m.qs; a.w1 = m2 ? (const __half *)m2->qs : nullptr; a.x = x; a.out = out; a.rows = m.rows; a.cols = m.cols;
+    a.seg = L.seg; a.nseg = L.nseg; a.stages = L.stages; a.tr = tr;
+    const int rw = 32 / lanes, mr = MODE == SF_GATEUP ? rw / 2 : rw;
+    int grid = L.ctas_per_sm * p->n_sms;
+    if (grid > m.rows / mr) grid = m.rows / mr;
+    if (lanes == 16) return launch_k(p, p->use_pdl, k_stream_matvec_f16<16, MODE>, dim3(grid), dim3(SF_THREADS), L.total, a);
+    return launch_k(p, p->use_pdl, k_stream_matvec_f16<8, MODE>, dim3(grid), dim3(SF_THREADS), L.total, a);
+}
+
 // Kernel launch with the programmatic-dependent-launch attribute (captured into the CUDA graph as
 // a programmatic edge): the kernel may become resident while its predecessor is still running.
 template <typename... KA, typename... A>
@@ -474,7 +492,9 @@ void read_knobs(b200_plan *p) {
     const char *v = getenv("B200_NORM_V2");
     p->norm_v2 = !(v && v[0] == '0');
     const char *d = getenv("B200_DECODE");
-    p->decode_mode = (d && !strcmp(d, "graph")) ? B200_DECODE_GRAPH : B200_DECODE_PERSISTENT;
+    // default: the CUDA graph -- measured faster than the persistent kernel on the same box (profiles/r2_final_a.log: 313.6 vs 285.1 tok/s,
+    // 8B Q8_0; under tensor parallelism by 10-21 %).  B200_DECODE=persistent or b200_set_decode_mode select the one-kernel-per-token path.
+    p->decode_mode = (d && !strcmp(d, "persistent")) ? B200_DECODE_PERSISTENT : B200_DECODE_GRAPH;
 }
 size_t smv_budget(const b200_plan *p, int cols) {
     if (p->smv_budget_cols && cols && p->smv_budget_cols != cols) return SMV_SMEM_BUDGET_MAX;
@@ -513,7 +533,7 @@ bool gateup_fits(int hidden, int n_sms) { // epilogue buffer holds this CTA's hi
 int enqueue_forward(b200_plan *p, bool with_logits, int *launches, bool trace = false) {
     const b200_config &c = p->cfg;
     const bool q8 = p->wtype == B200_GGML_Q8_0;
-    const bool st = p->use_stream, pdl = p->use_pdl;
+    const bool st = p->use_stream, pdl = p->use_pdl, sf = p->use_f16_stream;
     const bool tpar = p->tp.n > 1;
     int n = 0;
     auto TR = [&](int id) { return TraceBuf{trace ? p->trace_rec : nullptr, n, id}; };
@@ -538,6 +558,7 @@ int enqueue_forward(b200_plan *p, bool with_logits, int *launches, bool trace = 
         n++;
         if (st) rc = launch_stream<SMV_STORE>(p, L.tqkv, p->xq, p->xs, p->qkv, nullptr, nullptr, false, TR(2));
         else if (q8) rc = launch_matvec_q8<MODE_STORE>(p, L.qkv, p->xq, p->xs, p->qkv);
+        else if (sf) rc = launch_stream_f16<SF_STORE>(p, L.qkv, nullptr, p->xb, p->qkv, TR(2));
         else rc = launch_matvec_f16<MODE_STORE>(p, L.qkv, p->xb, p->qkv);
         if (rc) return rc; n++;
         float *kc = p->key_cache + (size_t)l * ctx_kv, *vc = p->value_cache + (size_t)l * ctx_kv;
@@ -558,6 +579,7 @@ int enqueue_forward(b200_plan *p, bool with_logits, int *launches, bool trace = 
         }
         if (st) rc = launch_stream<SMV_RESID>(p, L.two, p->attq, p->atts, p->x, nullptr, nullptr, false, TR(5), tpar ? TP_SLOT_ATT : -1, 4 * l + 0, tpar ? TP_SLOT_X : -1, 4 * l + 1, rank * p->dim_l);
         else if (q8) rc = launch_matvec_q8<MODE_RESID>(p, L.wo, p->xq, p->xs, p->x);
+        else if (sf) rc = launch_stream_f16<SF_RESID>(p, L.wo, nullptr, p->xb, p->x, TR(5));
         else rc = launch_matvec_f16<MODE_RESID>(p, L.wo, p->xb, p->x);
         if (rc) return rc; n++;
         if ((rc = norm(false, L.ffn_norm, 4 * l + 1))) return rc;
@@ -570,6 +592,9 @@ int enqueue_forward(b200_plan *p, bool with_logits, int *launches, bool trace = 
                 (const int8_t *)L.w1.qs, L.w1.sc, (const int8_t *)L.w3.qs, L.w3.sc, p->xq, p->xs, c.hidden_dim, c.dim, p->hq, p->hs, p->hb);
             CK(cudaGetLastError()); n++;
             if ((rc = launch_matvec_q8<MODE_RESID>(p, L.w2, p->hq, p->hs, p->x))) return rc; n++;
+        } else if (sf) { // gate, up and SwiGLU in one launch; then the down projection
+            if ((rc = launch_stream_f16<SF_GATEUP>(p, L.w1, &L.w3, p->xb, p->hb, TR(6)))) return rc; n++;
+            if ((rc = launch_stream_f16<SF_RESID>(p, L.w2, nullptr, p->hb, p->x, TR(7)))) return rc; n++;
         } else {
             if ((rc = launch_matvec_f16<MODE_STORE>(p, L.w1, p->xb, p->hb))) return rc; n++;
             if ((rc = launch_matvec_f16<MODE_STORE>(p, L.w3, p->xb, p->hb2))) return rc; n++;
@@ -586,6 +611,7 @@ int enqueue_forward(b200_plan *p, bool with_logits, int *launches, bool trace = 
         n++;
         if (st) rc = launch_stream<SMV_STORE>(p, p->tout, p->xq, p->xs, p->logits, nullptr, nullptr, true, TR(8), -1, 0, -1, 0, rank * p->voc_l);
         else if (q8) rc = launch_matvec_q8<MODE_STORE>(p, p->out, p->xq, p->xs, p->logits);
+        else if (sf) rc = launch_stream_f16<SF_STORE>(p, p->out, nullptr, p->xb, p->logits, TR(8));
         else rc = launch_matvec_f16<MODE_STORE>(p, p->out, p->xb, p->logits);
         if (rc) return rc; n++;
     }
@@ -761,6 +787,12 @@ int set_smem_attrs(b200_plan *p) {
     CK(cudaFuncSetAttribute(k_stream_matvec_q8<SMV_GATEUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMV_SMEM_BUDGET_MAX));
     CK(set_max_dyn(k_matvec_f16<MODE_STORE>, maxdyn));
     CK(set_max_dyn(k_matvec_f16<MODE_RESID>, maxdyn));
+    CK(set_max_dyn(k_stream_matvec_f16<16, SF_STORE>, maxdyn));
+    CK(set_max_dyn(k_stream_matvec_f16<16, SF_RESID>, maxdyn));
+    CK(set_max_dyn(k_stream_matvec_f16<16, SF_GATEUP>, maxdyn));
+    CK(set_max_dyn(k_stream_matvec_f16<8, SF_STORE>, maxdyn));
+    CK(set_max_dyn(k_stream_matvec_f16<8, SF_RESID>, maxdyn));
+    CK(set_max_dyn(k_stream_matvec_f16<8, SF_GATEUP>, maxdyn));
     done = true;
     return B200_OK;
 }
@@ -811,8 +843,12 @@ int build(b200_plan *p, const b200_tensor *tensors, int n_tensors) {
         p->use_stream = want && p->wtype == B200_GGML_Q8_0 && stream_shape_ok(p->qd_l + 2 * p->kvd_l, c.dim) && stream_shape_ok(p->dim_l, p->qd) &&
                         stream_shape_ok(2 * p->hid_l, c.dim) && stream_shape_ok(p->dim_l, c.hidden_dim) && stream_shape_ok(p->voc_l, c.dim) &&
                         gateup_fits(p->hid_l, p->n_sms);
+        const char *e3 = getenv("B200_F16_STREAM"); // FP16 plans: 0 = the round-1 k_matvec_f16 launches
+        p->use_f16_stream = !(e3 && e3[0] == '0') && p->wtype == B200_GGML_F16 && c.tp_size == 1 && sf_layout(p->qd + 2 * p->kvd, c.dim, c.fp16_lanes, false).ok &&
+                            sf_layout(c.dim, p->qd, c.fp16_lanes, false).ok && sf_layout(c.hidden_dim, c.dim, c.fp16_lanes, true).ok &&
+                            sf_layout(c.dim, c.hidden_dim, c.fp16_lanes, false).ok && sf_layout(c.vocab_size, c.dim, c.fp16_lanes, false).ok;
         const char *e2 = getenv("B200_PDL");
-        p->use_pdl = p->use_stream && !(e2 && e2[0] == '0');
+        p->use_pdl = (p->use_stream || p->use_f16_stream) && !(e2 && e2[0] == '0');
         if (c.tp_size > 1 && !p->use_stream) return fail(p, B200_ERR_UNSUPPORTED, "tensor parallelism needs the Q8_0 streaming path");
     }
     void *stage = nullptr;
@@ -1519,8 +1555,23 @@ int b200_time_kernel(b200_plan *p, int32_t which, int32_t reps, float *avg_ms, i
     };
     int64_t bytes = 0;
     int launches = 0;
+    const bool sf = p->use_f16_stream;
     auto one = [&](int l) -> int {
         LayerW &L = p->layers[l];
+        if (sf) { // FP16 streaming kernels, stand-alone (no PDL overlap)
+            const bool keep = p->use_pdl;
+            p->use_pdl = false;
+            int r;
+            switch (which) {
+            case 0: bytes = mat_bytes(L.w1) + mat_bytes(L.w3); r = launch_stream_f16<SF_GATEUP>(p, L.w1, &L.w3, p->xb, p->hb); break;
+            case 1: bytes = mat_bytes(L.w2); r = launch_stream_f16<SF_RESID>(p, L.w2, nullptr, p->hb, p->x); break;
+            case 2: bytes = mat_bytes(L.qkv); r = launch_stream_f16<SF_STORE>(p, L.qkv, nullptr, p->xb, p->qkv); break;
+            case 3: bytes = mat_bytes(L.wo); r = launch_stream_f16<SF_RESID>(p, L.wo, nullptr, p->xb, p->x); break;
+            default: bytes = mat_bytes(p->out); r = launch_stream_f16<SF_STORE>(p, p->out, nullptr, p->xb, p->logits); break;
+            }
+            p->use_pdl = keep;
+            return r;
+        }
         switch (which) {
         case 0:
             if (q8) {

@@ -134,11 +134,12 @@ int b200_prefill_info(b200_plan *plan, int32_t *mode, int32_t *launches, float *
 /* How the single-token forwards (b200_forward_decode / _prefill / b200_decode_sequence) run.  Both replace
  * TornadoVMMasterPlanSingleToken.tornadoVMForwardDecode's N+2 TaskGraph executions
  * (TornadoVMMasterPlanSingleToken.java:68-95) and produce bit-identical results:
- *   B200_DECODE_GRAPH       one CUDA graph of ~7 kernels per layer with programmatic-dependent-launch edges;
+ *   B200_DECODE_GRAPH       one CUDA graph of ~7 kernels per layer with programmatic-dependent-launch edges (the default:
+ *                           measured 3.19 ms vs 3.51 ms per token on Llama-3-8B Q8_0, profiles/r2_final_a.log);
  *   B200_DECODE_PERSISTENT  ONE persistent kernel per token (csrc/decode_persistent.cuh): one CTA per SM streams the
  *                           weights of every matrix through a shared-memory ring while epoch counters order the phases.
- *                           Default when the plan fits (Q8_0 streaming layout, head size 64/128); the environment
- *                           variable B200_DECODE=graph selects the graph at creation.
+ *                           Available when the plan fits (Q8_0 streaming layout, head size 64/128); the environment
+ *                           variable B200_DECODE=persistent selects it at creation.
  * Returns B200_ERR_UNSUPPORTED with the reason in b200_last_error when the plan cannot run the requested mode.
  * Under tensor parallelism every rank must switch at the same point of the call sequence. */
 #define B200_DECODE_GRAPH 0

@@ -74,6 +74,25 @@ def test_decode_f16_bit_exact(pkg, orc, make_model, shape, lanes):
     run_stream(pkg, orc, m, lanes, 12)
 
 
+@pytest.mark.parametrize("shape,lanes", [("mid-llama-1b", 16), ("mid-llama", 16), ("mid-llama", 8), ("mid-qwen3-4b", 16)])
+def test_decode_mid_geometries_f16(pkg, orc, shape, lanes):
+    """FP16 plans on the per-warp bulk-copy rings (csrc/stream_matvec_f16.cuh) at the real layer geometries, bit-exact vs the oracle:
+    Llama-3.2-1B (BASELINE config 1: dim 2048, hidden 8192, tied classifier), Llama-3-8B (config 3: hidden 14336 -> a 57 KB activation
+    next to the rings), Qwen3-4B (dim 2560 -> 256-column segments).  A warp laps its ring many times per matvec; the 8-lane species
+    puts four rows (two gate + two up) into one warp."""
+    sh = pkg.synth.SHAPES[shape]
+    F16 = pkg.gguf.GGMLType.F16
+    m = pkg.loader.model_from_tensors(sh, F16, pkg.synth.build_tensors_fast(sh, F16, seed=7), 16)
+    run_stream(pkg, orc, m, lanes, 4, check_kv=True)
+
+
+def test_decode_f16_round1_kernels_still_exact(pkg, orc, make_model, monkeypatch):
+    """B200_F16_STREAM=0 keeps the round-1 launches (k_matvec_f16 + separate SwiGLU), the fallback for shapes the rings do not fit."""
+    monkeypatch.setenv("B200_F16_STREAM", "0")
+    m = make_model("tiny-llama", pkg.gguf.GGMLType.F16, 24)
+    run_stream(pkg, orc, m, 16, 8)
+
+
 @pytest.mark.parametrize("mode", MODES)
 def test_decode_small_llama_q8(pkg, orc, make_model, mode):
     """dim 1536 (not a multiple of 512: exercises the column tail), 12 heads / 4 KV heads, 3 layers."""
