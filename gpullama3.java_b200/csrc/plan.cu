@@ -7,6 +7,7 @@
 #include "prefill.cuh"
 #include "stream_matvec.cuh"
 #include "stream_matvec_f16.cuh"
+#include "kquant.cuh"
 #include "decode_persistent.cuh"
 #include "sampler.cuh"
 
@@ -69,6 +70,7 @@ struct b200_plan {
     DevMat emb{}, out{};
     TileMat tout{};
     bool use_stream = false, use_pdl = false;
+    size_t kq_off = 0; // K-quant files: offset of the raw (K-quant bytes) area inside each staging buffer; 0 = no K-quant tensor in the file
     bool use_f16_stream = false; // FP16 plans: per-warp bulk-copy rings (stream_matvec_f16.cuh) instead of k_matvec_f16
     bool f16_copies = false; // Q8_0 plan that also holds f16 weight matrices for the tensor-core prefill
     int n_sms = 148;
@@ -283,33 +285,42 @@ int64_t n_elems(const b200_tensor *t) {
     return n;
 }
 
-// Upload rows [0, rows) of a [rows][cols] GGUF matrix into dst at row offset `row_off`.
-int upload_matrix(b200_plan *p, const b200_tensor *t, int rows, int cols, DevMat &dst, int row_off, void *stage,
-                  size_t stage_bytes) {
+static inline int eff_type(int t) { return kq_is_kquant(t) ? B200_GGML_Q8_0 : t; } // AbstractModelLoader.effectiveGpuWeightType (:58-64)
+
+// Upload rows [0, rows) of a [rows][cols] GGUF matrix into dst at row offset `row_off`.  K-quant sources are re-quantised to Q8_0 on
+// the device (kquant.cuh) between the copy and the repack.
+int upload_matrix(b200_plan *p, const b200_tensor *t, int rows, int cols, DevMat &dst, int row_off, void *stage, size_t stage_bytes) {
     if (!t) return fail(p, B200_ERR_BAD_ARG, "missing tensor");
     if (n_elems(t) != (int64_t)rows * cols)
         return fail(p, B200_ERR_BAD_ARG, "tensor %s has %lld elements, expected %lld", t->name, (long long)n_elems(t),
                     (long long)rows * cols);
-    if (t->ggml_type != dst.type)
+    if (eff_type(t->ggml_type) != dst.type)
         return fail(p, B200_ERR_UNSUPPORTED, "tensor %s has ggml type %d, plan weight type is %d", t->name, t->ggml_type,
                     dst.type);
     if (dst.type == B200_GGML_Q8_0) {
+        const bool kq = kq_is_kquant(t->ggml_type);
+        if (kq && (cols % 256 || !p->kq_off)) return fail(p, B200_ERR_BAD_ARG, "K-quant tensor %s: rows must be multiples of 256 elements", t->name);
+        const size_t kb = kq ? (size_t)kq_block_bytes(t->ggml_type) : 0;
         size_t nblk = (size_t)rows * cols / 32;
         int8_t *qs = (int8_t *)dst.qs + (size_t)row_off * cols;
         __half *sc = (__half *)dst.sc + (size_t)row_off * (cols / 32);
-        // chunked through the staging buffer (multiple of 34 bytes)
+        // chunked through the staging buffer (multiple of 34 bytes; of 8 blocks = one super-block for K-quants)
         if (p->up.on) stage_bytes = p->up.dst_bytes;
-        size_t blk_per_chunk = stage_bytes / 34;
+        const size_t q8_area = p->kq_off ? p->kq_off : stage_bytes;
+        size_t blk_per_chunk = (q8_area / 34) & ~(size_t)7;
         for (size_t b0 = 0; b0 < nblk; b0 += blk_per_chunk) {
             size_t nb = nblk - b0 < blk_per_chunk ? nblk - b0 : blk_per_chunk;
+            const unsigned char *hsrc = kq ? (const uint8_t *)t->data + b0 / 8 * kb : (const uint8_t *)t->data + b0 * 34;
+            const size_t hbytes = kq ? nb / 8 * kb : nb * 34;
             int rc;
             if (p->up.on) {
                 unsigned char *stg = nullptr;
                 if ((rc = up_stage_begin(p, &stg))) return rc;
-                if ((rc = up_h2d(p, stg, (const uint8_t *)t->data + b0 * 34, nb * 34))) return rc;
+                if ((rc = up_h2d(p, stg + (kq ? p->kq_off : 0), hsrc, hbytes))) return rc;
                 if ((rc = up_stage_ready(p))) return rc;
                 stage = stg;
-            } else CK(cudaMemcpyAsync(stage, (const uint8_t *)t->data + b0 * 34, nb * 34, cudaMemcpyHostToDevice, p->stream));
+            } else CK(cudaMemcpyAsync((unsigned char *)stage + (kq ? p->kq_off : 0), hsrc, hbytes, cudaMemcpyHostToDevice, p->stream));
+            if (kq) CK(launch_requant_kquant(t->ggml_type, (const unsigned char *)stage + p->kq_off, (unsigned char *)stage, (long long)nb, p->stream));
             size_t words = nb * 17;
             k_repack_q8<<<(unsigned)((words + 255) / 256), 256, 0, p->stream>>>((const uint16_t *)stage, (uint16_t *)(qs + b0 * 32),
                                                                                   (uint16_t *)(sc + b0), words);
@@ -339,6 +350,10 @@ int upload_tiles(b200_plan *p, const b200_tensor *t0, const b200_tensor *t1, con
         stage = stg;
         stage_bytes = p->up.dst_bytes;
     }
+    const size_t q8_area = p->kq_off ? p->kq_off : stage_bytes;
+    size_t roff = 0; // cursor inside the raw (K-quant) area
+    struct Requant { int type; const unsigned char *raw; unsigned char *q8; long long nblk; } rq[3];
+    int n_rq = 0;
     for (int k = 0; k < 3; k++) {
         src.raw[k] = nullptr;
         src.rows[k] = rs[k];
@@ -348,18 +363,32 @@ int upload_tiles(b200_plan *p, const b200_tensor *t0, const b200_tensor *t1, con
         const int first = row0 ? row0[k] : 0;
         const b200_tensor *t = ts[k];
         if (!t) return fail(p, B200_ERR_BAD_ARG, "missing tensor");
-        if (t->ggml_type != B200_GGML_Q8_0) return fail(p, B200_ERR_UNSUPPORTED, "tensor %s has ggml type %d, plan weight type is Q8_0", t->name, t->ggml_type);
+        const bool kq = kq_is_kquant(t->ggml_type);
+        if (t->ggml_type != B200_GGML_Q8_0 && !kq) return fail(p, B200_ERR_UNSUPPORTED, "tensor %s has ggml type %d, plan weight type is Q8_0", t->name, t->ggml_type);
+        if (kq && (cols % 256 || !p->kq_off)) return fail(p, B200_ERR_BAD_ARG, "K-quant tensor %s: rows must be multiples of 256 elements", t->name);
         if (n_elems(t) != (int64_t)full_rows * cols) return fail(p, B200_ERR_BAD_ARG, "tensor %s has %lld elements, expected %lld", t->name, (long long)n_elems(t), (long long)full_rows * cols);
         if (first < 0 || first + rs[k] > full_rows) return fail(p, B200_ERR_BAD_ARG, "row range of tensor %s out of bounds", t->name);
         const size_t row_bytes = (size_t)cols / 32 * 34, nbytes = (size_t)rs[k] * row_bytes;
-        const unsigned char *hsrc = (const unsigned char *)t->data + (size_t)first * row_bytes;
-        if (off + nbytes > stage_bytes) return fail(p, B200_ERR_STATE, "staging buffer too small");
-        if (p->up.on) { if ((rc = up_h2d(p, (unsigned char *)stage + off, hsrc, nbytes))) return rc; }
-        else CK(cudaMemcpyAsync((unsigned char *)stage + off, hsrc, nbytes, cudaMemcpyHostToDevice, p->stream));
+        if (off + nbytes > q8_area) return fail(p, B200_ERR_STATE, "staging buffer too small");
+        if (kq) { // the K-quant bytes land in the raw area; the Q8_0 blocks are produced on the device once the copies are in
+            const size_t raw_row = (size_t)cols / 256 * kq_block_bytes(t->ggml_type), raw_bytes = (size_t)rs[k] * raw_row;
+            const unsigned char *hsrc = (const unsigned char *)t->data + (size_t)first * raw_row;
+            if (p->kq_off + roff + raw_bytes > stage_bytes) return fail(p, B200_ERR_STATE, "staging buffer too small");
+            unsigned char *rdst = (unsigned char *)stage + p->kq_off + roff;
+            if (p->up.on) { if ((rc = up_h2d(p, rdst, hsrc, raw_bytes))) return rc; }
+            else CK(cudaMemcpyAsync(rdst, hsrc, raw_bytes, cudaMemcpyHostToDevice, p->stream));
+            rq[n_rq++] = Requant{t->ggml_type, rdst, (unsigned char *)stage + off, (long long)rs[k] * (cols / 32)};
+            roff += (raw_bytes + 255) & ~(size_t)255;
+        } else {
+            const unsigned char *hsrc = (const unsigned char *)t->data + (size_t)first * row_bytes;
+            if (p->up.on) { if ((rc = up_h2d(p, (unsigned char *)stage + off, hsrc, nbytes))) return rc; }
+            else CK(cudaMemcpyAsync((unsigned char *)stage + off, hsrc, nbytes, cudaMemcpyHostToDevice, p->stream));
+        }
         src.raw[k] = (const unsigned char *)stage + off;
         off += (nbytes + 255) & ~(size_t)255;
     }
     if (p->up.on && (rc = up_stage_ready(p))) return rc;
+    for (int i = 0; i < n_rq; i++) CK(launch_requant_kquant(rq[i].type, rq[i].raw, rq[i].q8, rq[i].nblk, p->stream));
     src.gateup = gateup ? 1 : 0;
     const int rows = gateup ? r0 + r1 : r0 + r1 + r2;
     out.rows = rows;
@@ -826,9 +855,11 @@ int build(b200_plan *p, const b200_tensor *tensors, int n_tensors) {
     if (!emb) return fail(p, B200_ERR_BAD_ARG, "missing tensor token_embd.weight");
     const b200_tensor *wq0 = find(tensors, n_tensors, "blk.0.attn_q.weight");
     if (!wq0) return fail(p, B200_ERR_BAD_ARG, "missing tensor blk.0.attn_q.weight");
-    p->wtype = wq0->ggml_type;
+    p->wtype = eff_type(wq0->ggml_type); // K-quant matrices become Q8_0 while they are uploaded (kquant.cuh)
     if (p->wtype != B200_GGML_Q8_0 && p->wtype != B200_GGML_F16)
-        return fail(p, B200_ERR_UNSUPPORTED, "Type: %d currently not supported for B200 weights (Q8_0 and F16 only)", p->wtype);
+        return fail(p, B200_ERR_UNSUPPORTED, "Type: %d currently not supported for B200 weights (Q8_0, F16 and the K-quants Q4_K/Q5_K/Q6_K only)", wq0->ggml_type);
+    bool any_kq = false;
+    for (int i = 0; i < n_tensors; i++) any_kq = any_kq || kq_is_kquant(tensors[i].ggml_type);
 
     CK(cudaSetDevice(p->device));
     read_knobs(p);
@@ -860,17 +891,22 @@ int build(b200_plan *p, const b200_tensor *tensors, int n_tensors) {
         size_t need = mx / 32 * 34 + 4096;
         if (need > stage_bytes) stage_bytes = need;
     }
+    if (any_kq) { // second half of each staging buffer receives the raw K-quant bytes (always fewer than their Q8_0 form)
+        stage_bytes = (stage_bytes + 255) & ~(size_t)255;
+        p->kq_off = stage_bytes;
+        stage_bytes *= 2;
+    }
     const auto t_up0 = std::chrono::steady_clock::now();
     if ((rc = up_init(p, stage_bytes))) return rc; // pipelined upload (B200_UPLOAD_SYNC=1: the blocking round-1 path)
-    if (!p->up.on && (p->wtype == B200_GGML_Q8_0 || emb->ggml_type == B200_GGML_Q8_0)) CK(cudaMalloc(&stage, stage_bytes));
+    if (!p->up.on && (p->wtype == B200_GGML_Q8_0 || eff_type(emb->ggml_type) == B200_GGML_Q8_0)) CK(cudaMalloc(&stage, stage_bytes));
     struct StageGuard { void *s; b200_plan *pl; ~StageGuard() { if (s) cudaFree(s); up_destroy(pl); } } guard{stage, p};
 
     // embedding table (+ tied classifier: AbstractModelLoader.java:186-195)
-    if ((rc = alloc_matrix(p, p->emb, c.vocab_size, c.dim, emb->ggml_type))) return rc;
+    if ((rc = alloc_matrix(p, p->emb, c.vocab_size, c.dim, eff_type(emb->ggml_type)))) return rc;
     if ((rc = upload_matrix(p, emb, c.vocab_size, c.dim, p->emb, 0, stage, stage_bytes))) return rc;
     const b200_tensor *outw = find(tensors, n_tensors, "output.weight");
     if (p->use_stream) {
-        if (!outw && emb->ggml_type != p->wtype) return fail(p, B200_ERR_UNSUPPORTED, "tied output weight type differs from the matrix type");
+        if (!outw && eff_type(emb->ggml_type) != p->wtype) return fail(p, B200_ERR_UNSUPPORTED, "tied output weight type differs from the matrix type");
         {
             const int r0[3] = {c.tp_rank * p->voc_l, 0, 0}, fu[3] = {c.vocab_size, 0, 0};
             if ((rc = upload_tiles(p, outw ? outw : emb, nullptr, nullptr, p->voc_l, 0, 0, c.dim, false, p->tout, stage, stage_bytes, r0, fu))) return rc;
@@ -884,7 +920,7 @@ int build(b200_plan *p, const b200_tensor *tensors, int n_tensors) {
         if ((rc = alloc_matrix(p, p->out, c.vocab_size, c.dim, p->wtype))) return rc;
         if ((rc = upload_matrix(p, outw, c.vocab_size, c.dim, p->out, 0, stage, stage_bytes))) return rc;
     } else {
-        if (emb->ggml_type != p->wtype) return fail(p, B200_ERR_UNSUPPORTED, "tied output weight type differs from the matrix type");
+        if (eff_type(emb->ggml_type) != p->wtype) return fail(p, B200_ERR_UNSUPPORTED, "tied output weight type differs from the matrix type");
         p->out = p->emb;
     }
     if ((rc = upload_f32(p, find(tensors, n_tensors, "output_norm.weight"), c.dim, &p->out_norm, "output_norm.weight"))) return rc;
@@ -1723,6 +1759,19 @@ int b200_test_seqsum(const float *terms, int32_t n, float *out, int32_t *info) {
 int b200_test_seqsum2(const float *terms, int32_t n, int32_t threads, float *out, int32_t *info) {
     if (threads != 256 && threads != 512 && threads != 1024) return B200_ERR_BAD_ARG;
     return run_seqsum_hook(terms, n, threads, out, info);
+}
+
+int b200_requant_kquant(int32_t ggml_type, const void *src, int64_t n_elems, void *dst_q8_0) {
+    if (!src || !dst_q8_0 || n_elems <= 0 || n_elems % 256 || !kq_is_kquant(ggml_type)) return B200_ERR_BAD_ARG;
+    const size_t raw = (size_t)(n_elems / 256) * kq_block_bytes(ggml_type), q8 = (size_t)(n_elems / 32) * 34;
+    unsigned char *ds = nullptr, *dd = nullptr;
+    int rc = B200_OK;
+    auto ok = [&](cudaError_t e) { if (e != cudaSuccess && rc == B200_OK) rc = e == cudaErrorMemoryAllocation ? B200_ERR_OOM : B200_ERR_CUDA; return rc == B200_OK; };
+    if (ok(cudaMalloc(&ds, raw)) && ok(cudaMalloc(&dd, q8)) && ok(cudaMemcpy(ds, src, raw, cudaMemcpyHostToDevice)) &&
+        ok(launch_requant_kquant(ggml_type, ds, dd, n_elems / 32, 0)) && ok(cudaDeviceSynchronize()))
+        ok(cudaMemcpy(dst_q8_0, dd, q8, cudaMemcpyDeviceToHost));
+    cudaFree(ds); cudaFree(dd);
+    return rc;
 }
 
 int b200_gemm_f16(const uint16_t *a, const uint16_t *b, float *c, int32_t m, int32_t n, int32_t k, int32_t iters, float *ms) {

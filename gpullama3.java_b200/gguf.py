@@ -25,9 +25,13 @@ class GGMLType:
     F32 = 0
     F16 = 1
     Q8_0 = 8
-    NAMES = {0: "F32", 1: "F16", 8: "Q8_0"}
+    Q4_K = 12  # K-quants: accepted for Q8_0 plans, re-quantised on the device at upload (ModelLoader.java:163, csrc/kquant.cuh)
+    Q5_K = 13
+    Q6_K = 14
+    NAMES = {0: "F32", 1: "F16", 8: "Q8_0", 12: "Q4_K", 13: "Q5_K", 14: "Q6_K"}
     # (type_size_bytes, block_size_elems), GGMLType.java:5-20
-    SIZES = {0: (4, 1), 1: (2, 1), 8: (34, 32)}
+    SIZES = {0: (4, 1), 1: (2, 1), 8: (34, 32), 12: (144, 256), 13: (176, 256), 14: (210, 256)}
+    K_QUANTS = (12, 13, 14)
 
     @staticmethod
     def byte_size_for(ggml_type: int, n_elements: int) -> int:

@@ -63,6 +63,8 @@ def _quantization(metadata: dict) -> str:
         return "FP16"
     if ft == 7:
         return "Q8_0"
+    if ft in (14, 15, 16, 17, 18):  # Q4_K_S/M, Q5_K_S/M, Q6_K: the accelerator path computes in Q8_0 (AbstractModelLoader.java:45-47)
+        return "Q8_0"
     raise UnsupportedModel(f"Unsupported quantization format: {ft} (as int).")
 
 

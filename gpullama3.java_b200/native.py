@@ -40,7 +40,7 @@ class Tensor(C.Structure):
 
 
 EXPORTS = ["b200_plan_create", "b200_forward_decode", "b200_forward_prefill", "b200_forward_batch_prefill", "b200_set_prefill_mode", "b200_prefill_info",
-           "b200_set_decode_mode", "b200_decode_info", "b200_trace_persistent", "b200_test_seqsum2", "b200_forward_decode_sample", "b200_upload_info",
+           "b200_set_decode_mode", "b200_decode_info", "b200_trace_persistent", "b200_test_seqsum2", "b200_forward_decode_sample", "b200_upload_info", "b200_requant_kquant",
            "b200_decode_sequence", "b200_time_kernel", "b200_tp_handle", "b200_tp_attach", "b200_trace_decode", "b200_profile_norm", "b200_test_seqsum", "b200_gemm_f16", "b200_kv_reset", "b200_read_buffer", "b200_launches_per_decode",
            "b200_device_bytes", "b200_plan_free", "b200_last_error", "b200_version"]
 
@@ -110,6 +110,17 @@ def test_seqsum(terms, want_info: bool = False, threads: int = 0):
     return (out.value, info[0], info[1]) if want_info else out.value
 
 
+def requant_kquant(ggml_type: int, raw, n_elems: int) -> np.ndarray:
+    """Device K-quant (Q4_K = 12 / Q5_K = 13 / Q6_K = 14) -> GGUF Q8_0 bytes (csrc/kquant.cuh; ModelLoader.java:173-224)."""
+    raw = np.ascontiguousarray(raw, dtype=np.uint8)
+    out = np.empty(n_elems // 32 * 34, dtype=np.uint8)
+    lib().b200_requant_kquant.argtypes = [C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]
+    rc = lib().b200_requant_kquant(int(ggml_type), raw.ctypes.data, int(n_elems), out.ctypes.data)
+    if rc != B200_OK:
+        _raise(rc, "b200_requant_kquant failed")
+    return out
+
+
 def gemm_f16(a, b, iters: int = 0):
     """C = A @ B.T on the tcgen05 prefill GEMM (A [m,k], B [n,k] float16) -> (C float32, ms per launch or None)."""
     a = np.ascontiguousarray(a, dtype=np.float16)
@@ -126,6 +137,9 @@ def gemm_f16(a, b, iters: int = 0):
     return c, (ms.value if iters > 0 else None)
 
 
+GGML_SIZES = {0: (4, 1), 1: (2, 1), 8: (34, 32), 12: (144, 256), 13: (176, 256), 14: (210, 256)}  # (bytes, elements) per block, GGMLType.java:5-20
+
+
 class NativePlan:
     """Owns one ``b200_plan*``."""
 
@@ -135,6 +149,11 @@ class NativePlan:
         self._keep = []
         for i, (name, (tt, dims, raw)) in enumerate(tensors.items()):
             raw = np.ascontiguousarray(raw)
+            ts_bs = GGML_SIZES.get(int(tt))
+            n_el = int(np.prod(dims))
+            if ts_bs is not None and (n_el % ts_bs[1] or raw.nbytes != n_el // ts_bs[1] * ts_bs[0]):
+                # the C ABI takes plain pointers: a short buffer would be read past its end on the device side of the upload
+                raise B200Error(-1, f"tensor {name}: {raw.nbytes} bytes do not hold {n_el} elements of ggml type {int(tt)}")
             self._keep.append(raw)
             arr[i].name = name.encode()
             arr[i].data = raw.ctypes.data

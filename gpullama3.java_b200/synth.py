@@ -246,6 +246,53 @@ def build_tensors(shape: Shape, quant: int, seed: int = 1234, w_std: float = 0.0
     return out
 
 
+def random_kquant(ggml_type: int, n_elems: int, rng, zero_blocks: int = 0) -> np.ndarray:
+    """Random but well-formed K-quant super-blocks (Q4_K / Q5_K / Q6_K): uniform random quants, sub-block scales and mins, and FP16 block
+    scales sized so the dequantised weights stay O(1/sqrt(fan-in))-ish.  There is no K-quant QUANTISER here (the hot path only ever reads
+    these formats); the test models need valid bytes, not a faithful compression of given floats.  `zero_blocks` leading super-blocks get
+    d = dmin = 0 (an all-zero Q8_0 block: scale 0, the re-quantiser's division guard)."""
+    ts, bs = GGMLType.SIZES[ggml_type]
+    assert ggml_type in GGMLType.K_QUANTS and n_elems % bs == 0
+    nb = n_elems // bs
+    raw = rng.integers(0, 256, size=(nb, ts), dtype=np.uint8)
+    if ggml_type == GGMLType.Q6_K:
+        d = rng.uniform(2e-5, 6e-5, nb).astype(np.float16)   # x int8 scale (<= 127) x 6-bit quant (<= 32)
+        d[:zero_blocks] = 0
+        raw[:, 208:210] = d.view(np.uint8).reshape(nb, 2)
+    else:
+        d = rng.uniform(1e-4, 4e-4, nb).astype(np.float16)   # x 6-bit scale (<= 63) x 4/5-bit quant (<= 15 / 31)
+        dmin = rng.uniform(1e-4, 4e-4, nb).astype(np.float16) * np.float16(4 if ggml_type == GGMLType.Q4_K else 8)
+        d[:zero_blocks] = 0
+        dmin[:zero_blocks] = 0
+        raw[:, 0:2] = d.view(np.uint8).reshape(nb, 2)
+        raw[:, 2:4] = dmin.view(np.uint8).reshape(nb, 2)
+    return raw.reshape(-1)
+
+
+def build_tensors_kquant(shape: Shape, seed: int = 1234, mix: str = "Q4_K_M") -> dict:
+    """{name: (ggml_type, dims, raw)} of a K-quant file in the layout llama.cpp's mixes use: "Q4_K_M" = Q4_K matrices with Q6_K for
+    attn_v / ffn_down / the classifier and a Q5_K attention output (to touch all three formats), "Q6_K" / "Q5_K" / "Q4_K" = one format
+    throughout.  Norms are F32 as always."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    pure = {"Q4_K": GGMLType.Q4_K, "Q5_K": GGMLType.Q5_K, "Q6_K": GGMLType.Q6_K}.get(mix)
+
+    def pick(name):
+        if pure is not None:
+            return pure
+        if "attn_v" in name or "ffn_down" in name or name in ("output.weight", "token_embd.weight"):
+            return GGMLType.Q6_K
+        return GGMLType.Q5_K if "attn_output" in name else GGMLType.Q4_K
+    out = {}
+    for name, _, dims, kind in tensor_plan(shape, GGMLType.Q8_0):
+        n = int(np.prod(dims))
+        if kind == "n":
+            out[name] = (GGMLType.F32, dims, (1.0 + 0.02 * rng.standard_normal(n, dtype=np.float32)).astype(np.float32).view(np.uint8))
+        else:
+            tt = pick(name)
+            out[name] = (tt, dims, random_kquant(tt, n, rng, zero_blocks=1 if "attn_q" in name else 0))
+    return out
+
+
 def write_model(path: str, shape_name: str, quant: int, seed: int = 1234, w_std: float = 0.0,
                 display_name: str | None = None):
     shape = SHAPES[shape_name]

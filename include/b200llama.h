@@ -42,6 +42,12 @@ extern "C" {
 #define B200_GGML_F32 0
 #define B200_GGML_F16 1
 #define B200_GGML_Q8_0 8
+/* K-quants are accepted for weight matrices and the embedding table of a Q8_0 plan: they are re-quantised to Q8_0 on the device while
+ * the upload pipeline streams them in, byte-identical to ModelLoader.dequantizeToQ8_0TornadoTensor (model/loader/ModelLoader.java:163,
+ * 173-224); the plan then computes exactly as for a Q8_0 file (AbstractModelLoader.java:45-59). */
+#define B200_GGML_Q4_K 12
+#define B200_GGML_Q5_K 13
+#define B200_GGML_Q6_K 14
 
 /* Model configuration: the fields of Configuration the forward pass reads
  * (LlamaModelLoader.java:47-63, Qwen3ModelLoader.java:48-74). */
@@ -217,6 +223,11 @@ int b200_test_seqsum(const float *terms, int32_t n, float *out, int32_t *info /*
 /* Same contract for the round-2 accumulator (csrc/seqsum2.cuh) run by `threads` = 1024 (the RMSNorm kernel's form), 512
  * (the persistent decode kernel's form) or 256 threads; info = {items walked, fallbacks}. */
 int b200_test_seqsum2(const float *terms, int32_t n, int32_t threads, float *out, int32_t *info /* nullable */);
+
+/* Test hook for the device-side K-quant -> Q8_0 re-quantiser the upload pipeline applies to Q4_K / Q5_K / Q6_K tensors (csrc/kquant.cuh;
+ * replaces ModelLoader.dequantizeToQ8_0TornadoTensor, model/loader/ModelLoader.java:173-224): host K-quant blocks in, host GGUF Q8_0
+ * blocks (34 bytes per 32 elements) out, byte-identical to the reference's.  n_elems % 256 == 0. */
+int b200_requant_kquant(int32_t ggml_type, const void *src, int64_t n_elems, void *dst_q8_0);
 
 /* Batched-prefill GEMM building block (csrc/prefill_gemm.cuh; replaces the reference's mma.sync GEMMs
  * gemmMMA / gemmMMAQKV / gemmMMAGateUp, TransformerBatchPrefillKernels.java:792-1132) exposed for

@@ -434,6 +434,91 @@ void oracle_quantize_q8_0(const float *x, int64_t n, uint8_t *out) {
 }
 
 /* ================================================================================================================
+ * K-quants: the reference's accelerator path never computes with Q4_K/Q5_K/Q6_K -- ModelLoader.loadTornadoTensor
+ * (model/loader/ModelLoader.java:163) re-quantises such tensors to Q8_0 at load time (dequantizeToQ8_0TornadoTensor, :173-224) and
+ * AbstractModelLoader.java:45-59 reports the model as Q8_0.  Restated here: the element read of each format (getFloat of
+ * tensor/standard/Q4_KFloatTensor.java:90-120, Q5_KFloatTensor.java:84-122, Q6_KFloatTensor.java:64-116; float products evaluated left
+ * to right, no contraction) and the re-quantiser (per 32 elements: maxAbs, scale = maxAbs / 127f stored as Float.floatToFloat16,
+ * q = clamp(Math.round(x * (1f / scale)), -128, 127) with Math.round = floor(x + 1/2) computed exactly).  The element reads are
+ * pinned against the gguf-py package (llama.cpp's own Python implementation of the formats, tests/test_kquants.py).
+ * ================================================================================================================ */
+static inline int k4_scale(int j, const uint8_t *sc) { return j < 4 ? (sc[j] & 63) : ((sc[j + 4] & 0xF) | ((sc[j - 4] >> 6) << 4)); }
+static inline int k4_min(int j, const uint8_t *sc) { return j < 4 ? (sc[j + 4] & 63) : ((sc[j + 4] >> 4) | ((sc[j] >> 6) << 4)); }
+static inline uint16_t rd16(const uint8_t *p) { return (uint16_t)(p[0] | (p[1] << 8)); }
+
+static float q4k_get(const uint8_t *base, int64_t index) {
+    const uint8_t *b = base + (index / 256) * 144;
+    const int within = (int)(index % 256), pair = within / 64, pos = within % 64;
+    const float d = f16_to_f32(rd16(b)), dmin = f16_to_f32(rd16(b + 2));
+    int sub, q;
+    if (pos < 32) { sub = pair * 2; q = b[16 + pair * 32 + pos] & 0xF; }
+    else { sub = pair * 2 + 1; q = (b[16 + pair * 32 + (pos - 32)] >> 4) & 0xF; }
+    const int sc = k4_scale(sub, b + 4), m = k4_min(sub, b + 4);
+    const float a = d * (float)sc, a2 = a * (float)q, c = dmin * (float)m;
+    return a2 - c;
+}
+static float q5k_get(const uint8_t *base, int64_t index) {
+    const uint8_t *b = base + (index / 256) * 176;
+    const int within = (int)(index % 256), pair = within / 64, pos = within % 64;
+    const float d = f16_to_f32(rd16(b)), dmin = f16_to_f32(rd16(b + 2));
+    int sub, q, hi;
+    if (pos < 32) { sub = pair * 2; q = b[48 + pair * 32 + pos] & 0xF; hi = (b[16 + pos] >> (pair * 2)) & 1; }
+    else { sub = pair * 2 + 1; q = (b[48 + pair * 32 + (pos - 32)] >> 4) & 0xF; hi = (b[16 + (pos - 32)] >> (pair * 2 + 1)) & 1; }
+    q += hi * 16;
+    const int sc = k4_scale(sub, b + 4), m = k4_min(sub, b + 4);
+    const float a = d * (float)sc, a2 = a * (float)q, c = dmin * (float)m;
+    return a2 - c;
+}
+static float q6k_get(const uint8_t *base, int64_t index) {
+    const uint8_t *b = base + (index / 256) * 210;
+    const int within = (int)(index % 256), half = within / 128, ph = within % 128, grp = ph / 32, pg = ph % 32, is = pg / 16;
+    const float d = f16_to_f32(rd16(b + 208));
+    const uint8_t *ql = b + half * 64, *qh = b + 128 + half * 32;
+    const int8_t *sc = (const int8_t *)(b + 192 + half * 8);
+    int qv, s;
+    switch (grp) {
+    case 0: qv = ((ql[pg] & 0xF) | (((qh[pg] >> 0) & 3) << 4)) - 32; s = sc[is]; break;
+    case 1: qv = ((ql[32 + pg] & 0xF) | (((qh[pg] >> 2) & 3) << 4)) - 32; s = sc[is + 2]; break;
+    case 2: qv = ((ql[pg] >> 4) | (((qh[pg] >> 4) & 3) << 4)) - 32; s = sc[is + 4]; break;
+    default: qv = ((ql[32 + pg] >> 4) | (((qh[pg] >> 6) & 3) << 4)) - 32; s = sc[is + 6]; break;
+    }
+    const float a = d * (float)s;
+    return a * (float)qv;
+}
+/* ggml type ids: Q4_K = 12, Q5_K = 13, Q6_K = 14 (tensor/GGMLType.java:18-20 in enum order) */
+float oracle_kquant_get(int type, const uint8_t *src, int64_t index) {
+    return type == 12 ? q4k_get(src, index) : type == 13 ? q5k_get(src, index) : q6k_get(src, index);
+}
+void oracle_kquant_dequantize(int type, const uint8_t *src, int64_t n, float *out) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; i++) out[i] = oracle_kquant_get(type, src, i);
+}
+static inline int java_round_f(float a) { /* Math.round(float): floor(a + 1/2), ties towards +infinity, NaN -> 0 */
+    if (a != a) return 0;
+    const float f = floorf(a);
+    return (int)f + ((a - f) >= 0.5f ? 1 : 0);
+}
+void oracle_kquant_to_q8_0(int type, const uint8_t *src, int64_t n, uint8_t *dst) { /* ModelLoader.java:184-212 */
+#pragma omp parallel for schedule(static)
+    for (int64_t b = 0; b < (n + 31) / 32; b++) {
+        const int64_t start = b * 32, end = start + 32 < n ? start + 32 : n;
+        float max_abs = 0.0f;
+        for (int64_t i = start; i < end; i++) { const float a = fabsf(oracle_kquant_get(type, src, i)); max_abs = a > max_abs ? a : max_abs; }
+        const float scale = max_abs / 127.0f;
+        const uint16_t h = f32_to_f16(scale);
+        dst[b * 34] = (uint8_t)(h & 0xFF);
+        dst[b * 34 + 1] = (uint8_t)(h >> 8);
+        const float inv = scale != 0.0f ? 1.0f / scale : 0.0f;
+        for (int64_t i = start; i < end; i++) {
+            int q = java_round_f(oracle_kquant_get(type, src, i) * inv);
+            q = q < -128 ? -128 : (q > 127 ? 127 : q);
+            dst[b * 34 + 2 + (i - start)] = (uint8_t)(int8_t)q;
+        }
+        for (int64_t i = end; i < start + 32; i++) dst[b * 34 + 2 + (i - start)] = 0;
+    }
+}
+
+/* ================================================================================================================
  * Sampler: Sampler.selectSampler (inference/sampler/Sampler.java:74-122), CategoricalSampler.java:28-40,
  * ToppSampler.java:26-156.  Temperature 0 -> FloatTensor.argmax; otherwise logits / temperature, softmaxInPlace, then
  * either the categorical walk or the top-p heap.  PARITY UNPINNED (no JDK here): the uniform numbers come from

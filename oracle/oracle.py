@@ -65,6 +65,8 @@ def lib() -> C.CDLL:
         L.oracle_rope_table.argtypes = [i32, i32, C.c_double, vp, vp]
         L.oracle_bench_tokens.argtypes = [C.c_int64, i32, i32, vp]
         L.oracle_quantize_q8_0.argtypes = [vp, C.c_int64, vp]
+        L.oracle_kquant_dequantize.argtypes = [i32, vp, C.c_int64, vp]
+        L.oracle_kquant_to_q8_0.argtypes = [i32, vp, C.c_int64, vp]
         L.oracle_f32_to_f16.argtypes = [f32]
         L.oracle_f32_to_f16.restype = C.c_uint16
         L.oracle_f16_to_f32.argtypes = [C.c_uint16]
@@ -285,6 +287,43 @@ def q8_quantize(x: np.ndarray):
     sc = np.empty(len(x) // 32, dtype=np.float32)
     lib().oracle_q8_quantize(x.ctypes.data, len(x), aq.ctypes.data, sc.ctypes.data)
     return aq, sc
+
+
+KQUANT_BLOCK_BYTES = {12: 144, 13: 176, 14: 210}  # Q4_K, Q5_K, Q6_K (tensor/GGMLType.java:18-20)
+
+
+def kquant_dequantize(ggml_type: int, raw: np.ndarray, n: int) -> np.ndarray:
+    """getFloat(i) of Q4_K/Q5_K/Q6_KFloatTensor for i in [0, n) (C restatement)."""
+    raw = np.ascontiguousarray(raw, dtype=np.uint8)
+    assert raw.size >= n // 256 * KQUANT_BLOCK_BYTES[ggml_type]
+    out = np.empty(n, dtype=np.float32)
+    lib().oracle_kquant_dequantize(ggml_type, raw.ctypes.data, n, out.ctypes.data)
+    return out
+
+
+def kquant_to_q8_0(ggml_type: int, raw: np.ndarray, n: int) -> np.ndarray:
+    """ModelLoader.dequantizeToQ8_0TornadoTensor (ModelLoader.java:173-224): the Q8_0 bytes the reference's accelerator path computes with."""
+    raw = np.ascontiguousarray(raw, dtype=np.uint8)
+    out = np.empty((n + 31) // 32 * 34, dtype=np.uint8)
+    lib().oracle_kquant_to_q8_0(ggml_type, raw.ctypes.data, n, out.ctypes.data)
+    return out
+
+
+def np_requant_q8_0(x: np.ndarray) -> np.ndarray:
+    """Second restatement (numpy, vectorised) of the re-quantiser applied to already dequantised floats: ModelLoader.java:184-212."""
+    x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1, 32)
+    max_abs = np.max(np.abs(x), axis=1)
+    scale = (max_abs / np.float32(127.0)).astype(np.float32)
+    with np.errstate(divide="ignore"):
+        inv = np.where(scale != 0, (np.float32(1.0) / scale).astype(np.float32), np.float32(0.0)).astype(np.float32)
+    t = (x * inv[:, None]).astype(np.float32)
+    f = np.floor(t)
+    q = f.astype(np.int64) + ((t - f) >= np.float32(0.5))  # Math.round(float): ties towards +infinity
+    q = np.clip(q, -128, 127).astype(np.int8)
+    out = np.empty((x.shape[0], 34), dtype=np.uint8)
+    out[:, :2] = scale.astype(np.float16).view(np.uint8).reshape(-1, 2)  # Float.floatToFloat16: round to nearest even
+    out[:, 2:] = q.view(np.uint8)
+    return out.reshape(-1)
 
 
 def rope_table(ctx: int, head_size: int, theta: float):
