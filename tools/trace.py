@@ -1,5 +1,5 @@
 """In-graph timeline of one decode step (PDL on) for the 8B-shaped model: per-launch
-entry / dependency-wait return / exit times from %globaltimer.  Usage: python tools/trace.py [shape] [pos]"""
+entry / dependency-wait return / exit times from %globaltimer.  Usage: python tools/trace.py [shape] [pos] [q8_0|f16]"""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -14,7 +14,8 @@ if world > 1:
     import torch, torch.distributed as dist
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-m = pkg.loader.model_from_tensors(sh, 8, pkg.synth.build_tensors_fast(sh, 8, seed=3, device=f"cuda:{local}"), pos + 16)
+qt = 1 if (len(sys.argv) > 3 and sys.argv[3] == "f16") else 8
+m = pkg.loader.model_from_tensors(sh, qt, pkg.synth.build_tensors_fast(sh, qt, seed=3, device=f"cuda:{local}"), pos + 16)
 plan = pkg.B200MasterPlan.initialize_plan(m, device=local, tp_rank=rank, tp_size=world)
 toks = pkg.llama_bench.synthetic_tokens(sh.vocab, pos + 2)
 plan.decode_sequence(toks[:pos], pos, 0)
@@ -31,7 +32,7 @@ for i, (kid, te, tw, tx) in enumerate(rec):
     run = (tx - tw) / 1e3
     early = (tw - te) / 1e3
     gap = (tw - prev_exit) / 1e3 if prev_exit is not None else 0.0
-    if 6 * 10 <= i < 6 * 12 or i >= len(rec) - 4 or i < 8:
+    if 7 * 8 <= i < 7 * 10 or i >= len(rec) - 4 or i < 8:
         print(f"{i:4d} {names.get(int(kid), '?'):10} {(te - t0) / 1e3:9.2f} {(tw - t0) / 1e3:9.2f} {(tx - t0) / 1e3:9.2f} {run:8.2f} {early:22.2f} {gap:24.2f}")
     a = agg.setdefault(int(kid), [0, 0.0, 0.0, 0.0])
     a[0] += 1; a[1] += run; a[2] += early; a[3] += gap
