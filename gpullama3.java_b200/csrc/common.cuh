@@ -107,6 +107,12 @@ __device__ __forceinline__ float ldcg_f32c(const float *p) {
     return v;
 }
 
+// What the attention prologues do per architecture (the kernels take these flags, not the architecture id):
+//   Llama / Mistral: interleaved-pair RoPE (InferenceCore.java:75-87); Qwen3: NeoX pairs + per-head q/k RMSNorm (:594-619);
+//   Phi-3: NeoX pairs, no q/k norm (forwardJavaPhi3, :726-742).
+#define KF_NEOX 1
+#define KF_QKNORM 2
+
 // In-graph timeline tracing (diagnostic graph only; rec == nullptr in the production graphs, so the
 // branch is uniform and free).  One record per launch: {kernel id, earliest CTA entry, latest
 // dependency-wait return, latest CTA exit} in %globaltimer nanoseconds.

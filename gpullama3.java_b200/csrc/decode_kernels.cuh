@@ -410,7 +410,7 @@ __global__ void k_swiglu(float *__restrict__ hb, const float *__restrict__ hb2, 
 template <int HS>
 __global__ void __launch_bounds__(ATT_THREADS) k_attention(float *__restrict__ qkv, float *__restrict__ kc, float *__restrict__ vc,
                                                           const StepState *__restrict__ st, const float *__restrict__ cr,
-                                                          const float *__restrict__ ci, int n_heads, int n_kv_heads, int arch,
+                                                          const float *__restrict__ ci, int n_heads, int n_kv_heads, int arch /* KF_* flags */,
                                                           const float *__restrict__ qnorm_w, const float *__restrict__ knorm_w,
                                                           float eps, float sqrt_hs, int8_t *__restrict__ xq,
                                                           float *__restrict__ xs, float *__restrict__ xb, TraceBuf tr, TpCtx tp,
@@ -445,14 +445,14 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attention(float *__restrict__ q
         const int p = is_q ? tid : tid - HALF;
         const float *src = is_q ? qsrc : ksrc;
         int i0, i1;
-        if (arch == 1) { i0 = p; i1 = p + HALF; } else { i0 = 2 * p; i1 = 2 * p + 1; }
+        if (arch & KF_NEOX) { i0 = p; i1 = p + HALF; } else { i0 = 2 * p; i1 = 2 * p + 1; }
         float v0 = src[i0], v1 = src[i1];
-        if (arch == 1) { // Qwen3 per-head RMSNorm: literal sequential sum over the head
+        if (arch & KF_QKNORM) { // Qwen3 per-head RMSNorm: literal sequential sum over the head
             float *sqr = is_q ? so : sk; // scratch: HS squares each
             sqr[i0] = __fmul_rn(v0, v0);
             sqr[i1] = __fmul_rn(v1, v1);
         }
-        if (arch == 1) {
+        if (arch & KF_QKNORM) {
             asm volatile("bar.sync 3, %0;" ::"n"(HS) : "memory");
             if (p == 0) {
                 const float *sqr = is_q ? so : sk;

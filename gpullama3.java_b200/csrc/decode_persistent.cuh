@@ -56,7 +56,7 @@ struct PdArgs {
     DevMat emb;
     int dim, hidden, qd;     // full widths (qd = columns of Wo)
     int n_heads, n_kv_heads; // of THIS rank
-    int head_size, arch, ctx;
+    int head_size, arch /* KF_* flags */, ctx;
     float eps, sqrt_hs;
     const float *rope_cr, *rope_ci;
     StepState *st;
@@ -656,14 +656,14 @@ __device__ __noinline__ void pd_attention_head(const PdArgs &a, const PdLayer &L
         const int p = is_q ? tid : tid - HALF;
         const float *src = is_q ? qsrc : ksrc;
         int i0, i1;
-        if (a.arch == 1) { i0 = p; i1 = p + HALF; } else { i0 = 2 * p; i1 = 2 * p + 1; }
+        if (a.arch & KF_NEOX) { i0 = p; i1 = p + HALF; } else { i0 = 2 * p; i1 = 2 * p + 1; }
         float v0 = ldcg_f32c(src + i0), v1 = ldcg_f32c(src + i1); // written by other CTAs in this kernel: bypass L1
         const float *srope = reinterpret_cast<const float *>(smem + L.off_rope); // this position's rope row, staged at kernel start
         const float fcr = srope[p], fci = srope[HALF + p];
         float cv0 = 0.f, cv1 = 0.f;
         const bool owner = (h % kv_mul == 0) && !is_q; // first query head of the KV group owns the cache write (InferenceCore.java:92-93)
         if (owner) { cv0 = ldcg_f32c(vsrc + i0); cv1 = ldcg_f32c(vsrc + i1); }
-        if (a.arch == 1) { // Qwen3 per-head RMSNorm: literal sequential sum over the head (InferenceCore.java:594-600)
+        if (a.arch & KF_QKNORM) { // Qwen3 per-head RMSNorm: literal sequential sum over the head (InferenceCore.java:594-600)
             float *sqr = is_q ? so : sk;
             sqr[i0] = __fmul_rn(v0, v0);
             sqr[i1] = __fmul_rn(v1, v1);

@@ -70,6 +70,7 @@ struct b200_plan {
     DevMat emb{}, out{};
     TileMat tout{};
     bool use_stream = false, use_pdl = false;
+    int kflags = 0; // KF_* (common.cuh): what the attention prologues do for this architecture
     size_t kq_off = 0; // K-quant files: offset of the raw (K-quant bytes) area inside each staging buffer; 0 = no K-quant tensor in the file
     bool use_f16_stream = false; // FP16 plans: per-warp bulk-copy rings (stream_matvec_f16.cuh) instead of k_matvec_f16
     bool f16_copies = false; // Q8_0 plan that also holds f16 weight matrices for the tensor-core prefill
@@ -289,11 +290,16 @@ static inline int eff_type(int t) { return kq_is_kquant(t) ? B200_GGML_Q8_0 : t;
 
 // Upload rows [0, rows) of a [rows][cols] GGUF matrix into dst at row offset `row_off`.  K-quant sources are re-quantised to Q8_0 on
 // the device (kquant.cuh) between the copy and the repack.
-int upload_matrix(b200_plan *p, const b200_tensor *t, int rows, int cols, DevMat &dst, int row_off, void *stage, size_t stage_bytes) {
+int upload_matrix(b200_plan *p, const b200_tensor *t, int rows, int cols, DevMat &dst, int row_off, void *stage, size_t stage_bytes, int src_row = 0,
+                  int src_full_rows = -1) { // rows [src_row, src_row + rows) of a source tensor with src_full_rows rows (Phi-3's fused wqkv / gate-up)
     if (!t) return fail(p, B200_ERR_BAD_ARG, "missing tensor");
-    if (n_elems(t) != (int64_t)rows * cols)
+    if (src_full_rows < 0) src_full_rows = rows;
+    if (n_elems(t) != (int64_t)src_full_rows * cols || src_row < 0 || src_row + rows > src_full_rows)
         return fail(p, B200_ERR_BAD_ARG, "tensor %s has %lld elements, expected %lld", t->name, (long long)n_elems(t),
-                    (long long)rows * cols);
+                    (long long)src_full_rows * cols);
+    const size_t src_row_bytes = kq_is_kquant(t->ggml_type) ? (size_t)cols / 256 * kq_block_bytes(t->ggml_type)
+                                 : t->ggml_type == B200_GGML_Q8_0 ? (size_t)cols / 32 * 34 : (size_t)cols * (t->ggml_type == B200_GGML_F16 ? 2 : 4);
+    const unsigned char *tdata = (const unsigned char *)t->data + (size_t)src_row * src_row_bytes;
     if (eff_type(t->ggml_type) != dst.type)
         return fail(p, B200_ERR_UNSUPPORTED, "tensor %s has ggml type %d, plan weight type is %d", t->name, t->ggml_type,
                     dst.type);
@@ -310,7 +316,7 @@ int upload_matrix(b200_plan *p, const b200_tensor *t, int rows, int cols, DevMat
         size_t blk_per_chunk = (q8_area / 34) & ~(size_t)7;
         for (size_t b0 = 0; b0 < nblk; b0 += blk_per_chunk) {
             size_t nb = nblk - b0 < blk_per_chunk ? nblk - b0 : blk_per_chunk;
-            const unsigned char *hsrc = kq ? (const uint8_t *)t->data + b0 / 8 * kb : (const uint8_t *)t->data + b0 * 34;
+            const unsigned char *hsrc = kq ? tdata + b0 / 8 * kb : tdata + b0 * 34;
             const size_t hbytes = kq ? nb / 8 * kb : nb * 34;
             int rc;
             if (p->up.on) {
@@ -330,8 +336,8 @@ int upload_matrix(b200_plan *p, const b200_tensor *t, int rows, int cols, DevMat
         }
     } else {
         size_t esz = dst.type == B200_GGML_F16 ? 2 : 4;
-        if (p->up.on) return up_h2d(p, (uint8_t *)dst.qs + (size_t)row_off * cols * esz, t->data, (size_t)rows * cols * esz); // ordered by the final synchronize
-        CK(cudaMemcpy((uint8_t *)dst.qs + (size_t)row_off * cols * esz, t->data, (size_t)rows * cols * esz, cudaMemcpyHostToDevice));
+        if (p->up.on) return up_h2d(p, (uint8_t *)dst.qs + (size_t)row_off * cols * esz, tdata, (size_t)rows * cols * esz); // ordered by the final synchronize
+        CK(cudaMemcpy((uint8_t *)dst.qs + (size_t)row_off * cols * esz, tdata, (size_t)rows * cols * esz, cudaMemcpyHostToDevice));
     }
     return B200_OK;
 }
@@ -475,7 +481,7 @@ template <int MODE> int launch_stream_f16(b200_plan *p, const DevMat &m, const D
     SfArgs a;
     a.w0 = (const __half *)m.qs; a.w1 = m2 ? (const __half *)m2->qs : nullptr; a.x = x; a.out = out; a.rows = m.rows; a.cols = m.cols;
     a.seg = L.seg; a.nseg = L.nseg; a.stages = L.stages; a.tr = tr;
-    const int rw = 32 / lanes, mr = MODE == SF_GATEUP ? rw / 2 : rw;
+    const int rw = 64 / lanes, mr = MODE == SF_GATEUP ? rw / 2 : rw;
     int grid = L.ctas_per_sm * p->n_sms;
     if (grid > m.rows / mr) grid = m.rows / mr;
     if (lanes == 16) return launch_k(p, p->use_pdl, k_stream_matvec_f16<16, MODE>, dim3(grid), dim3(SF_THREADS), L.total, a);
@@ -595,13 +601,14 @@ int enqueue_forward(b200_plan *p, bool with_logits, int *launches, bool trace = 
             const size_t att_smem = (size_t)(3 * c.head_size + (p->att_scratch ? 0 : c.context_length)) * 4;
             auto att = [&](auto kern) {
                 return launch_k(p, pdl, kern, dim3(p->nh_l), dim3(ATT_THREADS), att_smem, p->qkv, kc, vc, (const StepState *)p->st,
-                                (const float *)p->rope_cr, (const float *)p->rope_ci, p->nh_l, p->nkv_l, c.arch, (const float *)L.q_norm,
+                                (const float *)p->rope_cr, (const float *)p->rope_ci, p->nh_l, p->nkv_l, p->kflags, (const float *)L.q_norm,
                                 (const float *)L.k_norm, c.rms_norm_eps, (float)sqrt((double)c.head_size), q8 ? p->attq : nullptr, q8 ? p->atts : nullptr, xbf, TR(4),
                                 p->tp, (unsigned)(4 * l + 0), rank * p->nh_l, p->att_scratch, c.context_length);
             };
             if (c.head_size == 128) rc = att(k_attention<128>);
             else if (c.head_size == 64) rc = att(k_attention<64>);
             else if (c.head_size == 256) rc = att(k_attention<256>);
+            else if (c.head_size == 96) rc = att(k_attention<96>);
             else rc = att(k_attention<32>);
             if (rc) return rc;
             n++;
@@ -704,7 +711,7 @@ int enqueue_persistent(b200_plan *p, bool with_logits, int *launches, bool trace
     memset(&a, 0, sizeof a);
     a.layers = p->pd_layers; a.n_layers = c.n_layers; a.lm_head = p->tout; a.out_norm = p->out_norm; a.emb = p->emb;
     a.dim = c.dim; a.hidden = c.hidden_dim; a.qd = p->qd; a.n_heads = p->nh_l; a.n_kv_heads = p->nkv_l;
-    a.head_size = c.head_size; a.arch = c.arch; a.ctx = c.context_length;
+    a.head_size = c.head_size; a.arch = p->kflags; a.ctx = c.context_length;
     a.eps = c.rms_norm_eps; a.sqrt_hs = (float)sqrt((double)c.head_size);
     a.rope_cr = p->rope_cr; a.rope_ci = p->rope_ci;
     a.st = p->st; a.seq_tokens = p->seq_tokens; a.out_ids = p->out_ids;
@@ -752,7 +759,7 @@ int capture_all(b200_plan *p) {
     int rc;
     if ((rc = capture(p, true, &p->g_decode, &p->launches_decode))) return rc;
     if ((rc = capture(p, false, &p->g_prefill, nullptr))) return rc;
-    if (p->use_stream) {
+    if (p->use_stream || p->use_f16_stream) {
         if ((rc = dalloc(p, &p->trace_rec, (size_t)(p->launches_decode + 8) * 32))) return rc;
         if ((rc = capture(p, true, &p->g_trace, nullptr, true))) return rc;
     }
@@ -803,6 +810,7 @@ int set_smem_attrs(b200_plan *p) {
     CK(set_max_dyn(k_attention<32>, maxdyn));
     CK(set_max_dyn(k_attention<64>, maxdyn));
     CK(set_max_dyn(k_attention<128>, maxdyn));
+    CK(set_max_dyn(k_attention<96>, maxdyn));
     CK(set_max_dyn(k_attention<256>, maxdyn));
     CK(set_max_dyn(k_matvec_q8<1, MODE_STORE>, maxdyn));
     CK(set_max_dyn(k_matvec_q8<2, MODE_STORE>, maxdyn));
@@ -830,15 +838,16 @@ int prefill_init(b200_plan *p);
 
 int build(b200_plan *p, const b200_tensor *tensors, int n_tensors) {
     const b200_config &c = p->cfg;
-    if (c.arch != B200_ARCH_LLAMA && c.arch != B200_ARCH_QWEN3) return fail(p, B200_ERR_UNSUPPORTED, "unknown arch %d", c.arch);
-    if (c.dim <= 0 || c.dim % 32 || c.hidden_dim % 32 || (c.head_size != 32 && c.head_size != 64 && c.head_size != 128 && c.head_size != 256) || c.n_heads % c.n_kv_heads ||
+    if (c.arch != B200_ARCH_LLAMA && c.arch != B200_ARCH_QWEN3 && c.arch != B200_ARCH_PHI3) return fail(p, B200_ERR_UNSUPPORTED, "unknown arch %d", c.arch);
+    p->kflags = c.arch == B200_ARCH_QWEN3 ? (KF_NEOX | KF_QKNORM) : c.arch == B200_ARCH_PHI3 ? KF_NEOX : 0;
+    if (c.dim <= 0 || c.dim % 32 || c.hidden_dim % 32 || (c.head_size != 32 && c.head_size != 64 && c.head_size != 96 && c.head_size != 128 && c.head_size != 256) || c.n_heads % c.n_kv_heads ||
         c.n_layers <= 0 || c.vocab_size <= 0 || c.context_length <= 0)
-        return fail(p, B200_ERR_BAD_ARG, "unsupported shape (dim/hidden must be multiples of 32, head_size one of 32/64/128/256)");
+        return fail(p, B200_ERR_BAD_ARG, "unsupported shape (dim/hidden must be multiples of 32, head_size one of 32/64/96/128/256)");
     if (c.fp16_lanes != 0 && c.fp16_lanes != 8 && c.fp16_lanes != 16 && c.fp16_lanes != 4 && c.fp16_lanes != 32)
         return fail(p, B200_ERR_BAD_ARG, "fp16_lanes must be 0, 4, 8, 16 or 32");
     p->qd = c.n_heads * c.head_size;
     p->kvd = c.n_kv_heads * c.head_size;
-    if (c.arch == B200_ARCH_LLAMA && p->qd != c.dim) return fail(p, B200_ERR_BAD_ARG, "llama: n_heads*head_size must equal dim");
+    if (c.arch != B200_ARCH_QWEN3 && p->qd != c.dim) return fail(p, B200_ERR_BAD_ARG, "llama / phi3: n_heads*head_size must equal dim");
     {
         const int tn = c.tp_size;
         if (tn < 1 || tn > TP_MAX || c.tp_rank < 0 || c.tp_rank >= tn) return fail(p, B200_ERR_BAD_ARG, "bad tp_rank/tp_size %d/%d", c.tp_rank, tn);
@@ -853,8 +862,8 @@ int build(b200_plan *p, const b200_tensor *tensors, int n_tensors) {
 
     const b200_tensor *emb = find(tensors, n_tensors, "token_embd.weight");
     if (!emb) return fail(p, B200_ERR_BAD_ARG, "missing tensor token_embd.weight");
-    const b200_tensor *wq0 = find(tensors, n_tensors, "blk.0.attn_q.weight");
-    if (!wq0) return fail(p, B200_ERR_BAD_ARG, "missing tensor blk.0.attn_q.weight");
+    const b200_tensor *wq0 = find(tensors, n_tensors, c.arch == B200_ARCH_PHI3 ? "blk.0.attn_qkv.weight" : "blk.0.attn_q.weight");
+    if (!wq0) return fail(p, B200_ERR_BAD_ARG, "missing tensor blk.0.attn_q.weight (Phi-3: blk.0.attn_qkv.weight)");
     p->wtype = eff_type(wq0->ggml_type); // K-quant matrices become Q8_0 while they are uploaded (kquant.cuh)
     if (p->wtype != B200_GGML_Q8_0 && p->wtype != B200_GGML_F16)
         return fail(p, B200_ERR_UNSUPPORTED, "Type: %d currently not supported for B200 weights (Q8_0, F16 and the K-quants Q4_K/Q5_K/Q6_K only)", wq0->ggml_type);
@@ -936,28 +945,36 @@ int build(b200_plan *p, const b200_tensor *tensors, int n_tensors) {
             if ((rc = upload_f32(p, T("attn_q_norm.weight"), c.head_size, &L.q_norm, "attn_q_norm.weight"))) return rc;
             if ((rc = upload_f32(p, T("attn_k_norm.weight"), c.head_size, &L.k_norm, "attn_k_norm.weight"))) return rc;
         }
+        // Phi-3 stores wqkv and gate|up fused (Phi3StandardWeights: attn_qkv.weight = [q; k; v] rows, ffn_up.weight = [gate; up] rows,
+        // InferenceCore.java:718-724,779-781): the row ranges below address the same source tensor; rows are independent dot products, so
+        // splitting a fused matrix by rows changes nothing in the arithmetic.
+        const bool phi3 = c.arch == B200_ARCH_PHI3;
+        const b200_tensor *tq = T(phi3 ? "attn_qkv.weight" : "attn_q.weight"), *tk = phi3 ? tq : T("attn_k.weight"), *tv = phi3 ? tq : T("attn_v.weight");
+        const b200_tensor *tg = T(phi3 ? "ffn_up.weight" : "ffn_gate.weight"), *tu = T("ffn_up.weight");
+        const int q_full = phi3 ? p->qd + 2 * p->kvd : p->qd, k_full = phi3 ? q_full : p->kvd, g_full = phi3 ? 2 * c.hidden_dim : c.hidden_dim;
+        const int k_src = phi3 ? p->qd : 0, v_src = phi3 ? p->qd + p->kvd : 0, u_src = phi3 ? c.hidden_dim : 0;
         if (p->use_stream) {
             const int rk = c.tp_rank;
-            const int qr0[3] = {rk * p->qd_l, rk * p->kvd_l, rk * p->kvd_l}, qfu[3] = {p->qd, p->kvd, p->kvd};
-            if ((rc = upload_tiles(p, T("attn_q.weight"), T("attn_k.weight"), T("attn_v.weight"), p->qd_l, p->kvd_l, p->kvd_l, c.dim, false, L.tqkv, stage, stage_bytes, qr0, qfu))) return rc;
+            const int qr0[3] = {rk * p->qd_l, k_src + rk * p->kvd_l, v_src + rk * p->kvd_l}, qfu[3] = {q_full, k_full, k_full};
+            if ((rc = upload_tiles(p, tq, tk, tv, p->qd_l, p->kvd_l, p->kvd_l, c.dim, false, L.tqkv, stage, stage_bytes, qr0, qfu))) return rc;
             const int dr0[3] = {rk * p->dim_l, 0, 0}, dfu[3] = {c.dim, 0, 0};
             if ((rc = upload_tiles(p, T("attn_output.weight"), nullptr, nullptr, p->dim_l, 0, 0, p->qd, false, L.two, stage, stage_bytes, dr0, dfu))) return rc;
-            const int gr0[3] = {rk * p->hid_l, rk * p->hid_l, 0}, gfu[3] = {c.hidden_dim, c.hidden_dim, 0};
-            if ((rc = upload_tiles(p, T("ffn_gate.weight"), T("ffn_up.weight"), nullptr, p->hid_l, p->hid_l, 0, c.dim, true, L.tgu, stage, stage_bytes, gr0, gfu))) return rc;
+            const int gr0[3] = {rk * p->hid_l, u_src + rk * p->hid_l, 0}, gfu[3] = {g_full, g_full, 0};
+            if ((rc = upload_tiles(p, tg, tu, nullptr, p->hid_l, p->hid_l, 0, c.dim, true, L.tgu, stage, stage_bytes, gr0, gfu))) return rc;
             if ((rc = upload_tiles(p, T("ffn_down.weight"), nullptr, nullptr, p->dim_l, 0, 0, c.hidden_dim, false, L.tw2, stage, stage_bytes, dr0, dfu))) return rc;
             continue;
         }
         // fused [Wq; Wk; Wv] so one launch produces the packed q|k|v vector
         if ((rc = alloc_matrix(p, L.qkv, p->qd + 2 * p->kvd, c.dim, p->wtype))) return rc;
-        if ((rc = upload_matrix(p, T("attn_q.weight"), p->qd, c.dim, L.qkv, 0, stage, stage_bytes))) return rc;
-        if ((rc = upload_matrix(p, T("attn_k.weight"), p->kvd, c.dim, L.qkv, p->qd, stage, stage_bytes))) return rc;
-        if ((rc = upload_matrix(p, T("attn_v.weight"), p->kvd, c.dim, L.qkv, p->qd + p->kvd, stage, stage_bytes))) return rc;
+        if ((rc = upload_matrix(p, tq, p->qd, c.dim, L.qkv, 0, stage, stage_bytes, 0, q_full))) return rc;
+        if ((rc = upload_matrix(p, tk, p->kvd, c.dim, L.qkv, p->qd, stage, stage_bytes, k_src, k_full))) return rc;
+        if ((rc = upload_matrix(p, tv, p->kvd, c.dim, L.qkv, p->qd + p->kvd, stage, stage_bytes, v_src, k_full))) return rc;
         if ((rc = alloc_matrix(p, L.wo, c.dim, p->qd, p->wtype))) return rc;
         if ((rc = upload_matrix(p, T("attn_output.weight"), c.dim, p->qd, L.wo, 0, stage, stage_bytes))) return rc;
         if ((rc = alloc_matrix(p, L.w1, c.hidden_dim, c.dim, p->wtype))) return rc;
-        if ((rc = upload_matrix(p, T("ffn_gate.weight"), c.hidden_dim, c.dim, L.w1, 0, stage, stage_bytes))) return rc;
+        if ((rc = upload_matrix(p, tg, c.hidden_dim, c.dim, L.w1, 0, stage, stage_bytes, 0, g_full))) return rc;
         if ((rc = alloc_matrix(p, L.w3, c.hidden_dim, c.dim, p->wtype))) return rc;
-        if ((rc = upload_matrix(p, T("ffn_up.weight"), c.hidden_dim, c.dim, L.w3, 0, stage, stage_bytes))) return rc;
+        if ((rc = upload_matrix(p, tu, c.hidden_dim, c.dim, L.w3, 0, stage, stage_bytes, u_src, g_full))) return rc;
         if ((rc = alloc_matrix(p, L.w2, c.dim, c.hidden_dim, p->wtype))) return rc;
         if ((rc = upload_matrix(p, T("ffn_down.weight"), c.dim, c.hidden_dim, L.w2, 0, stage, stage_bytes))) return rc;
     }
@@ -1230,11 +1247,11 @@ int prefill_forward(b200_plan *p, int n, int start_pos, int *launches) {
             nl++;
         }
         if (g.head_size == 128) {
-            k_pf_rope_kv<128><<<n, 256, 0, s>>>(c.QKV, nqkv, kc, vc, c.KH, c.VH, p->kvd, g.n_heads, g.n_kv_heads, g.arch, L.q_norm, L.k_norm, g.rms_norm_eps, p->rope_cr, p->rope_ci, start_pos);
+            k_pf_rope_kv<128><<<n, 256, 0, s>>>(c.QKV, nqkv, kc, vc, c.KH, c.VH, p->kvd, g.n_heads, g.n_kv_heads, p->kflags, L.q_norm, L.k_norm, g.rms_norm_eps, p->rope_cr, p->rope_ci, start_pos);
             if (c.att_simt) k_pf_attention<128><<<ag, PA_THREADS, pa_smem_bytes<128>(), s>>>(c.QKV, nqkv, kc, vc, p->kvd, kv_mul, n, start_pos, inv_sqrt_hs, c.ATT16, p->qd);
             else k_pf_attention_mma<128><<<ag, PM_THREADS, pm_smem_bytes<128>(), s>>>(c.QKV, nqkv, c.KH, c.VH, p->kvd, kv_mul, n, start_pos, inv_sqrt_hs, c.ATT16, p->qd);
         } else {
-            k_pf_rope_kv<64><<<n, 256, 0, s>>>(c.QKV, nqkv, kc, vc, c.KH, c.VH, p->kvd, g.n_heads, g.n_kv_heads, g.arch, L.q_norm, L.k_norm, g.rms_norm_eps, p->rope_cr, p->rope_ci, start_pos);
+            k_pf_rope_kv<64><<<n, 256, 0, s>>>(c.QKV, nqkv, kc, vc, c.KH, c.VH, p->kvd, g.n_heads, g.n_kv_heads, p->kflags, L.q_norm, L.k_norm, g.rms_norm_eps, p->rope_cr, p->rope_ci, start_pos);
             if (c.att_simt) k_pf_attention<64><<<ag, PA_THREADS, pa_smem_bytes<64>(), s>>>(c.QKV, nqkv, kc, vc, p->kvd, kv_mul, n, start_pos, inv_sqrt_hs, c.ATT16, p->qd);
             else k_pf_attention_mma<64><<<ag, PM_THREADS, pm_smem_bytes<64>(), s>>>(c.QKV, nqkv, c.KH, c.VH, p->kvd, kv_mul, n, start_pos, inv_sqrt_hs, c.ATT16, p->qd);
         }
@@ -1679,7 +1696,7 @@ int b200_tp_attach(b200_plan *p, const void *handles, int32_t n) {
 
 int b200_trace_decode(b200_plan *p, int32_t token, int32_t position, uint64_t *records, int32_t cap, int32_t *n_out) {
     if (!p || !records || !n_out) return B200_ERR_BAD_ARG;
-    if (!p->g_trace) return fail(p, B200_ERR_UNSUPPORTED, "tracing needs the streaming (Q8_0) path");
+    if (!p->g_trace) return fail(p, B200_ERR_UNSUPPORTED, "tracing needs a streaming path (Q8_0 tiles or the FP16 rings)");
     int rc;
     if ((rc = check_pos(p, token, position))) return rc;
     CK(cudaSetDevice(p->device));

@@ -109,12 +109,12 @@ __global__ void __launch_bounds__(256) k_pf_rope_kv(float *__restrict__ qkv, int
 #pragma unroll
         for (int u = 0; u < PPL; u++) {
             const int p = lane + 32 * u;
-            if (arch == 1) { i0[u] = p; i1[u] = p + HALF; } else { i0[u] = 2 * p; i1[u] = 2 * p + 1; }
+            if (arch & KF_NEOX) { i0[u] = p; i1[u] = p + HALF; } else { i0[u] = 2 * p; i1[u] = 2 * p + 1; }
             v0[u] = src[i0[u]];
             v1[u] = src[i1[u]];
             ss += v0[u] * v0[u] + v1[u] * v1[u];
         }
-        if (arch == 1) {
+        if (arch & KF_QKNORM) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
             const float sc = (float)(1.0 / sqrt((double)(ss / (float)HS + eps)));

@@ -15,6 +15,7 @@ from .gguf import GGMLType, GGUFFile
 
 ARCH_LLAMA = 0
 ARCH_QWEN3 = 1
+ARCH_PHI3 = 2
 
 
 @dataclass
@@ -87,10 +88,11 @@ class Model:
 
 def model_from_tensors(shape, quant: int, tensors: dict, context_length: int) -> Model:
     """In-memory model (bench: synthetic weights never touch the disk)."""
-    cfg = Configuration(ARCH_QWEN3 if shape.arch == "qwen3" else ARCH_LLAMA, "Q8_0" if quant == GGMLType.Q8_0 else "FP16",
+    arch = {"llama": ARCH_LLAMA, "qwen3": ARCH_QWEN3, "phi3": ARCH_PHI3}[shape.arch]
+    cfg = Configuration(arch, "Q8_0" if quant == GGMLType.Q8_0 else "FP16",
                         shape.dim, shape.hidden, shape.n_layers, shape.n_heads, shape.n_kv_heads, shape.head_size,
                         shape.vocab, context_length, float(shape.eps), float(shape.rope_theta))
-    return Model(None, cfg, "QWEN_3" if shape.arch == "qwen3" else "LLAMA_3", tensors)
+    return Model(None, cfg, {"llama": "LLAMA_3", "qwen3": "QWEN_3", "phi3": "PHI_3"}[shape.arch], tensors)
 
 
 def load_model(path: str, context_length: int = -1) -> Model:
@@ -131,8 +133,19 @@ def load_model(path: str, context_length: int = -1) -> Model:
             int(md["qwen3.block_count"]), n_heads, int(md.get("qwen3.attention.head_count_kv", n_heads)),
             int(md["qwen3.attention.key_length"]), int(vocab), ctx,
             float(md["qwen3.attention.layer_norm_rms_epsilon"]), float(md["qwen3.rope.freq_base"]))
+    elif typ == "PHI_3":
+        # Phi3ModelLoader.createConfiguration (Phi3ModelLoader.java:51-71): head size = dim / heads, the context is the requested one
+        # (the RoPE table is precomputed for the model's), the vocabulary size is the token list's.
+        n_heads = int(md["phi3.attention.head_count"])
+        dim = int(md["phi3.embedding_length"])
+        model_ctx = int(md["phi3.context_length"])
+        vocab = len(md["tokenizer.ggml.tokens"]) if "tokenizer.ggml.tokens" in md else int(md["phi3.vocab_size"])
+        cfg = Configuration(
+            ARCH_PHI3, q, dim, int(md["phi3.feed_forward_length"]), int(md["phi3.block_count"]), n_heads,
+            int(md.get("phi3.attention.head_count_kv", n_heads)), dim // n_heads, int(vocab), model_ctx if context_length < 0 else context_length,
+            float(md.get("phi3.attention.layer_norm_rms_epsilon", 1e-5)), float(md.get("phi3.rope.freq_base", 10000.0)))
     else:
-        raise UnsupportedModel(f"model type {typ} is outside the B200 hot-path scope (Llama / Mistral / Qwen3 forward passes only)")
+        raise UnsupportedModel(f"model type {typ} is outside the B200 hot-path scope (Llama / Mistral / Qwen3 / Phi-3 forward passes only)")
     return Model(g, cfg, typ)
 
 

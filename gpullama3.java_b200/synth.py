@@ -15,7 +15,7 @@ from .gguf import GGMLType, write_gguf
 
 @dataclass(frozen=True)
 class Shape:
-    arch: str  # "llama" | "qwen3"
+    arch: str  # "llama" | "qwen3" | "phi3"
     dim: int
     hidden: int
     n_layers: int
@@ -51,6 +51,10 @@ SHAPES = {
     "tiny-llama": Shape("llama", 256, 512, 2, 4, 2, 64, 512, False, 500000.0, 1e-5),
     "tiny-llama-tied": Shape("llama", 256, 512, 2, 4, 2, 64, 512, True, 500000.0, 1e-5),
     "tiny-qwen3": Shape("qwen3", 256, 768, 2, 4, 2, 128, 640, True, 1000000.0, 1e-6),
+    # Phi-3 (forwardJavaPhi3: fused attn_qkv / gate-up tensors, NeoX-pair RoPE): mini-like (multi-head, head size 96) and medium-like (GQA, 128)
+    "tiny-phi3": Shape("phi3", 384, 768, 2, 4, 4, 96, 512, False, 10000.0, 1e-5, 4096),
+    "tiny-phi3-gqa": Shape("phi3", 512, 1024, 2, 4, 2, 128, 512, False, 10000.0, 1e-5, 4096),
+    "mid-phi3-mini": Shape("phi3", 3072, 8192, 2, 32, 32, 96, 8192, False, 10000.0, 1e-5, 4096),  # Phi-3-mini-4k layer geometry
     # mid shape: exercises column tails (dim not a multiple of 512) and several row tiles
     "small-llama": Shape("llama", 1536, 4096, 3, 12, 4, 128, 4096, False, 500000.0, 1e-5),
     # the real Llama-3-8B layer geometry (7 column segments in the down projection, 4 KB rows) with 2 layers / small vocab
@@ -207,6 +211,16 @@ def tensor_plan(shape: Shape, quant: int):
     t = [("token_embd.weight", quant, (shape.dim, shape.vocab), "w")]
     for i in range(shape.n_layers):
         p = f"blk.{i}."
+        if shape.arch == "phi3":  # Phi3ModelLoader.java:107-113: fused [q; k; v] and [gate; up] tensors
+            t += [
+                (p + "attn_norm.weight", GGMLType.F32, (shape.dim,), "n"),
+                (p + "attn_qkv.weight", quant, (shape.dim, shape.q_dim + 2 * shape.kv_dim), "w"),
+                (p + "attn_output.weight", quant, (shape.q_dim, shape.dim), "w"),
+                (p + "ffn_norm.weight", GGMLType.F32, (shape.dim,), "n"),
+                (p + "ffn_down.weight", quant, (shape.hidden, shape.dim), "w"),
+                (p + "ffn_up.weight", quant, (shape.dim, 2 * shape.hidden), "w"),
+            ]
+            continue
         t += [
             (p + "attn_norm.weight", GGMLType.F32, (shape.dim,), "n"),
             (p + "attn_q.weight", quant, (shape.dim, shape.q_dim), "w"),
@@ -296,7 +310,7 @@ def build_tensors_kquant(shape: Shape, seed: int = 1234, mix: str = "Q4_K_M") ->
 def write_model(path: str, shape_name: str, quant: int, seed: int = 1234, w_std: float = 0.0,
                 display_name: str | None = None):
     shape = SHAPES[shape_name]
-    name = display_name or {"llama": "Llama synthetic ", "qwen3": "Qwen3 synthetic "}[shape.arch] + shape_name
+    name = display_name or {"llama": "Llama synthetic ", "qwen3": "Qwen3 synthetic ", "phi3": "Phi3 synthetic "}[shape.arch] + shape_name
     write_gguf(path, metadata_for(shape, quant, name), build_tensors(shape, quant, seed, w_std))
     return shape
 

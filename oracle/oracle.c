@@ -12,6 +12,10 @@
  * file is a line-by-line restatement; every function cites the reference
  * file:line it follows (paths relative to
  * /root/reference/src/main/java/org/beehive/gpullama3/).
+ * What third parties pin instead (everything but the float summation order):
+ * the data formats against gguf-py (tests/test_kquants.py) and the structure
+ * of the forward pass against Hugging Face transformers in float64
+ * (tests/test_oracle_vs_transformers.py).
  *
  * Build: gcc -O2 -ffp-contract=off -fopenmp -shared -fPIC  (see Makefile)
  *   -ffp-contract=off is REQUIRED: Java never contracts a*b+c into an FMA;
@@ -37,6 +41,9 @@
 
 #define ARCH_LLAMA 0
 #define ARCH_QWEN3 1
+#define ARCH_PHI3 2 /* forwardJavaPhi3 (InferenceCore.java:699-800): the caller passes wq/wk/wv and w1/w3 as row ranges of the fused
+                     * attn_qkv / ffn_up tensors (rows of a matmul are independent dot products: wqkv.matmul + copyTo :718-724 and
+                     * wGateUp.matmul + copyChunk :779-781 produce exactly these vectors) */
 
 typedef struct {
     const void *data; /* raw GGUF tensor bytes (block layout for Q8_0) */
@@ -336,6 +343,19 @@ float *oracle_forward(const omodel *m, ostate *s, int token, int pos, int want_l
                         vec[h * hs + ic] = v0 * fcr - v1 * fci;
                         vec[h * hs + ic + half] = v0 * fci + v1 * fcr;
                     }
+                }
+            }
+        } else if (m->arch == ARCH_PHI3) {
+            /* InferenceCore.java:726-742: pairs (ic, ic + headSize/2) with ic = head base + head_dim/2, no q/k norm */
+            for (int i = 0; i < dim; i += 2) {
+                int head_dim = i % hs, base = i - head_dim, ic = base + head_dim / 2;
+                float fcr = s->rope_cr[pos * half + head_dim / 2], fci = s->rope_ci[pos * half + head_dim / 2];
+                int rotn = i < kvd ? 2 : 1;
+                for (int v = 0; v < rotn; v++) {
+                    float *vec = v == 0 ? s->q : s->k;
+                    float v0 = vec[ic], v1 = vec[ic + half];
+                    vec[ic] = v0 * fcr - v1 * fci;
+                    vec[ic + half] = v0 * fci + v1 * fcr;
                 }
             }
         } else {

@@ -209,11 +209,32 @@ class OracleModel:
             self._arrays[fmt] = a
             return a
 
+        def rows_of(fmt, key, row0, rows, cols):
+            """Rows [row0, row0 + rows) of a fused tensor as tensors of their own (Phi-3: wqkv.matmul + copyTo, wGateUp.matmul + copyChunk)."""
+            out = []
+            for i in range(c.n_layers):
+                tt, dims, raw = T[fmt.format(i)]
+                rb = {0: cols * 4, 1: cols * 2, 8: cols // 32 * 34}[int(tt)]
+                raw = np.asarray(raw).reshape(-1)
+                out.append(_ot((tt, (cols, rows), raw[row0 * rb:(row0 + rows) * rb])))
+            a = (OTensor * c.n_layers)(*out)
+            self._arrays[key] = a
+            return a
+
         m.attn_norm = arr("blk.{}.attn_norm.weight")
-        m.wq, m.wk, m.wv = arr("blk.{}.attn_q.weight"), arr("blk.{}.attn_k.weight"), arr("blk.{}.attn_v.weight")
+        if c.arch == 2:  # Phi-3: fused attn_qkv ([q; k; v] rows) and ffn_up ([gate; up] rows), InferenceCore.java:718-724,779-781
+            qd, kvd = c.n_heads * c.head_size, c.n_kv_heads * c.head_size
+            m.wq = rows_of("blk.{}.attn_qkv.weight", "q", 0, qd, c.dim)
+            m.wk = rows_of("blk.{}.attn_qkv.weight", "k", qd, kvd, c.dim)
+            m.wv = rows_of("blk.{}.attn_qkv.weight", "v", qd + kvd, kvd, c.dim)
+            m.w1 = rows_of("blk.{}.ffn_up.weight", "g", 0, c.hidden_dim, c.dim)
+            m.w3 = rows_of("blk.{}.ffn_up.weight", "u", c.hidden_dim, c.hidden_dim, c.dim)
+            m.w2 = arr("blk.{}.ffn_down.weight")
+        else:
+            m.wq, m.wk, m.wv = arr("blk.{}.attn_q.weight"), arr("blk.{}.attn_k.weight"), arr("blk.{}.attn_v.weight")
+            m.w1, m.w2, m.w3 = arr("blk.{}.ffn_gate.weight"), arr("blk.{}.ffn_down.weight"), arr("blk.{}.ffn_up.weight")
         m.wo = arr("blk.{}.attn_output.weight")
         m.ffn_norm = arr("blk.{}.ffn_norm.weight")
-        m.w1, m.w2, m.w3 = arr("blk.{}.ffn_gate.weight"), arr("blk.{}.ffn_down.weight"), arr("blk.{}.ffn_up.weight")
         if c.arch == 1:
             m.attn_q_norm, m.attn_k_norm = arr("blk.{}.attn_q_norm.weight"), arr("blk.{}.attn_k_norm.weight")
         self.m = m

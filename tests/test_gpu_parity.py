@@ -86,6 +86,26 @@ def test_decode_mid_geometries_f16(pkg, orc, shape, lanes):
     run_stream(pkg, orc, m, lanes, 4, check_kv=True)
 
 
+@pytest.mark.parametrize("shape,quant,mode", [("tiny-phi3", "Q8_0", "graph"), ("tiny-phi3", "F16", "graph"), ("tiny-phi3-gqa", "Q8_0", "graph"),
+                                              ("tiny-phi3-gqa", "Q8_0", "persistent"), ("tiny-phi3-gqa", "F16", "graph")])
+def test_decode_phi3_bit_exact(pkg, orc, make_model, shape, quant, mode):
+    """Phi-3 (InferenceCore.forwardJavaPhi3, InferenceCore.java:699-800): fused attn_qkv / gate-up tensors split by rows at upload,
+    NeoX-pair RoPE without q/k norm.  Mini-like (multi-head, head size 96: graph only, FP16 through the round-1 kernels since dim 384
+    is not a multiple of 256) and medium-like (GQA, head size 128: also the persistent kernel and the FP16 rings)."""
+    m = make_model(shape, getattr(pkg.gguf.GGMLType, quant), 24)
+    assert m.model_type == "PHI_3" and m.configuration.arch == 2
+    run_stream(pkg, orc, m, 16, 14, mode=mode)
+
+
+@pytest.mark.parametrize("quant", ["Q8_0", "F16"])
+def test_decode_phi3_mini_geometry(pkg, orc, quant):
+    """The Phi-3-mini layer geometry (dim 3072, hidden 8192, 32 heads of 96, fused 9216-row qkv and 16384-row gate-up), 2 layers."""
+    sh = pkg.synth.SHAPES["mid-phi3-mini"]
+    tt = getattr(pkg.gguf.GGMLType, quant)
+    m = pkg.loader.model_from_tensors(sh, tt, pkg.synth.build_tensors_fast(sh, tt, seed=9), 16)
+    run_stream(pkg, orc, m, 16, 4, check_kv=True)
+
+
 def test_decode_f16_round1_kernels_still_exact(pkg, orc, make_model, monkeypatch):
     """B200_F16_STREAM=0 keeps the round-1 launches (k_matvec_f16 + separate SwiGLU), the fallback for shapes the rings do not fit."""
     monkeypatch.setenv("B200_F16_STREAM", "0")

@@ -101,6 +101,23 @@ def test_mistral_loads_for_the_forward_pass_only(pkg, tmp_path):
         pkg.tokenizer.from_metadata(m.gguf.metadata, m.model_type)
 
 
+def test_phi3_loads_with_fused_tensors(pkg, tmp_path):
+    """a Phi-3 GGUF (Phi3ModelLoader.java:51-113): head size = dim / heads, the requested context length is kept, the
+    fused attn_qkv / ffn_up tensors are present instead of q/k/v/gate; its SentencePiece tokenizer is rejected up front."""
+    G = pkg.gguf.GGMLType
+    path = str(tmp_path / "phi3.gguf")
+    sh = pkg.synth.write_model(path, "tiny-phi3", G.Q8_0, seed=4)
+    m = pkg.load_model(path, 10 ** 5)
+    c = m.configuration
+    assert m.model_type == "PHI_3" and c.arch == 2 and c.head_size == sh.dim // sh.n_heads == 96
+    assert c.context_length == 10 ** 5 and pkg.load_model(path, -1).configuration.context_length == sh.model_ctx
+    qkv = m.tensors["blk.0.attn_qkv.weight"]
+    assert tuple(qkv[1]) == (sh.dim, sh.q_dim + 2 * sh.kv_dim) and tuple(m.tensors["blk.1.ffn_up.weight"][1]) == (sh.dim, 2 * sh.hidden)
+    assert "blk.0.attn_q.weight" not in m.tensors and "blk.0.ffn_gate.weight" not in m.tensors
+    with pytest.raises(pkg.tokenizer.UnsupportedTokenizer):
+        pkg.tokenizer.from_metadata(m.gguf.metadata, m.model_type)
+
+
 def test_batch_prefill_loop_conventions(pkg):
     """InferenceEngineWithBatchPrefillDecode.generateTokensGPULlama (:163-251): chunks are written at startPosition+chunkStart,
     clamped to the token budget, and decode starts at startPosition+N -- also for a continuation (startPosition > 0)."""

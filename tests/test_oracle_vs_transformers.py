@@ -3,7 +3,7 @@
 No JDK exists in this image, so the oracle cannot be compared with the reference's own output ("parity unpinned").  What can
 be checked here is everything except the float summation order: the oracle's forward pass (oracle/oracle.c, a restatement of
 InferenceCore.forwardJava / forwardJavaQwen3, inference/InferenceCore.java:39-172,565-697) is run on a seeded synthetic GGUF model and
-compared with Hugging Face transformers' LlamaForCausalLM / Qwen3ForCausalLM evaluating THE SAME weights in float64 -- an implementation
+compared with Hugging Face transformers' LlamaForCausalLM / Qwen3ForCausalLM / Phi3ForCausalLM evaluating THE SAME weights in float64 -- an implementation
 that shares no code with the reference or with this repository.  Any structural mistake (RoPE pairing or frequency, GQA head mapping, norm
 placement, q/k-norm, SwiGLU operand order, tied classifier, KV-cache indexing across positions) produces O(1) errors; agreement is at
 rounding level: <= 2e-4 of max|logit| for FP16 weights (fp32 arithmetic vs float64), <= 5e-2 for Q8_0 weights (the CPU path additionally
@@ -32,8 +32,12 @@ def _hf_model(pkg, m):
     common = dict(hidden_size=c.dim, intermediate_size=c.hidden_dim, num_hidden_layers=c.n_layers, num_attention_heads=c.n_heads,
                   num_key_value_heads=c.n_kv_heads, vocab_size=c.vocab_size, rms_norm_eps=c.rms_norm_eps, max_position_embeddings=c.context_length,
                   tie_word_embeddings=False, rope_theta=c.rope_theta, attention_bias=False, head_dim=c.head_size)
+    phi3 = m.model_type == "PHI_3"
     if qwen:
         hf = transformers.Qwen3ForCausalLM(transformers.Qwen3Config(**common))
+    elif phi3:
+        common.pop("head_dim"), common.pop("attention_bias")
+        hf = transformers.Phi3ForCausalLM(transformers.Phi3Config(**common, original_max_position_embeddings=c.context_length, pad_token_id=0))
     else:
         hf = transformers.LlamaForCausalLM(transformers.LlamaConfig(**common, mlp_bias=False))
 
@@ -47,6 +51,14 @@ def _hf_model(pkg, m):
     qd, kvd = c.n_heads * c.head_size, c.n_kv_heads * c.head_size
     for l in range(c.n_layers):
         g, h = f"blk.{l}.", f"model.layers.{l}."
+        if phi3:  # transformers keeps Phi-3's fused layout too: qkv_proj = [q; k; v] rows, gate_up_proj = [gate; up] rows, rotate-half RoPE
+            sd[h + "self_attn.qkv_proj.weight"] = W(g + "attn_qkv.weight", qd + 2 * kvd, c.dim)
+            sd[h + "self_attn.o_proj.weight"] = W(g + "attn_output.weight", c.dim, qd)
+            sd[h + "mlp.gate_up_proj.weight"] = W(g + "ffn_up.weight", 2 * c.hidden_dim, c.dim)
+            sd[h + "mlp.down_proj.weight"] = W(g + "ffn_down.weight", c.dim, c.hidden_dim)
+            sd[h + "input_layernorm.weight"] = V(g + "attn_norm.weight")
+            sd[h + "post_attention_layernorm.weight"] = V(g + "ffn_norm.weight")
+            continue
         wq, wk = W(g + "attn_q.weight", qd, c.dim), W(g + "attn_k.weight", kvd, c.dim)
         if not qwen:
             wq, wk = _unpermute(wq, c.n_heads), _unpermute(wk, c.n_kv_heads)
@@ -68,7 +80,8 @@ def _hf_model(pkg, m):
 
 
 @pytest.mark.parametrize("shape,quant,tol", [("tiny-llama", "F16", 2e-4), ("tiny-llama-tied", "F16", 2e-4), ("tiny-qwen3", "F16", 2e-4),
-                                             ("tiny-llama", "Q8_0", 5e-2), ("tiny-qwen3", "Q8_0", 5e-2)])
+                                             ("tiny-phi3", "F16", 2e-4), ("tiny-phi3-gqa", "F16", 2e-4),
+                                             ("tiny-llama", "Q8_0", 5e-2), ("tiny-qwen3", "Q8_0", 5e-2), ("tiny-phi3", "Q8_0", 5e-2)])
 def test_oracle_forward_agrees_with_transformers(pkg, orc, make_model, shape, quant, tol):
     n_tok = 20
     m = make_model(shape, getattr(pkg.gguf.GGMLType, quant), 32)
