@@ -474,16 +474,24 @@ template <int MODE> int launch_matvec_f16(b200_plan *p, const DevMat &m, const f
 
 // FP16 plans on the streaming path (stream_matvec_f16.cuh); m2 = ffn_up for SF_GATEUP.
 template <typename... KA, typename... A> int launch_k(b200_plan *p, bool pdl, void (*kern)(KA...), dim3 grid, dim3 block, size_t smem, A... args);
-template <int MODE> int launch_stream_f16(b200_plan *p, const DevMat &m, const DevMat *m2, const float *x, float *out, TraceBuf tr = TraceBuf{nullptr, 0, 0}) {
+int sf_grid(const b200_plan *p, int rows, int cols, bool gateup) { // CTAs of an FP16 streaming launch
+    const int lanes = p->cfg.fp16_lanes;
+    const SfLayout L = sf_layout(rows, cols, lanes, gateup);
+    const int rw = 64 / lanes, mr = gateup ? rw / 2 : rw;
+    const int grid = L.ctas_per_sm * p->n_sms;
+    return grid > rows / mr ? rows / mr : grid;
+}
+template <int MODE> int launch_stream_f16(b200_plan *p, const DevMat &m, const DevMat *m2, const float *x, float *out, TraceBuf tr = TraceBuf{nullptr, 0, 0},
+                                          bool argmax = false) {
     const int lanes = p->cfg.fp16_lanes;
     const SfLayout L = sf_layout(m.rows, m.cols, lanes, MODE == SF_GATEUP);
     if (!L.ok) return fail(p, B200_ERR_STATE, "f16 streaming layout does not fit %d x %d", m.rows, m.cols);
     SfArgs a;
     a.w0 = (const __half *)m.qs; a.w1 = m2 ? (const __half *)m2->qs : nullptr; a.x = x; a.out = out; a.rows = m.rows; a.cols = m.cols;
     a.seg = L.seg; a.nseg = L.nseg; a.stages = L.stages; a.tr = tr;
-    const int rw = 64 / lanes, mr = MODE == SF_GATEUP ? rw / 2 : rw;
-    int grid = L.ctas_per_sm * p->n_sms;
-    if (grid > m.rows / mr) grid = m.rows / mr;
+    a.part_val = argmax ? p->part_val : nullptr;
+    a.part_idx = argmax ? p->part_idx : nullptr;
+    const int grid = sf_grid(p, m.rows, m.cols, MODE == SF_GATEUP);
     if (lanes == 16) return launch_k(p, p->use_pdl, k_stream_matvec_f16<16, MODE>, dim3(grid), dim3(SF_THREADS), L.total, a);
     return launch_k(p, p->use_pdl, k_stream_matvec_f16<8, MODE>, dim3(grid), dim3(SF_THREADS), L.total, a);
 }
@@ -563,6 +571,13 @@ bool gateup_fits(int hidden, int n_sms) { // epilogue buffer holds this CTA's hi
     return 2 * ((hidden / 2) / n_sms + 1) <= SMV_HVALS;
 }
 
+// k_attention's dynamic shared memory: q | k | out | exact-accumulator scratch | score row padded to whole accumulator chunks (the row
+// lives in a global scratch buffer for long contexts).
+size_t att_smem_bytes(int head_size, int ctx, bool scratch) {
+    const int ctx_pad = (ctx + ATT_THREADS - 1) / ATT_THREADS * ATT_THREADS;
+    return (size_t)(3 * head_size + ATT_SEQ_FLOATS + (scratch ? 0 : ctx_pad)) * 4;
+}
+
 // Enqueue one single-token forward on p->stream (captured into a CUDA graph at creation).
 // with_logits=false is the prefill variant (InferenceCoreBatchPrefillDecode.java:166-167).
 int enqueue_forward(b200_plan *p, bool with_logits, int *launches, bool trace = false) {
@@ -598,7 +613,7 @@ int enqueue_forward(b200_plan *p, bool with_logits, int *launches, bool trace = 
         if (rc) return rc; n++;
         float *kc = p->key_cache + (size_t)l * ctx_kv, *vc = p->value_cache + (size_t)l * ctx_kv;
         {
-            const size_t att_smem = (size_t)(3 * c.head_size + (p->att_scratch ? 0 : c.context_length)) * 4;
+            const size_t att_smem = att_smem_bytes(c.head_size, c.context_length, p->att_scratch != nullptr);
             auto att = [&](auto kern) {
                 return launch_k(p, pdl, kern, dim3(p->nh_l), dim3(ATT_THREADS), att_smem, p->qkv, kc, vc, (const StepState *)p->st,
                                 (const float *)p->rope_cr, (const float *)p->rope_ci, p->nh_l, p->nkv_l, p->kflags, (const float *)L.q_norm,
@@ -647,14 +662,15 @@ int enqueue_forward(b200_plan *p, bool with_logits, int *launches, bool trace = 
         n++;
         if (st) rc = launch_stream<SMV_STORE>(p, p->tout, p->xq, p->xs, p->logits, nullptr, nullptr, true, TR(8), -1, 0, -1, 0, rank * p->voc_l);
         else if (q8) rc = launch_matvec_q8<MODE_STORE>(p, p->out, p->xq, p->xs, p->logits);
-        else if (sf) rc = launch_stream_f16<SF_STORE>(p, p->out, nullptr, p->xb, p->logits, TR(8));
+        else if (sf) rc = launch_stream_f16<SF_STORE>(p, p->out, nullptr, p->xb, p->logits, TR(8), true);
         else rc = launch_matvec_f16<MODE_STORE>(p, p->out, p->xb, p->logits);
         if (rc) return rc; n++;
     }
     {
         int rc;
         if ((rc = launch_k(p, pdl, k_argmax_advance, dim3(1), dim3(1024), (size_t)0, (const float *)p->logits, c.vocab_size, p->st, (const int *)p->seq_tokens, p->out_ids, with_logits ? 1 : 0,
-                           (const float *)(st ? p->part_val : nullptr), (const int *)(st ? p->part_idx : nullptr), p->n_sms, TR(9), p->tp, with_logits ? -1 : last_x_op))) return rc;
+                           (const float *)(st || sf ? p->part_val : nullptr), (const int *)(st || sf ? p->part_idx : nullptr),
+                           sf ? sf_grid(p, c.vocab_size, c.dim, false) : p->n_sms, TR(9), p->tp, with_logits ? -1 : last_x_op))) return rc;
         n++;
     }
     if (launches) *launches = n;
@@ -793,7 +809,7 @@ int set_smem_attrs(b200_plan *p) {
     CK(cudaDeviceGetAttribute(&maxdyn, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device));
     if (c.dim > 8192) return fail(p, B200_ERR_UNSUPPORTED, "dim > 8192 not supported by the RMSNorm kernel");
     size_t need_norm = norm_smem_bytes(c.dim, p->norm_v2);
-    size_t need_att = (size_t)(3 * c.head_size + (p->att_scratch ? 0 : c.context_length)) * 4;
+    size_t need_att = att_smem_bytes(c.head_size, c.context_length, p->att_scratch != nullptr);
     int maxcols = c.hidden_dim > c.dim ? c.hidden_dim : c.dim;
     if (p->qd > maxcols) maxcols = p->qd;
     size_t need_mv = q8_smem_bytes(maxcols, 4, 8);
@@ -926,11 +942,19 @@ int build(b200_plan *p, const b200_tensor *tensors, int n_tensors) {
         if ((rc = dalloc(p, &p->blk_cnt, (size_t)(c.hidden_dim / 32) * 4))) return rc;
         CK(cudaMemset(p->blk_cnt, 0, (size_t)(c.hidden_dim / 32) * 4));
     } else if (outw) {
+        if (p->use_f16_stream) { // per-CTA argmax partials of the classifier launch (at most 3 CTAs per SM)
+            if ((rc = dalloc(p, &p->part_val, (size_t)p->n_sms * 4 * 4))) return rc;
+            if ((rc = dalloc(p, &p->part_idx, (size_t)p->n_sms * 4 * 4))) return rc;
+        }
         if ((rc = alloc_matrix(p, p->out, c.vocab_size, c.dim, p->wtype))) return rc;
         if ((rc = upload_matrix(p, outw, c.vocab_size, c.dim, p->out, 0, stage, stage_bytes))) return rc;
     } else {
         if (eff_type(emb->ggml_type) != p->wtype) return fail(p, B200_ERR_UNSUPPORTED, "tied output weight type differs from the matrix type");
         p->out = p->emb;
+        if (p->use_f16_stream) {
+            if ((rc = dalloc(p, &p->part_val, (size_t)p->n_sms * 4 * 4))) return rc;
+            if ((rc = dalloc(p, &p->part_idx, (size_t)p->n_sms * 4 * 4))) return rc;
+        }
     }
     if ((rc = upload_f32(p, find(tensors, n_tensors, "output_norm.weight"), c.dim, &p->out_norm, "output_norm.weight"))) return rc;
 

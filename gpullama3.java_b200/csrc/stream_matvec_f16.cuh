@@ -36,6 +36,8 @@ struct SfArgs {
     int rows, cols;        // of ONE matrix
     int seg, nseg;         // columns per stage, stages per row
     int stages;            // ring depth per warp
+    float *part_val;       // SF_STORE on the classifier: per-CTA (max, first index) of the rows this CTA produced (FloatTensor.argmax, first
+    int *part_idx;         // strict maximum), merged by k_argmax_advance instead of a pass over all logits; nullptr otherwise
     TraceBuf tr;
 };
 
@@ -134,6 +136,8 @@ __global__ void __launch_bounds__(SF_THREADS) k_stream_matvec_f16(SfArgs a) {
 
     const int r = lane / LPR, u = lane % LPR;
     float acc0 = 0.0f, acc1 = 0.0f; // chains 2u and 2u+1 of row slot r
+    float best = -INFINITY;          // (a lane's rows ascend, so a strict comparison keeps the first maximum)
+    int best_i = 0x7fffffff;
     for (int k = 0; k < n_items; k++) {
         const int st = k % S, gi = k / nseg, s = k - gi * nseg;
         mbar_wait(bar0 + 8u * st, (unsigned)(k / S) & 1u);
@@ -162,8 +166,26 @@ __global__ void __launch_bounds__(SF_THREADS) k_stream_matvec_f16(SfArgs a) {
                 if (r < MR && u == 0) a.out[row] = swiglu(result, up);
             } else if (u == 0) {
                 a.out[row] = MODE == SF_RESID ? __fadd_rn(a.out[row], result) : result; // x[i] = x[i] + xb2[i] (InferenceCore.java:143,164)
+                if (MODE == SF_STORE && result > best) { best = result; best_i = (int)row; }
             }
             acc0 = acc1 = 0.0f;
+        }
+    }
+    if (MODE == SF_STORE && a.part_val) { // uniform over the grid
+        __shared__ float pv[SF_WARPS];
+        __shared__ int pi[SF_WARPS];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+            argmax_merge(best, best_i, ov, oi);
+        }
+        if (lane == 0) { pv[warp] = best; pi[warp] = best_i; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < SF_WARPS; w++) argmax_merge(best, best_i, pv[w], pi[w]);
+            a.part_val[blockIdx.x] = best;
+            a.part_idx[blockIdx.x] = best_i;
         }
     }
     trace_mark(a.tr, 3);

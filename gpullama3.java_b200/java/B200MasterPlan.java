@@ -69,7 +69,8 @@ public final class B200MasterPlan implements AutoCloseable {
     private final MemorySegment logits;   // vocab floats, reused every token (state.wrapLogits in the reference)
     private final MemorySegment argmax;
 
-    /** TornadoVMMasterPlan.initializeTornadoVMPlan(state, model): tensors are the plain mmap slices of GGUF.loadTensorsStandard. */
+    /** TornadoVMMasterPlan.initializeTornadoVMPlan(state, model): tensors are the plain mmap slices of GGUF.loadTensorsStandard.
+     *  archId: 0 = Llama / Mistral, 1 = Qwen3, 2 = Phi-3 (pass blk.N.attn_qkv.weight and blk.N.ffn_up.weight fused, as in the file). */
     public B200MasterPlan(State state, Model model, Map<String, GGMLTensorEntry> tensors, int archId, int headSize) throws Throwable {
         this(state, model, tensors, archId, headSize, 0, 1);
     }
@@ -93,7 +94,7 @@ public final class B200MasterPlan implements AutoCloseable {
             MemorySegment t = arr.asSlice((long) i * TENSOR.byteSize(), TENSOR.byteSize());
             t.set(ADDRESS, 0, arena.allocateFrom(e.getKey()));
             t.set(ADDRESS, 8, e.getValue().memorySegment());       // MemorySegment.address() of the mapping
-            t.set(JAVA_INT, 16, e.getValue().ggmlType().ordinal()); // GGMLType ordinal == ggml type id for F32/F16/Q8_0
+            t.set(JAVA_INT, 16, e.getValue().ggmlType().ordinal()); // GGMLType ordinal == ggml type id (F32 0, F16 1, Q8_0 8, Q4_K 12, Q5_K 13, Q6_K 14: GGMLType.java:5-20); K-quants are re-quantised on the device
             int[] shape = e.getValue().shape();
             t.set(JAVA_INT, 20, shape.length);
             for (int d = 0; d < shape.length; d++) t.set(JAVA_LONG, 24 + 8L * d, shape[d]);

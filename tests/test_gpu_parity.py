@@ -253,6 +253,44 @@ def test_long_context_score_row_in_global_memory(pkg, orc, make_model):
         run_stream(pkg, orc, m, 16, 6, check_kv=False, mode=mode)
 
 
+@pytest.mark.parametrize("shape,quant,ctx,mode", [("tiny-llama", "Q8_0", 704, "graph"), ("tiny-llama", "Q8_0", 704, "persistent"),
+                                                  ("tiny-qwen3", "Q8_0", 704, "graph"), ("tiny-qwen3", "Q8_0", 704, "persistent"),
+                                                  ("tiny-phi3", "Q8_0", 704, "graph"), ("tiny-llama", "F16", 704, "graph"),
+                                                  ("tiny-llama", "Q8_0", 20000, "graph"), ("tiny-qwen3", "Q8_0", 20000, "persistent")])
+def test_deep_context_bit_exact(pkg, orc, make_model, shape, quant, ctx, mode):
+    """Depth: 700 positions.  Past 128 keys the attention kernel's score and weighted-sum loops run several software-pipelined passes
+    (next pass's K / V rows in flight during the current chain), from 512 keys on the softmax sum is the exact parallel accumulator, the
+    K/V rows are bulk-prefetched into L2 ahead of the dependency wait; with a 20000-token context the score row lives in global memory.
+    Logits are compared on both sides of every switch-over (127|128|129 keys, 255|256|257, 511|512|513, ...) and at the end; the KV cache
+    of all 700 positions must be bit-equal.  Head sizes 64 (Llama), 128 (Qwen3: q/k norm, NeoX), 96 (Phi-3)."""
+    m = make_model(shape, getattr(pkg.gguf.GGMLType, quant), ctx)
+    c = m.configuration
+    plan = pkg.B200MasterPlan.initialize_plan(m)
+    set_mode(pkg, plan, mode)
+    om = orc.OracleModel(m, lanes=16)
+    n = 700
+    check = {0, 1, 126, 127, 128, 129, 254, 255, 256, 257, 383, 384, 510, 511, 512, 513, 639, 640, 641, 698, 699}
+    toks = orc.bench_tokens(c.vocab_size, n)
+    try:
+        for pos in range(n):
+            tok = int(toks[pos])
+            if pos in check:
+                lg, am = plan.forward_decode(tok, pos)
+                ref = om.forward(tok, pos)
+                assert_bit_equal(lg, ref, f"logits at position {pos}")
+                assert am == orc.argmax(ref)
+            else:
+                plan.forward_prefill(tok, pos)
+                om.forward(tok, pos, want_logits=False)
+        nkv = n * c.kv_dim
+        for l in range(c.n_layers):
+            assert_bit_equal(plan.read_buffer("key_cache", c.context_length * c.kv_dim, layer=l)[:nkv], om.key_cache(l)[:nkv], f"key cache layer {l}")
+            assert_bit_equal(plan.read_buffer("value_cache", c.context_length * c.kv_dim, layer=l)[:nkv], om.value_cache(l)[:nkv], f"value cache layer {l}")
+    finally:
+        plan.free()
+        om.close()
+
+
 @pytest.mark.parametrize("mode", MODES)
 def test_kv_reset_and_determinism(pkg, orc, make_model, mode):
     m = make_model("tiny-qwen3", pkg.gguf.GGMLType.Q8_0, 24)
