@@ -214,3 +214,27 @@ def test_native_is_faster_than_the_restatement(pkg, tor, vocabs):
     assert a == b
     print(f"\nnative {len(a) / (t1 - t0):,.0f} tok/s, restatement {len(b) / (t2 - t1):,.0f} tok/s on {len(text)} chars")
     assert (t1 - t0) < (t2 - t1)
+
+
+def test_encode_agrees_with_huggingface_tokenizers(pkg, tor, vocabs):
+    """THIRD-PARTY pin (SURVEY 8(f) N2 was checked only against this repository's own restatement): Hugging Face `tokenizers` (the Rust
+    BPE) configured with the reference's pipeline ORDER -- byte-level symbol mapping first, THEN the pre-tokenisation regex on the mapped
+    text (LlamaTokenizer.java:164-200 does exactly this, which is why words are not split at spaces there), then BPE over the chunk --
+    produces the same ids as the native tokenizer and as the oracle on the synthetic vocabularies (whose token ids are in merge order, so
+    'lowest merged-token id first' and 'lowest merge rank first' coincide).  Independent implementations of the regex (Oniguruma vs the
+    native matcher vs Python `regex`) and of the merge loop."""
+    hf = pytest.importorskip("tokenizers")
+    for arch in ("llama", "qwen3"):
+        tokens, merges, types, base = vocabs[arch]
+        ours, oracle = make_pair(pkg, tor, vocabs, arch)
+        pattern = tor.LLAMA_3_PATTERN if arch == "llama" else tor.QWEN3_PATTERN
+        tk = hf.Tokenizer(hf.models.BPE(vocab={t: i for i, t in enumerate(tokens)}, merges=[tuple(m.split(" ")) for m in merges]))
+        tk.pre_tokenizer = hf.pre_tokenizers.Sequence([hf.pre_tokenizers.ByteLevel(add_prefix_space=False, use_regex=False),
+                                                       hf.pre_tokenizers.Split(hf.Regex(pattern), behavior="isolated")])
+        n_tok = 0
+        for text in random_texts(300, 77):
+            want = tk.encode(text, add_special_tokens=False).ids
+            assert ours.encode(text) == want, (arch, text)
+            assert oracle.encode(text) == want, (arch, text)
+            n_tok += len(want)
+        assert n_tok > 5000
