@@ -406,7 +406,6 @@ __global__ void k_swiglu(float *__restrict__ hb, const float *__restrict__ hb2, 
 // FP32 cache.  Output as floats (xb) and/or quantised to Q8_0 (activation of the Wo matvec).
 // ------------------------------------------------------------------------------------------
 #define ATT_THREADS 512 // four threads per key (scores) and per output element (weighted sum): head size <= ATT_THREADS / 4
-#define ATT_SEQ_FLOATS ((int)((seqsum2_scratch_bytes(ATT_THREADS) + 15) / 16 * 4)) // exact-accumulator scratch in front of the score row
 
 template <int HS>
 __global__ void __launch_bounds__(ATT_THREADS) k_attention(float *__restrict__ qkv, float *__restrict__ kc, float *__restrict__ vc,
@@ -416,40 +415,29 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attention(float *__restrict__ q
                                                           float eps, float sqrt_hs, int8_t *__restrict__ xq,
                                                           float *__restrict__ xs, float *__restrict__ xb, TraceBuf tr, TpCtx tp,
                                                           unsigned tp_out_op, int head_base, float *att_scratch, int ctx) {
-    extern __shared__ __align__(16) float sm[]; // q[HS] | k[HS] | out[HS] | accumulator scratch | att[ctx_pad] (att in global scratch for long contexts)
+    extern __shared__ __align__(16) float sm[]; // q[HS] | k[HS] | out[HS] | att[ctx] (att in global scratch for long contexts)
     __shared__ float red[ATT_THREADS / 32];
     __shared__ float s_val[2];
     float *sq = sm, *sk = sm + HS, *so = sm + 2 * HS;
-    unsigned char *seq_scratch = reinterpret_cast<unsigned char *>(sm + 3 * HS);
-    const int ctx_pad = (ctx + ATT_THREADS - 1) / ATT_THREADS * ATT_THREADS; // score rows padded to whole accumulator chunks
-    float *att = att_scratch ? att_scratch + (size_t)blockIdx.x * ctx_pad : sm + 3 * HS + ATT_SEQ_FLOATS;
+    float *att = att_scratch ? att_scratch + (size_t)blockIdx.x * ctx : sm + 3 * HS;
     const int h = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int HALF = HS / 2;
     trace_entry(tr);
     pdl_launch_dependents();
     const int kv_mul = n_heads / n_kv_heads, kvh = h / kv_mul;
     const int qd = n_heads * HS, kvd = n_kv_heads * HS;
-    // K/V rows of the earlier positions -> L2 with a handful of bulk prefetches, BEFORE the dependency wait: those rows were written by
-    // earlier tokens (st->pos only changes between graph launches), so they can stream in while the QKV matvec is still running.  The
-    // rows [0, pos) of all KV heads are one contiguous span per cache; the CTAs split it.  (Round 2 first used one prefetch.global.L2
-    // per 128-byte line after the wait: at depth 4096 that is 32 Ki LSU requests per CTA in front of the first score load.)
-    {
-        const int ppos = st->pos;
-        const size_t span = (size_t)ppos * kvd * 4;
-        const size_t per = ((span + gridDim.x - 1) / gridDim.x + 15) & ~(size_t)15;
-        const size_t b0 = (size_t)blockIdx.x * per, b1 = b0 + per < span ? b0 + per : span;
-        constexpr size_t CH = 16384;
-        for (size_t o = b0 + (size_t)tid * CH; o < b1; o += (size_t)ATT_THREADS * CH) {
-            const unsigned n = (unsigned)((b1 - o < CH ? b1 - o : CH) & ~(size_t)15);
-            if (n) {
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const unsigned char *>(kc) + o), "r"(n) : "memory");
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const unsigned char *>(vc) + o), "r"(n) : "memory");
-            }
-        }
-    }
     pdl_wait();
     trace_mark(tr, 2);
     const int pos = st->pos, nt = pos + 1;
+    { // K/V rows of the earlier positions -> L2, one 128-byte line per request, so the score loads below hit L2 (the weight stream carries an
+      // evict_first policy; without the prefetch these rows come from HBM every layer)
+        constexpr int LINES = HS / 32;
+        for (int i = tid; i < pos * LINES; i += ATT_THREADS) {
+            const size_t off = (size_t)(i / LINES) * kvd + kvh * HS + (i % LINES) * 32;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(kc + off));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(vc + off));
+        }
+    }
     const float *qsrc = qkv + h * HS, *ksrc = qkv + qd + kvh * HS, *vsrc = qkv + qd + kvd + kvh * HS;
     // ---- prologue: threads [0,HALF) rotate q pairs, threads [HALF,HS) rotate k pairs
     if (tid < HS) {
@@ -502,48 +490,42 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attention(float *__restrict__ q
     }
     __syncthreads();
     // ---- scores (scalarDot, FloatTensor.java:86-92: one sequential unfused mul/add chain per key).  Four threads share a key: each loads
-    // ITS quarter of the K row at once, then the chain runs through the quad in element order, handed on by shuffle.
-    // Two register buffers, software-pipelined (deep contexts are otherwise one dependent L2 round trip per 128 keys / rows):
-    //   ka = the current K quarter during the scores, the NEXT V block during the weighted sum;
-    //   nb = the NEXT K quarter during the scores of a context deeper than one pass -- or, for a context of at most one pass, the V rows of
-    //        the first round of the weighted sum, requested before the scores (they do not depend on them) -- then the current V block.
+    // ITS quarter of the K row at once (one round trip per pass of ATT_THREADS/4 keys), then the chain runs through the quad in element
+    // order, handed on by shuffle.  The V rows of the first round of the weighted sum are requested here too (they do not depend on the scores).
     constexpr int QE = HS / 4, QV = HS / 16, VB = 32;
-    constexpr bool PIPE = HS <= 128; // (head size 256 would need 2 x 64 registers for the K buffers)
-    static_assert(!PIPE || QE <= VB, "the pipelined form keeps a K quarter in a V-block-sized buffer");
-    constexpr int KB = PIPE ? VB : QE;
     const int quad = tid & 3, qbase = lane & ~3, vd = tid >> 2;
     const bool vlive = vd < HS;
-    const bool deep = PIPE && nt > ATT_THREADS / 4;
-    float ka[KB], nb[VB];
-    auto load_k = [&](float *dst, int t) { // this thread's quarter of key t (cache, the current position from shared memory, or zeros past the end)
-        if (t < pos) {
-            const float4 *k = reinterpret_cast<const float4 *>(kc + (size_t)t * kvd + kvh * HS + quad * QE);
+    float vv[VB];
+    {
+        const float *vcol = vc + kvh * HS + vd;
 #pragma unroll
-            for (int u = 0; u < QV; u++) { const float4 v = __ldg(k + u); dst[4 * u] = v.x; dst[4 * u + 1] = v.y; dst[4 * u + 2] = v.z; dst[4 * u + 3] = v.w; }
-        } else {
-#pragma unroll
-            for (int u = 0; u < QE; u++) dst[u] = t == pos ? sk[quad * QE + u] : 0.0f;
-        }
-    };
-    auto load_v = [&](float *dst, const float *vcol, bool live, int vt0) { // rows [vt0, vt0 + 32) of this thread's output element
-#pragma unroll
-        for (int u = 0; u < VB; u++) dst[u] = (live && vt0 + u < pos) ? __ldg(vcol + (size_t)(vt0 + u) * kvd) : 0.0f;
-    };
-    load_k(ka, tid >> 2);
-    if (!deep) load_v(nb, vc + kvh * HS + vd, vlive, quad * VB);
+        for (int u = 0; u < VB; u++) vv[u] = (vlive && quad * VB + u < pos) ? __ldg(vcol + (size_t)(quad * VB + u) * kvd) : 0.0f;
+    }
     float lmax = -INFINITY;
 #pragma unroll 1
     for (int t0 = 0; t0 < nt; t0 += ATT_THREADS / 4) {
         const int t = t0 + (tid >> 2);
-        const bool more = t0 + ATT_THREADS / 4 < nt;
-        if (PIPE) { if (deep && more) load_k(nb, t + ATT_THREADS / 4); } // next pass: in flight while this pass's chain runs
+        float4 kk[QV];
+        if (t < pos) {
+            const float4 *k = reinterpret_cast<const float4 *>(kc + (size_t)t * kvd + kvh * HS + quad * QE);
+#pragma unroll
+            for (int u = 0; u < QV; u++) kk[u] = __ldg(k + u);
+        } else {
+#pragma unroll
+            for (int u = 0; u < QV; u++) kk[u] = t == pos ? *reinterpret_cast<const float4 *>(sk + quad * QE + 4 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         float acc = 0.0f;
 #pragma unroll 1
         for (int qd4 = 0; qd4 < 4; qd4++) {
             if (quad == qd4) {
                 const float *qq = sq + qd4 * QE;
 #pragma unroll
-                for (int u = 0; u < QE; u++) acc = __fadd_rn(acc, __fmul_rn(qq[u], ka[u]));
+                for (int u = 0; u < QV; u++) {
+                    acc = __fadd_rn(acc, __fmul_rn(qq[4 * u + 0], kk[u].x));
+                    acc = __fadd_rn(acc, __fmul_rn(qq[4 * u + 1], kk[u].y));
+                    acc = __fadd_rn(acc, __fmul_rn(qq[4 * u + 2], kk[u].z));
+                    acc = __fadd_rn(acc, __fmul_rn(qq[4 * u + 3], kk[u].w));
+                }
             }
             acc = __shfl_sync(0xffffffffu, acc, qbase + qd4);
         }
@@ -551,12 +533,6 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attention(float *__restrict__ q
             const float s = __fdiv_rn(acc, sqrt_hs);
             att[t] = s;
             lmax = fmaxf(lmax, s);
-        }
-        if (more) {
-            if (PIPE) {
-#pragma unroll
-                for (int u = 0; u < QE; u++) ka[u] = nb[u];
-            } else load_k(ka, t + ATT_THREADS / 4);
         }
     }
     lmax = warp_max_f(lmax);
@@ -566,25 +542,23 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attention(float *__restrict__ q
 #pragma unroll
     for (int w = 1; w < ATT_THREADS / 32; w++) mx = fmaxf(mx, red[w]);
     for (int t = tid; t < nt; t += ATT_THREADS) att[t] = (float)exp((double)__fsub_rn(att[t], mx));
-    // sequential float sum (FloatTensor.softmaxInPlace, FloatTensor.java:211-219): short rows by one thread, long rows with the exact
-    // parallel accumulator (seqsum2.cuh; the terms are non-negative), as in the persistent kernel
-    float sum;
-    if (nt >= 512) {
-        const int E = (nt + ATT_THREADS - 1) / ATT_THREADS;
-        for (int t = nt + tid; t < ATT_THREADS * E; t += ATT_THREADS) att[t] = 0.0f;
-        __syncthreads();
-        sum = block_seqsum_exact_v2_t<ATT_THREADS>(att, nt, seqsum2_carve(seq_scratch, ATT_THREADS), tid, SeqSum2BlockSync());
-    } else {
-        __syncthreads();
-        if (tid == 0) s_val[0] = seq2_literal(0.0f, att, nt, (reinterpret_cast<uintptr_t>(att) & 15) == 0);
-        __syncthreads();
-        sum = s_val[0];
+    __syncthreads();
+    if (tid == 0) {
+        float sum = 0.0f;
+        int t = 0;
+        for (; t + 4 <= nt; t += 4) {
+            const float a0 = att[t], a1 = att[t + 1], a2 = att[t + 2], a3 = att[t + 3];
+            sum = __fadd_rn(sum, a0); sum = __fadd_rn(sum, a1); sum = __fadd_rn(sum, a2); sum = __fadd_rn(sum, a3);
+        }
+        for (; t < nt; t++) sum = __fadd_rn(sum, att[t]);
+        s_val[0] = sum;
     }
+    __syncthreads();
+    const float sum = s_val[0];
     for (int t = tid; t < nt; t += ATT_THREADS) att[t] = __fdiv_rn(att[t], sum);
     __syncthreads();
     // ---- output: xb = sum_t a_t * v_t sequentially over t per element (saxpyInPlace, FloatTensor.java:221-227); four threads per element, thread
-    // `quad` holds rows [128 r + 32 quad, +32) of round r, the chain runs through the quad in row order; the next round's rows are requested
-    // before the chain of the current round starts
+    // `quad` holds rows [128 r + 32 quad, +32) of round r, the chain runs through the quad in row order
 #pragma unroll 1
     for (int vd0 = 0; vd0 < HS; vd0 += ATT_THREADS / 4) { // one pass for head sizes up to 128
         const int d = vd0 + vd;
@@ -592,26 +566,22 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attention(float *__restrict__ q
         const float *vcol = vc + kvh * HS + d;
         const float vcur = live ? vsrc[d] : 0.0f; // current position: straight from the packed qkv vector
         float acc = 0.0f;
-        if (deep || vd0 > 0) load_v(nb, vcol, live, quad * VB); // (a shallow context requested round 0 of the first pass before the scores)
 #pragma unroll 1
         for (int r0 = 0; r0 < pos; r0 += 4 * VB) {
-            const bool more = r0 + 4 * VB < pos;
-            if (PIPE) { if (more) load_v(ka, vcol, live, r0 + 4 * VB + quad * VB); }
+            if (r0 > 0 || vd0 > 0) { // (round 0 of the first pass was requested before the scores)
+                const int vt0 = r0 + quad * VB;
+#pragma unroll
+                for (int u = 0; u < VB; u++) vv[u] = (live && vt0 + u < pos) ? __ldg(vcol + (size_t)(vt0 + u) * kvd) : 0.0f;
+            }
 #pragma unroll 1
             for (int qd4 = 0; qd4 < 4; qd4++) {
                 if (quad == qd4) {
                     const int vt0 = r0 + qd4 * VB;
 #pragma unroll
                     for (int u = 0; u < VB; u++)
-                        if (vt0 + u < pos) acc = __fadd_rn(__fmul_rn(att[vt0 + u], nb[u]), acc);
+                        if (vt0 + u < pos) acc = __fadd_rn(__fmul_rn(att[vt0 + u], vv[u]), acc);
                 }
                 acc = __shfl_sync(0xffffffffu, acc, qbase + qd4);
-            }
-            if (more) {
-                if (PIPE) {
-#pragma unroll
-                    for (int u = 0; u < VB; u++) nb[u] = ka[u];
-                } else load_v(nb, vcol, live, r0 + 4 * VB + quad * VB);
             }
         }
         if (live && quad == 0) {

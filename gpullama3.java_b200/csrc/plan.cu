@@ -571,12 +571,8 @@ bool gateup_fits(int hidden, int n_sms) { // epilogue buffer holds this CTA's hi
     return 2 * ((hidden / 2) / n_sms + 1) <= SMV_HVALS;
 }
 
-// k_attention's dynamic shared memory: q | k | out | exact-accumulator scratch | score row padded to whole accumulator chunks (the row
-// lives in a global scratch buffer for long contexts).
-size_t att_smem_bytes(int head_size, int ctx, bool scratch) {
-    const int ctx_pad = (ctx + ATT_THREADS - 1) / ATT_THREADS * ATT_THREADS;
-    return (size_t)(3 * head_size + ATT_SEQ_FLOATS + (scratch ? 0 : ctx_pad)) * 4;
-}
+// k_attention's dynamic shared memory: q | k | out | score row (the row lives in a global scratch buffer for long contexts).
+size_t att_smem_bytes(int head_size, int ctx, bool scratch) { return (size_t)(3 * head_size + (scratch ? 0 : ctx)) * 4; }
 
 // Enqueue one single-token forward on p->stream (captured into a CUDA graph at creation).
 // with_logits=false is the prefill variant (InferenceCoreBatchPrefillDecode.java:166-167).
