@@ -9,9 +9,11 @@ LlamaBench.java:188-193) over a seeded synthetic GGUF-layout model of the real L
                CUDA-event time on the plan's stream, max over ranks)
   e2e          tok/s through the reference-facing call b200_forward_decode with HOST buffers:
                every step copies the token/position H2D and the argmax D2H inside the timed region
-  roofline     the WHOLE decode step (one persistent kernel per token: the dominant kernel IS the step):
+  roofline     the WHOLE decode step (default: one CUDA graph of 227 kernels per token; --decode-mode persistent: one kernel):
                achieved = algorithmic bytes per token / device time per token, peak = MEASURED_PEAKS.json
-               hbm_gbs; the stand-alone streaming matvecs are listed under roofline.other_kernels
+               hbm_gbs; per launch = per token / kernels per token; the stand-alone streaming matvecs (the dominant
+               kernels by bytes and time, timed live with CUDA events on the plan's stream) are listed under
+               roofline.other_kernels; traffic = measured DRAM bytes per launch from the committed ncu capture
   cpu_baseline the oracle (CPU restatement of the reference's onGPU=false path) on this box's
                host cores, bounded sample
   parity       in the same run: greedy ids of the first steps GPU == oracle, max|dlogit| of step 0
@@ -326,11 +328,11 @@ def main():
     if world == 1:  # the stand-alone streaming matvecs of the graph path, for context (b200_time_kernel, PDL off)
         for which, name in ((0, "gate_up"), (1, "down_proj"), (2, "qkv"), (3, "attn_out"), (4, "lm_head")):
             m, b = plan.time_kernel(which, reps=3 if which != 4 else 1)
-            per_kernel[name] = {"ms": m, "GB/s": b / (m / 1e3) / 1e9, "bytes": b}
+            per_kernel[name] = {"ms": m, "GB/s": b / (m / 1e3) / 1e9, "bytes": b, "frac": b / (m / 1e3) / 1e9 / peak}
     persistent = dmode == 1
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r2_decode_traffic.json")  # dram bytes per launch from the committed ncu --set full capture
-    if world == 1 and WORKLOAD == "llama-3-8b" and os.path.exists(tpath):
+    if world == 1 and WORKLOAD == "llama-3-8b" and QUANT == "q8_0" and os.path.exists(tpath):
         with open(tpath) as f:
             traffic = json.load(f).get("persistent" if persistent else "graph")
     line = {
