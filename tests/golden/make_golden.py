@@ -28,6 +28,7 @@ with tempfile.TemporaryDirectory() as d:
     out = {}
     for shape, quant, lanes in test_oracle._golden_cases(pkg):
         out[f"{shape}/{pkg.gguf.GGMLType.NAMES[quant]}/lanes{lanes}"] = test_oracle.golden_run(orc, pkg, make_model, shape, quant, lanes)
+    out["kquant_to_q8_0"] = test_oracle.kquant_golden(orc, pkg)
 with open(os.path.join(os.path.dirname(__file__), "oracle_golden.json"), "w") as f:
     json.dump(out, f, indent=1)
 print(json.dumps(out, indent=1))

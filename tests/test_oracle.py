@@ -164,7 +164,18 @@ def test_rope_table(orc):
 
 def _golden_cases(pkg):
     Q, F = pkg.gguf.GGMLType.Q8_0, pkg.gguf.GGMLType.F16
-    return [("tiny-llama", Q, 16), ("tiny-llama-tied", F, 16), ("tiny-llama", F, 8), ("tiny-llama", F, 0), ("tiny-qwen3", Q, 16), ("tiny-qwen3", F, 16)]
+    return [("tiny-llama", Q, 16), ("tiny-llama-tied", F, 16), ("tiny-llama", F, 8), ("tiny-llama", F, 0), ("tiny-qwen3", Q, 16), ("tiny-qwen3", F, 16),
+            ("tiny-phi3", Q, 16), ("tiny-phi3-gqa", F, 16)]
+
+
+def kquant_golden(orc, pkg):
+    """sha256 of the Q8_0 bytes the K-quant re-quantiser produces for seeded synthetic super-blocks (ModelLoader.java:173-224)."""
+    out = {}
+    for name in ("Q4_K", "Q5_K", "Q6_K"):
+        tt = getattr(pkg.gguf.GGMLType, name)
+        raw = pkg.synth.random_kquant(tt, 256 * 64, np.random.Generator(np.random.PCG64(tt)), zero_blocks=1)
+        out[name] = {"src_sha256": hashlib.sha256(raw.tobytes()).hexdigest(), "q8_0_sha256": hashlib.sha256(orc.kquant_to_q8_0(tt, raw, 256 * 64).tobytes()).hexdigest()}
+    return out
 
 
 def golden_run(orc, pkg, make_model, shape, quant, lanes, n=12):
@@ -189,6 +200,7 @@ def test_golden_fixture(orc, pkg, make_model):
         key = f"{shape}/{pkg.gguf.GGMLType.NAMES[quant]}/lanes{lanes}"
         got = golden_run(orc, pkg, make_model, shape, quant, lanes)
         assert got == gold[key], key
+    assert kquant_golden(orc, pkg) == gold["kquant_to_q8_0"]
 
 
 def test_sampler_restatements_agree(pkg, orc):
