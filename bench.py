@@ -351,6 +351,9 @@ def main():
                      "bytes_per_launch": step_bytes if persistent else step_bytes / launches_per_step, "ms_per_launch": ms / K if persistent else ms / K / launches_per_step,
                      "algorithmic_bytes_per_token": ab, "traffic": traffic,
                      "persistent_kernel": {"ring_stages": ring_stages, "smem_bytes": pd_smem} if persistent else None,
+                     "dominant_kernel": ({"name": ("k_stream_matvec_q8<GATEUP>" if QUANT == "q8_0" else "k_stream_matvec_f16<GATEUP>") + " (gate/up + SwiGLU: the largest share of the step's bytes and time), stand-alone, CUDA events on the plan's stream",
+                                          "achieved": per_kernel["gate_up"]["GB/s"], "peak": peak, "unit": "GB/s", "frac": per_kernel["gate_up"]["frac"],
+                                          "bytes_per_launch": per_kernel["gate_up"]["bytes"], "ms_per_launch": per_kernel["gate_up"]["ms"]} if "gate_up" in per_kernel else None),
                      "other_kernels": per_kernel},
         "load": {"synthesise_s": gen_s, "upload_repack_s": load_s, "device_bytes": plan.device_bytes, "pipeline": plan.upload_info()},
     }
